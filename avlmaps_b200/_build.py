@@ -1,0 +1,83 @@
+"""In-tree build of libavlmaps_b200.so (sm_100a only).
+
+`python -m avlmaps_b200._build` or `build()`; nvcc cross-compiles without a GPU.  The .so sits
+next to this file so that it travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OBJ = PKG.parent / "build" / "obj"
+LIB = PKG / "libavlmaps_b200.so"
+
+SOURCES = ["sim_screen.cu", "sim_exact.cu", "index_api.cu", "build_kernels.cu", "build_api.cu", "heat_kernels.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--cudart", "static",
+    # geometry kernels rely on exact, uncontracted fp64 arithmetic; they also use explicit
+    # __dmul_rn/__dadd_rn, this flag is the belt to those braces
+    "-fmad=false",
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: avlmaps_b200 has no CPU fallback and cannot be built")
+    return exe
+
+
+def _stamp(paths) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+    deps = srcs + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "avlmaps_b200.h"]
+    stamp_file = OBJ / "stamp"
+    stamp = _stamp(deps)
+    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return LIB
+    OBJ.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for s in srcs:
+        o = OBJ / (s.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for s, o, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s.name}")
+        objs.append(str(o))
+    cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC", "-o", str(LIB), *objs]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link of libavlmaps_b200.so failed")
+    stamp_file.write_text(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

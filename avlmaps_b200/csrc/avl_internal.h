@@ -1,0 +1,114 @@
+// Internal declarations shared by the translation units of libavlmaps_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/avlmaps_b200.h"
+
+namespace avl {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define AVL_CUDA(expr)                                                      \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) return ::avl::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define AVL_ARG(cond, msg)               \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::avl::set_error(msg);             \
+      return AVL_ERR_ARG;                \
+    }                                    \
+  } while (0)
+
+// ---- screen kernel (sim_screen.cu) -----------------------------------------
+enum ScreenMode : int32_t { kModeDense = 0, kModeArgmax = 1, kModeThresh = 2 };
+
+constexpr int kTileRows = 128;   // rows (voxels) per CTA per tile = UMMA M per CTA
+constexpr int kBlockK = 64;      // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kStageBytes = kTileRows * kBlockK * 2;  // 16 KiB of A per pipeline stage
+constexpr int kFlagWords = 8;    // candidate bitmask words per flagged row (256 queries)
+
+struct ScreenParams {
+  int64_t n_rows;        // rows of the map
+  int32_t kblocks;       // dpad / 64
+  int32_t nq;            // valid query columns
+  int32_t npad;          // UMMA N (multiple of 16, <= 256); B has npad rows
+  int32_t num_tiles;     // row tiles (of 128*CG rows) this launch processes
+  int32_t tile_stride;   // launch tile j covers map tile j * tile_stride (sampling)
+  int32_t stages;        // A pipeline depth
+  int32_t mode;          // ScreenMode
+  int32_t normalize;     // divide by the fp32 row norm
+  // per-row statistics (map_prepare): see DESIGN.md "error band"
+  const float* row_norm;   // ||a_i||  (fp32 row, fp64-accumulated)
+  const float* row_c;      // >= ||a_i - bf16(a_i)|| + kappa * ||bf16(a_i)||
+  const float* row_an;     // >= ||bf16(a_i)||
+  // per-query statistics (query_prepare)
+  const float* q_bn;       // >= ||b_q||
+  const float* q_glob;     // [0] rho >= max_q ||b_q - bf16(b_q)|| / ||b_q|| (+slack), [1] max_q q_bn
+  // kModeDense
+  float* dense_out;        // element (r, q) at r * dense_rs + q * dense_cs, r = compact row
+  int64_t dense_rs, dense_cs;
+  int32_t dense_cols;      // columns to store (nq or npad)
+  // kModeArgmax
+  int32_t* argmax_out;     // (n_rows,)
+  uint32_t* flag_count;    // [1]
+  uint32_t* flag_rows;     // [flag_cap]
+  uint32_t* flag_masks;    // [flag_cap][kFlagWords]
+  uint32_t flag_cap;
+  // kModeThresh
+  const float* thr_t;      // per query tau_q / scale_q  (+inf disables a query)
+  uint32_t* cand_cnt;      // [nq]
+  uint32_t* cand_idx;      // [nq][cand_cap]
+  float* cand_val;         // [nq][cand_cap]
+  uint32_t cand_cap;
+  // watchdog record (host-mapped), may be null
+  uint32_t* dbg;
+};
+
+// Launch the tcgen05 screen.  tmap_a / tmap_b are CUtensorMap (128 bytes each).
+int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const ScreenParams& p,
+                  int num_sms, size_t smem_bytes, cudaStream_t stream);
+size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages);
+int screen_pick_stages(int cta_group, int npad, int kblocks);  // <=0: does not fit
+
+// ---- exact / helper kernels (sim_exact.cu) --------------------------------
+int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
+                       float* row_norm, float* row_c, float* row_an, float kappa, cudaStream_t s);
+int launch_query_prepare(const float* q, int32_t nq, int32_t d, int32_t dpad, int32_t npad,
+                         __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s);
+int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq,
+                       const float* scale, const float* row_norm, int normalize, float* out,
+                       int64_t out_rs, int64_t out_cs, cudaStream_t s);
+int launch_argmax_rerank(const float* feat, int32_t d, const float* q, int32_t nq, const float* scale,
+                         const float* row_norm, int normalize, const uint32_t* flag_count,
+                         const uint32_t* flag_rows, const uint32_t* flag_masks, uint32_t flag_cap,
+                         int32_t* argmax_out, int num_sms, cudaStream_t s);
+int launch_select_threshold(float* sample_t, int32_t n_sample_rows, int64_t ld, int32_t nq, int32_t k,
+                            int32_t unit_rows, int32_t tile_stride, int64_t n_rows,
+                            const float* row_norm, const float* row_c, const float* row_an,
+                            const float* q_bn, const float* q_glob, int normalize, float* thr_t,
+                            cudaStream_t s);
+int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
+                         const float* scale, const float* row_norm, const float* row_c,
+                         const float* row_an, const float* q_bn, const float* q_glob, int normalize,
+                         int32_t k, const uint32_t* cand_cnt, const uint32_t* cand_idx, const float* cand_val,
+                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
+                         cudaStream_t s);
+int launch_topk_vector(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val,
+                       void* scratch, size_t scratch_bytes, cudaStream_t s);
+size_t topk_vector_scratch_bytes(int64_t n);
+size_t topk_finalize_smem(uint32_t cand_cap);
+int launch_minmax_cols(const float* m, int64_t n, int32_t cols, float* out_min, float* out_max,
+                       cudaStream_t s);
+int launch_fuse_heat(const float* sa, const float* sb, int64_t n, int32_t pair, int32_t cols,
+                     const float* min_a, const float* max_a, const float* min_b, const float* max_b,
+                     int32_t combine, float* heat, cudaStream_t s);
+
+}  // namespace avl

@@ -1,0 +1,725 @@
+// C-ABI of the landmark-index path: host orchestration around the tcgen05 screen and the exact
+// kernels.  No torch types, no CPU compute: every result is produced by the kernels in
+// sim_screen.cu / sim_exact.cu.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "avl_internal.h"
+
+namespace avl {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[1024];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e),
+           file, line, what);
+  g_err = buf;
+  return AVL_ERR_CUDA;
+}
+static bool g_profiling = false;
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major (rows x dpad) matrix, box = 64 columns (one 128-byte swizzle row) x box_rows.
+static int encode_kmajor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t dpad,
+                             uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return AVL_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {dpad, rows};
+  cuuint64_t strides[1] = {dpad * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    set_error(buf);
+    return AVL_ERR_CUDA;
+  }
+  return AVL_OK;
+}
+
+// ------------------------------------------------------------------ workspace
+struct Workspace {
+  float* q = nullptr;          // [256 x d] staged queries (host-pointer calls)
+  float* scale = nullptr;      // [256]
+  __nv_bfloat16* bq = nullptr; // [256 x dpad]
+  float* q_bn = nullptr;       // [256]
+  float* q_glob = nullptr;     // [2]
+  float* thr_t = nullptr;      // [256]
+  uint32_t* flag_count = nullptr;
+  uint32_t* flag_rows = nullptr;
+  uint32_t* flag_masks = nullptr;
+  uint32_t flag_cap = 0;
+  uint32_t* cand_cnt = nullptr;  // [256]
+  uint32_t* cand_idx = nullptr;
+  float* cand_val = nullptr;
+  uint32_t cand_cap = 0;
+  uint32_t* overflow = nullptr;  // [256]
+  float* sample_t = nullptr;
+  size_t sample_elems = 0;
+  int64_t* out_idx = nullptr;  // [256 x AVL_MAX_TOPK]
+  float* out_score = nullptr;
+  int32_t* argmax = nullptr;   // [n] (host-pointer calls)
+  float* column = nullptr;     // [n] scratch column (fallback / fusion)
+  void* topk_scratch = nullptr;
+  size_t topk_scratch_bytes = 0;
+  uint32_t* dbg_host = nullptr;
+  uint32_t* dbg_dev = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace avl
+
+struct avl_map {
+  int device = 0;
+  int num_sms = 0;
+  int64_t n = 0;
+  int32_t d = 0, dpad = 0;
+  float* feat = nullptr;
+  __nv_bfloat16* bf = nullptr;
+  float* row_norm = nullptr;
+  float* row_c = nullptr;
+  float* row_an = nullptr;
+  CUtensorMap tmap_a;
+  int64_t bytes = 0;
+  avl::Workspace ws;
+};
+
+namespace avl {
+
+template <typename T>
+static int dev_alloc(T** p, size_t count, int64_t* bytes) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  if (bytes) *bytes += static_cast<int64_t>(count * sizeof(T));
+  return AVL_OK;
+}
+
+static int ws_init(avl_map* m) {
+  Workspace& w = m->ws;
+  int rc;
+  if ((rc = dev_alloc(&w.q, static_cast<size_t>(AVL_MAX_QUERIES) * m->d, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.scale, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.bq, static_cast<size_t>(AVL_MAX_QUERIES) * m->dpad, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.q_bn, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.q_glob, 2, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.thr_t, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.flag_count, 1, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.cand_cnt, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.overflow, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
+  AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.dbg_host), 64, cudaHostAllocMapped));
+  memset(w.dbg_host, 0, 64);
+  AVL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.dbg_dev), w.dbg_host, 0));
+  for (int i = 0; i < 4; ++i) AVL_CUDA(cudaEventCreate(&w.ev[i]));
+  return AVL_OK;
+}
+
+static void ws_free(Workspace& w) {
+  cudaFree(w.q); cudaFree(w.scale); cudaFree(w.bq); cudaFree(w.q_bn); cudaFree(w.q_glob); cudaFree(w.thr_t);
+  cudaFree(w.flag_count); cudaFree(w.flag_rows); cudaFree(w.flag_masks); cudaFree(w.cand_cnt);
+  cudaFree(w.cand_idx); cudaFree(w.cand_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
+  cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
+  if (w.dbg_host) cudaFreeHost(w.dbg_host);
+  for (int i = 0; i < 4; ++i)
+    if (w.ev[i]) cudaEventDestroy(w.ev[i]);
+}
+
+static int ensure_flags(avl_map* m) {
+  Workspace& w = m->ws;
+  const uint32_t need = static_cast<uint32_t>(std::max<int64_t>(m->n, 1));
+  if (w.flag_cap >= need) return AVL_OK;
+  cudaFree(w.flag_rows); cudaFree(w.flag_masks);
+  int rc;
+  if ((rc = dev_alloc(&w.flag_rows, need, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.flag_masks, static_cast<size_t>(need) * kFlagWords, &m->bytes))) return rc;
+  w.flag_cap = need;
+  return AVL_OK;
+}
+static int ensure_cands(avl_map* m, uint32_t cap) {
+  Workspace& w = m->ws;
+  if (w.cand_cap >= cap) return AVL_OK;
+  cudaFree(w.cand_idx); cudaFree(w.cand_val);
+  int rc;
+  if ((rc = dev_alloc(&w.cand_idx, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.cand_val, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
+  w.cand_cap = cap;
+  return AVL_OK;
+}
+static int ensure_sample(avl_map* m, size_t elems) {
+  Workspace& w = m->ws;
+  if (w.sample_elems >= elems) return AVL_OK;
+  cudaFree(w.sample_t);
+  int rc;
+  if ((rc = dev_alloc(&w.sample_t, elems, &m->bytes))) return rc;
+  w.sample_elems = elems;
+  return AVL_OK;
+}
+static int ensure_column(avl_map* m) {
+  Workspace& w = m->ws;
+  int rc;
+  if (!w.column && (rc = dev_alloc(&w.column, static_cast<size_t>(std::max<int64_t>(m->n, 1)), &m->bytes)))
+    return rc;
+  const size_t need = topk_vector_scratch_bytes(m->n);
+  if (w.topk_scratch_bytes < need) {
+    cudaFree(w.topk_scratch);
+    AVL_CUDA(cudaMalloc(&w.topk_scratch, need));
+    w.topk_scratch_bytes = need;
+    m->bytes += static_cast<int64_t>(need);
+  }
+  return AVL_OK;
+}
+
+static int check_watchdog(avl_map* m, int rc) {
+  if (rc != AVL_OK && m->ws.dbg_host && (m->ws.dbg_host[0] >> 16) == 0xDEADu) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), " | screen watchdog: tag=0x%x block=%u thread=%u parity=%u",
+             m->ws.dbg_host[0] & 0xFFFFu, m->ws.dbg_host[1], m->ws.dbg_host[2], m->ws.dbg_host[3]);
+    g_err += buf;
+  }
+  return rc;
+}
+
+// which tcgen05 variant: 2 when B only fits the shared memory of an SM pair (or forced by env)
+static int pick_cta_group(int npad, int kblocks, int forced) {
+  if (forced == 1 || forced == 2) return screen_pick_stages(forced, npad, kblocks) >= 2 ? forced : 0;
+  const char* env = getenv("AVL_CTA_GROUP");
+  if (env && (env[0] == '1' || env[0] == '2')) {
+    const int f = env[0] - '0';
+    if (screen_pick_stages(f, npad, kblocks) >= 2) return f;
+  }
+  if (screen_pick_stages(1, npad, kblocks) >= 4) return 1;
+  if (screen_pick_stages(2, npad, kblocks) >= 2) return 2;
+  if (screen_pick_stages(1, npad, kblocks) >= 2) return 1;
+  return 0;
+}
+
+struct QuerySetup {
+  const float* q_dev = nullptr;      // fp32 queries on device
+  const float* scale_dev = nullptr;  // or null
+  int npad = 0;
+  int cg = 0;
+  int stages = 0;
+  size_t smem = 0;
+  CUtensorMap tmap_b;
+};
+
+// stage queries, build bf16 B + norms, pick the kernel variant
+static int setup_queries(avl_map* m, const float* queries, int32_t nq, const float* scale, int flags,
+                         int forced_cg, bool need_screen, cudaStream_t s, QuerySetup* qs) {
+  Workspace& w = m->ws;
+  AVL_ARG(queries != nullptr, "queries is NULL");
+  AVL_ARG(nq >= 1 && nq <= AVL_MAX_QUERIES, "nq must be in [1, AVL_MAX_QUERIES]");
+  if (flags & AVL_ON_DEVICE) {
+    qs->q_dev = queries;
+    qs->scale_dev = scale;
+  } else {
+    AVL_CUDA(cudaMemcpyAsync(w.q, queries, static_cast<size_t>(nq) * m->d * sizeof(float),
+                             cudaMemcpyHostToDevice, s));
+    qs->q_dev = w.q;
+    if (scale) {
+      AVL_CUDA(cudaMemcpyAsync(w.scale, scale, static_cast<size_t>(nq) * sizeof(float), cudaMemcpyHostToDevice, s));
+      qs->scale_dev = w.scale;
+    }
+  }
+  if (!need_screen) return AVL_OK;
+  qs->npad = (nq + 15) & ~15;
+  const int kblocks = m->dpad / kBlockK;
+  qs->cg = pick_cta_group(qs->npad, kblocks, forced_cg);
+  if (qs->cg == 0) {
+    set_error("query batch does not fit the shared memory of an SM pair (nq * dim too large); split the batch");
+    return AVL_ERR_UNSUPPORTED;
+  }
+  qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks);
+  qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages);
+  int rc = launch_query_prepare(qs->q_dev, nq, m->d, m->dpad, qs->npad, w.bq, w.q_bn, w.q_glob, s);
+  if (rc) return rc;
+  return encode_kmajor_map(&qs->tmap_b, w.bq, static_cast<uint64_t>(qs->npad), static_cast<uint64_t>(m->dpad),
+                           static_cast<uint32_t>(qs->npad / qs->cg));
+}
+
+static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int normalize, ScreenParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->n_rows = m->n;
+  p->kblocks = m->dpad / kBlockK;
+  p->nq = nq;
+  p->npad = qs.npad;
+  p->stages = qs.stages;
+  p->normalize = normalize;
+  p->row_norm = m->row_norm;
+  p->row_c = m->row_c;
+  p->row_an = m->row_an;
+  p->q_bn = m->ws.q_bn;
+  p->q_glob = m->ws.q_glob;
+  p->dbg = m->ws.dbg_dev;
+  p->tile_stride = 1;
+  const int64_t unit = static_cast<int64_t>(kTileRows) * qs.cg;
+  p->num_tiles = static_cast<int32_t>((m->n + unit - 1) / unit);
+}
+
+static int scale_positive(const float* scale, int32_t nq, int flags) {
+  // the threshold screen divides by scale; the host-pointer path can check it, the device path trusts it
+  if (scale && !(flags & AVL_ON_DEVICE))
+    for (int i = 0; i < nq; ++i)
+      if (!(scale[i] > 0.f) || !std::isfinite(scale[i])) {
+        set_error("scale entries must be finite and > 0");
+        return AVL_ERR_ARG;
+      }
+  return AVL_OK;
+}
+
+}  // namespace avl
+
+using namespace avl;
+
+extern "C" {
+
+int avl_version(void) { return 100; }
+const char* avl_last_error(void) { return g_err.c_str(); }
+
+int avl_device_count(int* count) {
+  AVL_ARG(count != nullptr, "count is NULL");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    c = 0;
+  }
+  *count = c;
+  return AVL_OK;
+}
+int avl_set_device(int device) {
+  AVL_CUDA(cudaSetDevice(device));
+  return AVL_OK;
+}
+int avl_set_profiling(int enabled) {
+  g_profiling = enabled != 0;
+  return AVL_OK;
+}
+
+int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, void* stream, avl_map** out) {
+  AVL_ARG(out != nullptr, "out is NULL");
+  *out = nullptr;
+  AVL_ARG(n >= 0 && n < (int64_t(1) << 31), "n must be in [0, 2^31)");
+  AVL_ARG(dim >= 1 && dim <= 4096, "dim must be in [1, 4096]");
+  AVL_ARG(n == 0 || grid_feat != nullptr, "grid_feat is NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  avl_map* m = new avl_map();
+  AVL_CUDA(cudaGetDevice(&m->device));
+  AVL_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device));
+  int major = 0;
+  AVL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, m->device));
+  if (major != 10) {
+    delete m;
+    set_error("avlmaps_b200 needs an sm_100a (B200) device");
+    return AVL_ERR_UNSUPPORTED;
+  }
+  m->n = n;
+  m->d = dim;
+  m->dpad = (dim + kBlockK - 1) / kBlockK * kBlockK;
+  int rc = AVL_OK;
+  const size_t rows = static_cast<size_t>(std::max<int64_t>(n, 1));
+  do {
+    if ((rc = dev_alloc(&m->feat, rows * dim, &m->bytes))) break;
+    if ((rc = dev_alloc(&m->bf, rows * m->dpad, &m->bytes))) break;
+    if ((rc = dev_alloc(&m->row_norm, rows, &m->bytes))) break;
+    if ((rc = dev_alloc(&m->row_c, rows, &m->bytes))) break;
+    if ((rc = dev_alloc(&m->row_an, rows, &m->bytes))) break;
+    if ((rc = ws_init(m))) break;
+    if (n > 0) {
+      cudaError_t e = cudaMemcpyAsync(m->feat, grid_feat, static_cast<size_t>(n) * dim * sizeof(float),
+                                      (flags & AVL_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "upload grid_feat", __FILE__, __LINE__); break; }
+    }
+    // kappa: fp32 accumulation slack of the tensor core over dpad products
+    const float kappa = static_cast<float>(m->dpad) * 2.4e-7f;
+    if ((rc = launch_map_prepare(m->feat, n, dim, m->dpad, m->bf, m->row_norm, m->row_c, m->row_an, kappa, s))) break;
+    if ((rc = encode_kmajor_map(&m->tmap_a, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
+                                kTileRows))) break;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
+  } while (0);
+  if (rc) {
+    avl_map_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return AVL_OK;
+}
+
+int avl_map_destroy(avl_map* m) {
+  if (!m) return AVL_OK;
+  ws_free(m->ws);
+  cudaFree(m->feat); cudaFree(m->bf); cudaFree(m->row_norm); cudaFree(m->row_c); cudaFree(m->row_an);
+  delete m;
+  return AVL_OK;
+}
+
+int avl_map_shape(const avl_map* m, int64_t* n, int32_t* dim) {
+  AVL_ARG(m != nullptr, "map is NULL");
+  if (n) *n = m->n;
+  if (dim) *dim = m->d;
+  return AVL_OK;
+}
+int64_t avl_map_device_bytes(const avl_map* m) { return m ? m->bytes : 0; }
+
+int avl_sim_dense(avl_map* m, const float* queries, int32_t nq, const float* scale, int normalize_map,
+                  float* out_scores, int flags, void* stream) {
+  AVL_ARG(m != nullptr && out_scores != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  QuerySetup qs;
+  int rc = setup_queries(m, queries, nq, scale, flags, 0, false, s, &qs);
+  if (rc) return rc;
+  if (m->n == 0) return AVL_OK;
+  if (flags & AVL_ON_DEVICE)
+    return launch_dense_exact(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map,
+                              out_scores, nq, 1, s);
+  // host output: row chunks through a bounded device buffer
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m->n, (int64_t(256) << 20) / (4 * nq)));
+  float* buf = nullptr;
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), static_cast<size_t>(chunk) * nq * sizeof(float)));
+  for (int64_t r0 = 0; r0 < m->n && rc == AVL_OK; r0 += chunk) {
+    const int64_t rows = std::min(chunk, m->n - r0);
+    rc = launch_dense_exact(m->feat + r0 * m->d, rows, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm + r0,
+                            normalize_map, buf, nq, 1, s);
+    if (rc) break;
+    cudaError_t e = cudaMemcpyAsync(out_scores + r0 * nq, buf, static_cast<size_t>(rows) * nq * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "dense D2H", __FILE__, __LINE__);
+  }
+  cudaFree(buf);
+  return rc;
+}
+
+int avl_sim_screen_dense(avl_map* m, const float* queries, int32_t nq, int32_t cta_group, float* out_scores,
+                         int flags, void* stream) {
+  AVL_ARG(m != nullptr && out_scores != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  QuerySetup qs;
+  int rc = setup_queries(m, queries, nq, nullptr, flags, cta_group, true, s, &qs);
+  if (rc) return rc;
+  if (m->n == 0) return AVL_OK;
+  float* dst = out_scores;
+  if (!(flags & AVL_ON_DEVICE))
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&dst), static_cast<size_t>(m->n) * nq * sizeof(float)));
+  ScreenParams p;
+  base_params(m, qs, nq, 0, &p);
+  p.mode = kModeDense;
+  p.dense_out = dst;
+  p.dense_rs = nq;
+  p.dense_cs = 1;
+  p.dense_cols = nq;
+  rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s);
+  if (rc == AVL_OK && !(flags & AVL_ON_DEVICE)) {
+    cudaError_t e = cudaMemcpyAsync(out_scores, dst, static_cast<size_t>(m->n) * nq * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "screen_dense", __FILE__, __LINE__);
+  }
+  if (!(flags & AVL_ON_DEVICE)) cudaFree(dst);
+  return check_watchdog(m, rc);
+}
+
+int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* scale, int normalize_map,
+                   int32_t* out_argmax, int flags, void* stream, avl_index_stats* stats) {
+  AVL_ARG(m != nullptr && out_argmax != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace& w = m->ws;
+  int rc = scale_positive(scale, nq, flags);
+  if (rc) return rc;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_rows = m->n;
+    stats->dim = m->d;
+    stats->n_queries = nq;
+  }
+  if (m->n == 0) return AVL_OK;
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
+  QuerySetup qs;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs))) return rc;
+  if ((rc = ensure_flags(m))) return rc;
+  int32_t* dst = out_argmax;
+  if (!(flags & AVL_ON_DEVICE)) {
+    if (!w.argmax && (rc = dev_alloc(&w.argmax, static_cast<size_t>(m->n), &m->bytes))) return rc;
+    dst = w.argmax;
+  }
+  AVL_CUDA(cudaMemsetAsync(w.flag_count, 0, sizeof(uint32_t), s));
+  ScreenParams p;
+  base_params(m, qs, nq, normalize_map, &p);
+  p.mode = kModeArgmax;
+  p.argmax_out = dst;
+  p.flag_count = w.flag_count;
+  p.flag_rows = w.flag_rows;
+  p.flag_masks = w.flag_masks;
+  p.flag_cap = w.flag_cap;
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
+  if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
+  if ((rc = launch_argmax_rerank(m->feat, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map,
+                                 w.flag_count, w.flag_rows, w.flag_masks, w.flag_cap, dst, m->num_sms, s)))
+    return rc;
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
+  if (!(flags & AVL_ON_DEVICE))
+    AVL_CUDA(cudaMemcpyAsync(out_argmax, dst, static_cast<size_t>(m->n) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (stats || !(flags & AVL_ON_DEVICE) || g_profiling) {
+    uint32_t nflag = 0;
+    cudaError_t e = cudaMemcpyAsync(&nflag, w.flag_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "argmax", __FILE__, __LINE__));
+    if (stats) {
+      stats->cta_group = qs.cg;
+      stats->n_launches = 3;  // query_prepare, screen, rerank
+      stats->n_flagged = nflag;
+      if (g_profiling) {
+        cudaEventElapsedTime(&stats->ms_screen, w.ev[1], w.ev[2]);
+        cudaEventElapsedTime(&stats->ms_total, w.ev[0], w.ev[3]);
+      }
+    }
+  }
+  return AVL_OK;
+}
+
+int avl_topk_f32(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val, int flags,
+                 void* stream) {
+  AVL_ARG(out_idx != nullptr && out_val != nullptr, "NULL output");
+  AVL_ARG(k >= 1 && k <= AVL_MAX_TOPK, "k must be in [1, AVL_MAX_TOPK]");
+  AVL_ARG(n >= 0 && n < (int64_t(1) << 32), "n out of range");
+  AVL_ARG(n == 0 || values != nullptr, "values is NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t sb = topk_vector_scratch_bytes(n);
+  void* scratch = nullptr;
+  float* dv = nullptr;
+  int64_t* di = nullptr;
+  float* dval = nullptr;
+  int rc = AVL_OK;
+  cudaError_t e = cudaMalloc(&scratch, sb);
+  if (e != cudaSuccess) return cuda_fail(e, "topk scratch", __FILE__, __LINE__);
+  const float* src = values;
+  if (!(flags & AVL_ON_DEVICE)) {
+    if (cudaMalloc(reinterpret_cast<void**>(&dv), std::max<size_t>(1, n) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&di), k * sizeof(int64_t)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&dval), k * sizeof(float)) != cudaSuccess) {
+      rc = cuda_fail(cudaGetLastError(), "topk staging", __FILE__, __LINE__);
+    } else {
+      e = cudaMemcpyAsync(dv, values, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) rc = cuda_fail(e, "topk H2D", __FILE__, __LINE__);
+      src = dv;
+    }
+  }
+  if (rc == AVL_OK)
+    rc = launch_topk_vector(src, n, k, (flags & AVL_ON_DEVICE) ? out_idx : di,
+                            (flags & AVL_ON_DEVICE) ? out_val : dval, scratch, sb, s);
+  if (rc == AVL_OK && !(flags & AVL_ON_DEVICE)) {
+    e = cudaMemcpyAsync(out_idx, di, k * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_val, dval, k * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "topk D2H", __FILE__, __LINE__);
+  }
+  e = cudaStreamSynchronize(s);  // scratch is freed below
+  if (e != cudaSuccess && rc == AVL_OK) rc = cuda_fail(e, "topk", __FILE__, __LINE__);
+  cudaFree(scratch); cudaFree(dv); cudaFree(di); cudaFree(dval);
+  return rc;
+}
+
+int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scale, int normalize_map,
+                 int32_t k, int64_t* out_idx, float* out_score, int flags, void* stream,
+                 avl_index_stats* stats) {
+  AVL_ARG(m != nullptr && out_idx != nullptr && out_score != nullptr, "NULL argument");
+  AVL_ARG(k >= 1 && k <= AVL_MAX_TOPK, "k must be in [1, AVL_MAX_TOPK]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace& w = m->ws;
+  int rc = scale_positive(scale, nq, flags);
+  if (rc) return rc;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_rows = m->n;
+    stats->dim = m->d;
+    stats->n_queries = nq;
+  }
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
+  QuerySetup qs;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs))) return rc;
+  int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
+  float* d_score = (flags & AVL_ON_DEVICE) ? out_score : w.out_score;
+
+  const int64_t unit = static_cast<int64_t>(kTileRows) * qs.cg;
+  const int64_t total_units = (m->n + unit - 1) / unit;
+  // rows sampled for the threshold: ~n/64, enough that ~k*n/n0 candidates per query stay << cand_cap
+  int64_t n0 = std::max<int64_t>(m->n / 64, static_cast<int64_t>(k) * m->n / 1024);
+  n0 = std::min<int64_t>(std::max<int64_t>(n0, 8192), std::max<int64_t>(m->n, 1));
+  int64_t sample_units = std::min<int64_t>(total_units, (n0 + unit - 1) / unit);
+  int64_t tile_stride = sample_units > 0 ? std::max<int64_t>(1, total_units / sample_units) : 1;
+  if (sample_units > 0) sample_units = std::min<int64_t>(sample_units, (total_units + tile_stride - 1) / tile_stride);
+  const int64_t n_sample = sample_units * unit;
+  const uint32_t cand_cap = 8192;
+  if ((rc = ensure_cands(m, cand_cap))) return rc;
+  if ((rc = ensure_sample(m, static_cast<size_t>(std::max<int64_t>(n_sample, 1)) * nq))) return rc;
+
+  ScreenParams p;
+  if (m->n > 0) {
+    // phase A: screen scores of the sampled tiles, transposed so that a query's column is contiguous
+    base_params(m, qs, nq, normalize_map, &p);
+    p.mode = kModeDense;
+    p.num_tiles = static_cast<int32_t>(sample_units);
+    p.tile_stride = static_cast<int32_t>(tile_stride);
+    p.dense_out = w.sample_t;
+    p.dense_rs = 1;
+    p.dense_cs = n_sample;
+    p.dense_cols = nq;
+    if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
+    if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_sample), n_sample, nq, k,
+                                      static_cast<int32_t>(unit), static_cast<int32_t>(tile_stride), m->n,
+                                      m->row_norm, m->row_c, m->row_an, w.q_bn, w.q_glob, normalize_map,
+                                      w.thr_t, s)))
+      return rc;
+  }
+  AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
+  AVL_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
+  if (m->n > 0) {
+    // phase B: full pass, candidates = rows whose upper bound reaches the threshold
+    base_params(m, qs, nq, normalize_map, &p);
+    p.mode = kModeThresh;
+    p.thr_t = w.thr_t;
+    p.cand_cnt = w.cand_cnt;
+    p.cand_idx = w.cand_idx;
+    p.cand_val = w.cand_val;
+    p.cand_cap = cand_cap;
+    if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
+    if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
+    if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
+  }
+  // phase C: exact re-score of the survivors, final order
+  if ((rc = launch_topk_finalize(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, m->row_c,
+                                 m->row_an, w.q_bn, w.q_glob, normalize_map, k, w.cand_cnt, w.cand_idx,
+                                 w.cand_val, cand_cap, d_idx, d_score, w.overflow, s)))
+    return rc;
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
+
+  // overflowed queries (adversarial data, massive ties): exact dense column + vector top-k
+  std::vector<uint32_t> ovf(nq), cnt(nq);
+  AVL_CUDA(cudaMemcpyAsync(ovf.data(), w.overflow, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s));
+  AVL_CUDA(cudaMemcpyAsync(cnt.data(), w.cand_cnt, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s));
+  {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk", __FILE__, __LINE__));
+  }
+  int n_fallback = 0;
+  int64_t n_cand = 0;
+  for (int q = 0; q < nq; ++q) {
+    n_cand += cnt[q];
+    if (!ovf[q]) continue;
+    ++n_fallback;
+    if ((rc = ensure_column(m))) return rc;
+    if ((rc = launch_dense_exact(m->feat, m->n, m->d, qs.q_dev + static_cast<size_t>(q) * m->d, 1,
+                                 qs.scale_dev ? qs.scale_dev + q : nullptr, m->row_norm, normalize_map,
+                                 w.column, 1, 1, s)))
+      return rc;
+    if ((rc = launch_topk_vector(w.column, m->n, k, d_idx + static_cast<size_t>(q) * k,
+                                 d_score + static_cast<size_t>(q) * k, w.topk_scratch, w.topk_scratch_bytes, s)))
+      return rc;
+  }
+  if (!(flags & AVL_ON_DEVICE)) {
+    AVL_CUDA(cudaMemcpyAsync(out_idx, d_idx, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, s));
+    AVL_CUDA(cudaMemcpyAsync(out_score, d_score, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, s));
+    AVL_CUDA(cudaStreamSynchronize(s));
+  }
+  if (stats) {
+    stats->cta_group = qs.cg;
+    stats->n_launches = 5 + 3 * n_fallback;  // query_prepare, sample screen, select, screen, finalize
+    stats->n_candidates = n_cand;
+    stats->n_fallback_queries = n_fallback;
+    stats->sample_rows = static_cast<int32_t>(std::min<int64_t>(n_sample, m->n));
+    if (g_profiling && m->n > 0) {
+      cudaEventElapsedTime(&stats->ms_screen, w.ev[1], w.ev[2]);
+      cudaEventElapsedTime(&stats->ms_total, w.ev[0], w.ev[3]);
+    }
+  }
+  return AVL_OK;
+}
+
+int avl_fuse_topk(avl_map* ma, const float* qa, const float* scale_a, int normalize_a, avl_map* mb,
+                  const float* qb, const float* scale_b, int normalize_b, int32_t n_pairs, int32_t combine,
+                  int32_t k, int64_t* out_idx, float* out_heat, int flags, void* stream) {
+  AVL_ARG(ma && mb && qa && qb && out_idx && out_heat, "NULL argument");
+  AVL_ARG(ma->n == mb->n, "both maps must have the same number of rows");
+  AVL_ARG(n_pairs >= 1 && n_pairs <= AVL_MAX_QUERIES, "n_pairs out of range");
+  AVL_ARG(k >= 1 && k <= AVL_MAX_TOPK, "k must be in [1, AVL_MAX_TOPK]");
+  AVL_ARG(combine >= AVL_FUSE_PRODUCT && combine <= AVL_FUSE_SUM, "unknown combine rule");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t n = ma->n;
+  QuerySetup sa, sb;
+  int rc;
+  if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, false, s, &sa))) return rc;
+  if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, false, s, &sb))) return rc;
+  if ((rc = ensure_column(ma))) return rc;
+  float *da = nullptr, *db = nullptr, *mm = nullptr;
+  const size_t elems = static_cast<size_t>(std::max<int64_t>(n, 1)) * n_pairs;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&da), elems * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&db), elems * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&mm), 4 * n_pairs * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(da); cudaFree(db); cudaFree(mm);
+    return cuda_fail(e, "fuse buffers", __FILE__, __LINE__);
+  }
+  int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : ma->ws.out_idx;
+  float* d_heat = (flags & AVL_ON_DEVICE) ? out_heat : ma->ws.out_score;
+  do {
+    // column-major (pair, row) exact scores of both modalities
+    if ((rc = launch_dense_exact(ma->feat, n, ma->d, sa.q_dev, n_pairs, sa.scale_dev, ma->row_norm, normalize_a,
+                                 da, 1, n, s))) break;
+    if ((rc = launch_dense_exact(mb->feat, n, mb->d, sb.q_dev, n_pairs, sb.scale_dev, mb->row_norm, normalize_b,
+                                 db, 1, n, s))) break;
+    if ((rc = launch_minmax_cols(da, n, n_pairs, mm, mm + n_pairs, s))) break;
+    if ((rc = launch_minmax_cols(db, n, n_pairs, mm + 2 * n_pairs, mm + 3 * n_pairs, s))) break;
+    for (int j = 0; j < n_pairs && rc == AVL_OK; ++j) {
+      rc = launch_fuse_heat(da, db, n, j, n_pairs, mm, mm + n_pairs, mm + 2 * n_pairs, mm + 3 * n_pairs, combine,
+                            ma->ws.column, s);
+      if (rc) break;
+      rc = launch_topk_vector(ma->ws.column, n, k, d_idx + static_cast<size_t>(j) * k,
+                              d_heat + static_cast<size_t>(j) * k, ma->ws.topk_scratch, ma->ws.topk_scratch_bytes, s);
+    }
+    if (rc) break;
+    if (!(flags & AVL_ON_DEVICE)) {
+      e = cudaMemcpyAsync(out_idx, d_idx, sizeof(int64_t) * n_pairs * k, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out_heat, d_heat, sizeof(float) * n_pairs * k, cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "fuse D2H", __FILE__, __LINE__); break; }
+    }
+  } while (0);
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess && rc == AVL_OK) rc = cuda_fail(e, "fuse", __FILE__, __LINE__);
+  cudaFree(da); cudaFree(db); cudaFree(mm);
+  return rc;
+}
+
+}  // extern "C"

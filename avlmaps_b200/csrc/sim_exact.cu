@@ -1,0 +1,599 @@
+// Exact (fp64-accumulated) kernels of the landmark-index path and the small selection
+// kernels around the tcgen05 screen.
+//
+// Canonical score (what oracle/ computes and what every index entry point returns):
+//     dot   = sum_k (double)a[k] * (double)b[k]        (each product exact in fp64)
+//     s     = (float)dot
+//     s     = s * inv_norm_i        if normalize_map   (inv_norm_i = 1.0f / (float)sqrt(sum a^2), 0 if the row is 0)
+//     s     = s * scale_q           if scale given
+// which restates `map_feats @ text_feats.T` (reference avlmaps/utils/clip_utils.py:229,240) and
+// `scale * audio_features @ text_features.T` (avlmaps/map/sound_map.py:109) with one rounding
+// instead of OpenBLAS' unknowable fp32 summation order.
+#include <algorithm>
+#include <cfloat>
+
+#include "avl_internal.h"
+
+namespace avl {
+
+namespace {
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b = __float_as_uint(f);
+  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float canon_score(double dot, float inv_norm, int normalize, const float* scale,
+                                             int q) {
+  float s = static_cast<float>(dot);
+  if (normalize) s = __fmul_rn(s, inv_norm);
+  if (scale) s = __fmul_rn(s, scale[q]);
+  return s;
+}
+__device__ __forceinline__ float inv_of_norm(float nrm) { return nrm > 0.f ? __fdiv_rn(1.0f, nrm) : 0.f; }
+
+// ------------------------------------------------------------------ map_prepare
+// One warp per row: bf16 copy (zero padded to dpad), fp32 norm, rounding residual norms.
+__global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, int32_t d, int32_t dpad,
+                                   __nv_bfloat16* __restrict__ bf, float* __restrict__ row_norm,
+                                   float* __restrict__ row_c, float* __restrict__ row_an, float kappa) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* a = feat + row * d;
+  __nv_bfloat16* o = bf + row * dpad;
+  double sa = 0.0, sd = 0.0, sb = 0.0;
+  for (int k = lane; k < dpad; k += 32) {
+    const float x = k < d ? a[k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    o[k] = h;
+    const float xb = __bfloat162float(h);
+    const float e = x - xb;  // exact
+    sa += static_cast<double>(x) * x;
+    sd += static_cast<double>(e) * e;
+    sb += static_cast<double>(xb) * xb;
+  }
+  sa = warp_sum(sa);
+  sd = warp_sum(sd);
+  sb = warp_sum(sb);
+  if (lane == 0) {
+    const float an = __double2float_ru(sqrt(sb) * (1.0 + 1e-7));
+    row_norm[row] = static_cast<float>(sqrt(sa));
+    row_an[row] = an;
+    row_c[row] = __double2float_ru(sqrt(sd) * (1.0 + 1e-7) + static_cast<double>(kappa) * an);
+  }
+}
+
+// ------------------------------------------------------------------ query_prepare
+// One block per padded query row: bf16 copy, ||b||, ||b - bf16(b)|| / ||b||.
+// glob[0] = max ratio (rho), glob[1] = max ||b|| (float bits, non-negative => uint order).
+__global__ void query_prepare_kernel(const float* __restrict__ q, int32_t nq, int32_t d, int32_t dpad,
+                                     __nv_bfloat16* __restrict__ bq, float* __restrict__ q_bn,
+                                     uint32_t* __restrict__ glob) {
+  const int r = blockIdx.x;
+  __shared__ double red[2][32];
+  double sb = 0.0, sd = 0.0;
+  for (int k = threadIdx.x; k < dpad; k += blockDim.x) {
+    const float x = (r < nq && k < d) ? q[static_cast<size_t>(r) * d + k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    bq[static_cast<size_t>(r) * dpad + k] = h;
+    const float e = x - __bfloat162float(h);
+    sb += static_cast<double>(x) * x;
+    sd += static_cast<double>(e) * e;
+  }
+  sb = warp_sum(sb);
+  sd = warp_sum(sd);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = sb; red[1][w] = sd; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tb = 0.0, td = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { tb += red[0][i]; td += red[1][i]; }
+    if (r < nq) {
+      const float bn = __double2float_ru(sqrt(tb) * (1.0 + 1e-7));
+      q_bn[r] = bn;
+      const float ratio = tb > 0.0 ? __double2float_ru(sqrt(td / tb) * (1.0 + 1e-6)) : 0.f;
+      atomicMax(glob + 0, __float_as_uint(ratio + 2e-6f));
+      atomicMax(glob + 1, __float_as_uint(bn));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dense exact scores
+// 64 rows x 64 queries per block, 4x4 outputs per thread, fp64 accumulators, k ascending.
+constexpr int kDT = 64, kDK = 16;
+__global__ void __launch_bounds__(256)
+dense_exact_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const float* __restrict__ q,
+                   int32_t nq, const float* __restrict__ scale, const float* __restrict__ row_norm,
+                   int normalize, float* __restrict__ out, int64_t out_rs, int64_t out_cs) {
+  __shared__ float As[kDK][kDT + 4];
+  __shared__ float Bs[kDK][kDT + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kDT;
+  const int q0 = blockIdx.y * kDT;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < d; k0 += kDK) {
+    // 64 x 16 tile of A and of B, one element (x4) per thread, coalesced along k
+    for (int e = threadIdx.x; e < kDT * kDK; e += 256) {
+      const int r = e / kDK, k = e % kDK;
+      const int64_t gr = row0 + r;
+      As[k][r] = (gr < n && k0 + k < d) ? feat[gr * d + k0 + k] : 0.f;
+      const int gq = q0 + r;
+      Bs[k][r] = (gq < nq && k0 + k < d) ? q[static_cast<size_t>(gq) * d + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kDK; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gr = row0 + ty * 4 + i;
+    if (gr >= n) continue;
+    const float inv = normalize ? inv_of_norm(row_norm[gr]) : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gq = q0 + tx * 4 + j;
+      if (gq < nq) out[gr * out_rs + gq * out_cs] = canon_score(acc[i][j], inv, normalize, scale, gq);
+    }
+  }
+}
+
+// warp-cooperative exact dot of fp32 row a (global) with fp32 row b (global)
+__device__ __forceinline__ double warp_dot(const float* __restrict__ a, const float* __restrict__ b, int d,
+                                           int lane) {
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) s = fma(static_cast<double>(a[k]), static_cast<double>(b[k]), s);
+  return warp_sum(s);
+}
+
+// ------------------------------------------------------------------ argmax re-rank
+// One warp per flagged row: exact scores of the queries in its band mask, first max wins.
+__global__ void argmax_rerank_kernel(const float* __restrict__ feat, int32_t d, const float* __restrict__ q,
+                                     int32_t nq, const float* __restrict__ scale,
+                                     const float* __restrict__ row_norm, int normalize,
+                                     const uint32_t* __restrict__ flag_count,
+                                     const uint32_t* __restrict__ flag_rows,
+                                     const uint32_t* __restrict__ flag_masks, uint32_t flag_cap,
+                                     int32_t* __restrict__ argmax_out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nflag = min(*flag_count, flag_cap);
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nflag; e += nwarps) {
+    const int64_t row = flag_rows[e];
+    const float* a = feat + row * d;
+    const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
+    float best = -FLT_MAX;
+    int best_q = -1;
+    for (int w = 0; w < kFlagWords; ++w) {
+      uint32_t m = flag_masks[static_cast<size_t>(e) * kFlagWords + w];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int qq = w * 32 + bit;
+        const double dot = warp_dot(a, q + static_cast<size_t>(qq) * d, d, lane);
+        const float s = canon_score(dot, inv, normalize, scale, qq);
+        if (best_q < 0 || s > best) { best = s; best_q = qq; }
+      }
+    }
+    if (lane == 0 && best_q >= 0) argmax_out[row] = best_q;
+  }
+}
+
+// ------------------------------------------------------------------ block-wide selection helpers
+// k-th largest (1-based) of keys[0..n) by bitwise bisection; every thread returns the value.
+template <typename KeyT, typename Fetch>
+__device__ KeyT block_kth_largest(Fetch fetch, int n, int k, int* sh_cnt) {
+  KeyT v = 0;
+  constexpr int kBits = sizeof(KeyT) * 8;
+  for (int bit = kBits - 1; bit >= 0; --bit) {
+    const KeyT cand = v | (static_cast<KeyT>(1) << bit);
+    int c = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) c += (fetch(j) >= cand) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (threadIdx.x == 0) *sh_cnt = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(sh_cnt, c);
+    __syncthreads();
+    if (*sh_cnt >= k) v = cand;
+    __syncthreads();
+  }
+  return v;
+}
+
+// map compact sample row -> map row (see ScreenParams::tile_stride)
+__device__ __forceinline__ int64_t sample_to_row(int64_t c, int32_t unit_rows, int32_t tile_stride) {
+  const int64_t u = c / unit_rows;
+  return u * tile_stride * unit_rows + (c - u * unit_rows);
+}
+
+// ------------------------------------------------------------------ threshold from a sample
+// sample_t[q][c]: screen scores of the sampled rows (transposed dense output).  Per query:
+// T_q = k-th largest of the LOWER bounds (s~ - eps)/w over the sample, a valid lower bound of the
+// k-th largest exact score over the whole map (in units of score / scale_q).
+__global__ void __launch_bounds__(256)
+select_threshold_kernel(float* __restrict__ sample_t, int32_t n_sample, int64_t ld, int32_t k,
+                        int32_t unit_rows, int32_t tile_stride, int64_t n_rows,
+                        const float* __restrict__ row_norm, const float* __restrict__ row_c,
+                        const float* __restrict__ row_an, const float* __restrict__ q_bn,
+                        const uint32_t* __restrict__ glob, int normalize, float* __restrict__ thr_t) {
+  __shared__ int sh_cnt;
+  __shared__ int sh_valid;
+  const int q = blockIdx.x;
+  const float rho = __uint_as_float(glob[0]);
+  const float bn = q_bn[q];
+  uint32_t* keys = reinterpret_cast<uint32_t*>(sample_t + static_cast<int64_t>(q) * ld);
+  if (threadIdx.x == 0) sh_valid = 0;
+  __syncthreads();
+  int nv = 0;
+  for (int c = threadIdx.x; c < n_sample; c += blockDim.x) {
+    const int64_t row = sample_to_row(c, unit_rows, tile_stride);
+    uint32_t key = 0u;
+    if (row < n_rows) {
+      const float s = __uint_as_float(keys[c]);
+      const float r_i = fmaf(rho, row_an[row], row_c[row]);
+      const float w_i = normalize ? fmaxf(row_norm[row], 1e-30f) : 1.f;
+      const float lo = __fdiv_rd(__fsub_rd(s, __fmul_ru(r_i, bn)), w_i);
+      key = f2ord(lo);
+      if (key == 0u) key = 1u;
+      ++nv;
+    }
+    keys[c] = key;
+  }
+  if (nv) atomicAdd(&sh_valid, nv);
+  __syncthreads();
+  const int valid = sh_valid;
+  __syncthreads();
+  if (valid < k) {
+    if (threadIdx.x == 0) thr_t[q] = -INFINITY;  // every row is a candidate (tiny maps)
+    return;
+  }
+  const uint32_t v = block_kth_largest<uint32_t>([&](int j) { return keys[j]; }, n_sample, k, &sh_cnt);
+  if (threadIdx.x == 0) thr_t[q] = ord2f(v);
+}
+
+// ------------------------------------------------------------------ top-k finalize
+// One block per query over its candidate list.
+__global__ void __launch_bounds__(256)
+topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, const float* __restrict__ q,
+                     const float* __restrict__ scale, const float* __restrict__ row_norm,
+                     const float* __restrict__ row_c, const float* __restrict__ row_an,
+                     const float* __restrict__ q_bn, const uint32_t* __restrict__ glob, int normalize,
+                     int32_t k, const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand_idx,
+                     const float* __restrict__ cand_val, uint32_t cand_cap, int64_t* __restrict__ out_idx,
+                     float* __restrict__ out_score, uint32_t* __restrict__ overflow_flags) {
+  extern __shared__ uint8_t sm[];
+  uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
+  uint32_t* Uk = Lk + cand_cap;
+  uint32_t* Ix = Uk + cand_cap;
+  unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Ix + cand_cap);
+  __shared__ int sh_cnt;
+  __shared__ int sh_ns;
+  const int qq = blockIdx.x;
+  const uint32_t cnt = cand_cnt[qq];
+  if (cnt > cand_cap) {
+    if (threadIdx.x == 0) overflow_flags[qq] = 1u;
+    return;
+  }
+  const int n = static_cast<int>(cnt);
+  const float rho = __uint_as_float(glob[0]);
+  const float bn = q_bn[qq];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const uint32_t i = cand_idx[static_cast<size_t>(qq) * cand_cap + j];
+    const float s = cand_val[static_cast<size_t>(qq) * cand_cap + j];
+    const float r_i = fmaf(rho, row_an[i], row_c[i]);
+    const float w_i = normalize ? fmaxf(row_norm[i], 1e-30f) : 1.f;
+    const float e = __fmul_ru(r_i, bn);
+    Lk[j] = max(f2ord(__fdiv_rd(__fsub_rd(s, e), w_i)), 1u);
+    Uk[j] = max(f2ord(__fdiv_ru(__fadd_ru(s, e), w_i)), 1u);
+    Ix[j] = i;
+  }
+  if (threadIdx.x == 0) sh_ns = 0;
+  __syncthreads();
+  const int kk = min(k, n);
+  uint32_t v = 0u;
+  if (kk > 0) v = block_kth_largest<uint32_t>([&](int j) { return Lk[j]; }, n, kk, &sh_cnt);
+  // survivors: upper bound reaches the k-th best lower bound.  Lk is dead now -> survivor list.
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    if (Uk[j] >= v) {
+      const int s = atomicAdd(&sh_ns, 1);
+      Lk[s] = static_cast<uint32_t>(j);
+    }
+  }
+  __syncthreads();
+  const int ns = sh_ns;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* b = q + static_cast<size_t>(qq) * d;
+  for (int s = warp; s < ns; s += nw) {
+    const uint32_t i = Ix[Lk[s]];
+    const double dot = warp_dot(feat + static_cast<int64_t>(i) * d, b, d, lane);
+    if (lane == 0) {
+      const float inv = normalize ? inv_of_norm(row_norm[i]) : 1.f;
+      const float f = canon_score(dot, inv, normalize, scale, qq);
+      K64[s] = (static_cast<unsigned long long>(f2ord(f)) << 32) | (0xFFFFFFFFu - i);
+    }
+  }
+  __syncthreads();
+  const int kf = min(k, ns);
+  unsigned long long v64 = 0ull;
+  if (kf > 0) v64 = block_kth_largest<unsigned long long>([&](int j) { return K64[j]; }, ns, kf, &sh_cnt);
+  for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+    const unsigned long long key = K64[s];
+    if (kf > 0 && key >= v64) {
+      int rank = 0;
+      for (int t = 0; t < ns; ++t) rank += (K64[t] > key) ? 1 : 0;
+      out_idx[static_cast<size_t>(qq) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+      out_score[static_cast<size_t>(qq) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
+    }
+  }
+  for (int s = kf + threadIdx.x; s < k; s += blockDim.x) {
+    out_idx[static_cast<size_t>(qq) * k + s] = -1;
+    out_score[static_cast<size_t>(qq) * k + s] = -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------ exact top-k of a vector
+// level 1: each block selects the k best of its chunk (keys in shared memory);
+// level 2: one block selects the k best of the survivors and sorts them.
+constexpr int kVecChunk = 4096;
+
+__device__ __forceinline__ unsigned long long vec_key(float f, int64_t i) {
+  return (static_cast<unsigned long long>(f2ord(f)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i));
+}
+
+__global__ void __launch_bounds__(256)
+topk_vec_l1_kernel(const float* __restrict__ v, int64_t n, int32_t k, unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long keys[kVecChunk];
+  __shared__ int sh_cnt;
+  __shared__ int sh_w;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kVecChunk;
+  const int m = static_cast<int>(min(static_cast<int64_t>(kVecChunk), n - base));
+  for (int j = threadIdx.x; j < m; j += blockDim.x) keys[j] = vec_key(v[base + j], base + j);
+  if (threadIdx.x == 0) sh_w = 0;
+  __syncthreads();
+  const int kk = min(k, m);
+  const unsigned long long t =
+      block_kth_largest<unsigned long long>([&](int j) { return keys[j]; }, m, kk, &sh_cnt);
+  unsigned long long* o = out + static_cast<size_t>(blockIdx.x) * k;
+  for (int j = threadIdx.x; j < m; j += blockDim.x)
+    if (keys[j] >= t) o[atomicAdd(&sh_w, 1)] = keys[j];
+  __syncthreads();
+  for (int j = sh_w + threadIdx.x; j < k; j += blockDim.x) o[j] = 0ull;  // 0 = "nothing"
+}
+
+__global__ void __launch_bounds__(1024)
+topk_vec_l2_kernel(const unsigned long long* __restrict__ keys, int m, int32_t k, int64_t n,
+                   int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  __shared__ int sh_cnt;
+  __shared__ unsigned long long sel[AVL_MAX_TOPK];
+  __shared__ int sh_w;
+  if (threadIdx.x == 0) sh_w = 0;
+  __syncthreads();
+  const int kk = static_cast<int>(min(static_cast<int64_t>(k), n));
+  const unsigned long long t =
+      block_kth_largest<unsigned long long>([&](int j) { return keys[j]; }, m, kk, &sh_cnt);
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const unsigned long long key = keys[j];
+    if (key >= t && key != 0ull) {
+      const int s = atomicAdd(&sh_w, 1);
+      if (s < AVL_MAX_TOPK) sel[s] = key;
+    }
+  }
+  __syncthreads();
+  const int ns = min(sh_w, kk);
+  for (int s = threadIdx.x; s < k; s += blockDim.x) {
+    if (s < ns) {
+      const unsigned long long key = sel[s];
+      int rank = 0;
+      for (int u = 0; u < ns; ++u) rank += (sel[u] > key) ? 1 : 0;
+      out_idx[rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+      out_val[rank] = ord2f(static_cast<uint32_t>(key >> 32));
+    }
+  }
+  __syncthreads();
+  for (int s = ns + threadIdx.x; s < k; s += blockDim.x) {
+    out_idx[s] = -1;
+    out_val[s] = -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------ fusion helpers
+// per-column min / max of a column-major matrix m[col][row] (each column contiguous).
+__global__ void __launch_bounds__(256)
+minmax_cols_kernel(const float* __restrict__ m, int64_t n, uint32_t* __restrict__ out_min,
+                   uint32_t* __restrict__ out_max) {
+  const int col = blockIdx.y;
+  const float* c = m + static_cast<int64_t>(col) * n;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t key = f2ord(c[i]);
+    lo = min(lo, key);
+    hi = max(hi, key);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(out_min + col, lo);
+    atomicMax(out_max + col, hi);
+  }
+}
+
+__device__ __forceinline__ float minmax_norm(float s, float lo, float hi) {
+  // (scores - min) / (max - min), fp32 like the reference's numpy float32 arithmetic
+  return __fdiv_rn(__fsub_rn(s, lo), __fsub_rn(hi, lo));
+}
+
+__global__ void __launch_bounds__(256)
+fuse_heat_kernel(const float* __restrict__ sa, const float* __restrict__ sb, int64_t n, int32_t pair,
+                 const uint32_t* __restrict__ min_a, const uint32_t* __restrict__ max_a,
+                 const uint32_t* __restrict__ min_b, const uint32_t* __restrict__ max_b, int32_t combine,
+                 float* __restrict__ heat) {
+  const float la = ord2f(min_a[pair]), ha = ord2f(max_a[pair]);
+  const float lb = ord2f(min_b[pair]), hb = ord2f(max_b[pair]);
+  const float* ca = sa + static_cast<int64_t>(pair) * n;
+  const float* cb = sb + static_cast<int64_t>(pair) * n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float x = minmax_norm(ca[i], la, ha);
+    const float y = minmax_norm(cb[i], lb, hb);
+    float h;
+    if (combine == AVL_FUSE_PRODUCT) h = __fmul_rn(x, y);
+    else if (combine == AVL_FUSE_MAX) h = fmaxf(x, y);
+    else h = __fadd_rn(x, y);
+    heat[i] = h;
+  }
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+// =================================================================== launchers
+int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
+                       float* row_norm, float* row_c, float* row_an, float kappa, cudaStream_t s) {
+  if (n == 0) return AVL_OK;
+  const int warps = 8;
+  const unsigned blocks = static_cast<unsigned>((n + warps - 1) / warps);
+  map_prepare_kernel<<<blocks, warps * 32, 0, s>>>(feat, n, d, dpad, bf, row_norm, row_c, row_an, kappa);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_query_prepare(const float* q, int32_t nq, int32_t d, int32_t dpad, int32_t npad,
+                         __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s) {
+  AVL_CUDA(cudaMemsetAsync(q_glob, 0, 2 * sizeof(float), s));
+  query_prepare_kernel<<<npad, 128, 0, s>>>(q, nq, d, dpad, bq, q_bn, reinterpret_cast<uint32_t*>(q_glob));
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq,
+                       const float* scale, const float* row_norm, int normalize, float* out,
+                       int64_t out_rs, int64_t out_cs, cudaStream_t s) {
+  if (n == 0 || nq == 0) return AVL_OK;
+  dim3 grid(static_cast<unsigned>((n + kDT - 1) / kDT), static_cast<unsigned>((nq + kDT - 1) / kDT));
+  dense_exact_kernel<<<grid, 256, 0, s>>>(feat, n, d, q, nq, scale, row_norm, normalize, out, out_rs, out_cs);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_argmax_rerank(const float* feat, int32_t d, const float* q, int32_t nq, const float* scale,
+                         const float* row_norm, int normalize, const uint32_t* flag_count,
+                         const uint32_t* flag_rows, const uint32_t* flag_masks, uint32_t flag_cap,
+                         int32_t* argmax_out, int num_sms, cudaStream_t s) {
+  argmax_rerank_kernel<<<num_sms * 8, 256, 0, s>>>(feat, d, q, nq, scale, row_norm, normalize, flag_count,
+                                                   flag_rows, flag_masks, flag_cap, argmax_out);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_select_threshold(float* sample_t, int32_t n_sample, int64_t ld, int32_t nq, int32_t k,
+                            int32_t unit_rows, int32_t tile_stride, int64_t n_rows, const float* row_norm,
+                            const float* row_c, const float* row_an, const float* q_bn, const float* q_glob,
+                            int normalize, float* thr_t, cudaStream_t s) {
+  select_threshold_kernel<<<nq, 256, 0, s>>>(sample_t, n_sample, ld, k, unit_rows, tile_stride, n_rows,
+                                             row_norm, row_c, row_an, q_bn,
+                                             reinterpret_cast<const uint32_t*>(q_glob), normalize, thr_t);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+size_t topk_finalize_smem(uint32_t cand_cap) { return static_cast<size_t>(cand_cap) * 20u; }
+
+int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
+                         const float* scale, const float* row_norm, const float* row_c, const float* row_an,
+                         const float* q_bn, const float* q_glob, int normalize, int32_t k,
+                         const uint32_t* cand_cnt, const uint32_t* cand_idx, const float* cand_val,
+                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
+                         cudaStream_t s) {
+  const size_t smem = topk_finalize_smem(cand_cap);
+  AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  topk_finalize_kernel<<<nq, 256, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
+                                             reinterpret_cast<const uint32_t*>(q_glob), normalize, k, cand_cnt,
+                                             cand_idx, cand_val, cand_cap, out_idx, out_score, overflow_flags);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+size_t topk_vector_scratch_bytes(int64_t n) {
+  const int64_t blocks = (n + kVecChunk - 1) / kVecChunk;
+  return static_cast<size_t>(blocks > 0 ? blocks : 1) * AVL_MAX_TOPK * sizeof(unsigned long long);
+}
+
+int launch_topk_vector(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val,
+                       void* scratch, size_t scratch_bytes, cudaStream_t s) {
+  const int64_t blocks = (n + kVecChunk - 1) / kVecChunk;
+  if (n <= 0) {
+    fill_u32_kernel<<<1, 256, 0, s>>>(reinterpret_cast<uint32_t*>(out_val), k, 0xFF800000u);
+    AVL_CUDA(cudaMemsetAsync(out_idx, 0xFF, sizeof(int64_t) * k, s));
+    return AVL_OK;
+  }
+  if (static_cast<size_t>(blocks) * k * sizeof(unsigned long long) > scratch_bytes) {
+    set_error("topk_vector: scratch too small");
+    return AVL_ERR_ARG;
+  }
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch);
+  topk_vec_l1_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(values, n, k, keys);
+  AVL_CUDA(cudaGetLastError());
+  topk_vec_l2_kernel<<<1, 1024, 0, s>>>(keys, static_cast<int>(blocks * k), k, n, out_idx, out_val);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_minmax_cols(const float* m, int64_t n, int32_t cols, float* out_min, float* out_max,
+                       cudaStream_t s) {
+  fill_u32_kernel<<<(cols + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(out_min), cols, 0xFFFFFFFFu);
+  fill_u32_kernel<<<(cols + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint32_t*>(out_max), cols, 0u);
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 592)), static_cast<unsigned>(cols));
+  minmax_cols_kernel<<<grid, 256, 0, s>>>(m, n, reinterpret_cast<uint32_t*>(out_min),
+                                          reinterpret_cast<uint32_t*>(out_max));
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_fuse_heat(const float* sa, const float* sb, int64_t n, int32_t pair, int32_t cols,
+                     const float* min_a, const float* max_a, const float* min_b, const float* max_b,
+                     int32_t combine, float* heat, cudaStream_t s) {
+  (void)cols;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 1184));
+  fuse_heat_kernel<<<blocks, 256, 0, s>>>(sa, sb, n, pair, reinterpret_cast<const uint32_t*>(min_a),
+                                          reinterpret_cast<const uint32_t*>(max_a),
+                                          reinterpret_cast<const uint32_t*>(min_b),
+                                          reinterpret_cast<const uint32_t*>(max_b), combine, heat);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+}  // namespace avl

@@ -1,0 +1,373 @@
+// Voxel x query similarity screen: S~ = bf16(A) . bf16(B)^T on the 5th-gen tensor cores.
+//
+//   A  = voxel features  (n_rows x dpad bf16, K-major)   streamed once from HBM by TMA
+//   B  = query embeddings (npad   x dpad bf16, K-major)   resident in shared memory
+//   S~ = 128-row x npad accumulator tiles in TMEM, consumed in place by a fused epilogue
+//
+// Replaces the OpenBLAS sgemm behind `map_feats @ text_feats.T`
+// (reference avlmaps/utils/clip_utils.py:227-229) plus the argmax / selection that follows it
+// (avlmaps/map/vlmap.py:123-124, avlmaps/robot/habitat_lang_robot.py:427-430); the (N, Q) score
+// matrix never exists in HBM.
+//
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue
+// (warp w owns TMEM lanes 32*(w%4)..+31, i.e. one voxel row per thread).
+// CG = 2 pairs two SMs (tcgen05 cta_group::2): UMMA M = 256, each CTA stages its own 128 voxel
+// rows and HALF of B, so a 256-query x 512-d B (256 KiB) is resident across the pair.
+#include <cuda.h>
+
+#include "avl_internal.h"
+#include "ptx_sm100.cuh"
+
+namespace avl {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 12;
+constexpr int kCtrlBytes = 1024;   // barriers + tmem slot
+constexpr int kQConstBytes = 2048; // float2[256]
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccumStride = 256;  // columns between the two accumulator stages
+
+__device__ __forceinline__ uint32_t f2ord(uint32_t b) {
+  // monotone map float bits -> uint32 (larger float <=> larger uint)
+  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+  return __uint_as_float(b);
+}
+
+struct TileCtx {
+  int64_t row;    // map row of this thread
+  int64_t crow;   // compact row (dense output of sampled launches)
+  bool valid;
+  uint32_t taddr; // TMEM address of column 0 of this thread's row
+};
+
+// ---- epilogue: dense store ------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void dense_chunk(const ScreenParams& p, const TileCtx& t, int c0) {
+  uint32_t v[W];
+  if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
+  ptx::tmem_ld_wait();
+  if (t.valid) {
+    float* o = p.dense_out + t.crow * p.dense_rs + static_cast<int64_t>(c0) * p.dense_cs;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (c0 + j < p.dense_cols) o[j * p.dense_cs] = __uint_as_float(v[j]);
+  }
+}
+
+// ---- epilogue: per-row top-2 keys -------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void argmax_chunk(const ScreenParams& p, const TileCtx& t, int c0,
+                                             uint32_t& best, uint32_t& second) {
+  uint32_t v[W];
+  if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
+  ptx::tmem_ld_wait();
+  if (c0 + W <= p.nq) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      uint32_t key = (f2ord(v[j]) & 0xFFFFFF00u) | static_cast<uint32_t>(255 - (c0 + j));
+      second = max(second, min(best, key));
+      best = max(best, key);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      if (c0 + j < p.nq) {
+        uint32_t key = (f2ord(v[j]) & 0xFFFFFF00u) | static_cast<uint32_t>(255 - (c0 + j));
+        second = max(second, min(best, key));
+        best = max(best, key);
+      }
+    }
+  }
+}
+
+template <int W>
+__device__ __forceinline__ uint32_t mask_chunk(const TileCtx& t, int c0, float thr) {
+  uint32_t v[W];
+  if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
+  ptx::tmem_ld_wait();
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < W; ++j) m |= (__uint_as_float(v[j]) >= thr ? 1u : 0u) << j;
+  return m;
+}
+
+// ---- epilogue: threshold screen ---------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void thresh_chunk(const ScreenParams& p, const TileCtx& t, int c0,
+                                             const float2* qc, float w_i, float r_i) {
+  uint32_t v[W];
+  if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const float2 c = qc[c0 + j];                       // (tau_q / scale_q, ||b_q||), smem broadcast
+    const float thr = fmaf(c.x, w_i, -r_i * c.y);      // candidate iff s~ + eps_iq >= T_q * w_i
+    const float s = __uint_as_float(v[j]);
+    if (t.valid && s >= thr) {
+      const int q = c0 + j;
+      const uint32_t slot = atomicAdd(p.cand_cnt + q, 1u);
+      if (slot < p.cand_cap) {
+        p.cand_idx[static_cast<size_t>(q) * p.cand_cap + slot] = static_cast<uint32_t>(t.row);
+        p.cand_val[static_cast<size_t>(q) * p.cand_cap + slot] = s;
+      }
+    }
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+              const ScreenParams p) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment; the offset is identical in both CTAs of a pair.
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t rank = 0;
+  if constexpr (CG == 2) rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  const uint32_t b_rows = static_cast<uint32_t>(p.npad) / CG;
+  const uint32_t bblk = b_rows * 128u;                       // bytes of one resident k-block of B
+  const uint32_t b_bytes = bblk * static_cast<uint32_t>(p.kblocks);
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + ((b_bytes + 1023u) & ~1023u);
+  uint8_t* ctrl = smem_a + static_cast<uint32_t>(p.stages) * kStageBytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(ctrl);    // [kMaxStages]
+  uint64_t* bar_empty = bar_full + kMaxStages;               // [kMaxStages]
+  uint64_t* bar_tfull = bar_empty + kMaxStages;              // [2]
+  uint64_t* bar_tempty = bar_tfull + 2;                      // [2]
+  uint64_t* bar_bfull = bar_tempty + 2;                      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_bfull + 1);
+  float2* qc = reinterpret_cast<float2*>(ctrl + kCtrlBytes);
+
+  if constexpr (CG == 2) ptx::cluster_sync_all();  // both CTAs resident before the paired TMEM alloc
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(bar_full + i), CG);   // leader's expect_tx arrive (+ peer's arrive)
+      ptx::mbar_init(ptx::smem_u32(bar_empty + i), 1);   // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(bar_tfull + i), 1);          // one tcgen05.commit
+      ptx::mbar_init(ptx::smem_u32(bar_tempty + i), CG * 128);  // every epilogue thread of the pair
+    }
+    ptx::mbar_init(ptx::smem_u32(bar_bfull), CG);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<CG>(ptx::smem_u32(tmem_slot), kTmemCols);
+  // per-query constants of the threshold screen
+  if (threadIdx.x < 256) {
+    const int q = threadIdx.x;
+    float2 c = make_float2(__int_as_float(0x7f800000), 0.f);  // +inf: padded column never passes
+    if (q < p.nq) {
+      c.x = (p.mode == kModeThresh) ? p.thr_t[q] : 0.f;
+      c.y = p.q_bn[q];
+    }
+    qc[q] = c;
+  }
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_units = static_cast<int>(gridDim.x) / CG;
+  const int unit = static_cast<int>(blockIdx.x) / CG;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < p.kblocks; ++kb)
+        ptx::tma_load_2d<CG>(ptx::smem_u32(smem_b + kb * bblk), &tmap_b, ptx::smem_u32(bar_bfull),
+                             kb * kBlockK, static_cast<int32_t>(rank * b_rows), ptx::kEvictLast);
+      if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_bfull), b_bytes * CG);
+      else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_bfull), 0);
+
+      uint32_t stage = 0, phase = 0;
+      for (int j = unit; j < p.num_tiles; j += num_units) {
+        const int64_t row0 = (static_cast<int64_t>(j) * p.tile_stride * CG + rank) * kTileRows;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(bar_empty + stage), phase ^ 1u, p.dbg, 0x10u + stage);
+          ptx::tma_load_2d<CG>(ptx::smem_u32(smem_a + stage * kStageBytes), &tmap_a,
+                               ptx::smem_u32(bar_full + stage), kb * kBlockK,
+                               static_cast<int32_t>(row0), ptx::kEvictFirst);
+          if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_full + stage), kStageBytes * CG);
+          else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_full + stage), 0);
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(kTileRows * CG, static_cast<uint32_t>(p.npad));
+      ptx::mbar_wait(ptx::smem_u32(bar_bfull), 0, p.dbg, 0x20u);
+      ptx::tc_fence_after();
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(bar_tempty + as), aphase ^ 1u, p.dbg, 0x30u + as);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccumStride;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(bar_full + stage), phase, p.dbg, 0x40u + stage);
+          ptx::tc_fence_after();
+          const uint64_t a0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_a + stage * kStageBytes));
+          const uint64_t b0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_b + kb * bblk));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes inside the swizzle row
+            ptx::umma_bf16<CG>(tmem_d, a0 + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit<CG>(ptx::smem_u32(bar_empty + stage));   // frees the A stage in both CTAs
+          if (kb == p.kblocks - 1) ptx::umma_commit<CG>(ptx::smem_u32(bar_tfull + as));
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (TMEM -> registers -> fused reduction) =====================
+    const uint32_t lane_base = (warp & 3u) * 32u;
+    const float rho = p.q_glob[0], bn_max = p.q_glob[1];
+    uint32_t it = 0;
+    for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
+      const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      ptx::mbar_wait(ptx::smem_u32(bar_tfull + as), aphase, p.dbg, 0x50u + as);
+      ptx::tc_fence_after();
+      TileCtx t;
+      t.row = (static_cast<int64_t>(j) * p.tile_stride * CG + rank) * kTileRows + lane_base + lane;
+      t.crow = (static_cast<int64_t>(j) * CG + rank) * kTileRows + lane_base + lane;
+      t.valid = t.row < p.n_rows;
+      t.taddr = tmem_base + as * kAccumStride + (lane_base << 16);
+      const int n32 = p.npad & ~31;
+
+      if (p.mode == kModeDense) {
+        for (int c0 = 0; c0 < n32; c0 += 32) dense_chunk<32>(p, t, c0);
+        if (n32 < p.npad) dense_chunk<16>(p, t, n32);
+      } else if (p.mode == kModeArgmax) {
+        uint32_t best = 0, second = 0;
+        for (int c0 = 0; c0 < n32; c0 += 32) argmax_chunk<32>(p, t, c0, best, second);
+        if (n32 < p.npad) argmax_chunk<16>(p, t, n32, best, second);
+        float r_i = 0.f, an_i = 0.f;
+        if (t.valid) {
+          an_i = p.row_an[t.row];
+          r_i = fmaf(rho, an_i, p.row_c[t.row]);
+        }
+        // eps_i = r_i * bn_max bounds |s~ - s| for every query; 2^-15 relative is lost by the key
+        const float tol = (2.f * r_i + 6.2e-5f * an_i) * bn_max * 1.0001f;
+        const float s1 = ord2f(best & 0xFFFFFF00u);
+        const float s2 = ord2f(second & 0xFFFFFF00u);
+        const float thr = s1 - tol;
+        const bool flagged = t.valid && second != 0u && (s2 >= thr);
+        if (t.valid) p.argmax_out[t.row] = 255 - static_cast<int32_t>(best & 0xFFu);
+        const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
+        if (fl != 0u) {
+          // second pass over the accumulator: bitmask of every query inside the band
+          uint32_t m[kFlagWords];
+#pragma unroll
+          for (int cb = 0; cb < kFlagWords; ++cb) {
+            m[cb] = 0u;
+            const int c0 = cb * 32;
+            if (c0 + 32 <= p.npad) m[cb] = mask_chunk<32>(t, c0, thr);
+            else if (c0 < p.npad) m[cb] = mask_chunk<16>(t, c0, thr);
+            const int nv = p.nq - c0;  // valid columns in this word
+            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv > 0 ? ((1u << nv) - 1u) : 0u);
+            m[cb] &= vm;
+          }
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(p.flag_count, static_cast<uint32_t>(__popc(fl)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (flagged) {
+            const uint32_t slot = base + __popc(fl & ((1u << lane) - 1u));
+            if (slot < p.flag_cap) {
+              p.flag_rows[slot] = static_cast<uint32_t>(t.row);
+              uint4* dst = reinterpret_cast<uint4*>(p.flag_masks + static_cast<size_t>(slot) * kFlagWords);
+              dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
+              dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
+            }
+          }
+        }
+      } else {  // kModeThresh
+        float r_i = 0.f, w_i = 1.f;
+        if (t.valid) {
+          r_i = fmaf(rho, p.row_an[t.row], p.row_c[t.row]);
+          if (p.normalize) w_i = fmaxf(p.row_norm[t.row], 1e-30f);
+        }
+        for (int c0 = 0; c0 < n32; c0 += 32) thresh_chunk<32>(p, t, c0, qc, w_i, r_i);
+        if (n32 < p.npad) thresh_chunk<16>(p, t, n32, qc, w_i, r_i);
+      }
+
+      // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+      ptx::tc_fence_before();
+      if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::smem_u32(bar_tempty + as), 0);
+      else ptx::mbar_arrive(ptx::smem_u32(bar_tempty + as));
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+#endif
+}
+
+}  // namespace
+
+size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages) {
+  const size_t b_bytes = static_cast<size_t>(npad / cta_group) * 128u * kblocks;
+  size_t total = ((b_bytes + 1023u) & ~size_t(1023)) + static_cast<size_t>(stages) * kStageBytes + kCtrlBytes +
+                 kQConstBytes + 1024u /* alignment slack */;
+  // > half of the SM's shared memory, so exactly one CTA (and one 512-column TMEM owner) per SM
+  if (total < 120u * 1024u) total = 120u * 1024u;
+  return total;
+}
+
+int screen_pick_stages(int cta_group, int npad, int kblocks) {
+  const size_t limit = 227u * 1024u;
+  for (int s = kMaxStages; s >= 2; --s)
+    if (screen_smem_bytes(cta_group, npad, kblocks, s) <= limit) return s;
+  return 0;
+}
+
+int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const ScreenParams& p,
+                  int num_sms, size_t smem_bytes, cudaStream_t stream) {
+  if (p.num_tiles <= 0) return AVL_OK;
+  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(tmap_a);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(tmap_b);
+  int units = num_sms / cta_group;
+  if (units > p.num_tiles) units = p.num_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(units * cta_group));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cta_group);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cta_group == 2) {
+    AVL_CUDA(cudaFuncSetAttribute(screen_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes)));
+    AVL_CUDA(cudaLaunchKernelEx(&cfg, screen_kernel<2>, ta, tb, p));
+  } else {
+    AVL_CUDA(cudaFuncSetAttribute(screen_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes)));
+    AVL_CUDA(cudaLaunchKernelEx(&cfg, screen_kernel<1>, ta, tb, p));
+  }
+  return AVL_OK;
+}
+
+}  // namespace avl

@@ -1,0 +1,186 @@
+/*
+ * avlmaps_b200 -- C-ABI of the B200-native AVLMaps hot paths.
+ *
+ * The reference (avlmaps/AVLMaps, pure Python) has no FFI; the boundary it
+ * offers is the Python surface of `avlmaps.map`.  The
+ * entry points below are what a ctypes stub inside those reference files
+ * would bind; each one names the reference lines whose body it replaces
+ * (paths relative to /root/reference).  INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C types only; every function returns AVL_OK (0) or an AVL_ERR_*
+ *     code and leaves a message for avl_last_error() (thread-local).
+ *   - `flags & AVL_ON_DEVICE`: the data pointers of that call are device
+ *     pointers (HBM-resident, e.g. torch tensors' data_ptr()); otherwise they
+ *     are host pointers and the call performs the H2D / D2H copies itself.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Host-pointer calls synchronise the stream before returning; device-
+ *     pointer calls only enqueue work (except where a count must be read
+ *     back, which is documented per call).
+ *   - inputs are borrowed for the duration of the call; handles own their
+ *     device memory; outputs are caller-allocated.
+ *   - there is NO CPU implementation behind any entry point: without a
+ *     CUDA device every compute call fails with AVL_ERR_CUDA.
+ */
+#ifndef AVLMAPS_B200_H_
+#define AVLMAPS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVL_OK 0
+#define AVL_ERR_CUDA 1        /* CUDA runtime/driver error (message has the cudaError string) */
+#define AVL_ERR_ARG 2         /* invalid argument */
+#define AVL_ERR_UNSUPPORTED 3 /* shape outside what the kernels support */
+#define AVL_ERR_STATE 4       /* call order violated (e.g. export before finalize) */
+
+#define AVL_ON_DEVICE 1 /* data pointers of this call are device pointers */
+
+#define AVL_MAX_QUERIES 256 /* per call; larger batches are chunked by the host layer */
+#define AVL_MAX_TOPK 128
+
+/* combine rules of avl_fuse_topk (habitat_lang_robot.py:223, avlmap.py:92-97,124-131; paper: product) */
+#define AVL_FUSE_PRODUCT 0
+#define AVL_FUSE_MAX 1
+#define AVL_FUSE_SUM 2
+
+/* feature layouts accepted by avl_builder_add_frame */
+#define AVL_FEAT_CHW 0 /* (1, D, FH, FW) fp32, what get_lseg_feat returns (lseg_utils.py:101-102) */
+#define AVL_FEAT_HWC 1 /* (FH, FW, D) fp32 pixel-major, the B200-friendly hand-off */
+
+typedef struct avl_map avl_map;         /* device-resident voxel feature map (grid_feat) */
+typedef struct avl_builder avl_builder; /* device-resident map under construction */
+
+/* Filled by the index calls when a non-NULL pointer is passed. */
+typedef struct avl_index_stats {
+  int64_t n_rows;
+  int32_t dim;
+  int32_t n_queries;
+  int32_t cta_group;          /* tcgen05 variant that ran: 1 or 2 (0 = no tensor-core kernel) */
+  int32_t n_launches;         /* kernels launched by the call */
+  int64_t n_flagged;          /* argmax: rows whose bf16 margin was inside the error band (re-ranked exactly) */
+  int64_t n_candidates;       /* top-k: (row, query) pairs that passed the screen threshold */
+  int32_t n_fallback_queries; /* top-k: queries that overflowed the candidate list -> exact dense path */
+  int32_t sample_rows;        /* top-k: rows used for the threshold estimate */
+  float ms_screen;            /* CUDA-event time of the main tcgen05 launch (avl_set_profiling(1)), else 0 */
+  float ms_total;             /* CUDA-event time of the whole call's device work, else 0 */
+} avl_index_stats;
+
+/* ---- library -------------------------------------------------------------------------- */
+int avl_version(void);              /* 100*major + minor; no CUDA call */
+const char* avl_last_error(void);   /* thread-local message of the last failing call */
+int avl_device_count(int* count);   /* number of CUDA devices (0 on a CPU box) */
+int avl_set_device(int device);     /* cudaSetDevice for the calling thread */
+int avl_set_profiling(int enabled); /* record CUDA events inside index calls (adds a stream sync) */
+
+/* ---- landmark-index path ------------------------------------------------------------- */
+
+/* Upload (or adopt a device copy of) grid_feat (n, dim) fp32 C-contiguous, build the bf16
+ * tensor-core copy and the per-row norms / rounding residuals.
+ * Replaces the host-RAM residency of VLMap.grid_feat after load_3d_map
+ * (avlmaps/map/vlmap.py:50-65, avlmaps/utils/mapping_utils.py:508-541). */
+int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, void* stream, avl_map** out);
+int avl_map_destroy(avl_map* map);
+int avl_map_shape(const avl_map* map, int64_t* n, int32_t* dim);
+int64_t avl_map_device_bytes(const avl_map* map);
+
+/* scores[i, q] = scale[q] * inv_norm[i] * <grid_feat[i], queries[q]>   (fp32, (n, nq) C-contiguous)
+ * inv_norm = 1 unless normalize_map; scale = 1 if NULL.  Accumulated in fp64, rounded once.
+ * Replaces `scores_list = map_feats @ text_feats.T` (avlmaps/utils/clip_utils.py:227-229,236-240;
+ * duplicate avlmaps/utils/index_utils.py:93-106) and the scaled audio form
+ * (avlmaps/map/sound_map.py:108-109). */
+int avl_sim_dense(avl_map* map, const float* queries, int32_t nq, const float* scale, int normalize_map,
+                  float* out_scores, int flags, void* stream);
+
+/* out_argmax[i] = argmax_q scores[i, q], ties -> lowest q (numpy argmax).  int32 (n,).
+ * Replaces get_lseg_score + `np.argmax(scores_mat, axis=1)` (avlmaps/map/vlmap.py:113-124,
+ * avlmaps/utils/index_utils.py:153-161, avlmaps/robot/habitat_lang_robot.py:243).
+ * tcgen05 bf16 screen; rows whose top-2 margin is inside the rigorous bf16 error band are
+ * re-scored exactly, so the result equals the argmax of avl_sim_dense's scores.
+ * Device-pointer calls read one counter back (stream sync). */
+int avl_sim_argmax(avl_map* map, const float* queries, int32_t nq, const float* scale, int normalize_map,
+                   int32_t* out_argmax, int flags, void* stream, avl_index_stats* stats);
+
+/* Per query the k best rows: out_idx (nq, k) int64, out_score (nq, k) fp32, sorted by
+ * (score desc, row asc); slots past n are idx -1 / score -inf.  Scores are the exact ones.
+ * Generalises `grid_pos[np.argmax(heat)]` (avlmaps/robot/habitat_lang_robot.py:427-430) and the
+ * argsort retrieval precedent (avlmaps/utils/clip_utils.py:86-93) to k > 1. */
+int avl_sim_topk(avl_map* map, const float* queries, int32_t nq, const float* scale, int normalize_map,
+                 int32_t k, int64_t* out_idx, float* out_score, int flags, void* stream,
+                 avl_index_stats* stats);
+
+/* Diagnostic: the raw bf16 tensor-core scores (n, nq) fp32 of the screen kernel, no correction.
+ * cta_group = 1 or 2 selects the tcgen05 variant (0 = the one the engine would pick). */
+int avl_sim_screen_dense(avl_map* map, const float* queries, int32_t nq, int32_t cta_group,
+                         float* out_scores, int flags, void* stream);
+
+/* Exact top-k of a vector: (value desc, index asc).  Serves get_max_pos_3d on any fused heat. */
+int avl_topk_f32(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val, int flags,
+                 void* stream);
+
+/* Cross-modal goal selection (BASELINE config 3).  For pair j < n_pairs:
+ *   h_a = minmax_i(score_a[:, j]), h_b = minmax_i(score_b[:, j])   (sound_map.py:151-152,
+ *   habitat_lang_robot.py:213-214), heat = combine(h_a, h_b), result = top-k(heat).
+ * map_a / map_b must have the same number of rows. out_idx/out_heat are (n_pairs, k). */
+int avl_fuse_topk(avl_map* map_a, const float* queries_a, const float* scale_a, int normalize_a,
+                  avl_map* map_b, const float* queries_b, const float* scale_b, int normalize_b,
+                  int32_t n_pairs, int32_t combine, int32_t k, int64_t* out_idx, float* out_heat,
+                  int flags, void* stream);
+
+/* ---- map-build path ------------------------------------------------------------------ */
+
+typedef struct avl_grid_spec {
+  int32_t gs;       /* grid_size: rows = cols = gs            (vlmap_builder.py:62)  */
+  int32_t vh;       /* int(camera_height / cs)                (vlmap_builder.py:201) */
+  double cs;        /* cell_size in metres                    (vlmap_builder.py:61)  */
+  int32_t dim;      /* feature dim D                          (vlmap_builder.py:202) */
+  int64_t capacity; /* initial voxel rows (reference: gs*gs, doubled on demand :151-152,286-311) */
+} avl_grid_spec;
+
+typedef struct avl_frame {
+  const float* depth; /* (h, w) fp32 metres (mapping_utils.py:231)                              */
+  int32_t h, w;
+  const float* feat; /* per-pixel features, layout below (vlmap_builder.py:123-126)             */
+  int32_t fh, fw;
+  int32_t feat_layout;       /* AVL_FEAT_CHW | AVL_FEAT_HWC                                     */
+  const uint8_t* rgb;        /* (h, w, 3) u8 or NULL (vlmap_builder.py:118-119)                 */
+  const int32_t* sample_idx; /* pixel ids v*w+u in the order `shuffle_mask[::rate]` yields
+                                (vlmap_builder.py:275-277); NULL = every pixel in raster order  */
+  int32_t n_samples;
+  double kinv[9];  /* np.linalg.inv(cam_calib_mat), row-major (mapping_utils.py:237)            */
+  double k[9];     /* cam_calib_mat (vlmap_builder.py:98,141)                                   */
+  double kfeat[9]; /* get_sim_cam_mat(fh, fw) (mapping_utils.py:591-596)                        */
+  double tf[16];   /* pc_transform = tf @ base_transform @ base2cam_tf (vlmap_builder.py:133)   */
+  double min_depth, max_depth; /* 0.1, 6 at the reference call site (vlmap_builder.py:129)      */
+} avl_frame;
+
+int avl_builder_create(const avl_grid_spec* spec, avl_builder** out);
+int avl_builder_destroy(avl_builder* b);
+
+/* Back-project one frame and fuse it (vlmap_builder.py:129-178): fp64 geometry without FMA
+ * contraction, first-touch voxel ids in (frame, sample) order, alpha-weighted accumulation.
+ * Frames must be added in the reference's frame order. */
+int avl_builder_add_frame(avl_builder* b, const avl_frame* frame, int flags, void* stream);
+
+/* voxels created so far (max_id, vlmap_builder.py:164-170); synchronises the stream. */
+int avl_builder_num_voxels(avl_builder* b, int64_t* n, void* stream);
+/* points that passed the depth / grid / feature-bounds tests so far (P_acc of SURVEY 8d). */
+int avl_builder_num_accepted(avl_builder* b, int64_t* n, void* stream);
+
+/* Export arrays[:max_id] + occupied_ids like _save_3d_map (vlmap_builder.py:313-327):
+ * grid_feat (V, D) f32, grid_pos (V, 3) i32, weight (V,) f32, occupied_ids (gs, gs, vh) i32,
+ * grid_rgb (V, 3) u8 (may be NULL).  Any pointer may be NULL to skip that array.  Can be
+ * called repeatedly (the reference saves every 100 frames, :181-183). */
+int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, float* weight,
+                       int32_t* occupied_ids, uint8_t* grid_rgb, int flags, void* stream);
+
+/* Hand the finished map to the index path without leaving HBM. */
+int avl_builder_to_map(avl_builder* b, void* stream, avl_map** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVLMAPS_B200_H_ */
