@@ -161,11 +161,24 @@ dense_exact_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const f
   }
 }
 
-// warp-cooperative exact dot of fp32 row a (global) with fp32 row b (global)
+// warp-cooperative exact dot of fp32 row a (global) with fp32 row b (global).  Lane l sums
+// k = l, l+32, ... in ascending order; 512-element chunks are loaded with 32 independent
+// requests in flight before the fp64 FMA chain starts (the loop is latency-bound otherwise).
 __device__ __forceinline__ double warp_dot(const float* __restrict__ a, const float* __restrict__ b, int d,
                                            int lane) {
   double s = 0.0;
-  for (int k = lane; k < d; k += 32) s = fma(static_cast<double>(a[k]), static_cast<double>(b[k]), s);
+  int k0 = 0;
+  for (; k0 + 512 <= d; k0 += 512) {
+    float av[16], bv[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      av[t] = __ldg(a + k0 + t * 32 + lane);
+      bv[t] = __ldg(b + k0 + t * 32 + lane);
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) s = fma(static_cast<double>(av[t]), static_cast<double>(bv[t]), s);
+  }
+  for (int k = k0 + lane; k < d; k += 32) s = fma(static_cast<double>(a[k]), static_cast<double>(b[k]), s);
   return warp_sum(s);
 }
 
@@ -232,58 +245,57 @@ __device__ __forceinline__ int64_t sample_to_row(int64_t c, int32_t unit_rows, i
 
 // ------------------------------------------------------------------ threshold from a sample
 // sample_t[q][c]: screen scores of the sampled rows (transposed dense output).  Per query:
-// T_q = k-th largest of the LOWER bounds (s~ - eps)/w over the sample, a valid lower bound of the
-// k-th largest exact score over the whole map (in units of score / scale_q).
-__global__ void __launch_bounds__(256)
-select_threshold_kernel(float* __restrict__ sample_t, int32_t n_sample, int64_t ld, int32_t k,
+// T_q = k-th largest of the per-thread maxima of the LOWER bounds (s~ - eps)/w over the sample.
+// The maxima belong to distinct rows, so T_q <= k-th largest lower bound over the sample <=
+// k-th largest exact score over the whole map (in units of score / scale_q): a valid threshold
+// from ONE pass over the sample.
+constexpr int kSelThreads = 1024;
+__global__ void __launch_bounds__(kSelThreads)
+select_threshold_kernel(const float* __restrict__ sample_t, int32_t n_sample, int64_t ld, int32_t k,
                         int32_t unit_rows, int32_t tile_stride, int64_t n_rows,
                         const float* __restrict__ row_norm, const float* __restrict__ row_c,
                         const float* __restrict__ row_an, const float* __restrict__ q_bn,
                         const uint32_t* __restrict__ glob, int normalize, float* __restrict__ thr_t) {
-  __shared__ int sh_cnt;
-  __shared__ int sh_valid;
   const int q = blockIdx.x;
   const float rho = __uint_as_float(glob[0]);
   const float bn = q_bn[q];
-  uint32_t* keys = reinterpret_cast<uint32_t*>(sample_t + static_cast<int64_t>(q) * ld);
-  if (threadIdx.x == 0) sh_valid = 0;
-  __syncthreads();
-  int nv = 0;
-  for (int c = threadIdx.x; c < n_sample; c += blockDim.x) {
+  const float* col = sample_t + static_cast<int64_t>(q) * ld;
+  uint32_t best = 0u;  // 0 = this thread saw no valid row
+  for (int c = threadIdx.x; c < n_sample; c += kSelThreads) {
     const int64_t row = sample_to_row(c, unit_rows, tile_stride);
-    uint32_t key = 0u;
     if (row < n_rows) {
-      const float s = __uint_as_float(keys[c]);
+      const float s = col[c];
       const float r_i = fmaf(rho, row_an[row], row_c[row]);
       const float w_i = normalize ? fmaxf(row_norm[row], 1e-30f) : 1.f;
       const float lo = __fdiv_rd(__fsub_rd(s, __fmul_ru(r_i, bn)), w_i);
-      key = f2ord(lo);
-      if (key == 0u) key = 1u;
-      ++nv;
+      best = max(best, max(f2ord(lo), 1u));
     }
-    keys[c] = key;
   }
-  if (nv) atomicAdd(&sh_valid, nv);
-  __syncthreads();
-  const int valid = sh_valid;
-  __syncthreads();
-  if (valid < k) {
-    if (threadIdx.x == 0) thr_t[q] = -INFINITY;  // every row is a candidate (tiny maps)
+  const int groups = __syncthreads_count(best != 0u);
+  if (groups < k) {
+    if (threadIdx.x == 0) thr_t[q] = -INFINITY;  // tiny maps: every row is a candidate
     return;
   }
-  const uint32_t v = block_kth_largest<uint32_t>([&](int j) { return keys[j]; }, n_sample, k, &sh_cnt);
+  uint32_t v = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = v | (1u << bit);
+    if (__syncthreads_count(best >= cand) >= k) v = cand;
+  }
   if (threadIdx.x == 0) thr_t[q] = ord2f(v);
 }
 
 // ------------------------------------------------------------------ top-k finalize
-// One block per query over its candidate list.
+// One block per query.  Gathers its entries from the unified candidate list, finds the k-th best
+// LOWER bound, keeps the entries whose UPPER bound reaches it, re-scores those exactly (fp64) and
+// orders them by (score desc, row asc).
 __global__ void __launch_bounds__(256)
 topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, const float* __restrict__ q,
                      const float* __restrict__ scale, const float* __restrict__ row_norm,
                      const float* __restrict__ row_c, const float* __restrict__ row_an,
                      const float* __restrict__ q_bn, const uint32_t* __restrict__ glob, int normalize,
-                     int32_t k, const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand_idx,
-                     const float* __restrict__ cand_val, uint32_t cand_cap, int64_t* __restrict__ out_idx,
+                     int32_t k, const uint32_t* __restrict__ list_total, const uint32_t* __restrict__ list_row,
+                     const uint8_t* __restrict__ list_q, const float* __restrict__ list_val, uint32_t list_cap,
+                     uint32_t cand_cap, uint32_t* __restrict__ cand_cnt, int64_t* __restrict__ out_idx,
                      float* __restrict__ out_score, uint32_t* __restrict__ overflow_flags) {
   extern __shared__ uint8_t sm[];
   uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
@@ -292,8 +304,36 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Ix + cand_cap);
   __shared__ int sh_cnt;
   __shared__ int sh_ns;
+  __shared__ unsigned int sh_n;
   const int qq = blockIdx.x;
-  const uint32_t cnt = cand_cnt[qq];
+  const uint32_t total = *list_total;
+  if (total > list_cap) {  // the list itself overflowed: every query takes the exact fallback
+    if (threadIdx.x == 0) { overflow_flags[qq] = 1u; cand_cnt[qq] = 0u; }
+    return;
+  }
+  if (threadIdx.x == 0) { sh_n = 0u; sh_ns = 0; }
+  __syncthreads();
+  // gather: 16 query bytes per load
+  const uint32_t nvec = (total + 15u) / 16u;
+  const uint4* lq4 = reinterpret_cast<const uint4*>(list_q);
+  for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 w = lq4[v];
+    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t e = v * 16u + a * 4u + b;
+        if (((words[a] >> (8 * b)) & 0xFFu) == static_cast<uint32_t>(qq) && e < total) {
+          const uint32_t s = atomicAdd(&sh_n, 1u);
+          if (s < cand_cap) { Ix[s] = list_row[e]; Lk[s] = __float_as_uint(list_val[e]); }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t cnt = sh_n;
+  if (threadIdx.x == 0) cand_cnt[qq] = cnt;
   if (cnt > cand_cap) {
     if (threadIdx.x == 0) overflow_flags[qq] = 1u;
     return;
@@ -302,16 +342,14 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   const float rho = __uint_as_float(glob[0]);
   const float bn = q_bn[qq];
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const uint32_t i = cand_idx[static_cast<size_t>(qq) * cand_cap + j];
-    const float s = cand_val[static_cast<size_t>(qq) * cand_cap + j];
+    const uint32_t i = Ix[j];
+    const float s = __uint_as_float(Lk[j]);
     const float r_i = fmaf(rho, row_an[i], row_c[i]);
     const float w_i = normalize ? fmaxf(row_norm[i], 1e-30f) : 1.f;
     const float e = __fmul_ru(r_i, bn);
     Lk[j] = max(f2ord(__fdiv_rd(__fsub_rd(s, e), w_i)), 1u);
     Uk[j] = max(f2ord(__fdiv_ru(__fadd_ru(s, e), w_i)), 1u);
-    Ix[j] = i;
   }
-  if (threadIdx.x == 0) sh_ns = 0;
   __syncthreads();
   const int kk = min(k, n);
   uint32_t v = 0u;
@@ -339,15 +377,17 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   }
   __syncthreads();
   const int kf = min(k, ns);
-  unsigned long long v64 = 0ull;
-  if (kf > 0) v64 = block_kth_largest<unsigned long long>([&](int j) { return K64[j]; }, ns, kf, &sh_cnt);
+  unsigned long long v64 = 0ull;  // keys are unique (row id in the low word): rank by counting
+  if (kf > 0 && ns > 2048) v64 = block_kth_largest<unsigned long long>([&](int j) { return K64[j]; }, ns, kf, &sh_cnt);
   for (int s = threadIdx.x; s < ns; s += blockDim.x) {
     const unsigned long long key = K64[s];
     if (kf > 0 && key >= v64) {
       int rank = 0;
       for (int t = 0; t < ns; ++t) rank += (K64[t] > key) ? 1 : 0;
-      out_idx[static_cast<size_t>(qq) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
-      out_score[static_cast<size_t>(qq) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
+      if (rank < kf) {
+        out_idx[static_cast<size_t>(qq) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+        out_score[static_cast<size_t>(qq) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
+      }
     }
   }
   for (int s = kf + threadIdx.x; s < k; s += blockDim.x) {
@@ -518,11 +558,15 @@ int launch_argmax_rerank(const float* feat, int32_t d, const float* q, int32_t n
   return AVL_OK;
 }
 
-int launch_select_threshold(float* sample_t, int32_t n_sample, int64_t ld, int32_t nq, int32_t k,
+int launch_select_threshold(const float* sample_t, int32_t n_sample, int64_t ld, int32_t nq, int32_t k,
                             int32_t unit_rows, int32_t tile_stride, int64_t n_rows, const float* row_norm,
                             const float* row_c, const float* row_an, const float* q_bn, const float* q_glob,
                             int normalize, float* thr_t, cudaStream_t s) {
-  select_threshold_kernel<<<nq, 256, 0, s>>>(sample_t, n_sample, ld, k, unit_rows, tile_stride, n_rows,
+  if (k > kSelThreads) {
+    set_error("select_threshold: k too large");
+    return AVL_ERR_ARG;
+  }
+  select_threshold_kernel<<<nq, kSelThreads, 0, s>>>(sample_t, n_sample, ld, k, unit_rows, tile_stride, n_rows,
                                              row_norm, row_c, row_an, q_bn,
                                              reinterpret_cast<const uint32_t*>(q_glob), normalize, thr_t);
   AVL_CUDA(cudaGetLastError());
@@ -534,15 +578,16 @@ size_t topk_finalize_smem(uint32_t cand_cap) { return static_cast<size_t>(cand_c
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c, const float* row_an,
                          const float* q_bn, const float* q_glob, int normalize, int32_t k,
-                         const uint32_t* cand_cnt, const uint32_t* cand_idx, const float* cand_val,
-                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
-                         cudaStream_t s) {
+                         const uint32_t* list_total, const uint32_t* list_row, const uint8_t* list_q,
+                         const float* list_val, uint32_t list_cap, uint32_t cand_cap, uint32_t* cand_cnt,
+                         int64_t* out_idx, float* out_score, uint32_t* overflow_flags, cudaStream_t s) {
   const size_t smem = topk_finalize_smem(cand_cap);
   AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   topk_finalize_kernel<<<nq, 256, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
-                                             reinterpret_cast<const uint32_t*>(q_glob), normalize, k, cand_cnt,
-                                             cand_idx, cand_val, cand_cap, out_idx, out_score, overflow_flags);
+                                             reinterpret_cast<const uint32_t*>(q_glob), normalize, k, list_total,
+                                             list_row, list_q, list_val, list_cap, cand_cap, cand_cnt, out_idx,
+                                             out_score, overflow_flags);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

@@ -22,10 +22,13 @@ namespace avl {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kThreads = 128 + kEpiWarps * 32;     // 384
 constexpr int kMaxStages = 12;
 constexpr int kCtrlBytes = 1024;   // barriers + tmem slot
 constexpr int kQConstBytes = 2048; // float2[256]
+constexpr int kRingEntries = 64;   // per epilogue warp: staged candidates before a 32-entry flush
+constexpr int kRingBytes = kEpiWarps * kRingEntries * 12;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccumStride = 256;  // columns between the two accumulator stages
 
@@ -97,26 +100,112 @@ __device__ __forceinline__ uint32_t mask_chunk(const TileCtx& t, int c0, float t
 }
 
 // ---- epilogue: threshold screen ---------------------------------------------------------
-template <int W>
-__device__ __forceinline__ void thresh_chunk(const ScreenParams& p, const TileCtx& t, int c0,
-                                             const float2* qc, float w_i, float r_i) {
+// candidate (row i, query q)  <=>  upper bound of the exact score reaches the threshold:
+//     (s~ + r_i * ||b_q||) / w_i  >=  T_q          (w_i = ||a_i|| if normalize_map else 1)
+// Fast path: one predicate bit per score, no branch.  qc[q] = (T_q, ||b_q||) in shared memory.
+template <int W, bool kNorm>
+__device__ __forceinline__ uint32_t thresh_mask_chunk(const TileCtx& t, int c0, const float2* qc, float iw,
+                                                      float ri) {
   uint32_t v[W];
   if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
   ptx::tmem_ld_wait();
+  const float4* qc4 = reinterpret_cast<const float4*>(qc + c0);
+  uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < W; ++j) {
-    const float2 c = qc[c0 + j];                       // (tau_q / scale_q, ||b_q||), smem broadcast
-    const float thr = fmaf(c.x, w_i, -r_i * c.y);      // candidate iff s~ + eps_iq >= T_q * w_i
-    const float s = __uint_as_float(v[j]);
-    if (t.valid && s >= thr) {
-      const int q = c0 + j;
-      const uint32_t slot = atomicAdd(p.cand_cnt + q, 1u);
-      if (slot < p.cand_cap) {
-        p.cand_idx[static_cast<size_t>(q) * p.cand_cap + slot] = static_cast<uint32_t>(t.row);
-        p.cand_val[static_cast<size_t>(q) * p.cand_cap + slot] = s;
-      }
+  for (int j = 0; j < W; j += 2) {
+    const float4 c = qc4[j >> 1];  // two queries per 16-byte broadcast load
+    float u0, u1;
+    if constexpr (kNorm) {
+      u0 = fmaf(ri, c.y, __uint_as_float(v[j]) * iw);       // ri = r_i / w_i, iw = 1 / w_i
+      u1 = fmaf(ri, c.w, __uint_as_float(v[j + 1]) * iw);
+    } else {
+      u0 = fmaf(ri, c.y, __uint_as_float(v[j]));
+      u1 = fmaf(ri, c.w, __uint_as_float(v[j + 1]));
+    }
+    m |= (u0 >= c.x ? 1u : 0u) << j;
+    m |= (u1 >= c.z ? 1u : 0u) << (j + 1);
+  }
+  return m;
+}
+
+// Slow path (rare, ~3 scores per warp and tile).  Kept tiny on purpose: an unrolled per-bit version
+// thrashed the instruction cache, and one global atomic per candidate cost ~2000 cycles each.
+// Marked scores are staged in a per-warp shared-memory ring and written to ONE global list in
+// 32-entry bursts (one atomicAdd per burst); the finalize kernel regroups them by query.
+struct Ring {
+  uint32_t* row;   // [kRingEntries]
+  uint32_t* q;     // [kRingEntries]
+  float* val;      // [kRingEntries]
+};
+
+__device__ __noinline__ uint32_t ring_flush(const ScreenParams& p, Ring r, uint32_t pend, uint32_t count,
+                                            uint32_t lane) {
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(p.list_total, count);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (lane < count && base + lane < p.list_cap) {
+    p.list_row[base + lane] = r.row[lane];
+    p.list_q[base + lane] = static_cast<uint8_t>(r.q[lane]);
+    p.list_val[base + lane] = r.val[lane];
+  }
+  __syncwarp();
+  const uint32_t rem = pend - count;
+  uint32_t a = 0, b = 0;
+  float c = 0.f;
+  if (lane < rem) { a = r.row[count + lane]; b = r.q[count + lane]; c = r.val[count + lane]; }
+  __syncwarp();
+  if (lane < rem) { r.row[lane] = a; r.q[lane] = b; r.val[lane] = c; }
+  __syncwarp();
+  return rem;
+}
+
+__device__ __forceinline__ uint32_t thresh_emit_word(const ScreenParams& p, uint32_t taddr, int64_t row, int c0,
+                                                     uint32_t m, Ring r, uint32_t pend, uint32_t lane) {
+  uint32_t u = __reduce_or_sync(0xffffffffu, m);
+  while (u) {  // warp-uniform loop over the columns any lane marked
+    const int j = __ffs(u) - 1;
+    u &= u - 1;
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr + c0 + j) : "memory");
+    ptx::tmem_ld_wait();
+    const bool mine = (m >> j) & 1u;
+    const uint32_t b = __ballot_sync(0xffffffffu, mine);
+    if (mine) {
+      const uint32_t slot = pend + __popc(b & ((1u << lane) - 1u));
+      r.row[slot] = static_cast<uint32_t>(row);
+      r.q[slot] = static_cast<uint32_t>(c0 + j);
+      r.val[slot] = __uint_as_float(v);
+    }
+    pend += __popc(b);
+    __syncwarp();
+    if (pend >= 32u) pend = ring_flush(p, r, pend, 32u, lane);
+  }
+  return pend;
+}
+
+// One epilogue warp handles the 32-column words cb = half, half + 2, ... of its 32 rows.
+template <bool kNorm>
+__device__ __forceinline__ uint32_t thresh_tile(const ScreenParams& p, const TileCtx& t, const float2* qc,
+                                                float iw, float ri, int half, Ring r, uint32_t pend,
+                                                uint32_t lane) {
+  uint32_t m[kFlagWords / 2];
+  uint32_t any = 0;
+#pragma unroll
+  for (int i = 0; i < kFlagWords / 2; ++i) {
+    m[i] = 0u;
+    const int c0 = (2 * i + half) * 32;
+    if (c0 + 32 <= p.npad) m[i] = thresh_mask_chunk<32, kNorm>(t, c0, qc, iw, ri);
+    else if (c0 < p.npad) m[i] = thresh_mask_chunk<16, kNorm>(t, c0, qc, iw, ri);
+    any |= m[i];
+  }
+  if (__any_sync(0xffffffffu, any != 0u)) {
+#pragma unroll
+    for (int i = 0; i < kFlagWords / 2; ++i) {
+      const int c0 = (2 * i + half) * 32;
+      if (c0 < p.npad) pend = thresh_emit_word(p, t.taddr, t.row, c0, m[i], r, pend, lane);
     }
   }
+  return pend;
 }
 
 template <int CG>
@@ -147,6 +236,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   uint64_t* bar_bfull = bar_tempty + 2;                      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_bfull + 1);
   float2* qc = reinterpret_cast<float2*>(ctrl + kCtrlBytes);
+  uint8_t* ring_base = ctrl + kCtrlBytes + kQConstBytes;
 
   if constexpr (CG == 2) ptx::cluster_sync_all();  // both CTAs resident before the paired TMEM alloc
 
@@ -161,7 +251,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(bar_tfull + i), 1);          // one tcgen05.commit
-      ptx::mbar_init(ptx::smem_u32(bar_tempty + i), CG * 128);  // every epilogue thread of the pair
+      ptx::mbar_init(ptx::smem_u32(bar_tempty + i), CG * kEpiWarps * 32);  // every epilogue thread of the pair
     }
     ptx::mbar_init(ptx::smem_u32(bar_bfull), CG);
     ptx::fence_barrier_init();
@@ -239,7 +329,16 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   } else if (warp >= 4) {
     // ===================== epilogue (TMEM -> registers -> fused reduction) =====================
     const uint32_t lane_base = (warp & 3u) * 32u;
+    const int half = static_cast<int>((warp - 4u) >> 2);  // which interleaved set of 32-column words
     const float rho = p.q_glob[0], bn_max = p.q_glob[1];
+    Ring ring;
+    {
+      uint8_t* rb = ring_base + (warp - 4u) * (kRingEntries * 12);
+      ring.row = reinterpret_cast<uint32_t*>(rb);
+      ring.q = ring.row + kRingEntries;
+      ring.val = reinterpret_cast<float*>(ring.q + kRingEntries);
+    }
+    uint32_t pend = 0;
     uint32_t it = 0;
     for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
@@ -253,59 +352,65 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       const int n32 = p.npad & ~31;
 
       if (p.mode == kModeDense) {
-        for (int c0 = 0; c0 < n32; c0 += 32) dense_chunk<32>(p, t, c0);
-        if (n32 < p.npad) dense_chunk<16>(p, t, n32);
+        for (int c0 = half * 32; c0 < n32; c0 += 64) dense_chunk<32>(p, t, c0);
+        if (n32 < p.npad && ((n32 >> 5) & 1) == half) dense_chunk<16>(p, t, n32);
       } else if (p.mode == kModeArgmax) {
-        uint32_t best = 0, second = 0;
-        for (int c0 = 0; c0 < n32; c0 += 32) argmax_chunk<32>(p, t, c0, best, second);
-        if (n32 < p.npad) argmax_chunk<16>(p, t, n32, best, second);
-        float r_i = 0.f, an_i = 0.f;
-        if (t.valid) {
-          an_i = p.row_an[t.row];
-          r_i = fmaf(rho, an_i, p.row_c[t.row]);
-        }
-        // eps_i = r_i * bn_max bounds |s~ - s| for every query; 2^-15 relative is lost by the key
-        const float tol = (2.f * r_i + 6.2e-5f * an_i) * bn_max * 1.0001f;
-        const float s1 = ord2f(best & 0xFFFFFF00u);
-        const float s2 = ord2f(second & 0xFFFFFF00u);
-        const float thr = s1 - tol;
-        const bool flagged = t.valid && second != 0u && (s2 >= thr);
-        if (t.valid) p.argmax_out[t.row] = 255 - static_cast<int32_t>(best & 0xFFu);
-        const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
-        if (fl != 0u) {
-          // second pass over the accumulator: bitmask of every query inside the band
-          uint32_t m[kFlagWords];
-#pragma unroll
-          for (int cb = 0; cb < kFlagWords; ++cb) {
-            m[cb] = 0u;
-            const int c0 = cb * 32;
-            if (c0 + 32 <= p.npad) m[cb] = mask_chunk<32>(t, c0, thr);
-            else if (c0 < p.npad) m[cb] = mask_chunk<16>(t, c0, thr);
-            const int nv = p.nq - c0;  // valid columns in this word
-            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv > 0 ? ((1u << nv) - 1u) : 0u);
-            m[cb] &= vm;
+        if (half == 0) {  // the per-row reduction stays inside one thread: 4 of the 8 warps do it
+          uint32_t best = 0, second = 0;
+          for (int c0 = 0; c0 < n32; c0 += 32) argmax_chunk<32>(p, t, c0, best, second);
+          if (n32 < p.npad) argmax_chunk<16>(p, t, n32, best, second);
+          float r_i = 0.f, an_i = 0.f;
+          if (t.valid) {
+            an_i = p.row_an[t.row];
+            r_i = fmaf(rho, an_i, p.row_c[t.row]);
           }
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(p.flag_count, static_cast<uint32_t>(__popc(fl)));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (flagged) {
-            const uint32_t slot = base + __popc(fl & ((1u << lane) - 1u));
-            if (slot < p.flag_cap) {
-              p.flag_rows[slot] = static_cast<uint32_t>(t.row);
-              uint4* dst = reinterpret_cast<uint4*>(p.flag_masks + static_cast<size_t>(slot) * kFlagWords);
-              dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
-              dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
+          // eps_i = r_i * bn_max bounds |s~ - s| for every query; 2^-15 relative is lost by the key
+          const float tol = (2.f * r_i + 6.2e-5f * an_i) * bn_max * 1.0001f;
+          const float s1 = ord2f(best & 0xFFFFFF00u);
+          const float s2 = ord2f(second & 0xFFFFFF00u);
+          const float thr = s1 - tol;
+          const bool flagged = t.valid && second != 0u && (s2 >= thr);
+          if (t.valid) p.argmax_out[t.row] = 255 - static_cast<int32_t>(best & 0xFFu);
+          const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
+          if (fl != 0u) {
+            // second pass over the accumulator: bitmask of every query inside the band
+            uint32_t m[kFlagWords];
+#pragma unroll
+            for (int cb = 0; cb < kFlagWords; ++cb) {
+              m[cb] = 0u;
+              const int c0 = cb * 32;
+              if (c0 + 32 <= p.npad) m[cb] = mask_chunk<32>(t, c0, thr);
+              else if (c0 < p.npad) m[cb] = mask_chunk<16>(t, c0, thr);
+              const int nv = p.nq - c0;  // valid columns in this word
+              const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv > 0 ? ((1u << nv) - 1u) : 0u);
+              m[cb] &= vm;
+            }
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(p.flag_count, static_cast<uint32_t>(__popc(fl)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (flagged) {
+              const uint32_t slot = base + __popc(fl & ((1u << lane) - 1u));
+              if (slot < p.flag_cap) {
+                p.flag_rows[slot] = static_cast<uint32_t>(t.row);
+                uint4* dst = reinterpret_cast<uint4*>(p.flag_masks + static_cast<size_t>(slot) * kFlagWords);
+                dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
+                dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
+              }
             }
           }
         }
       } else {  // kModeThresh
-        float r_i = 0.f, w_i = 1.f;
+        // invalid rows: ri = -inf makes every upper bound -inf (or NaN), never a candidate
+        float ri = -INFINITY, iw = 1.f;
         if (t.valid) {
-          r_i = fmaf(rho, p.row_an[t.row], p.row_c[t.row]);
-          if (p.normalize) w_i = fmaxf(p.row_norm[t.row], 1e-30f);
+          ri = fmaf(rho, p.row_an[t.row], p.row_c[t.row]);
+          if (p.normalize) {
+            iw = 1.f / fmaxf(p.row_norm[t.row], 1e-30f);
+            ri *= iw;
+          }
         }
-        for (int c0 = 0; c0 < n32; c0 += 32) thresh_chunk<32>(p, t, c0, qc, w_i, r_i);
-        if (n32 < p.npad) thresh_chunk<16>(p, t, n32, qc, w_i, r_i);
+        if (p.normalize) pend = thresh_tile<true>(p, t, qc, iw, ri, half, ring, pend, lane);
+        else pend = thresh_tile<false>(p, t, qc, iw, ri, half, ring, pend, lane);
       }
 
       // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
@@ -313,6 +418,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::smem_u32(bar_tempty + as), 0);
       else ptx::mbar_arrive(ptx::smem_u32(bar_tempty + as));
     }
+    if (p.mode == kModeThresh && pend > 0u) pend = ring_flush(p, ring, pend, pend, lane);
   }
 
   ptx::tc_fence_before();
@@ -326,7 +432,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages) {
   const size_t b_bytes = static_cast<size_t>(npad / cta_group) * 128u * kblocks;
   size_t total = ((b_bytes + 1023u) & ~size_t(1023)) + static_cast<size_t>(stages) * kStageBytes + kCtrlBytes +
-                 kQConstBytes + 1024u /* alignment slack */;
+                 kQConstBytes + kRingBytes + 1024u /* alignment slack */;
   // > half of the SM's shared memory, so exactly one CTA (and one 512-column TMEM owner) per SM
   if (total < 120u * 1024u) total = 120u * 1024u;
   return total;

@@ -1,0 +1,177 @@
+"""ORACLE -- test infrastructure only (see oracle/README.md).
+
+Loads the UNMODIFIED reference files from /root/reference and runs the reference's own hot-path
+functions, so that golden vectors can be generated in the build container (the reference tree does
+not exist on the GPU box; nothing that runs there imports this module).
+
+The package `avlmaps.map` cannot be imported as a whole (its __init__ pulls hloc, librosa,
+audioclip, shapely ...), so single files are loaded with importlib after empty stub modules are put
+in sys.modules for the third-party imports that are absent here.
+Only three names are monkey-patched, all of them I/O or model loading, never arithmetic:
+  VLMapBuilder._init_lseg   (would load the LSeg checkpoint)   -> sets device / clip_feat_dim
+  get_lseg_feat             (would run LSeg)                   -> returns the synthetic (1,D,FH,FW) features
+  save_3d_map               (would write HDF5 through h5py)    -> captures the arrays
+and `get_text_feats` (would run CLIP) for the index path -> returns the synthetic embeddings.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+
+REF_ROOT = Path(os.environ.get("AVL_REFERENCE_ROOT", "/root/reference"))
+_STUBS = ["h5py", "matplotlib", "matplotlib.patches", "matplotlib.pyplot", "clip", "open3d", "omegaconf",
+          "gdown", "timm"]
+_loaded = {}
+
+
+def available() -> bool:
+    return (REF_ROOT / "avlmaps" / "map" / "vlmap_builder.py").exists()
+
+
+def _install_stubs():
+    for name in _STUBS:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["omegaconf"].DictConfig = dict
+    sys.modules["omegaconf"].OmegaConf = object
+    sys.modules["matplotlib"].patches = sys.modules["matplotlib.patches"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if str(REF_ROOT) not in sys.path:
+        sys.path.insert(0, str(REF_ROOT))
+
+
+def load(name: str, rel: str):
+    if name in _loaded:
+        return _loaded[name]
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REF_ROOT}")
+    _install_stubs()
+    spec = importlib.util.spec_from_file_location(name, REF_ROOT / rel)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _loaded[name] = mod
+    return mod
+
+
+class AttrDict(dict):
+    """dict with attribute access, what the reference expects from an OmegaConf node."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:  # pragma: no cover
+            raise AttributeError(k) from e
+        return AttrDict(v) if isinstance(v, dict) else v
+
+
+# ------------------------------------------------------------------------------------------ index path
+def ref_get_lseg_score(feat: np.ndarray, text_feats: np.ndarray) -> np.ndarray:
+    """The reference's get_lseg_score (avlmaps/utils/clip_utils.py:196-242) with
+    use_multiple_templates=False; the CLIP text encoder is replaced by `text_feats`."""
+    cu = load("ref_clip_utils", "avlmaps/utils/clip_utils.py")
+    names = [f"q{i}" for i in range(text_feats.shape[0] - 1)] + ["other"]
+    saved = cu.get_text_feats
+    cu.get_text_feats = lambda in_text, clip_model, clip_feat_dim, batch_size=64: text_feats
+    try:
+        return cu.get_lseg_score(None, names, feat, feat.shape[-1], use_multiple_templates=False)
+    finally:
+        cu.get_text_feats = saved
+
+
+def ref_index_mask(scores: np.ndarray, cat_id: int) -> np.ndarray:
+    """avlmaps/map/vlmap.py:123-124"""
+    max_ids = np.argmax(scores, axis=1)
+    return max_ids == cat_id
+
+
+def ref_heatmap_from_mask_3d(grid_pos, mask, cell_size=0.05, decay_rate=0.01):
+    vu = load("ref_visualize_utils", "avlmaps/utils/visualize_utils.py")
+    return vu.get_heatmap_from_mask_3d(grid_pos, mask, cell_size=cell_size, decay_rate=decay_rate)
+
+
+# ------------------------------------------------------------------------------------------ build path
+def ref_transforms(map_config):
+    """Map._setup_transforms (avlmaps/map/map.py:54-68), restated because map.py needs shapely."""
+    base2cam_tf = np.eye(4)
+    base2cam_tf[:3, :3] = np.array([map_config["pose_info"]["base2cam_rot"]]).reshape((3, 3))
+    base2cam_tf[1, 3] = map_config["pose_info"]["camera_height"]
+    base_transform = np.eye(4)
+    base_transform[0, :3] = map_config["pose_info"]["base_forward_axis"]
+    base_transform[1, :3] = map_config["pose_info"]["base_left_axis"]
+    base_transform[2, :3] = map_config["pose_info"]["base_up_axis"]
+    return base2cam_tf, base_transform
+
+
+def ref_build(map_config: dict, poses: np.ndarray, depths, rgbs, feats, seed: int):
+    """Run the reference's VLMapBuilder.create_mobile_base_map (vlmap_builder.py:54-185) on synthetic
+    frames.  depths[i] (H,W) f32, rgbs[i] (H,W,3) u8 RGB, feats[i] (1,D,FH,FW) f32.
+    Returns dict(grid_feat, grid_pos, weight, occupied_ids, grid_rgb, sample_idx) where sample_idx[i]
+    is the pixel order the reference's global-RNG shuffle produced for frame i."""
+    import cv2
+
+    vb = load("ref_vlmap_builder", "avlmaps/map/vlmap_builder.py")
+    cfg = AttrDict(map_config)
+    base2cam_tf, base_transform = ref_transforms(map_config)
+    D = feats[0].shape[1]
+    captured = {}
+    frame_counter = {"i": 0}
+    sample_orders = []
+
+    def fake_init_lseg(self):
+        self.device = "cpu"
+        self.clip_feat_dim = D
+        return None, None, 480, 520, [0.5] * 3, [0.5] * 3
+
+    def fake_get_lseg_feat(*a, **k):
+        i = frame_counter["i"]
+        frame_counter["i"] += 1
+        return feats[i]
+
+    def fake_save(path, grid_feat, grid_pos, weight, occupied_ids, mapped_iter_list, grid_rgb=None,
+                  init_height_id=None):
+        captured.update(grid_feat=np.array(grid_feat), grid_pos=np.array(grid_pos), weight=np.array(weight),
+                        occupied_ids=np.array(occupied_ids), grid_rgb=np.array(grid_rgb),
+                        mapped_iter_list=list(mapped_iter_list))
+
+    # record the permutation np.random.shuffle produces inside _backproject_depth without touching it
+    orig_shuffle = np.random.shuffle
+
+    def recording_shuffle(x):
+        orig_shuffle(x)
+        sample_orders.append(np.array(x))
+
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        (td / "rgb").mkdir()
+        (td / "depth").mkdir()
+        rgb_paths, depth_paths = [], []
+        for i, (d, c) in enumerate(zip(depths, rgbs)):
+            rp = td / "rgb" / f"{i:06d}.png"
+            dp = td / "depth" / f"{i:06d}.npy"
+            cv2.imwrite(str(rp), cv2.cvtColor(c, cv2.COLOR_RGB2BGR))
+            np.save(dp, d)
+            rgb_paths.append(rp)
+            depth_paths.append(dp)
+        pose_path = td / "poses.txt"
+        np.savetxt(pose_path, poses)
+        saved = (vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map)
+        vb.VLMapBuilder._init_lseg = fake_init_lseg
+        vb.get_lseg_feat = fake_get_lseg_feat
+        vb.save_3d_map = fake_save
+        np.random.shuffle = recording_shuffle
+        try:
+            np.random.seed(seed)
+            b = vb.VLMapBuilder(td, cfg, pose_path, rgb_paths, depth_paths, base2cam_tf, base_transform)
+            b.create_mobile_base_map()
+        finally:
+            vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map = saved
+            np.random.shuffle = orig_shuffle
+    rate = map_config["depth_sample_rate"]
+    captured["sample_idx"] = [s[::rate].astype(np.int32) for s in sample_orders]
+    return captured
