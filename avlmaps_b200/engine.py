@@ -1,0 +1,312 @@
+"""Pythonic handles over the C-ABI (include/avlmaps_b200.h): `DeviceMap` for the landmark-index
+path, `DeviceBuilder` for the map-build path.  Inputs may be numpy arrays (host pointers, the
+library does the H2D / D2H copies) or torch CUDA tensors (device pointers, nothing leaves HBM).
+
+PyTorch is only plumbing here (device memory, streams, torch.distributed); every result comes from
+the hand-written kernels in csrc/.  There is no CPU path: without a CUDA device every method raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+def _current_torch_stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Arg:
+    """Uniform view of a numpy / torch argument: pointer + whether it is a device pointer."""
+
+    def __init__(self, x, dtype, name):
+        self.keep = None
+        self.device = False
+        self.ptr = None
+        self.shape = None
+        if x is None:
+            return
+        if _is_torch(x):
+            import torch
+
+            want = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8}[dtype]
+            if x.dtype != want or not x.is_contiguous():
+                x = x.to(want).contiguous()
+            if not x.is_cuda:
+                x = x.numpy()
+            else:
+                self.keep, self.device, self.ptr, self.shape = x, True, C.c_void_p(x.data_ptr()), tuple(x.shape)
+                return
+        a = np.ascontiguousarray(x, dtype=dtype)
+        self.keep, self.ptr, self.shape = a, a.ctypes.data_as(C.c_void_p), a.shape
+
+
+def _flags(*args: _Arg) -> int:
+    dev = [a.device for a in args if a.ptr is not None]
+    if any(dev) and not all(dev):
+        raise ValueError("all array arguments of one call must be on the same side (all numpy or all torch.cuda)")
+    return L.AVL_ON_DEVICE if dev and dev[0] else 0
+
+
+class DeviceMap:
+    """grid_feat (N, D) resident in HBM: fp32 copy (exact re-scoring), bf16 copy (tcgen05 screen),
+    per-row norms and bf16 rounding residuals.  Created once per loaded map (VLMap.load_map)."""
+
+    def __init__(self, grid_feat, stream=None, _handle=None):
+        self._lib = L.load()
+        L.require_device()
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            a = _Arg(grid_feat, np.float32, "grid_feat")
+            if len(a.shape) != 2:
+                raise ValueError("grid_feat must be (N, D)")
+            L.check(self._lib.avl_map_create(a.ptr, a.shape[0], a.shape[1], _flags(a), _stream_ptr(stream), C.byref(self._h)))
+        n, d = C.c_int64(), C.c_int32()
+        L.check(self._lib.avl_map_shape(self._h, C.byref(n), C.byref(d)))
+        self.n, self.dim = n.value, d.value
+        self.last_stats = None
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.avl_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.avl_map_device_bytes(self._h))
+
+    def _queries(self, queries, scale):
+        q = _Arg(queries, np.float32, "queries")
+        if len(q.shape) != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be (Q, {self.dim}), got {q.shape}")
+        s = _Arg(scale, np.float32, "scale")
+        if s.ptr is not None and tuple(s.shape) != (q.shape[0],):
+            raise ValueError("scale must be (Q,)")
+        return q, s
+
+    def _out(self, like_device: bool, shape, dtype):
+        if like_device:
+            import torch
+
+            t = torch.empty(shape, dtype={np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64}[dtype],
+                            device="cuda")
+            return t, C.c_void_p(t.data_ptr())
+        a = np.empty(shape, dtype)
+        return a, a.ctypes.data_as(C.c_void_p)
+
+    # -- scores (N, Q): the reference's `map_feats @ text_feats.T`
+    def scores(self, queries, scale=None, normalize_map: bool = False, stream=None):
+        q, s = self._queries(queries, scale)
+        out = []
+        for c0 in range(0, q.shape[0], L.AVL_MAX_QUERIES):
+            qc = q.keep[c0:c0 + L.AVL_MAX_QUERIES]
+            sc = None if s.ptr is None else s.keep[c0:c0 + L.AVL_MAX_QUERIES]
+            qa, sa = _Arg(qc, np.float32, "q"), _Arg(sc, np.float32, "s")
+            o, optr = self._out(q.device, (self.n, qa.shape[0]), np.float32)
+            L.check(self._lib.avl_sim_dense(self._h, qa.ptr, qa.shape[0], sa.ptr, int(normalize_map), optr,
+                                            _flags(qa, sa), _stream_ptr(stream)))
+            out.append(o)
+        if len(out) == 1:
+            return out[0]
+        if q.device:
+            import torch
+
+            return torch.cat(out, dim=1)
+        return np.concatenate(out, axis=1)
+
+    def screen_scores(self, queries, cta_group: int = 0, stream=None):
+        """Diagnostic: raw bf16 tensor-core scores of the screen kernel."""
+        q, _ = self._queries(queries, None)
+        o, optr = self._out(q.device, (self.n, q.shape[0]), np.float32)
+        L.check(self._lib.avl_sim_screen_dense(self._h, q.ptr, q.shape[0], cta_group, optr, _flags(q), _stream_ptr(stream)))
+        return o
+
+    # -- per-voxel argmax over the query batch (index_map)
+    def argmax(self, queries, scale=None, normalize_map: bool = False, stream=None, want_stats: bool = False):
+        q, s = self._queries(queries, scale)
+        if q.shape[0] > L.AVL_MAX_QUERIES:
+            raise ValueError(f"at most {L.AVL_MAX_QUERIES} queries per argmax call")
+        o, optr = self._out(q.device, (self.n,), np.int32)
+        st = L.IndexStats()
+        L.check(self._lib.avl_sim_argmax(self._h, q.ptr, q.shape[0], s.ptr, int(normalize_map), optr, _flags(q, s),
+                                         _stream_ptr(stream), C.byref(st) if (want_stats or not q.device) else None))
+        self.last_stats = st.as_dict()
+        return o
+
+    # -- per-query top-k rows
+    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None):
+        q, s = self._queries(queries, scale)
+        outs_i, outs_s = [], []
+        stats = None
+        for c0 in range(0, q.shape[0], L.AVL_MAX_QUERIES):
+            qa = _Arg(q.keep[c0:c0 + L.AVL_MAX_QUERIES], np.float32, "q")
+            sa = _Arg(None if s.ptr is None else s.keep[c0:c0 + L.AVL_MAX_QUERIES], np.float32, "s")
+            oi, oiptr = self._out(q.device, (qa.shape[0], k), np.int64)
+            os_, osptr = self._out(q.device, (qa.shape[0], k), np.float32)
+            st = L.IndexStats()
+            L.check(self._lib.avl_sim_topk(self._h, qa.ptr, qa.shape[0], sa.ptr, int(normalize_map), k, oiptr, osptr,
+                                           _flags(qa, sa), _stream_ptr(stream), C.byref(st)))
+            stats = st.as_dict()
+            outs_i.append(oi)
+            outs_s.append(os_)
+        self.last_stats = stats
+        if len(outs_i) == 1:
+            return outs_i[0], outs_s[0]
+        if q.device:
+            import torch
+
+            return torch.cat(outs_i), torch.cat(outs_s)
+        return np.concatenate(outs_i), np.concatenate(outs_s)
+
+
+def topk_vector(values, k: int, stream=None):
+    """Exact top-k of a heat vector, (value desc, index asc): k = 1 is get_max_pos_3d's np.argmax."""
+    lib = L.load()
+    L.require_device()
+    v = _Arg(values, np.float32, "values")
+    n = int(np.prod(v.shape))
+    if v.device:
+        import torch
+
+        oi = torch.empty(k, dtype=torch.int64, device="cuda")
+        ov = torch.empty(k, dtype=torch.float32, device="cuda")
+        L.check(lib.avl_topk_f32(v.ptr, n, k, C.c_void_p(oi.data_ptr()), C.c_void_p(ov.data_ptr()), L.AVL_ON_DEVICE,
+                                 _stream_ptr(stream)))
+        return oi, ov
+    oi, ov = np.empty(k, np.int64), np.empty(k, np.float32)
+    L.check(lib.avl_topk_f32(v.ptr, n, k, L.np_ptr(oi), L.np_ptr(ov), 0, _stream_ptr(stream)))
+    return oi, ov
+
+
+def fuse_topk(map_a: DeviceMap, queries_a, map_b: DeviceMap, queries_b, k: int, scale_a=None, scale_b=None,
+              normalize_a: bool = False, normalize_b: bool = False, combine: int = L.FUSE_PRODUCT, stream=None):
+    """Cross-modal goal: per pair j, heat = combine(minmax(score_a[:, j]), minmax(score_b[:, j])) -> top-k."""
+    lib = L.load()
+    qa, sa = map_a._queries(queries_a, scale_a)
+    qb, sb = map_b._queries(queries_b, scale_b)
+    if qa.shape[0] != qb.shape[0]:
+        raise ValueError("fuse_topk needs the same number of queries per modality (pairs)")
+    n_pairs = qa.shape[0]
+    oi, oiptr = map_a._out(qa.device, (n_pairs, k), np.int64)
+    oh, ohptr = map_a._out(qa.device, (n_pairs, k), np.float32)
+    L.check(lib.avl_fuse_topk(map_a._h, qa.ptr, sa.ptr, int(normalize_a), map_b._h, qb.ptr, sb.ptr, int(normalize_b),
+                              n_pairs, combine, k, oiptr, ohptr, _flags(qa, sa, qb, sb), _stream_ptr(stream)))
+    return oi, oh
+
+
+class DeviceBuilder:
+    """Voxel map under construction in HBM (the arrays of VLMapBuilder._init_map, vlmap_builder.py:195-224)."""
+
+    def __init__(self, gs: int, vh: int, cs: float, dim: int, capacity: Optional[int] = None):
+        self._lib = L.load()
+        L.require_device()
+        self.gs, self.vh, self.cs, self.dim = int(gs), int(vh), float(cs), int(dim)
+        spec = L.GridSpec(self.gs, self.vh, self.cs, self.dim, int(capacity or 0))
+        self._h = C.c_void_p()
+        L.check(self._lib.avl_builder_create(C.byref(spec), C.byref(self._h)))
+        self.n_frames = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.avl_builder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def add_frame(self, depth, feat, kinv, k, kfeat, tf, rgb=None, sample_idx=None, feat_layout: int = L.FEAT_CHW,
+                  min_depth: float = 0.1, max_depth: float = 6.0, stream=None):
+        """depth (H, W) f32; feat (1, D, FH, FW) [CHW] or (FH, FW, D) [HWC] f32; rgb (H, W, 3) u8 or None;
+        sample_idx int32 pixel ids in the reference's sample order or None for every pixel."""
+        d_ = _Arg(depth, np.float32, "depth")
+        f_ = _Arg(feat, np.float32, "feat")
+        r_ = _Arg(rgb, np.uint8, "rgb")
+        s_ = _Arg(sample_idx, np.int32, "sample_idx")
+        if len(d_.shape) != 2:
+            raise ValueError("depth must be (H, W)")
+        if feat_layout == L.FEAT_CHW:
+            if len(f_.shape) == 4 and f_.shape[0] == 1:
+                _, dd, fh, fw = f_.shape
+            elif len(f_.shape) == 3:
+                dd, fh, fw = f_.shape
+            else:
+                raise ValueError("CHW features must be (1, D, FH, FW)")
+        else:
+            if len(f_.shape) != 3:
+                raise ValueError("HWC features must be (FH, FW, D)")
+            fh, fw, dd = f_.shape
+        if dd != self.dim:
+            raise ValueError(f"feature dim {dd} != builder dim {self.dim}")
+        fr = L.Frame()
+        fr.depth, fr.h, fr.w = d_.ptr, d_.shape[0], d_.shape[1]
+        fr.feat, fr.fh, fr.fw, fr.feat_layout = f_.ptr, fh, fw, feat_layout
+        fr.rgb = r_.ptr
+        fr.sample_idx = s_.ptr
+        fr.n_samples = 0 if s_.ptr is None else int(np.prod(s_.shape))
+        for name, m, n in (("kinv", kinv, 9), ("k", k, 9), ("kfeat", kfeat, 9), ("tf", tf, 16)):
+            arr = np.ascontiguousarray(m, np.float64).reshape(-1)
+            if arr.size != n:
+                raise ValueError(f"{name} must have {n} elements")
+            getattr(fr, name)[:] = arr.tolist()
+        fr.min_depth, fr.max_depth = float(min_depth), float(max_depth)
+        L.check(self._lib.avl_builder_add_frame(self._h, C.byref(fr), _flags(d_, f_, r_, s_), _stream_ptr(stream)))
+        self.n_frames += 1
+
+    @property
+    def num_voxels(self) -> int:
+        n = C.c_int64()
+        L.check(self._lib.avl_builder_num_voxels(self._h, C.byref(n), None))
+        return n.value
+
+    @property
+    def num_accepted(self) -> int:
+        n = C.c_int64()
+        L.check(self._lib.avl_builder_num_accepted(self._h, C.byref(n), None))
+        return n.value
+
+    def export(self, want_rgb: bool = True):
+        """numpy arrays[:max_id] + occupied_ids, like _save_3d_map (vlmap_builder.py:313-327)."""
+        v = self.num_voxels
+        out = dict(
+            grid_feat=np.zeros((v, self.dim), np.float32),
+            grid_pos=np.zeros((v, 3), np.int32),
+            weight=np.zeros((v,), np.float32),
+            occupied_ids=np.empty((self.gs, self.gs, self.vh), np.int32),
+            grid_rgb=np.zeros((v, 3), np.uint8),
+        )
+        L.check(self._lib.avl_builder_export(self._h, L.np_ptr(out["grid_feat"]), L.np_ptr(out["grid_pos"]),
+                                             L.np_ptr(out["weight"]), L.np_ptr(out["occupied_ids"]),
+                                             L.np_ptr(out["grid_rgb"]) if want_rgb else None, 0, None))
+        return out
+
+    def to_map(self) -> DeviceMap:
+        h = C.c_void_p()
+        L.check(self._lib.avl_builder_to_map(self._h, None, C.byref(h)))
+        return DeviceMap(None, _handle=h)

@@ -1,0 +1,113 @@
+"""Host-side geometry and map I/O with the reference's names and signatures
+(reference avlmaps/utils/mapping_utils.py).  Scalar fp64 pose/camera math stays on the host exactly as
+the reference computes it (numpy + scipy), because the kernels take these matrices as inputs
+(SURVEY.md section 0.6); per-point work happens in csrc/build_path.cu."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import List, Optional, Set, Tuple
+
+import numpy as np
+
+
+def cvt_pose_vec2tf(pos_quat_vec: np.ndarray) -> np.ndarray:
+    """(px, py, pz, qx, qy, qz, qw) -> 4x4.  Reference mapping_utils.py:18-26."""
+    from scipy.spatial.transform import Rotation as R
+
+    pose_tf = np.eye(4)
+    pose_tf[:3, 3] = pos_quat_vec[:3].flatten()
+    pose_tf[:3, :3] = R.from_quat(pos_quat_vec[3:].flatten()).as_matrix()
+    return pose_tf
+
+
+def load_depth_npy(depth_filepath) -> np.ndarray:
+    """Reference mapping_utils.py (load_depth_npy): depth in metres, (H, W) float32."""
+    with open(depth_filepath, "rb") as f:
+        return np.load(f)
+
+
+def get_sim_cam_mat(h: int, w: int) -> np.ndarray:
+    """Reference mapping_utils.py:591-596."""
+    cam_mat = np.eye(3)
+    cam_mat[0, 0] = cam_mat[1, 1] = w / 2.0
+    cam_mat[0, 2] = w / 2.0
+    cam_mat[1, 2] = h / 2.0
+    return cam_mat
+
+
+def base_pos2grid_id_3d(gs, cs, x_base, y_base, z_base):
+    """Reference mapping_utils.py:345-349 (scalar helper; the kernels do this per point)."""
+    row = int(gs / 2 - int(x_base / cs))
+    col = int(gs / 2 - int(y_base / cs))
+    h = int(z_base / cs)
+    return [row, col, h]
+
+
+def grid_id2base_pos_3d(row, col, height, cs, gs):
+    base_x = (gs / 2 - row) * cs
+    base_y = (gs / 2 - col) * cs
+    base_z = height * cs
+    return [base_x, base_y, base_z]
+
+
+# ---------------------------------------------------------------------------------------------- map files
+# The reference writes HDF5 through h5py (mapping_utils.py:469-505).  h5py is used when it is
+# importable (same dataset names and dtypes, so files interchange with the reference); otherwise the
+# same arrays go to an .npz twin next to the requested path (`<path>.npz`).
+_FIELDS = ("mapped_iter_list", "grid_feat", "grid_pos", "weight", "occupied_ids", "grid_rgb", "init_height_id")
+
+
+def _have_h5py() -> bool:
+    try:
+        import h5py  # noqa: F401
+
+        return hasattr(h5py, "File")
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _npz_twin(path) -> Path:
+    return Path(str(path) + ".npz")
+
+
+def map_file_exists(path) -> bool:
+    return Path(path).exists() or _npz_twin(path).exists()
+
+
+def save_3d_map(save_path, grid_feat: np.ndarray, grid_pos: np.ndarray, weight: np.ndarray, occupied_ids: np.ndarray,
+                mapped_iter_list: Set[int], grid_rgb: Optional[np.ndarray] = None, init_height_id: Optional[int] = None) -> None:
+    """Reference mapping_utils.py:469-505: same arguments, same dataset names."""
+    data = {
+        "mapped_iter_list": np.array(list(mapped_iter_list), dtype=np.int32),
+        "grid_feat": grid_feat, "grid_pos": grid_pos, "weight": weight, "occupied_ids": occupied_ids,
+    }
+    if init_height_id is not None:
+        data["init_height_id"] = np.array(init_height_id, dtype=np.int32)
+    if grid_rgb is not None:
+        data["grid_rgb"] = grid_rgb
+    if _have_h5py():
+        import h5py
+
+        with h5py.File(save_path, "w") as f:
+            for k, v in data.items():
+                f.create_dataset(k, data=v)
+    else:
+        with open(_npz_twin(save_path), "wb") as f:
+            np.savez(f, **data)
+
+
+def load_3d_map(map_path) -> Tuple:
+    """Reference mapping_utils.py:508-541: returns the 6-tuple (7 with init_height_id)."""
+    if Path(map_path).exists() and _have_h5py():
+        import h5py
+
+        with h5py.File(map_path, "r") as f:
+            d = {k: f[k][()] for k in _FIELDS if k in f}
+    else:
+        with np.load(_npz_twin(map_path)) as z:
+            d = {k: z[k] for k in _FIELDS if k in z.files}
+    mapped_iter_list = d["mapped_iter_list"].tolist()
+    out = (mapped_iter_list, d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], d.get("grid_rgb"))
+    if "init_height_id" in d:
+        return out + (d["init_height_id"],)
+    return out
