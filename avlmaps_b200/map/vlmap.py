@@ -1,0 +1,145 @@
+"""`VLMap` with the reference's method surface (reference avlmaps/map/vlmap.py:27-187).
+
+After `load_map` the numpy attributes the reference exposes (grid_feat, grid_pos, weight, occupied_ids,
+grid_rgb) are populated as before AND grid_feat is made resident in HBM (engine.DeviceMap), so that
+`init_categories` / `index_map` run on the B200: one fused tcgen05 pass gives the per-voxel argmax
+that `index_map` needs, without materialising the (N, C) score matrix.  `scores_mat` is still
+available (computed exactly, on demand) because callers of the reference read it."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import List, Optional, Union
+
+import numpy as np
+
+from ..engine import DeviceMap
+from ..utils.clip_utils import get_lseg_score, landmark_text_feats
+from ..utils.mapping_utils import load_3d_map, map_file_exists
+from .map import Map, cfg_get
+from .vlmap_builder import VLMapBuilder
+
+
+def find_similar_category_id(class_name: str, classes_list: List[str]) -> int:
+    """Reference avlmaps/utils/index_utils.py:8-32.  The literal match is kept; the reference's fallback
+    (an OpenAI completion call) is a network service outside this engine."""
+    if class_name in classes_list:
+        return classes_list.index(class_name)
+    raise KeyError(f"'{class_name}' is not one of the initialised categories {classes_list}; the reference "
+                   "would ask an OpenAI model for the closest name here")
+
+
+class VLMap(Map):
+    def __init__(self, map_config, data_dir: str = "", feature_fn=None):
+        super().__init__(map_config, data_dir=data_dir)
+        self._scores_mat = None
+        self.categories = None
+        self._argmax = None          # (N,) int32 cache: argmax over categories + "other"
+        self._cat_text_feats = None
+        self.device_map: Optional[DeviceMap] = None
+        self.feature_fn = feature_fn
+
+    # ------------------------------------------------------------------ build
+    def create_map(self, data_dir: Union[Path, str]) -> None:
+        """Reference vlmap.py:33-48."""
+        print("Creating map for scene at: ", data_dir)
+        self._setup_paths(data_dir)
+        self.map_builder = VLMapBuilder(self.data_dir, self.map_config, self.pose_path, self.rgb_paths,
+                                        self.depth_paths, self.base2cam_tf, self.base_transform,
+                                        feature_fn=self.feature_fn)
+        pose_type = cfg_get(cfg_get(self.map_config, "pose_info"), "pose_type")
+        if pose_type == "mobile_base":
+            self.map_builder.create_mobile_base_map()
+        elif pose_type == "camera":
+            self.map_builder.create_camera_map()
+
+    # ------------------------------------------------------------------ load
+    def load_map(self, data_dir: str) -> bool:
+        """Reference vlmap.py:50-65: False + message when the file is missing."""
+        self._setup_paths(data_dir)
+        self.map_save_path = Path(data_dir) / "vlmap" / "vlmaps.h5df"
+        if not map_file_exists(self.map_save_path):
+            print("Loading VLMap failed because the file doesn't exist.")
+            return False
+        (self.mapped_iter_list, self.grid_feat, self.grid_pos, self.weight, self.occupied_ids,
+         self.grid_rgb) = load_3d_map(self.map_save_path)[:6]
+        self.set_map_arrays(self.grid_feat)
+        return True
+
+    def set_map_arrays(self, grid_feat, grid_pos=None, weight=None, occupied_ids=None, grid_rgb=None) -> None:
+        """Adopt in-memory arrays (what load_map does after reading the file) and upload grid_feat."""
+        self.grid_feat = grid_feat
+        if grid_pos is not None:
+            self.grid_pos = grid_pos
+        if weight is not None:
+            self.weight = weight
+        if occupied_ids is not None:
+            self.occupied_ids = occupied_ids
+        if grid_rgb is not None:
+            self.grid_rgb = grid_rgb
+        if self.device_map is not None:
+            self.device_map.close()
+        self.device_map = DeviceMap(grid_feat)
+        self._scores_mat, self._argmax, self.categories = None, None, None
+
+    # ------------------------------------------------------------------ CLIP
+    def _init_clip(self, clip_version="ViT-B/32"):
+        """Reference vlmap.py:67-90 (needs the `clip` package, which is the caller's dependency)."""
+        if hasattr(self, "clip_model"):
+            print("clip model is already initialized")
+            return
+        import clip
+        import torch
+
+        self.device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.clip_version = clip_version
+        self.clip_feat_dim = {"RN50": 1024, "RN101": 512, "RN50x4": 640, "RN50x16": 768, "RN50x64": 1024,
+                              "ViT-B/32": 512, "ViT-B/16": 512, "ViT-L/14": 768}[self.clip_version]
+        print("Loading CLIP model...")
+        self.clip_model, self.preprocess = clip.load(self.clip_version)
+        self.clip_model.to(self.device).eval()
+
+    def set_text_encoder(self, encoder, clip_feat_dim: int) -> None:
+        """Use any callable `texts -> (len, D)` in place of CLIP (tests; other encoders)."""
+        self.clip_model, self.clip_feat_dim = encoder, clip_feat_dim
+
+    # ------------------------------------------------------------------ index
+    @property
+    def scores_mat(self):
+        """(N, C+1) float32 like the reference caches (vlmap.py:94-101); computed exactly on first access."""
+        if self._scores_mat is None and self._cat_text_feats is not None:
+            self._scores_mat = self.device_map.scores(self._cat_text_feats)
+        return self._scores_mat
+
+    @scores_mat.setter
+    def scores_mat(self, v):
+        self._scores_mat = v
+
+    def init_categories(self, categories: List[str], return_scores: bool = True):
+        """Reference vlmap.py:92-102.  One fused pass caches the per-voxel argmax; the score matrix
+        itself is returned (reference contract) unless return_scores=False."""
+        self.categories = categories
+        self._cat_text_feats, _, _ = landmark_text_feats(self.clip_model, self.categories, self.clip_feat_dim,
+                                                         use_multiple_templates=True, avg_mode=0, add_other=True)
+        self._scores_mat = None
+        self._argmax = self.device_map.argmax(self._cat_text_feats)
+        return self.scores_mat if return_scores else None
+
+    def index_map(self, language_desc: str, with_init_cat: bool = True) -> np.ndarray:
+        """Reference vlmap.py:104-125: mask = argmax(scores, 1) == cat_id."""
+        if with_init_cat and self._argmax is not None and self.categories is not None:
+            cat_id = find_similar_category_id(language_desc, self.categories)
+            max_ids = self._argmax
+        else:
+            if with_init_cat:
+                raise Exception(
+                    "Categories are not preloaded. Call init_categories(categories: List[str]) to initialize categories."
+                )
+            text_feats, _, _ = landmark_text_feats(self.clip_model, [language_desc], self.clip_feat_dim,
+                                                   use_multiple_templates=True, avg_mode=0, add_other=True)
+            max_ids = self.device_map.argmax(text_feats)  # score for name and other
+            cat_id = 0
+        return max_ids == cat_id
+
+    def get_lseg_score(self, landmarks: List[str], use_multiple_templates: bool = True, add_other: bool = True):
+        return get_lseg_score(self.clip_model, landmarks, self.device_map, self.clip_feat_dim,
+                              use_multiple_templates=use_multiple_templates, add_other=add_other)

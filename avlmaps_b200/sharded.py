@@ -1,0 +1,89 @@
+"""Slab-sharded map over the GPUs of one box: one process per GPU (torchrun), each rank owns a
+contiguous slab of voxel rows; a query batch is scored against every slab independently and the
+per-slab top-k are exchanged with ONE small NCCL all-gather (world * Q * k * 12 bytes) and merged
+locally.  The per-voxel argmax needs no exchange at all (it stays sharded).
+
+torch.distributed is plumbing only; scoring runs in the C-ABI library."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def merge_topk(idx: np.ndarray, val: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Merge per-shard results (S, Q, k) with GLOBAL row ids into the global top-k (Q, k), ordered by
+    (score desc, row asc) -- the order each shard already uses, so ties stay on the lowest row."""
+    s, q, kk = idx.shape
+    fi = np.transpose(idx, (1, 0, 2)).reshape(q, s * kk)
+    fv = np.transpose(val, (1, 0, 2)).reshape(q, s * kk).astype(np.float32)
+    out_i = np.full((q, k), -1, np.int64)
+    out_v = np.full((q, k), -np.inf, np.float32)
+    for j in range(q):
+        valid = fi[j] >= 0
+        ci, cv = fi[j][valid], fv[j][valid]
+        order = np.lexsort((ci, -cv.astype(np.float64)))[:k]
+        out_i[j, :order.size] = ci[order]
+        out_v[j, :order.size] = cv[order]
+    return out_i, out_v
+
+
+def merge_topk_torch(idx, val, k: int):
+    """Same merge on device tensors (S, Q, k): sort by (score desc, row asc) with two stable sorts."""
+    import torch
+
+    s, q, kk = idx.shape
+    fi = idx.permute(1, 0, 2).reshape(q, s * kk)
+    fv = val.permute(1, 0, 2).reshape(q, s * kk)
+    big = torch.iinfo(torch.int64).max
+    key_i = torch.where(fi >= 0, fi, torch.full_like(fi, big))
+    o1 = torch.argsort(key_i, dim=1, stable=True)
+    fi, fv = torch.gather(fi, 1, o1), torch.gather(fv, 1, o1)
+    o2 = torch.argsort(fv, dim=1, descending=True, stable=True)
+    fi, fv = torch.gather(fi, 1, o2), torch.gather(fv, 1, o2)
+    return fi[:, :k].contiguous(), fv[:, :k].contiguous()
+
+
+def slab_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row slab of `rank` (the last slabs are one row shorter when world does not divide n)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedMap:
+    """`local` is anything with .topk(queries, k, scale=, normalize_map=) and .argmax(...) over this
+    rank's slab (an engine.DeviceMap in production); `row_offset` is the slab's first global row."""
+
+    def __init__(self, local, row_offset: int, group=None):
+        import torch.distributed as dist
+
+        self.local = local
+        self.row_offset = int(row_offset)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def topk(self, queries, k: int, scale=None, normalize_map: bool = False):
+        import torch
+        import torch.distributed as dist
+
+        idx, val = self.local.topk(queries, k, scale=scale, normalize_map=normalize_map)
+        as_numpy = isinstance(idx, np.ndarray)
+        ti = torch.from_numpy(idx) if as_numpy else idx
+        tv = torch.from_numpy(val) if as_numpy else val
+        ti = torch.where(ti >= 0, ti + self.row_offset, ti)
+        if self.world > 1:
+            gi = torch.empty((self.world,) + tuple(ti.shape), dtype=ti.dtype, device=ti.device)
+            gv = torch.empty((self.world,) + tuple(tv.shape), dtype=tv.dtype, device=tv.device)
+            # the one collective of the path (ids and scores; concatenated along dim 0)
+            dist.all_gather_into_tensor(gi.view(-1, ti.shape[-1]), ti.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(gv.view(-1, tv.shape[-1]), tv.contiguous(), group=self.group)
+        else:
+            gi, gv = ti[None], tv[None]
+        mi, mv = merge_topk_torch(gi, gv, k)
+        return (mi.numpy(), mv.numpy()) if as_numpy else (mi, mv)
+
+    def argmax(self, queries, scale=None, normalize_map: bool = False):
+        """Per-voxel argmax of this rank's slab; rows are independent, nothing to exchange."""
+        return self.local.argmax(queries, scale=scale, normalize_map=normalize_map)

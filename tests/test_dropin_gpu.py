@@ -1,0 +1,80 @@
+"""GPU: the drop-in classes (VLMapBuilder / VLMap) used the way application/create_map.py and
+application/index_map.py use the reference's, on a synthetic scene written to disk."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import avl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def write_scene(root: Path, poses, depths, rgbs):
+    import cv2
+
+    (root / "rgb").mkdir(parents=True)
+    (root / "depth").mkdir()
+    for i, (d, c) in enumerate(zip(depths, rgbs)):
+        cv2.imwrite(str(root / "rgb" / f"{i:06d}.png"), cv2.cvtColor(c, cv2.COLOR_RGB2BGR))
+        np.save(root / "depth" / f"{i:06d}.npy", d)
+    np.savetxt(root / "poses.txt", poses)
+
+
+def fake_encoder(dim):
+    def enc(texts):
+        out = np.zeros((len(texts), dim), np.float32)
+        for i, t in enumerate(texts):
+            out[i] = np.random.default_rng(abs(hash(t)) % (2 ** 32)).standard_normal(dim)
+        return out
+
+    return enc
+
+
+def test_create_load_index_like_the_applications(lib, tmp_path):
+    from avlmaps_b200.map import VLMap
+
+    n_frames, h, w, fh, fw, d = 4, 60, 80, 49, 65, 32
+    cfg = synth.map_config(48, 0.1, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], 2)
+    poses = synth.circle_poses(n_frames, radius=0.3)
+    depths, rgbs, feats = synth.build_inputs(n_frames, h, w, fh, fw, d, seed=3)
+    write_scene(tmp_path, poses, depths, rgbs)
+    it = iter(feats)
+    vlmap = VLMap(cfg, feature_fn=lambda rgb: next(it))
+    np.random.seed(21)
+    vlmap.create_map(tmp_path)                    # create_map.py:17 -> vlmap.py:33-48
+    assert vlmap.grid_feat is None                # the reference does not populate memory on create either
+    assert vlmap.load_map(tmp_path) is True       # index_map.py:27
+    np.random.seed(21)
+    sidx = [O.sample_order(h * w, 2) for _ in range(n_frames)]
+    ref = O.build_map(cfg, poses, depths, rgbs, feats, sidx, capacity=48 * 48 * 16)
+    assert np.array_equal(vlmap.grid_pos, ref["grid_pos"]) and np.array_equal(vlmap.occupied_ids, ref["occupied_ids"])
+    assert np.allclose(vlmap.grid_feat, ref["grid_feat"], rtol=1e-3, atol=1e-5)
+    assert vlmap.mapped_iter_list == list(range(n_frames))
+
+    # ---- index like index_map.py / AVLMap.index_object
+    enc = fake_encoder(d)
+    vlmap.set_text_encoder(enc, d)
+    with pytest.raises(Exception, match="Categories are not preloaded"):
+        vlmap.index_map("chair", with_init_cat=True)
+    mask = vlmap.index_map("chair", with_init_cat=False)           # vlmap.py:113-124
+    from avlmaps_b200.utils.clip_utils import landmark_text_feats
+
+    tf, _, _ = landmark_text_feats(enc, ["chair"], d, True, 0, True)
+    want = O.index_mask(O.scores(vlmap.grid_feat, tf), 0)
+    assert mask.dtype == bool and np.array_equal(mask, want)
+    cats = ["chair", "table", "sofa", "plant"]
+    sm = vlmap.init_categories(cats)                                # vlmap.py:92-102
+    tfc, _, _ = landmark_text_feats(enc, cats, d, True, 0, True)
+    ref_scores = O.scores(vlmap.grid_feat, tfc)
+    assert sm.shape == (vlmap.grid_feat.shape[0], 5) and np.array_equal(sm, ref_scores)
+    for i, c in enumerate(cats):
+        assert np.array_equal(vlmap.index_map(c, with_init_cat=True), O.index_mask(ref_scores, i))
+    # get_lseg_score keeps the reference signature (numpy map in, (N, C+1) scores out)
+    from avlmaps_b200.utils.clip_utils import get_lseg_score
+
+    s2 = get_lseg_score(enc, cats, vlmap.grid_feat, d, use_multiple_templates=True, add_other=True)
+    assert np.array_equal(s2, ref_scores)
+    s3 = get_lseg_score(enc, cats, vlmap.grid_feat, d, use_multiple_templates=True, avg_mode=1)
+    assert s3.shape == (vlmap.grid_feat.shape[0], 5)

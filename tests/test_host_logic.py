@@ -1,0 +1,92 @@
+"""CPU: host-side logic of the drop-in classes against the oracle / the reference's conventions."""
+import numpy as np
+import pytest
+
+import synth
+from avlmaps_b200.map.map import Map
+from avlmaps_b200.map.vlmap import VLMap, find_similar_category_id
+from avlmaps_b200.map.vlmap_builder import VLMapBuilder
+from avlmaps_b200.utils import clip_utils, mapping_utils
+from oracle import avl_oracle as O
+
+
+def cfg():
+    return synth.map_config(64, 0.05, 1.6, [32, 0, 32, 0, 32, 24, 0, 0, 1], 3)
+
+
+def test_transforms_match_oracle():
+    m = Map(cfg())
+    b2c, bt = O.setup_transforms(cfg()["pose_info"])
+    assert np.array_equal(m.base2cam_tf, b2c) and np.array_equal(m.base_transform, bt)
+    poses = synth.circle_poses(5, 0.7)
+    vb = VLMapBuilder("/tmp", cfg(), None, [], [], m.base2cam_tf, m.base_transform)
+    got = vb._frame_transforms(poses)
+    want = O.frame_transforms(poses, b2c, bt)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)  # same numpy operations in the same order: bit-equal
+    assert np.array_equal(mapping_utils.get_sim_cam_mat(390, 520), O.get_sim_cam_mat(390, 520))
+    assert np.array_equal(mapping_utils.cvt_pose_vec2tf(poses[2]), O.cvt_pose_vec2tf(poses[2]))
+
+
+def test_sample_order_uses_global_rng_like_reference():
+    np.random.seed(11)
+    a = [VLMapBuilder._sample_order(1000, 7) for _ in range(3)]
+    np.random.seed(11)
+    b = [O.sample_order(1000, 7) for _ in range(3)]
+    for x, y in zip(a, b):
+        assert x.dtype == np.int32 and np.array_equal(x, y)
+    assert len(a[0]) == len(range(0, 1000, 7))
+
+
+def test_prompt_templates():
+    assert len(clip_utils.multiple_templates) == 63
+    assert clip_utils.multiple_templates[0] == "There is {} in the scene."
+    assert clip_utils.multiple_templates[-1] == "a painting of a {}."
+    enc = lambda texts: np.random.default_rng(len(texts)).standard_normal((len(texts), 16))  # noqa: E731
+    f = clip_utils.get_text_feats(["a", "b", "c"], enc, 16)
+    assert np.allclose(np.linalg.norm(f, axis=1), 1.0, atol=1e-6)  # rows L2-normalised (clip_utils.py:145)
+    fm = clip_utils.get_text_feats_multiple_templates(["chair", "other"], enc, 16)
+    assert fm.shape == (2, 16) and np.all(np.linalg.norm(fm, axis=1) < 1.0)  # mean of unit rows, not re-normalised
+    tf, names, n_tmp = clip_utils.landmark_text_feats(enc, ["chair"], 16, True, 0, True)
+    assert names == ["chair", "other"] and tf.shape == (2, 16) and n_tmp == 63
+    tf, names, _ = clip_utils.landmark_text_feats(enc, ["chair", "other"], 16, False, 0, True)
+    assert names == ["chair", "other"]  # "other" is not appended twice (clip_utils.py:213-215)
+
+
+def test_save_load_roundtrip(tmp_path):
+    p = tmp_path / "vlmaps.h5df"
+    gf = np.arange(12, dtype=np.float32).reshape(3, 4)
+    gp = np.arange(9, dtype=np.int32).reshape(3, 3)
+    w = np.ones(3, np.float32)
+    occ = -np.ones((2, 2, 2), np.int32)
+    rgb = np.zeros((3, 3), np.uint8)
+    assert not mapping_utils.map_file_exists(p)
+    mapping_utils.save_3d_map(p, gf, gp, w, occ, [0, 1], rgb)
+    assert mapping_utils.map_file_exists(p)
+    it, gf2, gp2, w2, occ2, rgb2 = mapping_utils.load_3d_map(p)
+    assert it == [0, 1] and np.array_equal(gf, gf2) and np.array_equal(gp, gp2) and np.array_equal(occ, occ2)
+    assert w2.dtype == np.float32 and rgb2.dtype == np.uint8
+
+
+def test_reference_conventions():
+    m = VLMap(cfg())
+    assert m.grid_feat is None and m.scores_mat is None and m.categories is None
+    assert Map(cfg()).create_map("x") is NotImplementedError  # returned, not raised (map.py:70-77)
+    assert m.load_map("/nonexistent/dir") is False            # vlmap.py:53-55
+    with pytest.raises(Exception, match="Categories are not preloaded"):
+        m.index_map("chair", with_init_cat=True)              # vlmap.py:109-112
+    with pytest.raises(AttributeError):
+        m.index_map("chair", with_init_cat=False)             # needs _init_clip first, like the reference
+    assert find_similar_category_id("b", ["a", "b"]) == 1
+    assert VLMapBuilder("/tmp", cfg(), None, [], [], None, None).create_camera_map() is NotImplementedError
+
+
+def test_generate_obstacle_map_quirk():
+    m = Map(cfg())
+    occ = -np.ones((4, 4, 32), np.int32)
+    occ[1, 1, 5] = 0   # voxel id 0 counts as free in the reference (occupied_ids > 0)
+    occ[2, 2, 5] = 7
+    m.occupied_ids = occ
+    obs = m.generate_obstacle_map()
+    assert obs[1, 1] and not obs[2, 2]
+    assert (m.rmin, m.rmax, m.cmin, m.cmax) == (2, 2, 2, 2)

@@ -1,0 +1,255 @@
+"""GPU parity of the landmark-index path: CUDA (through the C-ABI) vs the oracle and the reference's
+golden vectors.  Bar: indices bit-exact; scores within 1e-3 relative (scale-aware) -- in
+practice they are the same bits because both sides round one fp64-accumulated dot."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import avl_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+SCORE_RTOL = 1e-3  # the tolerance north_star states for fp32 similarity scores
+
+
+def assert_scores_close(got, ref, feat, q):
+    floor = (np.linalg.norm(feat, axis=1)[:, None] * np.linalg.norm(q, axis=1)[None, :]) / np.sqrt(feat.shape[1])
+    assert np.all(np.abs(got - ref) <= SCORE_RTOL * np.maximum(np.abs(ref), floor))
+
+
+@pytest.fixture(scope="module")
+def eng(lib):
+    from avlmaps_b200 import engine
+
+    return engine
+
+
+@pytest.mark.parametrize("name", ["c1_10k_q2", "4k_q64", "3k_d768_q9", "odd_1001_d100_q3"])
+def test_golden_reference_vectors(eng, name):
+    """BASELINE config 1 and friends: identical mask/argmax to the reference's own output."""
+    g = np.load(G / f"index_{name}.npz")
+    feat, q = synth.index_inputs(int(g["n"]), int(g["d"]), int(g["nq"]), int(g["seed"]))
+    m = eng.DeviceMap(feat)
+    am = m.argmax(q)
+    assert am.dtype == np.int32 and np.array_equal(am, g["argmax"])       # vlmap.py:123
+    assert np.array_equal(am == 0, g["mask0"])                              # vlmap.py:124
+    sc = m.scores(q)
+    assert_scores_close(sc, g["scores"], feat, q)                           # vs the reference's float32 BLAS
+    assert np.array_equal(sc, O.scores(feat, q))                            # vs the oracle: same bits
+    assert np.array_equal(np.argmax(sc, axis=1), am)                        # fused argmax == argmax of dense scores
+    m.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,normalize,use_scale", [
+    (1000, 512, 1, 1, False, False),
+    (1000, 512, 2, 16, False, False),
+    (5000, 512, 9, 16, False, False),
+    (70_001, 512, 64, 16, False, False),
+    (33_333, 512, 65, 5, True, True),
+    (20_000, 512, 256, 16, False, False),
+    (9_000, 768, 33, 8, True, False),
+    (9_000, 1024, 32, 16, True, True),     # AudioCLIP-like: unit rows, scale 100
+    (777, 100, 3, 128, False, False),       # D not a multiple of 64, k > typical
+    (50, 512, 3, 16, False, False),         # fewer rows than k
+])
+def test_topk_and_argmax_vs_oracle(eng, n, d, nq, k, normalize, use_scale):
+    feat, q = synth.index_inputs(n, d, nq, seed=n % 97, unit_rows=(d == 1024))
+    scale = np.random.default_rng(5).uniform(0.5, 100.0, nq).astype(np.float32) if use_scale else None
+    ref = O.scores(feat, q, scale=scale, normalize=normalize)
+    m = eng.DeviceMap(feat)
+    idx, val = m.topk(q, k, scale=scale, normalize_map=normalize)
+    ri, rv = O.topk(ref, k)
+    assert idx.dtype == np.int64 and np.array_equal(idx, ri)
+    assert np.array_equal(val, rv)
+    am = m.argmax(q, scale=scale, normalize_map=normalize)
+    assert np.array_equal(am, O.argmax(ref))
+    assert np.array_equal(m.scores(q, scale=scale, normalize_map=normalize), ref)
+    m.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_tensor_core_screen_matches_bf16_model(eng, cg):
+    """The raw tcgen05 output equals the exact product of the bf16-rounded operands (fp32 accumulate)."""
+    feat, q = synth.index_inputs(3000, 512, 48, seed=3)
+
+    def bf16(x):
+        b = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+        return ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+    m = eng.DeviceMap(feat)
+    got = m.screen_scores(q, cta_group=cg)
+    ref = bf16(feat).astype(np.float64) @ bf16(q).astype(np.float64).T
+    scale = np.linalg.norm(feat, axis=1)[:, None] * np.linalg.norm(q, axis=1)[None, :]
+    assert np.max(np.abs(got - ref) / scale) < 2e-6
+    m.close()
+
+
+def test_ties_resolve_to_lowest_index(eng):
+    feat, q = synth.index_inputs(4096, 512, 4, seed=1)
+    feat[100:110] = feat[7]          # ten exact copies of row 7
+    feat[2000] = feat[7]
+    q[1] = q[0]                      # two identical queries: argmax must pick the lower id
+    m = eng.DeviceMap(feat)
+    ref = O.scores(feat, q)
+    idx, val = m.topk(q, 32)
+    ri, rv = O.topk(ref, 32)
+    assert np.array_equal(idx, ri) and np.array_equal(val, rv)
+    am = m.argmax(q)
+    assert np.array_equal(am, O.argmax(ref)) and not np.any(am == 1)
+    m.close()
+
+
+def test_massive_ties_take_the_exact_fallback(eng):
+    """All rows identical: every row is a candidate, the candidate list overflows, the exact dense
+    fallback must still return rows 0..k-1."""
+    row = synth.index_inputs(1, 512, 1, seed=2)[0]
+    feat = np.repeat(row, 20_000, axis=0)
+    q = synth.index_inputs(1, 512, 3, seed=4)[1]
+    m = eng.DeviceMap(feat)
+    idx, val = m.topk(q, 8)
+    assert np.array_equal(idx, np.tile(np.arange(8), (3, 1)))
+    assert m.last_stats["n_fallback_queries"] == 3
+    assert np.array_equal(val, O.topk(O.scores(feat, q), 8)[1])
+    m.close()
+
+
+def test_zero_rows_and_empty_map(eng):
+    feat, q = synth.index_inputs(2000, 512, 5, seed=9)
+    feat[::7] = 0.0
+    ref = O.scores(feat, q, normalize=True)
+    m = eng.DeviceMap(feat)
+    idx, val = m.topk(q, 16, normalize_map=True)
+    ri, rv = O.topk(ref, 16)
+    assert np.array_equal(idx, ri) and np.array_equal(val, rv)
+    m.close()
+    e = eng.DeviceMap(np.zeros((0, 512), np.float32))
+    idx, val = e.topk(q, 4)
+    assert np.all(idx == -1) and np.all(np.isneginf(val))
+    assert e.argmax(q).shape == (0,)
+    e.close()
+
+
+def test_deterministic(eng):
+    feat, q = synth.index_inputs(50_000, 512, 64, seed=12)
+    m = eng.DeviceMap(feat)
+    a1, a2 = m.argmax(q), m.argmax(q)
+    i1, v1 = m.topk(q, 16)
+    i2, v2 = m.topk(q, 16)
+    assert np.array_equal(a1, a2) and np.array_equal(i1, i2) and np.array_equal(v1, v2)
+    m.close()
+
+
+def test_shard_merge_equals_single_map(eng):
+    """Slab sharding property: merging per-shard top-k equals the top-k of the whole map."""
+    from avlmaps_b200.sharded import merge_topk
+
+    feat, q = synth.index_inputs(30_000, 512, 16, seed=21)
+    whole = eng.DeviceMap(feat)
+    wi, wv = whole.topk(q, 16)
+    cuts = [0, 7_000, 7_100, 19_999, 30_000]
+    parts_i, parts_v = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s = eng.DeviceMap(feat[a:b])
+        i, v = s.topk(q, 16)
+        parts_i.append(np.where(i >= 0, i + a, -1))
+        parts_v.append(v)
+        s.close()
+    mi, mv = merge_topk(np.stack(parts_i), np.stack(parts_v), 16)
+    assert np.array_equal(mi, wi) and np.array_equal(mv, wv)
+    whole.close()
+
+
+def test_vector_topk_and_fusion(eng):
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(1_000_003).astype(np.float32)
+    v[rng.integers(0, v.size, v.size // 3)] = 1.0
+    gi, gv = eng.topk_vector(v, 16)
+    ri, rv = O.topk_vector(v, 16)
+    assert np.array_equal(gi, ri) and np.array_equal(gv, rv)
+    # BASELINE config 3, reduced: LSeg-512 x AudioCLIP-1024, min-max, product, top-16
+    n = 40_000
+    fv, qv = synth.index_inputs(n, 512, 6, seed=30)
+    fa, qa = synth.index_inputs(n, 1024, 6, seed=31, unit_rows=True)
+    sa = np.full(6, 100.0, np.float32)  # clamp ceiling of the AudioCLIP logit scale (audioclip.py:174)
+    mv_, ma_ = eng.DeviceMap(fv), eng.DeviceMap(fa)
+    for combine in (O.FUSE_PRODUCT, O.FUSE_MAX, O.FUSE_SUM):
+        gi, gh = eng.fuse_topk(mv_, qv, ma_, qa, 16, scale_b=sa, combine=combine)
+        ri, rh = O.fuse_topk(O.scores(fv, qv), O.scores(fa, qa, scale=sa), combine, 16)
+        assert np.array_equal(gi, ri)
+        assert np.allclose(gh, rh, rtol=0, atol=2e-7)
+    mv_.close()
+    ma_.close()
+
+
+def test_device_pointer_path_matches_host_path(eng):
+    import torch
+
+    feat, q = synth.index_inputs(20_000, 512, 40, seed=5)
+    m = eng.DeviceMap(torch.from_numpy(feat).cuda())
+    qi = torch.from_numpy(q).cuda()
+    i_d, v_d = m.topk(qi, 16)
+    a_d = m.argmax(qi)
+    i_h, v_h = m.topk(q, 16)
+    assert np.array_equal(i_d.cpu().numpy(), i_h) and np.array_equal(v_d.cpu().numpy(), v_h)
+    assert np.array_equal(a_d.cpu().numpy(), m.argmax(q))
+    m.close()
+
+
+def test_capi_argument_errors(eng, lib):
+    import ctypes as C
+
+    from avlmaps_b200 import _lib as L
+
+    feat, q = synth.index_inputs(100, 512, 4, seed=0)
+    m = eng.DeviceMap(feat)
+    oi, ov = np.empty((4, 200), np.int64), np.empty((4, 200), np.float32)
+    assert lib.avl_sim_topk(m._h, L.np_ptr(q), 4, None, 0, 200, L.np_ptr(oi), L.np_ptr(ov), 0, None, None) == 2
+    assert lib.avl_sim_topk(m._h, L.np_ptr(q), 0, None, 0, 4, L.np_ptr(oi), L.np_ptr(ov), 0, None, None) == 2
+    bad_scale = np.array([1, -1, 1, 1], np.float32)
+    assert lib.avl_sim_topk(m._h, L.np_ptr(q), 4, L.np_ptr(bad_scale), 0, 4, L.np_ptr(oi), L.np_ptr(ov), 0, None, None) == 2
+    with pytest.raises(ValueError):
+        m.topk(q[:, :100], 4)
+    m.close()
+
+
+def test_full_size_c2_properties(eng):
+    """BASELINE config 2 at full size (1M x 512, Q = 64) through size-independent properties: the
+    argmax equals the oracle on a row sample; every returned top-k score is the exact score of its
+    row; no sampled row beats the k-th score; the two halves merge to the whole."""
+    import torch
+
+    from avlmaps_b200.sharded import merge_topk
+
+    n, d, nq, k = 1_000_000, 512, 64, 16
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feat_t = torch.randn((n, d), device="cuda", generator=g) * (torch.rand((n, 1), device="cuda", generator=g) * 13.5 + 0.7)
+    q_t = torch.randn((nq, d), device="cuda", generator=g)
+    q_t = q_t / q_t.norm(dim=1, keepdim=True)
+    m = eng.DeviceMap(feat_t)
+    am = m.argmax(q_t, want_stats=True).cpu().numpy()
+    idx, val = m.topk(q_t, k)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    q = q_t.cpu().numpy()
+    rows = np.unique(np.concatenate([np.random.default_rng(0).integers(0, n, 20_000), idx.reshape(-1)]))
+    sub = feat_t[torch.from_numpy(rows).cuda()].cpu().numpy()
+    ref = O.scores(sub, q)
+    assert np.array_equal(am[rows], O.argmax(ref))
+    pos = {r: i for i, r in enumerate(rows)}
+    for j in range(nq):
+        exact = np.array([ref[pos[r], j] for r in idx[j]])
+        assert np.array_equal(val[j], exact)
+        assert np.all(np.diff(val[j]) <= 0)
+        beaten = ref[:, j] > val[j, -1]
+        assert set(rows[beaten]).issubset(set(idx[j]))
+    h = n // 2
+    parts = []
+    for a, b in ((0, h), (h, n)):
+        s = eng.DeviceMap(feat_t[a:b])
+        i, v = s.topk(q_t, k)
+        parts.append((np.where(i.cpu().numpy() >= 0, i.cpu().numpy() + a, -1), v.cpu().numpy()))
+        s.close()
+    mi, mv = merge_topk(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), k)
+    assert np.array_equal(mi, idx) and np.array_equal(mv, val)
+    m.close()
