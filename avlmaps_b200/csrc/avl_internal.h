@@ -82,8 +82,8 @@ int screen_pick_stages(int cta_group, int npad, int kblocks);  // <=0: does not 
 // ---- exact / helper kernels (sim_exact.cu) --------------------------------
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
                        float* row_norm, float* row_c, float* row_an, float kappa, cudaStream_t s);
-int launch_query_prepare(const float* q, int32_t nq, int32_t d, int32_t dpad, int32_t npad,
-                         __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s);
+int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, int32_t d, int32_t dpad,
+                         int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s);
 int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq,
                        const float* scale, const float* row_norm, int normalize, float* out,
                        int64_t out_rs, int64_t out_cs, cudaStream_t s);

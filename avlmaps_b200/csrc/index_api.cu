@@ -241,7 +241,8 @@ struct QuerySetup {
 
 // stage queries, build bf16 B + norms, pick the kernel variant
 static int setup_queries(avl_map* m, const float* queries, int32_t nq, const float* scale, int flags,
-                         int forced_cg, bool need_screen, cudaStream_t s, QuerySetup* qs) {
+                         int forced_cg, bool need_screen, cudaStream_t s, QuerySetup* qs,
+                         bool fold_scale = false) {
   Workspace& w = m->ws;
   AVL_ARG(queries != nullptr, "queries is NULL");
   AVL_ARG(nq >= 1 && nq <= AVL_MAX_QUERIES, "nq must be in [1, AVL_MAX_QUERIES]");
@@ -267,7 +268,8 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
   }
   qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks);
   qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages);
-  int rc = launch_query_prepare(qs->q_dev, nq, m->d, m->dpad, qs->npad, w.bq, w.q_bn, w.q_glob, s);
+  int rc = launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
+                                w.q_bn, w.q_glob, s);
   if (rc) return rc;
   return encode_kmajor_map(&qs->tmap_b, w.bq, static_cast<uint64_t>(qs->npad), static_cast<uint64_t>(m->dpad),
                            static_cast<uint32_t>(qs->npad / qs->cg));
@@ -472,7 +474,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
   if (m->n == 0) return AVL_OK;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
   QuerySetup qs;
-  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs))) return rc;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs, /*fold_scale=*/true))) return rc;
   if ((rc = ensure_flags(m))) return rc;
   int32_t* dst = out_argmax;
   if (!(flags & AVL_ON_DEVICE)) {

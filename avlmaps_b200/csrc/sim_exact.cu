@@ -75,14 +75,17 @@ __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, in
 // ------------------------------------------------------------------ query_prepare
 // One block per padded query row: bf16 copy, ||b||, ||b - bf16(b)|| / ||b||.
 // glob[0] = max ratio (rho), glob[1] = max ||b|| (float bits, non-negative => uint order).
-__global__ void query_prepare_kernel(const float* __restrict__ q, int32_t nq, int32_t d, int32_t dpad,
-                                     __nv_bfloat16* __restrict__ bq, float* __restrict__ q_bn,
-                                     uint32_t* __restrict__ glob) {
+__global__ void query_prepare_kernel(const float* __restrict__ q, const float* __restrict__ fold_scale, int32_t nq,
+                                     int32_t d, int32_t dpad, __nv_bfloat16* __restrict__ bq,
+                                     float* __restrict__ q_bn, uint32_t* __restrict__ glob) {
   const int r = blockIdx.x;
   __shared__ double red[2][32];
   double sb = 0.0, sd = 0.0;
   for (int k = threadIdx.x; k < dpad; k += blockDim.x) {
-    const float x = (r < nq && k < d) ? q[static_cast<size_t>(r) * d + k] : 0.f;
+    float x = (r < nq && k < d) ? q[static_cast<size_t>(r) * d + k] : 0.f;
+    // argmax mode compares ACROSS queries, so the per-query scale is folded into B (the bounds below
+    // are then those of the scaled vector); top-k mode keeps B unscaled and divides its threshold
+    if (fold_scale && r < nq) x = __fmul_rn(x, fold_scale[r]);
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     bq[static_cast<size_t>(r) * dpad + k] = h;
     const float e = x - __bfloat162float(h);
@@ -530,10 +533,11 @@ int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __
   return AVL_OK;
 }
 
-int launch_query_prepare(const float* q, int32_t nq, int32_t d, int32_t dpad, int32_t npad,
-                         __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s) {
+int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, int32_t d, int32_t dpad,
+                         int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s) {
   AVL_CUDA(cudaMemsetAsync(q_glob, 0, 2 * sizeof(float), s));
-  query_prepare_kernel<<<npad, 128, 0, s>>>(q, nq, d, dpad, bq, q_bn, reinterpret_cast<uint32_t*>(q_glob));
+  query_prepare_kernel<<<npad, 128, 0, s>>>(q, fold_scale, nq, d, dpad, bq, q_bn,
+                                            reinterpret_cast<uint32_t*>(q_glob));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

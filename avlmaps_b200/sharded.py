@@ -79,8 +79,8 @@ class ShardedMap:
             # the one collective of the path (ids and scores; concatenated along dim 0)
             dist.all_gather_into_tensor(gi.view(-1, ti.shape[-1]), ti.contiguous(), group=self.group)
             dist.all_gather_into_tensor(gv.view(-1, tv.shape[-1]), tv.contiguous(), group=self.group)
-        else:
-            gi, gv = ti[None], tv[None]
+        else:  # a single slab is already in final order
+            return (ti.numpy(), tv.numpy()) if as_numpy else (ti, tv)
         mi, mv = merge_topk_torch(gi, gv, k)
         return (mi.numpy(), mv.numpy()) if as_numpy else (mi, mv)
 
