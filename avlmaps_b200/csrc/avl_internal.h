@@ -45,6 +45,8 @@ struct ScreenParams {
   int32_t stages;        // A pipeline depth
   int32_t mode;          // ScreenMode
   int32_t normalize;     // divide by the fp32 row norm
+  int32_t prefetch_tiles; // L2 prefetch distance of the A stream, in tiles per unit
+  int32_t debug_flags;    // perf triage only (AVL_DEBUG_FLAGS): 1 = no MMA, 2 = no A loads, 4 = no epilogue work
   // per-row statistics (map_prepare): see DESIGN.md "error band"
   const float* row_norm;   // ||a_i||  (fp32 row, fp64-accumulated)
   const float* row_c;      // >= ||a_i - bf16(a_i)|| + kappa * ||bf16(a_i)||
@@ -56,6 +58,7 @@ struct ScreenParams {
   float* dense_out;        // element (r, q) at r * dense_rs + q * dense_cs, r = compact row
   int64_t dense_rs, dense_cs;
   int32_t dense_cols;      // columns to store (nq or npad)
+  int32_t dense_lb;        // store lower bounds (s~ - eps)/w instead of s~ (rows past n_rows: -inf)
   // kModeArgmax
   int32_t* argmax_out;     // (n_rows,)
   uint32_t* flag_count;    // [1]
@@ -87,15 +90,14 @@ int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, in
 int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq,
                        const float* scale, const float* row_norm, int normalize, float* out,
                        int64_t out_rs, int64_t out_cs, cudaStream_t s);
-int launch_argmax_rerank(const float* feat, int32_t d, const float* q, int32_t nq, const float* scale,
+int launch_column_exact(const float* feat, int64_t n, int32_t d, const float* q, const float* scale,
+                        const float* row_norm, int normalize, float* out, int num_sms, cudaStream_t s);
+int launch_argmax_rerank(const float* feat, int32_t d, const float* q, double* q64, int32_t nq, const float* scale,
                          const float* row_norm, int normalize, const uint32_t* flag_count,
                          const uint32_t* flag_rows, const uint32_t* flag_masks, uint32_t flag_cap,
                          int32_t* argmax_out, int num_sms, cudaStream_t s);
-int launch_select_threshold(const float* sample_t, int32_t n_sample_rows, int64_t ld, int32_t nq, int32_t k,
-                            int32_t unit_rows, int32_t tile_stride, int64_t n_rows,
-                            const float* row_norm, const float* row_c, const float* row_an,
-                            const float* q_bn, const float* q_glob, int normalize, float* thr_t,
-                            cudaStream_t s);
+int launch_select_threshold(const float* sample_lb, int32_t n_sample_rows, int64_t ld, int32_t nq, int32_t k,
+                            float* thr_t, cudaStream_t s);
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c,
                          const float* row_an, const float* q_bn, const float* q_glob, int normalize,

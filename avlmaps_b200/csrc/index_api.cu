@@ -70,6 +70,7 @@ static int encode_kmajor_map(CUtensorMap* out, const void* base, uint64_t rows, 
 // ------------------------------------------------------------------ workspace
 struct Workspace {
   float* q = nullptr;          // [256 x d] staged queries (host-pointer calls)
+  double* q64 = nullptr;       // [256 x d] queries in fp64 for the exact re-rank
   float* scale = nullptr;      // [256]
   __nv_bfloat16* bq = nullptr; // [256 x dpad]
   float* q_bn = nullptr;       // [256]
@@ -131,6 +132,7 @@ static int ws_init(avl_map* m) {
   Workspace& w = m->ws;
   int rc;
   if ((rc = dev_alloc(&w.q, static_cast<size_t>(AVL_MAX_QUERIES) * m->d, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.q64, static_cast<size_t>(AVL_MAX_QUERIES) * m->d, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.scale, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.bq, static_cast<size_t>(AVL_MAX_QUERIES) * m->dpad, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.q_bn, AVL_MAX_QUERIES, &m->bytes))) return rc;
@@ -150,7 +152,7 @@ static int ws_init(avl_map* m) {
 }
 
 static void ws_free(Workspace& w) {
-  cudaFree(w.q); cudaFree(w.scale); cudaFree(w.bq); cudaFree(w.q_bn); cudaFree(w.q_glob); cudaFree(w.thr_t);
+  cudaFree(w.q); cudaFree(w.q64); cudaFree(w.scale); cudaFree(w.bq); cudaFree(w.q_bn); cudaFree(w.q_glob); cudaFree(w.thr_t);
   cudaFree(w.flag_count); cudaFree(w.flag_rows); cudaFree(w.flag_masks); cudaFree(w.cand_cnt);
   cudaFree(w.list_total); cudaFree(w.list_row); cudaFree(w.list_q); cudaFree(w.list_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
@@ -290,6 +292,21 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->q_glob = m->ws.q_glob;
   p->dbg = m->ws.dbg_dev;
   p->tile_stride = 1;
+  {
+    static int pf = -1;  // L2 prefetch distance of the A stream (tiles per unit); AVL_PREFETCH_TILES overrides
+    if (pf < 0) {
+      const char* e = getenv("AVL_PREFETCH_TILES");
+      pf = e ? atoi(e) : 0;  // measured on B200: 0.90 ms without, 1.02-1.31 ms with 1-8 tiles of prefetch
+      if (pf < 0 || pf > 16) pf = 0;
+    }
+    p->prefetch_tiles = pf;
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e2 = getenv("AVL_DEBUG_FLAGS");
+      dbg = e2 ? atoi(e2) : 0;
+    }
+    p->debug_flags = dbg;
+  }
   const int64_t unit = static_cast<int64_t>(kTileRows) * qs.cg;
   p->num_tiles = static_cast<int32_t>((m->n + unit - 1) / unit);
 }
@@ -493,7 +510,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
   if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
-  if ((rc = launch_argmax_rerank(m->feat, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map,
+  if ((rc = launch_argmax_rerank(m->feat, m->d, qs.q_dev, w.q64, nq, qs.scale_dev, m->row_norm, normalize_map,
                                  w.flag_count, w.flag_rows, w.flag_masks, w.flag_cap, dst, m->num_sms, s)))
     return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
@@ -506,7 +523,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
     if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "argmax", __FILE__, __LINE__));
     if (stats) {
       stats->cta_group = qs.cg;
-      stats->n_launches = 3;  // query_prepare, screen, rerank
+      stats->n_launches = 4;  // query_prepare, screen, f32->f64, rerank
       stats->n_flagged = nflag;
       if (g_profiling) {
         cudaEventElapsedTime(&stats->ms_screen, w.ev[1], w.ev[2]);
@@ -604,11 +621,10 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     p.dense_rs = 1;
     p.dense_cs = n_sample;
     p.dense_cols = nq;
+    p.dense_lb = 1;
+    p.prefetch_tiles = 0;  // sampled tiles are strided: nothing sequential to prefetch
     if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
-    if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_sample), n_sample, nq, k,
-                                      static_cast<int32_t>(unit), static_cast<int32_t>(tile_stride), m->n,
-                                      m->row_norm, m->row_c, m->row_an, w.q_bn, w.q_glob, normalize_map,
-                                      w.thr_t, s)))
+    if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_sample), n_sample, nq, k, w.thr_t, s)))
       return rc;
   }
   AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
@@ -651,9 +667,9 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     if (!ovf[q]) continue;
     ++n_fallback;
     if ((rc = ensure_column(m))) return rc;
-    if ((rc = launch_dense_exact(m->feat, m->n, m->d, qs.q_dev + static_cast<size_t>(q) * m->d, 1,
-                                 qs.scale_dev ? qs.scale_dev + q : nullptr, m->row_norm, normalize_map,
-                                 w.column, 1, 1, s)))
+    if ((rc = launch_column_exact(m->feat, m->n, m->d, qs.q_dev + static_cast<size_t>(q) * m->d,
+                                  qs.scale_dev ? qs.scale_dev + q : nullptr, m->row_norm, normalize_map, w.column,
+                                  m->num_sms, s)))
       return rc;
     if ((rc = launch_topk_vector(w.column, m->n, k, d_idx + static_cast<size_t>(q) * k,
                                  d_score + static_cast<size_t>(q) * k, w.topk_scratch, w.topk_scratch_bytes, s)))

@@ -128,6 +128,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
   }
 }
 
+// L2 prefetch of a tile that a later TMA load will fetch: hides HBM latency beyond what the shared
+// memory ring can keep in flight.
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -187,13 +187,19 @@ __device__ __forceinline__ double warp_dot(const float* __restrict__ a, const fl
 
 // ------------------------------------------------------------------ argmax re-rank
 // One warp per flagged row: exact scores of the queries in its band mask, first max wins.
-__global__ void argmax_rerank_kernel(const float* __restrict__ feat, int32_t d, const float* __restrict__ q,
-                                     int32_t nq, const float* __restrict__ scale,
-                                     const float* __restrict__ row_norm, int normalize,
-                                     const uint32_t* __restrict__ flag_count,
-                                     const uint32_t* __restrict__ flag_rows,
-                                     const uint32_t* __restrict__ flag_masks, uint32_t flag_cap,
-                                     int32_t* __restrict__ argmax_out) {
+// float->double conversions run at a quarter of the FMA rate, so the queries are converted once per
+// call (q64) and the row once per flagged row (registers) instead of once per product.
+__global__ void f32_to_f64_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = static_cast<double>(src[i]);
+}
+
+__global__ void __launch_bounds__(256)
+argmax_rerank_kernel(const float* __restrict__ feat, int32_t d, const float* __restrict__ q,
+                     const double* __restrict__ q64, int32_t nq, const float* __restrict__ scale,
+                     const float* __restrict__ row_norm, int normalize, const uint32_t* __restrict__ flag_count,
+                     const uint32_t* __restrict__ flag_rows, const uint32_t* __restrict__ flag_masks,
+                     uint32_t flag_cap, int32_t* __restrict__ argmax_out) {
   const int lane = threadIdx.x & 31;
   const uint32_t nflag = min(*flag_count, flag_cap);
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -201,20 +207,66 @@ __global__ void argmax_rerank_kernel(const float* __restrict__ feat, int32_t d, 
     const int64_t row = flag_rows[e];
     const float* a = feat + row * d;
     const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
+    const uint4 m0 = *reinterpret_cast<const uint4*>(flag_masks + static_cast<size_t>(e) * kFlagWords);
+    const uint4 m1 = *reinterpret_cast<const uint4*>(flag_masks + static_cast<size_t>(e) * kFlagWords + 4);
+    const uint32_t masks[kFlagWords] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
     float best = -FLT_MAX;
     int best_q = -1;
-    for (int w = 0; w < kFlagWords; ++w) {
-      uint32_t m = flag_masks[static_cast<size_t>(e) * kFlagWords + w];
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const int qq = w * 32 + bit;
-        const double dot = warp_dot(a, q + static_cast<size_t>(qq) * d, d, lane);
-        const float s = canon_score(dot, inv, normalize, scale, qq);
-        if (best_q < 0 || s > best) { best = s; best_q = qq; }
+    if (d == 512) {
+      double ad[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) ad[t] = static_cast<double>(__ldg(a + t * 32 + lane));
+#pragma unroll
+      for (int w = 0; w < kFlagWords; ++w) {
+        uint32_t m = masks[w];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int qq = w * 32 + bit;
+          const double* b = q64 + static_cast<size_t>(qq) * 512;
+          double bd[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) bd[t] = __ldg(b + t * 32 + lane);
+          double sum = 0.0;
+#pragma unroll
+          for (int t = 0; t < 16; ++t) sum = fma(ad[t], bd[t], sum);  // k ascending per lane, like warp_dot
+          const float sc = canon_score(warp_sum(sum), inv, normalize, scale, qq);
+          if (best_q < 0 || sc > best) { best = sc; best_q = qq; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < kFlagWords; ++w) {
+        uint32_t m = masks[w];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int qq = w * 32 + bit;
+          const double dot = warp_dot(a, q + static_cast<size_t>(qq) * d, d, lane);
+          const float sc = canon_score(dot, inv, normalize, scale, qq);
+          if (best_q < 0 || sc > best) { best = sc; best_q = qq; }
+        }
       }
     }
     if (lane == 0 && best_q >= 0) argmax_out[row] = best_q;
+  }
+}
+
+// ------------------------------------------------------------------ one exact score column
+// out[i] = canonical score of row i against ONE query (warp per row).  Used by the top-k fallback,
+// where the 64x64-tile dense kernel would waste 63/64 of its work.
+__global__ void __launch_bounds__(256)
+column_exact_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const float* __restrict__ q,
+                    const float* __restrict__ scale, const float* __restrict__ row_norm, int normalize,
+                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += nwarps) {
+    const double dot = warp_dot(feat + row * d, q, d, lane);
+    if (lane == 0) {
+      const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
+      out[row] = canon_score(dot, inv, normalize, scale, 0);
+    }
   }
 }
 
@@ -240,39 +292,28 @@ __device__ KeyT block_kth_largest(Fetch fetch, int n, int k, int* sh_cnt) {
   return v;
 }
 
-// map compact sample row -> map row (see ScreenParams::tile_stride)
-__device__ __forceinline__ int64_t sample_to_row(int64_t c, int32_t unit_rows, int32_t tile_stride) {
-  const int64_t u = c / unit_rows;
-  return u * tile_stride * unit_rows + (c - u * unit_rows);
-}
-
 // ------------------------------------------------------------------ threshold from a sample
-// sample_t[q][c]: screen scores of the sampled rows (transposed dense output).  Per query:
-// T_q = k-th largest of the per-thread maxima of the LOWER bounds (s~ - eps)/w over the sample.
-// The maxima belong to distinct rows, so T_q <= k-th largest lower bound over the sample <=
-// k-th largest exact score over the whole map (in units of score / scale_q): a valid threshold
-// from ONE pass over the sample.
+// sample_lb[q][c]: LOWER bounds (s~ - eps)/w of the sampled rows, written transposed by the screen
+// kernel (dense_lb; rows past the end of the map are -inf).  Per query: T_q = k-th largest of the
+// per-thread maxima.  The maxima belong to distinct rows, so T_q <= k-th largest lower bound over the
+// sample <= k-th largest exact score over the whole map (in units of score / scale_q): a valid
+// threshold from ONE coalesced pass over the sample.
 constexpr int kSelThreads = 1024;
 __global__ void __launch_bounds__(kSelThreads)
-select_threshold_kernel(const float* __restrict__ sample_t, int32_t n_sample, int64_t ld, int32_t k,
-                        int32_t unit_rows, int32_t tile_stride, int64_t n_rows,
-                        const float* __restrict__ row_norm, const float* __restrict__ row_c,
-                        const float* __restrict__ row_an, const float* __restrict__ q_bn,
-                        const uint32_t* __restrict__ glob, int normalize, float* __restrict__ thr_t) {
+select_threshold_kernel(const float* __restrict__ sample_lb, int32_t n_sample, int64_t ld, int32_t k,
+                        float* __restrict__ thr_t) {
   const int q = blockIdx.x;
-  const float rho = __uint_as_float(glob[0]);
-  const float bn = q_bn[q];
-  const float* col = sample_t + static_cast<int64_t>(q) * ld;
+  const float* col = sample_lb + static_cast<int64_t>(q) * ld;
   uint32_t best = 0u;  // 0 = this thread saw no valid row
-  for (int c = threadIdx.x; c < n_sample; c += kSelThreads) {
-    const int64_t row = sample_to_row(c, unit_rows, tile_stride);
-    if (row < n_rows) {
-      const float s = col[c];
-      const float r_i = fmaf(rho, row_an[row], row_c[row]);
-      const float w_i = normalize ? fmaxf(row_norm[row], 1e-30f) : 1.f;
-      const float lo = __fdiv_rd(__fsub_rd(s, __fmul_ru(r_i, bn)), w_i);
-      best = max(best, max(f2ord(lo), 1u));
-    }
+  int c = threadIdx.x;
+  for (; c + 3 * kSelThreads < n_sample; c += 4 * kSelThreads) {  // 4 independent loads in flight
+    const float a0 = col[c], a1 = col[c + kSelThreads], a2 = col[c + 2 * kSelThreads], a3 = col[c + 3 * kSelThreads];
+    const float m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+    if (m > -INFINITY) best = max(best, max(f2ord(m), 1u));
+  }
+  for (; c < n_sample; c += kSelThreads) {
+    const float a0 = col[c];
+    if (a0 > -INFINITY) best = max(best, max(f2ord(a0), 1u));
   }
   const int groups = __syncthreads_count(best != 0u);
   if (groups < k) {
@@ -291,7 +332,8 @@ select_threshold_kernel(const float* __restrict__ sample_t, int32_t n_sample, in
 // One block per query.  Gathers its entries from the unified candidate list, finds the k-th best
 // LOWER bound, keeps the entries whose UPPER bound reaches it, re-scores those exactly (fp64) and
 // orders them by (score desc, row asc).
-__global__ void __launch_bounds__(256)
+constexpr int kFinThreads = 1024;
+__global__ void __launch_bounds__(kFinThreads)
 topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, const float* __restrict__ q,
                      const float* __restrict__ scale, const float* __restrict__ row_norm,
                      const float* __restrict__ row_c, const float* __restrict__ row_an,
@@ -319,17 +361,29 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   // gather: 16 query bytes per load
   const uint32_t nvec = (total + 15u) / 16u;
   const uint4* lq4 = reinterpret_cast<const uint4*>(list_q);
-  for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
-    const uint4 w = lq4[v];
-    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+  const uint32_t pat = static_cast<uint32_t>(qq) * 0x01010101u;
+  for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += 4 * blockDim.x) {
+    uint4 w[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int u = 0; u < 4; ++u) {  // 4 independent 16-byte loads in flight
+      const uint32_t v = v0 + u * blockDim.x;
+      w[u] = v < nvec ? lq4[v] : make_uint4(~pat, ~pat, ~pat, ~pat);
+    }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t e = v * 16u + a * 4u + b;
-        if (((words[a] >> (8 * b)) & 0xFFu) == static_cast<uint32_t>(qq) && e < total) {
-          const uint32_t s = atomicAdd(&sh_n, 1u);
-          if (s < cand_cap) { Ix[s] = list_row[e]; Lk[s] = __float_as_uint(list_val[e]); }
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t v = v0 + u * blockDim.x;
+      const uint32_t words[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        uint32_t x = words[a] ^ pat;  // a zero byte marks an entry of this query
+        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t e = v * 16u + a * 4u + b;
+          if (((x >> (8 * b)) & 0xFFu) == 0u && e < total) {
+            const uint32_t s = atomicAdd(&sh_n, 1u);
+            if (s < cand_cap) { Ix[s] = list_row[e]; Lk[s] = __float_as_uint(list_val[e]); }
+          }
         }
       }
     }
@@ -552,27 +606,33 @@ int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, 
   return AVL_OK;
 }
 
-int launch_argmax_rerank(const float* feat, int32_t d, const float* q, int32_t nq, const float* scale,
+int launch_column_exact(const float* feat, int64_t n, int32_t d, const float* q, const float* scale,
+                        const float* row_norm, int normalize, float* out, int num_sms, cudaStream_t s) {
+  if (n == 0) return AVL_OK;
+  column_exact_kernel<<<num_sms * 8, 256, 0, s>>>(feat, n, d, q, scale, row_norm, normalize, out);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_argmax_rerank(const float* feat, int32_t d, const float* q, double* q64, int32_t nq, const float* scale,
                          const float* row_norm, int normalize, const uint32_t* flag_count,
                          const uint32_t* flag_rows, const uint32_t* flag_masks, uint32_t flag_cap,
                          int32_t* argmax_out, int num_sms, cudaStream_t s) {
-  argmax_rerank_kernel<<<num_sms * 8, 256, 0, s>>>(feat, d, q, nq, scale, row_norm, normalize, flag_count,
+  const int64_t nel = static_cast<int64_t>(nq) * d;
+  f32_to_f64_kernel<<<static_cast<unsigned>((nel + 255) / 256), 256, 0, s>>>(q, q64, nel);
+  argmax_rerank_kernel<<<num_sms * 8, 256, 0, s>>>(feat, d, q, q64, nq, scale, row_norm, normalize, flag_count,
                                                    flag_rows, flag_masks, flag_cap, argmax_out);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
 
-int launch_select_threshold(const float* sample_t, int32_t n_sample, int64_t ld, int32_t nq, int32_t k,
-                            int32_t unit_rows, int32_t tile_stride, int64_t n_rows, const float* row_norm,
-                            const float* row_c, const float* row_an, const float* q_bn, const float* q_glob,
-                            int normalize, float* thr_t, cudaStream_t s) {
+int launch_select_threshold(const float* sample_lb, int32_t n_sample, int64_t ld, int32_t nq, int32_t k,
+                            float* thr_t, cudaStream_t s) {
   if (k > kSelThreads) {
     set_error("select_threshold: k too large");
     return AVL_ERR_ARG;
   }
-  select_threshold_kernel<<<nq, kSelThreads, 0, s>>>(sample_t, n_sample, ld, k, unit_rows, tile_stride, n_rows,
-                                             row_norm, row_c, row_an, q_bn,
-                                             reinterpret_cast<const uint32_t*>(q_glob), normalize, thr_t);
+  select_threshold_kernel<<<nq, kSelThreads, 0, s>>>(sample_lb, n_sample, ld, k, thr_t);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
@@ -588,7 +648,7 @@ int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const flo
   const size_t smem = topk_finalize_smem(cand_cap);
   AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-  topk_finalize_kernel<<<nq, 256, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
+  topk_finalize_kernel<<<nq, kFinThreads, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
                                              reinterpret_cast<const uint32_t*>(q_glob), normalize, k, list_total,
                                              list_row, list_q, list_val, list_cap, cand_cap, cand_cnt, out_idx,
                                              out_score, overflow_flags);

@@ -49,13 +49,23 @@ struct TileCtx {
 };
 
 // ---- epilogue: dense store ------------------------------------------------------------
+// dense_lb: store the LOWER bound of the exact score in threshold units, (s~ - r_i ||b_q||) / w_i
+// (directed rounding), instead of s~ -- what the sampled threshold pass needs.
 template <int W>
-__device__ __forceinline__ void dense_chunk(const ScreenParams& p, const TileCtx& t, int c0) {
+__device__ __forceinline__ void dense_chunk(const ScreenParams& p, const TileCtx& t, int c0, const float2* qc,
+                                            float r_i, float w_i) {
   uint32_t v[W];
   if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
   ptx::tmem_ld_wait();
-  if (t.valid) {
-    float* o = p.dense_out + t.crow * p.dense_rs + static_cast<int64_t>(c0) * p.dense_cs;
+  float* o = p.dense_out + t.crow * p.dense_rs + static_cast<int64_t>(c0) * p.dense_cs;
+  if (p.dense_lb) {
+    // rows past the end of the map store -inf so that they never raise a threshold
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (c0 + j < p.dense_cols)
+        o[j * p.dense_cs] = t.valid ? __fdiv_rd(__fsub_rd(__uint_as_float(v[j]), __fmul_ru(r_i, qc[c0 + j].y)), w_i)
+                                    : -INFINITY;
+  } else if (t.valid) {
 #pragma unroll
     for (int j = 0; j < W; ++j)
       if (c0 + j < p.dense_cols) o[j * p.dense_cs] = __uint_as_float(v[j]);
@@ -285,15 +295,34 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_bfull), 0);
 
       uint32_t stage = 0, phase = 0;
+      // The ring holds `stages` x 16 KiB per CTA, not enough bytes in flight to cover HBM latency at
+      // full rate when B takes most of the shared memory; so the A tiles of the next
+      // `prefetch_tiles` tiles are pulled into L2 ahead of the loads that will need them.
+      for (int t = 0; t < p.prefetch_tiles; ++t) {
+        const int jj = unit + t * num_units;
+        if (jj < p.num_tiles) {
+          const int64_t r0 = (static_cast<int64_t>(jj) * p.tile_stride * CG + rank) * kTileRows;
+          for (int kb = 0; kb < p.kblocks; ++kb) ptx::tma_prefetch_2d(&tmap_a, kb * kBlockK, static_cast<int32_t>(r0));
+        }
+      }
       for (int j = unit; j < p.num_tiles; j += num_units) {
         const int64_t row0 = (static_cast<int64_t>(j) * p.tile_stride * CG + rank) * kTileRows;
+        const int jp = j + p.prefetch_tiles * num_units;
+        const int64_t rowp = (static_cast<int64_t>(jp) * p.tile_stride * CG + rank) * kTileRows;
+        const bool do_pf = p.prefetch_tiles > 0 && jp < p.num_tiles;
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (do_pf) ptx::tma_prefetch_2d(&tmap_a, kb * kBlockK, static_cast<int32_t>(rowp));
           ptx::mbar_wait(ptx::smem_u32(bar_empty + stage), phase ^ 1u, p.dbg, 0x10u + stage);
-          ptx::tma_load_2d<CG>(ptx::smem_u32(smem_a + stage * kStageBytes), &tmap_a,
-                               ptx::smem_u32(bar_full + stage), kb * kBlockK,
-                               static_cast<int32_t>(row0), ptx::kEvictFirst);
-          if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_full + stage), kStageBytes * CG);
-          else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_full + stage), 0);
+          if (!(p.debug_flags & 2)) {
+            ptx::tma_load_2d<CG>(ptx::smem_u32(smem_a + stage * kStageBytes), &tmap_a,
+                                 ptx::smem_u32(bar_full + stage), kb * kBlockK,
+                                 static_cast<int32_t>(row0), ptx::kEvictFirst);
+            if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_full + stage), kStageBytes * CG);
+            else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_full + stage), 0);
+          } else {  // triage: barrier protocol only
+            if (leader) ptx::mbar_arrive(ptx::smem_u32(bar_full + stage));
+            else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_full + stage), 0);
+          }
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1u; }
         }
       }
@@ -318,7 +347,8 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           const uint64_t b0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_b + kb * bblk));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes inside the swizzle row
-            ptx::umma_bf16<CG>(tmem_d, a0 + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (!(p.debug_flags & 1))
+              ptx::umma_bf16<CG>(tmem_d, a0 + 2u * k, b0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           ptx::umma_commit<CG>(ptx::smem_u32(bar_empty + stage));   // frees the A stage in both CTAs
           if (kb == p.kblocks - 1) ptx::umma_commit<CG>(ptx::smem_u32(bar_tfull + as));
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1u; }
@@ -351,9 +381,16 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       t.taddr = tmem_base + as * kAccumStride + (lane_base << 16);
       const int n32 = p.npad & ~31;
 
-      if (p.mode == kModeDense) {
-        for (int c0 = half * 32; c0 < n32; c0 += 64) dense_chunk<32>(p, t, c0);
-        if (n32 < p.npad && ((n32 >> 5) & 1) == half) dense_chunk<16>(p, t, n32);
+      if (p.debug_flags & 4) {
+        // triage: drain nothing
+      } else if (p.mode == kModeDense) {
+        float r_i = 0.f, w_i = 1.f;
+        if (p.dense_lb && t.valid) {
+          r_i = fmaf(rho, p.row_an[t.row], p.row_c[t.row]);
+          if (p.normalize) w_i = fmaxf(p.row_norm[t.row], 1e-30f);
+        }
+        for (int c0 = half * 32; c0 < n32; c0 += 64) dense_chunk<32>(p, t, c0, qc, r_i, w_i);
+        if (n32 < p.npad && ((n32 >> 5) & 1) == half) dense_chunk<16>(p, t, n32, qc, r_i, w_i);
       } else if (p.mode == kModeArgmax) {
         if (half == 0) {  // the per-row reduction stays inside one thread: 4 of the 8 warps do it
           uint32_t best = 0, second = 0;

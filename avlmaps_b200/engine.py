@@ -218,6 +218,34 @@ def fuse_topk(map_a: DeviceMap, queries_a, map_b: DeviceMap, queries_b, k: int, 
     return oi, oh
 
 
+def heat_from_mask_3d(grid_pos, mask, cell_size: float = 0.05, decay_rate: float = 0.01, stream=None):
+    """get_heatmap_from_mask_3d (visualize_utils.py:29-49) on the device: (N,) float32 heat."""
+    lib = L.load()
+    L.require_device()
+    p = _Arg(grid_pos, np.int32, "grid_pos")
+    if _is_torch(mask):
+        import torch
+
+        mask = mask.to(torch.uint8)
+    else:
+        mask = np.ascontiguousarray(mask).astype(np.uint8)
+    m = _Arg(mask, np.uint8, "mask")
+    n = p.shape[0]
+    if len(p.shape) != 2 or p.shape[1] != 3 or tuple(m.shape) != (n,):
+        raise ValueError("grid_pos must be (N, 3) and mask (N,)")
+    if p.device:
+        import torch
+
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        optr = C.c_void_p(out.data_ptr())
+    else:
+        out = np.empty(n, np.float32)
+        optr = out.ctypes.data_as(C.c_void_p)
+    L.check(lib.avl_heat_from_mask_3d(p.ptr, m.ptr, n, float(cell_size), float(decay_rate), optr, _flags(p, m),
+                                      _stream_ptr(stream)))
+    return out
+
+
 class DeviceBuilder:
     """Voxel map under construction in HBM (the arrays of VLMapBuilder._init_map, vlmap_builder.py:195-224)."""
 

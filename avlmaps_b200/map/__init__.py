@@ -4,5 +4,6 @@ part of the accelerated path; their similarity call sites map to engine.DeviceMa
 from .map import Map
 from .vlmap import VLMap
 from .vlmap_builder import VLMapBuilder
+from .avlmap import AVLMap
 
-__all__ = ["Map", "VLMap", "VLMapBuilder"]
+__all__ = ["Map", "VLMap", "VLMapBuilder", "AVLMap"]

@@ -69,6 +69,8 @@ class ShardedMap:
         import torch.distributed as dist
 
         idx, val = self.local.topk(queries, k, scale=scale, normalize_map=normalize_map)
+        if self.world == 1 and self.row_offset == 0:
+            return idx, val  # one slab: already global ids in final order
         as_numpy = isinstance(idx, np.ndarray)
         ti = torch.from_numpy(idx) if as_numpy else idx
         tv = torch.from_numpy(val) if as_numpy else val

@@ -130,6 +130,14 @@ int avl_fuse_topk(avl_map* map_a, const float* queries_a, const float* scale_a, 
                   int32_t n_pairs, int32_t combine, int32_t k, int64_t* out_idx, float* out_heat,
                   int flags, void* stream);
 
+/* heat[i] = 1 on target voxels (mask[i] != 0), else clip(1 - min_t ||pos_i - pos_t|| / cell_size * decay_rate, 0, 1).
+ * grid_pos (n, 3) int32, mask (n,) uint8 (numpy bool), out_heat (n,) fp32.  Bit-exact restatement of
+ * get_heatmap_from_mask_3d (avlmaps/utils/visualize_utils.py:29-49; twin habitat_lang_robot.py:242-265),
+ * the O(N_other * N_target) Python loop behind AVLMap.index_object (avlmaps/map/avlmap.py:67-76).
+ * An empty mask is an argument error (the reference's np.argmin raises). */
+int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mask, int64_t n, double cell_size,
+                          double decay_rate, float* out_heat, int flags, void* stream);
+
 /* ---- map-build path ------------------------------------------------------------------ */
 
 typedef struct avl_grid_spec {

@@ -78,3 +78,30 @@ def test_create_load_index_like_the_applications(lib, tmp_path):
     assert np.array_equal(s2, ref_scores)
     s3 = get_lseg_score(enc, cats, vlmap.grid_feat, d, use_multiple_templates=True, avg_mode=1)
     assert s3.shape == (vlmap.grid_feat.shape[0], 5)
+
+
+def test_avlmap_index_object(lib):
+    """AVLMap.index_object (avlmap.py:67-76): mask -> nearest-target distance decay, incl. the
+    `init_categories[1:-1]` quirk, and get_max_pos_3d."""
+    from avlmaps_b200.map import AVLMap
+    from avlmaps_b200.utils.clip_utils import landmark_text_feats
+
+    d = 32
+    feat, _ = synth.index_inputs(3000, d, 1, seed=2)
+    pos = np.random.default_rng(0).integers(0, 40, (3000, 3)).astype(np.int32)
+    cfg = {"map_config": synth.map_config(48, 0.05, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1), "params": {"cs": 0.05}}
+    av = AVLMap(cfg)
+    av.vlmap.set_map_arrays(feat, grid_pos=pos)
+    enc = fake_encoder(d)
+    av.vlmap.set_text_encoder(enc, d)
+    heat = av.index_object("chair", decay_rate=0.1)
+    tf, _, _ = landmark_text_feats(enc, ["chair"], d, True, 0, True)
+    mask = O.index_mask(O.scores(feat, tf), 0)
+    assert np.array_equal(heat, O.heatmap_from_mask_3d(pos, mask, 0.05, 0.1))
+    cats = ["void", "chair", "table", "sofa", "misc"]
+    heat2 = av.index_object("table", init_categories=cats, decay_rate=0.1)
+    assert av.vlmap.categories == ["chair", "table", "sofa"]
+    tf2, _, _ = landmark_text_feats(enc, cats[1:-1], d, True, 0, True)
+    mask2 = O.index_mask(O.scores(feat, tf2), 1)
+    assert np.array_equal(heat2, O.heatmap_from_mask_3d(pos, mask2, 0.05, 0.1))
+    assert np.array_equal(av.get_max_pos_3d(heat2), pos[int(np.argmax(heat2))])

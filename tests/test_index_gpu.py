@@ -253,3 +253,19 @@ def test_full_size_c2_properties(eng):
     mi, mv = merge_topk(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), k)
     assert np.array_equal(mi, idx) and np.array_equal(mv, val)
     m.close()
+
+
+def test_heat_from_mask_bit_exact(eng):
+    """get_heatmap_from_mask_3d (visualize_utils.py:29-49): golden vector of the reference + a larger oracle case."""
+    g = np.load(G / "heat_n600.npz")
+    h = eng.heat_from_mask_3d(g["pos"], g["mask"], float(g["cell_size"]), float(g["decay_rate"]))
+    assert h.dtype == np.float32 and np.array_equal(h, g["heat"])
+    rng = np.random.default_rng(1)
+    pos = rng.integers(0, 300, (30_000, 3)).astype(np.int32)
+    mask = rng.uniform(size=30_000) < 0.02
+    want = O.heatmap_from_mask_3d(pos, mask, 0.05, 0.01)
+    assert np.array_equal(eng.heat_from_mask_3d(pos, mask, 0.05, 0.01), want)
+    from avlmaps_b200 import _lib as L
+
+    with pytest.raises(L.AvlError, match="selects no voxel"):
+        eng.heat_from_mask_3d(pos, np.zeros(30_000, bool))
