@@ -53,6 +53,7 @@ struct ScreenParams {
   const float* row_an;     // >= ||bf16(a_i)||
   // per-query statistics (query_prepare)
   const float* q_bn;       // >= ||b_q||
+  const __nv_bfloat16* bq; // bf16 queries (256 zero-padded rows x dpad), read by the query-stationary kernel
   const float* q_glob;     // [0] rho >= max_q ||b_q - bf16(b_q)|| / ||b_q|| (+slack), [1] max_q q_bn
   // kModeDense
   float* dense_out;        // element (r, q) at r * dense_rs + q * dense_cs, r = compact row
@@ -81,6 +82,11 @@ int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const S
                   int num_sms, size_t smem_bytes, cudaStream_t stream);
 size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages);
 int screen_pick_stages(int cta_group, int npad, int kblocks);  // <=0: does not fit
+// query-stationary variant (sim_screen_ts.cu): queries in TMEM, 128-voxel tiles, cta_group::2 only
+int launch_screen_ts(const void* tmap_v64, const ScreenParams& p, int num_sms, size_t smem_bytes,
+                     cudaStream_t stream);
+size_t screen_ts_smem_bytes(int stages);
+int screen_ts_pick_stages();
 
 // ---- exact / helper kernels (sim_exact.cu) --------------------------------
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
@@ -109,6 +115,8 @@ int launch_topk_vector(const float* values, int64_t n, int32_t k, int64_t* out_i
                        void* scratch, size_t scratch_bytes, cudaStream_t s);
 size_t topk_vector_scratch_bytes(int64_t n);
 size_t topk_finalize_smem(uint32_t cand_cap);
+int launch_merge_topk(const int64_t* idx, const float* val, int32_t n_shards, int32_t nq, int32_t k,
+                      int64_t* out_idx, float* out_val, cudaStream_t s);
 int launch_minmax_cols(const float* m, int64_t n, int32_t cols, float* out_min, float* out_max,
                        cudaStream_t s);
 int launch_fuse_heat(const float* sa, const float* sb, int64_t n, int32_t pair, int32_t cols,

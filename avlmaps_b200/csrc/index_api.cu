@@ -112,7 +112,8 @@ struct avl_map {
   float* row_norm = nullptr;
   float* row_c = nullptr;
   float* row_an = nullptr;
-  CUtensorMap tmap_a;
+  CUtensorMap tmap_a;     // box 64 x 128 rows (sim_screen.cu)
+  CUtensorMap tmap_a64;   // box 64 x 64 rows  (sim_screen_ts.cu)
   int64_t bytes = 0;
   avl::Workspace ws;
 };
@@ -231,11 +232,25 @@ static int pick_cta_group(int npad, int kblocks, int forced) {
   return 0;
 }
 
+// query-stationary kernel: 128 < nq <= 256 and D <= 512 (AVL_TS=0 disables, AVL_TS=1 forces for any nq)
+static bool want_ts(int nq, int dpad, int forced_cg, bool allow_ts) {
+  if (forced_cg == 3) return dpad <= 512;
+  if (!allow_ts || forced_cg != 0 || dpad > 512) return false;
+  const char* e = getenv("AVL_TS");
+  // Measured on B200 (4M x 512 x 256): 1.15 ms vs 0.90 ms for the shared-memory-operand kernel -- the
+  // M=256 x N=128 A-from-TMEM MMAs retire at ~106 cycles instead of the 64 the tile shape suggests, so the
+  // deeper ring does not pay.  Kept as an opt-in variant (AVL_TS=1), parity-tested like the default.
+  (void)nq;
+  return e && e[0] == '1';
+}
+
 struct QuerySetup {
   const float* q_dev = nullptr;      // fp32 queries on device
   const float* scale_dev = nullptr;  // or null
   int npad = 0;
   int cg = 0;
+  bool ts = false;                   // query-stationary kernel (queries in TMEM)
+  int unit_rows = 0;                 // voxel rows per tile unit of the chosen kernel
   int stages = 0;
   size_t smem = 0;
   CUtensorMap tmap_b;
@@ -244,7 +259,7 @@ struct QuerySetup {
 // stage queries, build bf16 B + norms, pick the kernel variant
 static int setup_queries(avl_map* m, const float* queries, int32_t nq, const float* scale, int flags,
                          int forced_cg, bool need_screen, cudaStream_t s, QuerySetup* qs,
-                         bool fold_scale = false) {
+                         bool fold_scale = false, bool allow_ts = false) {
   Workspace& w = m->ws;
   AVL_ARG(queries != nullptr, "queries is NULL");
   AVL_ARG(nq >= 1 && nq <= AVL_MAX_QUERIES, "nq must be in [1, AVL_MAX_QUERIES]");
@@ -263,11 +278,23 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
   if (!need_screen) return AVL_OK;
   qs->npad = (nq + 15) & ~15;
   const int kblocks = m->dpad / kBlockK;
+  if (want_ts(nq, m->dpad, forced_cg, allow_ts)) {
+    // large batches: queries live in TMEM, all of shared memory streams voxel tiles
+    qs->ts = true;
+    qs->cg = 2;
+    qs->npad = AVL_MAX_QUERIES;
+    qs->unit_rows = 128;
+    qs->stages = screen_ts_pick_stages();
+    qs->smem = screen_ts_smem_bytes(qs->stages);
+    return launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
+                                w.q_bn, w.q_glob, s);
+  }
   qs->cg = pick_cta_group(qs->npad, kblocks, forced_cg);
   if (qs->cg == 0) {
     set_error("query batch does not fit the shared memory of an SM pair (nq * dim too large); split the batch");
     return AVL_ERR_UNSUPPORTED;
   }
+  qs->unit_rows = kTileRows * qs->cg;
   qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks);
   qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages);
   int rc = launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
@@ -289,6 +316,7 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->row_c = m->row_c;
   p->row_an = m->row_an;
   p->q_bn = m->ws.q_bn;
+  p->bq = m->ws.bq;
   p->q_glob = m->ws.q_glob;
   p->dbg = m->ws.dbg_dev;
   p->tile_stride = 1;
@@ -307,8 +335,13 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
     }
     p->debug_flags = dbg;
   }
-  const int64_t unit = static_cast<int64_t>(kTileRows) * qs.cg;
+  const int64_t unit = qs.unit_rows;
   p->num_tiles = static_cast<int32_t>((m->n + unit - 1) / unit);
+}
+
+static int run_screen(avl_map* m, const QuerySetup& qs, const ScreenParams& p, cudaStream_t s) {
+  if (qs.ts) return launch_screen_ts(&m->tmap_a64, p, m->num_sms, qs.smem, s);
+  return launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s);
 }
 
 static int scale_positive(const float* scale, int32_t nq, int flags) {
@@ -390,6 +423,8 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
     if ((rc = launch_map_prepare(m->feat, n, dim, m->dpad, m->bf, m->row_norm, m->row_c, m->row_an, kappa, s))) break;
     if ((rc = encode_kmajor_map(&m->tmap_a, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
                                 kTileRows))) break;
+    if ((rc = encode_kmajor_map(&m->tmap_a64, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
+                                64))) break;
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
   } while (0);
@@ -464,7 +499,7 @@ int avl_sim_screen_dense(avl_map* m, const float* queries, int32_t nq, int32_t c
   p.dense_rs = nq;
   p.dense_cs = 1;
   p.dense_cols = nq;
-  rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s);
+  rc = run_screen(m, qs, p, s);
   if (rc == AVL_OK && !(flags & AVL_ON_DEVICE)) {
     cudaError_t e = cudaMemcpyAsync(out_scores, dst, static_cast<size_t>(m->n) * nq * sizeof(float),
                                     cudaMemcpyDeviceToHost, s);
@@ -508,7 +543,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
   p.flag_masks = w.flag_masks;
   p.flag_cap = w.flag_cap;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
-  if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
+  if ((rc = run_screen(m, qs, p, s))) return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
   if ((rc = launch_argmax_rerank(m->feat, m->d, qs.q_dev, w.q64, nq, qs.scale_dev, m->row_norm, normalize_map,
                                  w.flag_count, w.flag_rows, w.flag_masks, w.flag_cap, dst, m->num_sms, s)))
@@ -592,11 +627,11 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   }
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
   QuerySetup qs;
-  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs))) return rc;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs, false, /*allow_ts=*/true))) return rc;
   int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
   float* d_score = (flags & AVL_ON_DEVICE) ? out_score : w.out_score;
 
-  const int64_t unit = static_cast<int64_t>(kTileRows) * qs.cg;
+  const int64_t unit = qs.unit_rows;
   const int64_t total_units = (m->n + unit - 1) / unit;
   // rows sampled for the threshold: ~n/64, enough that ~k*n/n0 candidates per query stay << cand_cap
   int64_t n0 = std::max<int64_t>(m->n / 64, static_cast<int64_t>(k) * m->n / 1024);
@@ -623,7 +658,7 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     p.dense_cols = nq;
     p.dense_lb = 1;
     p.prefetch_tiles = 0;  // sampled tiles are strided: nothing sequential to prefetch
-    if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
+    if ((rc = run_screen(m, qs, p, s))) return rc;
     if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_sample), n_sample, nq, k, w.thr_t, s)))
       return rc;
   }
@@ -641,7 +676,7 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     p.list_val = w.list_val;
     p.list_cap = w.list_cap;
     if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
-    if ((rc = launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s))) return rc;
+    if ((rc = run_screen(m, qs, p, s))) return rc;
     if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
   }
   // phase C: exact re-score of the survivors, final order
@@ -681,7 +716,7 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     AVL_CUDA(cudaStreamSynchronize(s));
   }
   if (stats) {
-    stats->cta_group = qs.cg;
+    stats->cta_group = qs.ts ? 3 : qs.cg;
     stats->n_launches = 5 + 3 * n_fallback;  // query_prepare, sample screen, select, screen, finalize
     stats->n_candidates = n_cand;
     stats->n_fallback_queries = n_fallback;
@@ -692,6 +727,17 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     }
   }
   return AVL_OK;
+}
+
+int avl_merge_topk(const int64_t* idx, const float* val, int32_t n_shards, int32_t nq, int32_t k,
+                   int64_t* out_idx, float* out_val, int flags, void* stream) {
+  AVL_ARG(idx && val && out_idx && out_val, "NULL argument");
+  AVL_ARG(n_shards >= 1 && nq >= 1 && k >= 1 && k <= AVL_MAX_TOPK, "invalid shape");
+  if (!(flags & AVL_ON_DEVICE)) {
+    set_error("avl_merge_topk takes device pointers (the gathered NCCL buffer)");
+    return AVL_ERR_UNSUPPORTED;
+  }
+  return launch_merge_topk(idx, val, n_shards, nq, k, out_idx, out_val, static_cast<cudaStream_t>(stream));
 }
 
 int avl_fuse_topk(avl_map* ma, const float* qa, const float* scale_a, int normalize_a, avl_map* mb,

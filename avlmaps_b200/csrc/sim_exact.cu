@@ -518,6 +518,44 @@ topk_vec_l2_kernel(const unsigned long long* __restrict__ keys, int m, int32_t k
   }
 }
 
+// ------------------------------------------------------------------ merge of per-shard top-k
+// idx/val: (S, Q, k) per-shard results with GLOBAL row ids (-1 = empty slot).  One block per query:
+// rank every entry by (score desc, row asc) by counting -- S*k <= 1024 entries.
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const int64_t* __restrict__ idx, const float* __restrict__ val, int32_t n_shards, int32_t nq,
+                  int32_t k, int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  __shared__ int64_t si[1024];
+  __shared__ float sv[1024];
+  const int q = blockIdx.x;
+  const int m = n_shards * k;
+  for (int e = threadIdx.x; e < m; e += blockDim.x) {
+    const int s = e / k, j = e - s * k;
+    const size_t off = (static_cast<size_t>(s) * nq + q) * k + j;
+    si[e] = idx[off];
+    sv[e] = val[off];
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    out_idx[static_cast<size_t>(q) * k + j] = -1;
+    out_val[static_cast<size_t>(q) * k + j] = -INFINITY;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < m; e += blockDim.x) {
+    const int64_t i = si[e];
+    if (i < 0) continue;
+    const float v = sv[e];
+    int rank = 0;
+    for (int t = 0; t < m; ++t) {
+      const int64_t it = si[t];
+      const float vt = sv[t];
+      rank += (it >= 0 && (vt > v || (vt == v && it < i))) ? 1 : 0;
+    }
+    if (rank < k) {
+      out_idx[static_cast<size_t>(q) * k + rank] = i;
+      out_val[static_cast<size_t>(q) * k + rank] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ fusion helpers
 // per-column min / max of a column-major matrix m[col][row] (each column contiguous).
 __global__ void __launch_bounds__(256)
@@ -677,6 +715,17 @@ int launch_topk_vector(const float* values, int64_t n, int32_t k, int64_t* out_i
   topk_vec_l1_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(values, n, k, keys);
   AVL_CUDA(cudaGetLastError());
   topk_vec_l2_kernel<<<1, 1024, 0, s>>>(keys, static_cast<int>(blocks * k), k, n, out_idx, out_val);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+int launch_merge_topk(const int64_t* idx, const float* val, int32_t n_shards, int32_t nq, int32_t k,
+                      int64_t* out_idx, float* out_val, cudaStream_t s) {
+  if (n_shards * k > 1024) {
+    set_error("merge_topk: n_shards * k must be <= 1024");
+    return AVL_ERR_UNSUPPORTED;
+  }
+  merge_topk_kernel<<<nq, 256, 0, s>>>(idx, val, n_shards, nq, k, out_idx, out_val);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

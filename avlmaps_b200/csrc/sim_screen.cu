@@ -261,7 +261,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(bar_tfull + i), 1);          // one tcgen05.commit
-      ptx::mbar_init(ptx::smem_u32(bar_tempty + i), CG * kEpiWarps * 32);  // every epilogue thread of the pair
+      ptx::mbar_init(ptx::smem_u32(bar_tempty + i), CG * kEpiWarps);  // one arrive per epilogue warp of the pair
     }
     ptx::mbar_init(ptx::smem_u32(bar_bfull), CG);
     ptx::fence_barrier_init();
@@ -272,7 +272,8 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     const int q = threadIdx.x;
     float2 c = make_float2(__int_as_float(0x7f800000), 0.f);  // +inf: padded column never passes
     if (q < p.nq) {
-      c.x = (p.mode == kModeThresh) ? p.thr_t[q] : 0.f;
+      c.x = (p.mode == kModeThresh && !(p.debug_flags & 3)) ? p.thr_t[q]
+            : (p.mode == kModeThresh ? __int_as_float(0x7f800000) : 0.f);  // triage modes emit nothing
       c.y = p.q_bn[q];
     }
     qc[q] = c;
@@ -450,10 +451,14 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         else pend = thresh_tile<false>(p, t, qc, iw, ri, half, ring, pend, lane);
       }
 
-      // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+      // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier); one arrive
+      // per warp -- per-thread remote arrives serialise on the barrier (see sim_screen_ts.cu)
       ptx::tc_fence_before();
-      if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::smem_u32(bar_tempty + as), 0);
-      else ptx::mbar_arrive(ptx::smem_u32(bar_tempty + as));
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::smem_u32(bar_tempty + as), 0);
+        else ptx::mbar_arrive(ptx::smem_u32(bar_tempty + as));
+      }
     }
     if (p.mode == kModeThresh && pend > 0u) pend = ring_flush(p, ring, pend, pend, lane);
   }

@@ -158,8 +158,18 @@ class DeviceMap:
         return o
 
     # -- per-query top-k rows
-    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None):
+    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None, out=None):
+        """out=(idx int64 (Q, k), score float32 (Q, k)) torch CUDA tensors: write there (device path, Q <= 256)."""
         q, s = self._queries(queries, scale)
+        if out is not None:
+            if not q.device or q.shape[0] > L.AVL_MAX_QUERIES:
+                raise ValueError("out= needs CUDA queries and at most 256 of them")
+            st = L.IndexStats()
+            L.check(self._lib.avl_sim_topk(self._h, q.ptr, q.shape[0], s.ptr, int(normalize_map), k,
+                                           C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                           _flags(q, s), _stream_ptr(stream), C.byref(st)))
+            self.last_stats = st.as_dict()
+            return out
         outs_i, outs_s = [], []
         stats = None
         for c0 in range(0, q.shape[0], L.AVL_MAX_QUERIES):
@@ -181,6 +191,19 @@ class DeviceMap:
 
             return torch.cat(outs_i), torch.cat(outs_s)
         return np.concatenate(outs_i), np.concatenate(outs_s)
+
+
+def merge_topk_device(gathered_idx, gathered_val, k: int, stream=None):
+    """(S, Q, k) torch CUDA tensors with global row ids -> merged (Q, k) by (score desc, row asc)."""
+    import torch
+
+    lib = L.load()
+    s_, q_, kk = gathered_idx.shape
+    oi = torch.empty((q_, k), dtype=torch.int64, device=gathered_idx.device)
+    ov = torch.empty((q_, k), dtype=torch.float32, device=gathered_idx.device)
+    L.check(lib.avl_merge_topk(C.c_void_p(gathered_idx.data_ptr()), C.c_void_p(gathered_val.data_ptr()), s_, q_, kk,
+                               C.c_void_p(oi.data_ptr()), C.c_void_p(ov.data_ptr()), L.AVL_ON_DEVICE, _stream_ptr(stream)))
+    return oi, ov
 
 
 def topk_vector(values, k: int, stream=None):

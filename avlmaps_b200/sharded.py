@@ -68,6 +68,25 @@ class ShardedMap:
         import torch
         import torch.distributed as dist
 
+        on_device = type(queries).__module__.startswith("torch") and queries.is_cuda
+        if on_device and self.world > 1 and queries.shape[0] <= 256:
+            # device path: the slab's result is written straight into a packed (ids | scores) buffer, ONE
+            # NCCL all-gather moves world * Q * k * 12 bytes, one kernel of the library merges.
+            nq = queries.shape[0]
+            nb_i, nb_v = nq * k * 8, nq * k * 4
+            mine = torch.empty(nb_i + nb_v, dtype=torch.uint8, device=queries.device)
+            ti = mine[:nb_i].view(torch.int64).view(nq, k)
+            tv = mine[nb_i:].view(torch.float32).view(nq, k)
+            self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv))
+            if self.row_offset:
+                ti += (ti >= 0) * self.row_offset
+            gathered = torch.empty((self.world, nb_i + nb_v), dtype=torch.uint8, device=queries.device)
+            dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)   # the one collective
+            gi = gathered[:, :nb_i].contiguous().view(torch.int64).view(self.world, nq, k)
+            gv = gathered[:, nb_i:].contiguous().view(torch.float32).view(self.world, nq, k)
+            from .engine import merge_topk_device
+
+            return merge_topk_device(gi, gv, k)
         idx, val = self.local.topk(queries, k, scale=scale, normalize_map=normalize_map)
         if self.world == 1 and self.row_offset == 0:
             return idx, val  # one slab: already global ids in final order
@@ -78,11 +97,10 @@ class ShardedMap:
         if self.world > 1:
             gi = torch.empty((self.world,) + tuple(ti.shape), dtype=ti.dtype, device=ti.device)
             gv = torch.empty((self.world,) + tuple(tv.shape), dtype=tv.dtype, device=tv.device)
-            # the one collective of the path (ids and scores; concatenated along dim 0)
             dist.all_gather_into_tensor(gi.view(-1, ti.shape[-1]), ti.contiguous(), group=self.group)
             dist.all_gather_into_tensor(gv.view(-1, tv.shape[-1]), tv.contiguous(), group=self.group)
-        else:  # a single slab is already in final order
-            return (ti.numpy(), tv.numpy()) if as_numpy else (ti, tv)
+        else:
+            gi, gv = ti[None], tv[None]
         mi, mv = merge_topk_torch(gi, gv, k)
         return (mi.numpy(), mv.numpy()) if as_numpy else (mi, mv)
 

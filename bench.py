@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -164,18 +164,19 @@ def make_shard(torch, n, d, seed, device):
 def build_extra(torch, engine, L, frames=24, reps=3):
     """BASELINE config 4 geometry: 480x640 RGB-D -> 390x520 feature map -> 2M-cell grid, rate 1."""
     import synth
-    from oracle import avl_oracle as O  # host geometry helpers only (pose chain), not on the timed path
+    from avlmaps_b200.map import Map, VLMapBuilder
+    from avlmaps_b200.utils.mapping_utils import get_sim_cam_mat
 
     h, w, fh, fw, d, gs, cs, cam_h = 480, 640, 390, 520, DIM, 256, 0.05, 1.6
     cfg = synth.map_config(gs, cs, cam_h, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
     poses = synth.circle_poses(frames, radius=2.0)
-    b2c, bt = O.setup_transforms(cfg["pose_info"])
-    tfs = O.frame_transforms(poses, b2c, bt)
+    host = Map(cfg)  # the product's own host-side pose chain (reference arithmetic)
+    tfs = VLMapBuilder("", cfg, None, [], [], host.base2cam_tf, host.base_transform)._frame_transforms(poses)
     calib = np.array(cfg["cam_calib_mat"]).reshape(3, 3)
-    kinv, kfeat = np.linalg.inv(calib), O.get_sim_cam_mat(fh, fw)
+    kinv, kfeat = np.linalg.inv(calib), get_sim_cam_mat(fh, fw)
     gen = torch.Generator(device="cuda").manual_seed(0)
     np.random.seed(7)
-    sidx = [torch.from_numpy(O.sample_order(h * w, 1)).cuda() for _ in range(4)]
+    sidx = [torch.from_numpy(VLMapBuilder._sample_order(h * w, 1)).cuda() for _ in range(4)]
     depths = [torch.rand((h, w), device="cuda", generator=gen) * 5.5 + 0.5 for _ in range(4)]
     out = {}
     for name, layout in (("hwc", L.FEAT_HWC), ("chw_reference_layout", L.FEAT_CHW)):
@@ -310,7 +311,9 @@ def run_gpu(args):
     achieved = flops / (ms_k * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": None,
-                "kernel": "screen_kernel<cta_group::2> (tcgen05 bf16, M=256 N=256 K=512 per tile pair)",
+                "kernel": {3: "screen_ts_kernel (tcgen05 cta_group::2, queries resident in TMEM, M=256 N=128 K=512 per tile)",
+                           2: "screen_kernel<cta_group::2> (tcgen05 bf16, M=256 N=256 K=512 per tile pair)",
+                           1: "screen_kernel<cta_group::1>"}.get(dmap.last_stats["cta_group"], "?"),
                 "kernel_ms": ms_k, "peak_source": peaks["source"] + ", burst figure",
                 "algorithmic_flops": flops, "algorithmic_bytes": N_VOX * DIM * 2 + NQ * DIM * 4 + NQ * TOPK * 12,
                 "hbm_GBps": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9, "hbm_frac": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -380,7 +383,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-build", action="store_true", help="skip the back-projection section")

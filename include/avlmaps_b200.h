@@ -59,7 +59,8 @@ typedef struct avl_index_stats {
   int64_t n_rows;
   int32_t dim;
   int32_t n_queries;
-  int32_t cta_group;          /* tcgen05 variant that ran: 1 or 2 (0 = no tensor-core kernel) */
+  int32_t cta_group;          /* tcgen05 variant that ran: 1 / 2 = cta_group of sim_screen.cu, 3 = query-stationary
+                                 2-CTA kernel (queries in TMEM, sim_screen_ts.cu), 0 = no tensor-core kernel */
   int32_t n_launches;         /* kernels launched by the call */
   int64_t n_flagged;          /* argmax: rows whose bf16 margin was inside the error band (re-ranked exactly) */
   int64_t n_candidates;       /* top-k: (row, query) pairs that passed the screen threshold */
@@ -113,13 +114,19 @@ int avl_sim_topk(avl_map* map, const float* queries, int32_t nq, const float* sc
                  avl_index_stats* stats);
 
 /* Diagnostic: the raw bf16 tensor-core scores (n, nq) fp32 of the screen kernel, no correction.
- * cta_group = 1 or 2 selects the tcgen05 variant (0 = the one the engine would pick). */
+ * cta_group = 1 or 2 selects the tcgen05 variant, 3 the query-stationary kernel (0 = engine's choice). */
 int avl_sim_screen_dense(avl_map* map, const float* queries, int32_t nq, int32_t cta_group,
                          float* out_scores, int flags, void* stream);
 
 /* Exact top-k of a vector: (value desc, index asc).  Serves get_max_pos_3d on any fused heat. */
 int avl_topk_f32(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val, int flags,
                  void* stream);
+
+/* Multi-GPU: merge per-slab top-k results (n_shards, nq, k) carrying GLOBAL row ids (-1 = empty) into the
+ * global (nq, k), same (score desc, row asc) order.  Device pointers only: the input is the buffer the
+ * one NCCL all-gather of the path filled.  n_shards * k <= 1024. */
+int avl_merge_topk(const int64_t* idx, const float* val, int32_t n_shards, int32_t nq, int32_t k,
+                   int64_t* out_idx, float* out_val, int flags, void* stream);
 
 /* Cross-modal goal selection (BASELINE config 3).  For pair j < n_pairs:
  *   h_a = minmax_i(score_a[:, j]), h_b = minmax_i(score_b[:, j])   (sound_map.py:151-152,

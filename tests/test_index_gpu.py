@@ -48,7 +48,8 @@ def test_golden_reference_vectors(eng, name):
     (5000, 512, 9, 16, False, False),
     (70_001, 512, 64, 16, False, False),
     (33_333, 512, 65, 5, True, True),
-    (20_000, 512, 256, 16, False, False),
+    (20_000, 512, 256, 16, False, False),   # 256 queries: cta_group::2, B resident across the SM pair
+    (50_001, 448, 200, 16, True, True),
     (9_000, 768, 33, 8, True, False),
     (9_000, 1024, 32, 16, True, True),     # AudioCLIP-like: unit rows, scale 100
     (777, 100, 3, 128, False, False),       # D not a multiple of 64, k > typical
@@ -69,9 +70,10 @@ def test_topk_and_argmax_vs_oracle(eng, n, d, nq, k, normalize, use_scale):
     m.close()
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3])
 def test_tensor_core_screen_matches_bf16_model(eng, cg):
-    """The raw tcgen05 output equals the exact product of the bf16-rounded operands (fp32 accumulate)."""
+    """The raw tcgen05 output equals the exact product of the bf16-rounded operands (fp32 accumulate);
+    cg 1/2: operands from shared memory, 3: query-stationary kernel (queries in TMEM)."""
     feat, q = synth.index_inputs(3000, 512, 48, seed=3)
 
     def bf16(x):
@@ -269,3 +271,16 @@ def test_heat_from_mask_bit_exact(eng):
 
     with pytest.raises(L.AvlError, match="selects no voxel"):
         eng.heat_from_mask_3d(pos, np.zeros(30_000, bool))
+
+
+def test_query_stationary_variant_matches(eng, monkeypatch):
+    """The opt-in kernel with the queries resident in TMEM (AVL_TS=1) returns the same top-k."""
+    feat, q = synth.index_inputs(40_001, 512, 200, seed=44)
+    scale = np.random.default_rng(5).uniform(0.5, 3.0, 200).astype(np.float32)
+    ref = O.topk(O.scores(feat, q, scale=scale, normalize=True), 16)
+    m = eng.DeviceMap(feat)
+    monkeypatch.setenv("AVL_TS", "1")
+    idx, val = m.topk(q, 16, scale=scale, normalize_map=True)
+    assert m.last_stats["cta_group"] == 3
+    assert np.array_equal(idx, ref[0]) and np.array_equal(val, ref[1])
+    m.close()
