@@ -68,11 +68,10 @@ struct ScreenParams {
   uint32_t flag_cap;
   // kModeThresh
   const float* thr_t;      // per query tau_q / scale_q  (+inf disables a query)
-  uint32_t* list_total;    // [1] entries appended to the candidate list (may exceed list_cap)
-  uint32_t* list_row;      // [list_cap] map row
-  uint8_t* list_q;         // [list_cap] query
-  float* list_val;         // [list_cap] screen score s~
-  uint32_t list_cap;
+  uint32_t* cand_cnt;      // [nq] entries appended per query (may exceed cand_cap)
+  uint32_t* cand_row;      // [nq][cand_cap] map row
+  float* cand_val;         // [nq][cand_cap] screen score s~
+  uint32_t cand_cap;
   // watchdog record (host-mapped), may be null
   uint32_t* dbg;
 };
@@ -107,9 +106,8 @@ int launch_select_threshold(const float* sample_lb, int32_t n_sample_rows, int64
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c,
                          const float* row_an, const float* q_bn, const float* q_glob, int normalize,
-                         int32_t k, const uint32_t* list_total, const uint32_t* list_row,
-                         const uint8_t* list_q, const float* list_val, uint32_t list_cap, uint32_t cand_cap,
-                         uint32_t* cand_cnt, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
+                         int32_t k, const uint32_t* cand_cnt, const uint32_t* cand_row, const float* cand_val,
+                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
                          cudaStream_t s);
 int launch_topk_vector(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val,
                        void* scratch, size_t scratch_bytes, cudaStream_t s);

@@ -196,23 +196,56 @@ assign_ids_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_
 }
 
 // ---------------------------------------------------------------- feature layout
-// (D, P) -> (P, D), P = FH*FW pixels: 32x32 tiles through shared memory, coalesced both ways.
+// (D, P) -> (P, D), P = FH*FW pixels.  64 pixels x 64 channels per block through shared memory:
+// 256-byte contiguous reads per channel row, 256-byte contiguous writes per pixel row (float4 both
+// ways when P and D allow it).
 __global__ void __launch_bounds__(256)
 chw_to_hwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int32_t d, int64_t p) {
-  __shared__ float tile[32][33];
-  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r;
-    const int64_t pp = p0 + tx;
-    tile[r][tx] = (c < d && pp < p) ? src[static_cast<int64_t>(c) * p + pp] : 0.f;
+  __shared__ float tile[64][65];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int c0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  const bool vec_in = (p & 3) == 0, vec_out = (d & 3) == 0;
+  // load: row = channel, 16 threads x float4 cover 64 pixels
+  {
+    const int q4 = (t & 15) * 4, r0 = t >> 4;
+#pragma unroll
+    for (int rr = 0; rr < 64; rr += 16) {
+      const int c = c0 + r0 + rr;
+      const int64_t pp = p0 + q4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        const float* s = src + static_cast<int64_t>(c) * p + pp;
+        if (vec_in && pp + 3 < p) v = __ldg(reinterpret_cast<const float4*>(s));
+        else {
+          if (pp < p) v.x = s[0];
+          if (pp + 1 < p) v.y = s[1];
+          if (pp + 2 < p) v.z = s[2];
+          if (pp + 3 < p) v.w = s[3];
+        }
+      }
+      tile[r0 + rr][q4] = v.x; tile[r0 + rr][q4 + 1] = v.y; tile[r0 + rr][q4 + 2] = v.z; tile[r0 + rr][q4 + 3] = v.w;
+    }
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t pp = p0 + r;
-    const int c = c0 + tx;
-    if (pp < p && c < d) dst[pp * d + c] = tile[tx][r];
+  // store: row = pixel, 16 threads x float4 cover 64 channels
+  {
+    const int c4 = (t & 15) * 4, r0 = t >> 4;
+#pragma unroll
+    for (int rr = 0; rr < 64; rr += 16) {
+      const int64_t pp = p0 + r0 + rr;
+      const int c = c0 + c4;
+      if (pp >= p) continue;
+      const float4 v = make_float4(tile[c4][r0 + rr], tile[c4 + 1][r0 + rr], tile[c4 + 2][r0 + rr], tile[c4 + 3][r0 + rr]);
+      float* o = dst + pp * d + c;
+      if (vec_out && c + 3 < d) *reinterpret_cast<float4*>(o) = v;
+      else {
+        if (c < d) o[0] = v.x;
+        if (c + 1 < d) o[1] = v.y;
+        if (c + 2 < d) o[2] = v.z;
+        if (c + 3 < d) o[3] = v.w;
+      }
+    }
   }
 }
 
@@ -483,7 +516,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   }
   if (f->feat_layout == AVL_FEAT_CHW) {  // (1, D, FH, FW) -> pixel-major rows for the coalesced gather
     if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, fpix * d))) return rc;
-    dim3 grid(static_cast<unsigned>((fpix + 31) / 32), static_cast<unsigned>((d + 31) / 32));
+    dim3 grid(static_cast<unsigned>((fpix + 63) / 64), static_cast<unsigned>((d + 63) / 64));
     chw_to_hwc_kernel<<<grid, 256, 0, s>>>(feat, b->d_feat_t, d, static_cast<int64_t>(fpix));
     AVL_CUDA(cudaGetLastError());
     feat = b->d_feat_t;

@@ -80,12 +80,10 @@ struct Workspace {
   uint32_t* flag_rows = nullptr;
   uint32_t* flag_masks = nullptr;
   uint32_t flag_cap = 0;
-  uint32_t* cand_cnt = nullptr;  // [256] per-query candidates seen by finalize
-  uint32_t* list_total = nullptr;  // [1]
-  uint32_t* list_row = nullptr;
-  uint8_t* list_q = nullptr;
-  float* list_val = nullptr;
-  uint32_t list_cap = 0;
+  uint32_t* cand_cnt = nullptr;  // [256] per-query candidate counters
+  uint32_t* cand_row = nullptr;  // [256][cand_cap]
+  float* cand_val = nullptr;
+  uint32_t cand_cap = 0;
   uint32_t* overflow = nullptr;  // [256]
   float* sample_t = nullptr;
   size_t sample_elems = 0;
@@ -141,7 +139,6 @@ static int ws_init(avl_map* m) {
   if ((rc = dev_alloc(&w.thr_t, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.flag_count, 1, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.cand_cnt, AVL_MAX_QUERIES, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.list_total, 1, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.overflow, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
@@ -155,7 +152,7 @@ static int ws_init(avl_map* m) {
 static void ws_free(Workspace& w) {
   cudaFree(w.q); cudaFree(w.q64); cudaFree(w.scale); cudaFree(w.bq); cudaFree(w.q_bn); cudaFree(w.q_glob); cudaFree(w.thr_t);
   cudaFree(w.flag_count); cudaFree(w.flag_rows); cudaFree(w.flag_masks); cudaFree(w.cand_cnt);
-  cudaFree(w.list_total); cudaFree(w.list_row); cudaFree(w.list_q); cudaFree(w.list_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
+  cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
   for (int i = 0; i < 4; ++i)
@@ -173,15 +170,14 @@ static int ensure_flags(avl_map* m) {
   w.flag_cap = need;
   return AVL_OK;
 }
-static int ensure_list(avl_map* m, uint32_t cap) {
+static int ensure_cands(avl_map* m, uint32_t cap) {
   Workspace& w = m->ws;
-  if (w.list_cap >= cap) return AVL_OK;
-  cudaFree(w.list_row); cudaFree(w.list_q); cudaFree(w.list_val);
+  if (w.cand_cap >= cap) return AVL_OK;
+  cudaFree(w.cand_row); cudaFree(w.cand_val);
   int rc;
-  if ((rc = dev_alloc(&w.list_row, cap, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.list_q, static_cast<size_t>(cap) + 16, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.list_val, cap, &m->bytes))) return rc;
-  w.list_cap = cap;
+  if ((rc = dev_alloc(&w.cand_row, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.cand_val, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
+  w.cand_cap = cap;
   return AVL_OK;
 }
 static int ensure_sample(avl_map* m, size_t elems) {
@@ -640,9 +636,8 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   int64_t tile_stride = sample_units > 0 ? std::max<int64_t>(1, total_units / sample_units) : 1;
   if (sample_units > 0) sample_units = std::min<int64_t>(sample_units, (total_units + tile_stride - 1) / tile_stride);
   const int64_t n_sample = sample_units * unit;
-  const uint32_t cand_cap = 8192;            // per-query entries the finalize block can hold
-  const uint32_t list_cap = 4u << 20;        // whole-call candidate list (~10x the expected load)
-  if ((rc = ensure_list(m, list_cap))) return rc;
+  const uint32_t cand_cap = 8192;            // per-query entries the finalize block can hold (~4x the expected load)
+  if ((rc = ensure_cands(m, cand_cap))) return rc;
   if ((rc = ensure_sample(m, static_cast<size_t>(std::max<int64_t>(n_sample, 1)) * nq))) return rc;
 
   ScreenParams p;
@@ -663,27 +658,24 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
       return rc;
   }
   AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
-  AVL_CUDA(cudaMemsetAsync(w.list_total, 0, sizeof(uint32_t), s));
   AVL_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
   if (m->n > 0) {
     // phase B: full pass, candidates = rows whose upper bound reaches the threshold
     base_params(m, qs, nq, normalize_map, &p);
     p.mode = kModeThresh;
     p.thr_t = w.thr_t;
-    p.list_total = w.list_total;
-    p.list_row = w.list_row;
-    p.list_q = w.list_q;
-    p.list_val = w.list_val;
-    p.list_cap = w.list_cap;
+    p.cand_cnt = w.cand_cnt;
+    p.cand_row = w.cand_row;
+    p.cand_val = w.cand_val;
+    p.cand_cap = cand_cap;
     if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
     if ((rc = run_screen(m, qs, p, s))) return rc;
     if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
   }
   // phase C: exact re-score of the survivors, final order
   if ((rc = launch_topk_finalize(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, m->row_c,
-                                 m->row_an, w.q_bn, w.q_glob, normalize_map, k, w.list_total, w.list_row,
-                                 w.list_q, w.list_val, w.list_cap, cand_cap, w.cand_cnt, d_idx, d_score,
-                                 w.overflow, s)))
+                                 m->row_an, w.q_bn, w.q_glob, normalize_map, k, w.cand_cnt, w.cand_row,
+                                 w.cand_val, cand_cap, d_idx, d_score, w.overflow, s)))
     return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
 

@@ -338,9 +338,8 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
                      const float* __restrict__ scale, const float* __restrict__ row_norm,
                      const float* __restrict__ row_c, const float* __restrict__ row_an,
                      const float* __restrict__ q_bn, const uint32_t* __restrict__ glob, int normalize,
-                     int32_t k, const uint32_t* __restrict__ list_total, const uint32_t* __restrict__ list_row,
-                     const uint8_t* __restrict__ list_q, const float* __restrict__ list_val, uint32_t list_cap,
-                     uint32_t cand_cap, uint32_t* __restrict__ cand_cnt, int64_t* __restrict__ out_idx,
+                     int32_t k, const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand_row,
+                     const float* __restrict__ cand_val, uint32_t cand_cap, int64_t* __restrict__ out_idx,
                      float* __restrict__ out_score, uint32_t* __restrict__ overflow_flags) {
   extern __shared__ uint8_t sm[];
   uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
@@ -349,52 +348,18 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Ix + cand_cap);
   __shared__ int sh_cnt;
   __shared__ int sh_ns;
-  __shared__ unsigned int sh_n;
   const int qq = blockIdx.x;
-  const uint32_t total = *list_total;
-  if (total > list_cap) {  // the list itself overflowed: every query takes the exact fallback
-    if (threadIdx.x == 0) { overflow_flags[qq] = 1u; cand_cnt[qq] = 0u; }
-    return;
-  }
-  if (threadIdx.x == 0) { sh_n = 0u; sh_ns = 0; }
-  __syncthreads();
-  // gather: 16 query bytes per load
-  const uint32_t nvec = (total + 15u) / 16u;
-  const uint4* lq4 = reinterpret_cast<const uint4*>(list_q);
-  const uint32_t pat = static_cast<uint32_t>(qq) * 0x01010101u;
-  for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += 4 * blockDim.x) {
-    uint4 w[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {  // 4 independent 16-byte loads in flight
-      const uint32_t v = v0 + u * blockDim.x;
-      w[u] = v < nvec ? lq4[v] : make_uint4(~pat, ~pat, ~pat, ~pat);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t v = v0 + u * blockDim.x;
-      const uint32_t words[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        uint32_t x = words[a] ^ pat;  // a zero byte marks an entry of this query
-        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0u) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t e = v * 16u + a * 4u + b;
-          if (((x >> (8 * b)) & 0xFFu) == 0u && e < total) {
-            const uint32_t s = atomicAdd(&sh_n, 1u);
-            if (s < cand_cap) { Ix[s] = list_row[e]; Lk[s] = __float_as_uint(list_val[e]); }
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  const uint32_t cnt = sh_n;
-  if (threadIdx.x == 0) cand_cnt[qq] = cnt;
-  if (cnt > cand_cap) {
+  const uint32_t cnt = cand_cnt[qq];
+  if (cnt > cand_cap) {  // list overflow (adversarial data, massive ties): exact fallback on the host side
     if (threadIdx.x == 0) overflow_flags[qq] = 1u;
     return;
   }
+  if (threadIdx.x == 0) sh_ns = 0;
+  for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+    Ix[j] = cand_row[static_cast<size_t>(qq) * cand_cap + j];
+    Lk[j] = __float_as_uint(cand_val[static_cast<size_t>(qq) * cand_cap + j]);
+  }
+  __syncthreads();
   const int n = static_cast<int>(cnt);
   const float rho = __uint_as_float(glob[0]);
   const float bn = q_bn[qq];
@@ -680,16 +645,16 @@ size_t topk_finalize_smem(uint32_t cand_cap) { return static_cast<size_t>(cand_c
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c, const float* row_an,
                          const float* q_bn, const float* q_glob, int normalize, int32_t k,
-                         const uint32_t* list_total, const uint32_t* list_row, const uint8_t* list_q,
-                         const float* list_val, uint32_t list_cap, uint32_t cand_cap, uint32_t* cand_cnt,
-                         int64_t* out_idx, float* out_score, uint32_t* overflow_flags, cudaStream_t s) {
+                         const uint32_t* cand_cnt, const uint32_t* cand_row, const float* cand_val,
+                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
+                         cudaStream_t s) {
   const size_t smem = topk_finalize_smem(cand_cap);
   AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   topk_finalize_kernel<<<nq, kFinThreads, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
-                                             reinterpret_cast<const uint32_t*>(q_glob), normalize, k, list_total,
-                                             list_row, list_q, list_val, list_cap, cand_cap, cand_cnt, out_idx,
-                                             out_score, overflow_flags);
+                                                     reinterpret_cast<const uint32_t*>(q_glob), normalize, k,
+                                                     cand_cnt, cand_row, cand_val, cand_cap, out_idx, out_score,
+                                                     overflow_flags);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

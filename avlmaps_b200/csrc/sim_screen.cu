@@ -61,10 +61,14 @@ __device__ __forceinline__ void dense_chunk(const ScreenParams& p, const TileCtx
   if (p.dense_lb) {
     // rows past the end of the map store -inf so that they never raise a threshold
 #pragma unroll
-    for (int j = 0; j < W; ++j)
-      if (c0 + j < p.dense_cols)
-        o[j * p.dense_cs] = t.valid ? __fdiv_rd(__fsub_rd(__uint_as_float(v[j]), __fmul_ru(r_i, qc[c0 + j].y)), w_i)
-                                    : -INFINITY;
+    for (int j = 0; j < W; ++j) {
+      if (c0 + j < p.dense_cols) {
+        // (s~ - r ||b||) / w with the rounding pushed DOWN by a relative 2^-20 instead of directed-rounding
+        // divides (the threshold only has to be a lower bound)
+        const float x = (__uint_as_float(v[j]) - r_i * qc[c0 + j].y) * w_i;  // w_i holds 1 / w here
+        o[j * p.dense_cs] = t.valid ? fmaf(-fabsf(x), 9.5367431640625e-7f, x) : -INFINITY;
+      }
+    }
   } else if (t.valid) {
 #pragma unroll
     for (int j = 0; j < W; ++j)
@@ -150,13 +154,15 @@ struct Ring {
 
 __device__ __noinline__ uint32_t ring_flush(const ScreenParams& p, Ring r, uint32_t pend, uint32_t count,
                                             uint32_t lane) {
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(p.list_total, count);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (lane < count && base + lane < p.list_cap) {
-    p.list_row[base + lane] = r.row[lane];
-    p.list_q[base + lane] = static_cast<uint8_t>(r.q[lane]);
-    p.list_val[base + lane] = r.val[lane];
+  // every lane appends one staged entry to its query's list: 32 independent atomics in flight, one
+  // round trip per 32 candidates (a per-candidate atomic in the epilogue cost ~2000 cycles each)
+  if (lane < count) {
+    const uint32_t q = r.q[lane];
+    const uint32_t slot = atomicAdd(p.cand_cnt + q, 1u);
+    if (slot < p.cand_cap) {
+      p.cand_row[static_cast<size_t>(q) * p.cand_cap + slot] = r.row[lane];
+      p.cand_val[static_cast<size_t>(q) * p.cand_cap + slot] = r.val[lane];
+    }
   }
   __syncwarp();
   const uint32_t rem = pend - count;
@@ -387,8 +393,8 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       } else if (p.mode == kModeDense) {
         float r_i = 0.f, w_i = 1.f;
         if (p.dense_lb && t.valid) {
-          r_i = fmaf(rho, p.row_an[t.row], p.row_c[t.row]);
-          if (p.normalize) w_i = fmaxf(p.row_norm[t.row], 1e-30f);
+          r_i = fmaf(rho, p.row_an[t.row], p.row_c[t.row]) * 1.000001f;
+          if (p.normalize) w_i = 1.f / fmaxf(p.row_norm[t.row], 1e-30f);  // reciprocal: dense_chunk multiplies
         }
         for (int c0 = half * 32; c0 < n32; c0 += 64) dense_chunk<32>(p, t, c0, qc, r_i, w_i);
         if (n32 < p.npad && ((n32 >> 5) & 1) == half) dense_chunk<16>(p, t, n32, qc, r_i, w_i);

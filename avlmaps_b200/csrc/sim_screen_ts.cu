@@ -45,13 +45,15 @@ struct Ring {
 
 __device__ __noinline__ uint32_t ring_flush(const ScreenParams& p, Ring r, uint32_t pend, uint32_t count,
                                             uint32_t lane) {
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(p.list_total, count);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (lane < count && base + lane < p.list_cap) {
-    p.list_row[base + lane] = r.row[lane];
-    p.list_q[base + lane] = static_cast<uint8_t>(r.q[lane]);
-    p.list_val[base + lane] = r.val[lane];
+  // every lane appends one staged entry to its query's list: 32 independent atomics in flight, one
+  // round trip per 32 candidates (a per-candidate atomic in the epilogue cost ~2000 cycles each)
+  if (lane < count) {
+    const uint32_t q = r.q[lane];
+    const uint32_t slot = atomicAdd(p.cand_cnt + q, 1u);
+    if (slot < p.cand_cap) {
+      p.cand_row[static_cast<size_t>(q) * p.cand_cap + slot] = r.row[lane];
+      p.cand_val[static_cast<size_t>(q) * p.cand_cap + slot] = r.val[lane];
+    }
   }
   __syncwarp();
   const uint32_t rem = pend - count;
@@ -247,13 +249,13 @@ screen_ts_kernel(const __grid_constant__ CUtensorMap tmap_v, const ScreenParams 
             if (p.normalize) w = fmaxf(p.row_norm[row], 1e-30f);
           }
         }
+        const float iw = 1.f / w;
         if (p.mode == kModeThresh) {
-          const float iw = 1.f / w;
           sr[cc] = r * iw;
           sw[cc] = iw;
-        } else {
-          sr[cc] = r;
-          sw[cc] = w;
+        } else {  // dense: keep r (slightly inflated for the lower bound) and 1 / w
+          sr[cc] = r * 1.000001f;
+          sw[cc] = iw;
         }
       }
     };
@@ -337,9 +339,9 @@ screen_ts_kernel(const __grid_constant__ CUtensorMap tmap_v, const ScreenParams 
           if (p.dense_lb) {
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
-              const float r = st_r[t], w = st_w[t];
-              o[t * p.dense_rs] = (r == -INFINITY) ? -INFINITY
-                                                   : __fdiv_rd(__fsub_rd(__uint_as_float(v[t]), __fmul_ru(r, bn_q)), w);
+              const float r = st_r[t], iw = st_w[t];  // iw = 1 / w for dense_lb too
+              const float x = (__uint_as_float(v[t]) - r * bn_q) * iw;
+              o[t * p.dense_rs] = (r == -INFINITY) ? -INFINITY : fmaf(-fabsf(x), 9.5367431640625e-7f, x);
             }
           } else {
 #pragma unroll
