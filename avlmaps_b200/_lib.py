@@ -26,7 +26,7 @@ EXPORTS = [
     "avl_version", "avl_last_error", "avl_device_count", "avl_set_device", "avl_set_profiling",
     "avl_map_create", "avl_map_destroy", "avl_map_shape", "avl_map_device_bytes",
     "avl_sim_dense", "avl_sim_argmax", "avl_sim_topk", "avl_sim_screen_dense", "avl_topk_f32", "avl_fuse_topk",
-    "avl_heat_from_mask_3d", "avl_merge_topk",
+    "avl_heat_from_mask_3d", "avl_merge_topk", "avl_heat2d_sources",
     "avl_builder_create", "avl_builder_destroy", "avl_builder_add_frame", "avl_builder_num_voxels",
     "avl_builder_num_accepted", "avl_builder_export", "avl_builder_to_map",
 ]
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
     lib.avl_topk_f32.argtypes = [f32p, i64, i32, vp, vp, C.c_int, vp]
     lib.avl_fuse_topk.argtypes = [vp, f32p, f32p, C.c_int, vp, f32p, f32p, C.c_int, i32, i32, i32, vp, vp,
                                   C.c_int, vp]
+    lib.avl_heat2d_sources.argtypes = [vp, vp, vp, i32, i32, i32, C.c_double, i32, vp, C.c_int, vp]
     lib.avl_merge_topk.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.c_int, vp]
     lib.avl_heat_from_mask_3d.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp, C.c_int, vp]
     if hasattr(lib, "avl_builder_create"):

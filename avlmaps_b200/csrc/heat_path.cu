@@ -131,3 +131,103 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
   cudaFree(d_pos); cudaFree(d_mask); cudaFree(d_heat); cudaFree(d_targets); cudaFree(d_count);
   return rc;
 }
+
+// ------------------------------------------------------------------------------------------------
+// 2-D heat from point sources: the per-frame / per-segment full-grid distance_transform_edt loops of
+// AVLMap.index_area_2d (reference avlmaps/map/avlmap.py:78-98, combine = max, float64 result) and
+// AVLMap.index_sound_2d (avlmap.py:111-133, combine = sum accumulated in float32, in segment order).
+// The EDT of a map with a few marked cells is the distance to the nearest marked cell: one thread per
+// grid cell, sources staged in shared memory, integer squared distances, float64 tail in the
+// reference's operation order.
+namespace avl {
+namespace {
+
+constexpr int kSrcTile = 1024;
+
+// sources are sorted by group; group g owns sources [gstart[g], gstart[g+1])
+__global__ void __launch_bounds__(256)
+heat2d_kernel(const int32_t* __restrict__ cells, const int32_t* __restrict__ gstart, const float* __restrict__ conf,
+              int32_t n_groups, int32_t rows, int32_t cols, double decay_rate, int32_t mode, void* __restrict__ out) {
+  __shared__ int2 tile[kSrcTile];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool active = i < static_cast<int64_t>(rows) * cols;
+  const int r = active ? static_cast<int>(i / cols) : 0, c = active ? static_cast<int>(i % cols) : 0;
+  double acc_max = 0.0;  // dist_map starts at zeros (avlmap.py:79)
+  float acc_sum = 0.f;   // avlmap.py:113
+  for (int g = 0; g < n_groups; ++g) {
+    const int s0 = gstart[g], s1 = gstart[g + 1];
+    if (s1 <= s0) continue;  // frame outside the grid: `continue` (avlmap.py:88-89)
+    unsigned long long best = ~0ull;
+    for (int t0 = s0; t0 < s1; t0 += kSrcTile) {
+      const int m = min(kSrcTile, s1 - t0);
+      __syncthreads();
+      for (int j = threadIdx.x; j < m; j += blockDim.x) tile[j] = make_int2(cells[2 * (t0 + j)], cells[2 * (t0 + j) + 1]);
+      __syncthreads();
+      if (active)
+        for (int j = 0; j < m; ++j) {
+          const long long dr = tile[j].x - r, dc = tile[j].y - c;
+          best = min(best, static_cast<unsigned long long>(dr * dr + dc * dc));
+        }
+    }
+    if (!active) continue;
+    const double dist = __dsqrt_rn(static_cast<double>(best));
+    const float con = conf[g];
+    if (mode == 0) {
+      // area: tmp = ones * s - dists * decay; clip(tmp, 0, 1); dist_map = max(dist_map, tmp)   (avlmap.py:93-97)
+      // (a source with s == 0 leaves tmp_dist_map all zero; the reference's EDT then measures to a virtual
+      //  background cell, but -dists * decay clips to 0 either way)
+      double v = __dsub_rn(static_cast<double>(con), __dmul_rn(dist, decay_rate));
+      v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+      acc_max = acc_max > v ? acc_max : v;
+    } else {
+      // sound: reduct = con * dists * decay; tmp = ones * con - reduct; tmp[tmp < 0] = 0; dist_map += tmp
+      // (float32 accumulator, float64 addend: avlmap.py:124-131)
+      const double reduct = __dmul_rn(__dmul_rn(static_cast<double>(con), dist), decay_rate);
+      double v = __dsub_rn(static_cast<double>(con), reduct);
+      if (v < 0.0) v = 0.0;
+      acc_sum = static_cast<float>(__dadd_rn(static_cast<double>(acc_sum), v));
+    }
+  }
+  if (!active) return;
+  if (mode == 0) reinterpret_cast<double*>(out)[i] = acc_max;
+  else reinterpret_cast<float*>(out)[i] = acc_sum;
+}
+
+}  // namespace
+}  // namespace avl
+
+extern "C" int avl_heat2d_sources(const int32_t* cells, const int32_t* group_start, const float* conf, int32_t n_groups,
+                                  int32_t rows, int32_t cols, double decay_rate, int32_t mode, void* out_heat,
+                                  int flags, void* stream) {
+  AVL_ARG(rows >= 1 && cols >= 1 && n_groups >= 0 && (mode == 0 || mode == 1), "invalid argument");
+  AVL_ARG(out_heat != nullptr && (n_groups == 0 || (group_start && conf)), "NULL argument");
+  if (flags & AVL_ON_DEVICE) {
+    set_error("avl_heat2d_sources takes host pointers (a handful of sources, one small grid)");
+    return AVL_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t n = static_cast<int64_t>(rows) * cols;
+  const size_t esz = mode == 0 ? sizeof(double) : sizeof(float);
+  const int n_src = n_groups > 0 ? group_start[n_groups] : 0;
+  AVL_ARG(n_src == 0 || cells != nullptr, "cells is NULL");
+  int32_t *d_cells = nullptr, *d_gs = nullptr;
+  float* d_conf = nullptr;
+  void* d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, n * esz);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_cells), std::max(1, n_src) * 2 * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_gs), (n_groups + 1) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_conf), std::max(1, n_groups) * sizeof(float));
+  if (e == cudaSuccess && n_src) e = cudaMemcpyAsync(d_cells, cells, static_cast<size_t>(n_src) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && n_groups) e = cudaMemcpyAsync(d_gs, group_start, (n_groups + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && n_groups) e = cudaMemcpyAsync(d_conf, conf, n_groups * sizeof(float), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    heat2d_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(d_cells, d_gs, d_conf, n_groups, rows, cols,
+                                                                         decay_rate, mode, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_heat, d_out, n * esz, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_cells); cudaFree(d_gs); cudaFree(d_conf); cudaFree(d_out);
+  if (e != cudaSuccess) return cuda_fail(e, "heat2d_sources", __FILE__, __LINE__);
+  return AVL_OK;
+}

@@ -269,6 +269,30 @@ def heat_from_mask_3d(grid_pos, mask, cell_size: float = 0.05, decay_rate: float
     return out
 
 
+def heat2d_sources(shape, cells_per_group, conf, decay_rate: float, mode: str):
+    """2-D source heat before the final min-max.  mode "area": max-combine, float64 (avlmap.py:78-97);
+    mode "sound": float32 running sum in group order (avlmap.py:111-131).  cells_per_group: list of (n_i, 2)
+    int arrays of (row, col); an empty array is a frame that fell outside the grid."""
+    lib = L.load()
+    L.require_device()
+    rows, cols = int(shape[0]), int(shape[1])
+    starts = np.zeros(len(cells_per_group) + 1, np.int32)
+    flat = []
+    for i, c in enumerate(cells_per_group):
+        c = np.asarray(c, np.int32).reshape(-1, 2)
+        flat.append(c)
+        starts[i + 1] = starts[i] + c.shape[0]
+    cells = np.ascontiguousarray(np.concatenate(flat) if flat else np.zeros((0, 2), np.int32), np.int32)
+    conf = np.ascontiguousarray(conf, np.float32)
+    if conf.shape != (len(cells_per_group),):
+        raise ValueError("one confidence per group")
+    m = {"area": 0, "sound": 1}[mode]
+    out = np.empty((rows, cols), np.float64 if m == 0 else np.float32)
+    L.check(lib.avl_heat2d_sources(L.np_ptr(cells), L.np_ptr(starts), L.np_ptr(conf), len(cells_per_group), rows, cols,
+                                   float(decay_rate), m, L.np_ptr(out), 0, None))
+    return out
+
+
 class DeviceBuilder:
     """Voxel map under construction in HBM (the arrays of VLMapBuilder._init_map, vlmap_builder.py:195-224)."""
 

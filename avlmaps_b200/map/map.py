@@ -96,6 +96,19 @@ class Map:
         return self.obstacles_cropped
 
     @staticmethod
+    def _dilate_map(binary_map: np.ndarray, dilate_iter: int = 0, gaussian_sigma: float = 1.0):
+        """Reference map.py:170-181 (host-side 2-D morphology on the small cropped obstacle map)."""
+        import cv2
+        from scipy.ndimage import binary_dilation, gaussian_filter
+
+        h, w = binary_map.shape
+        binary_map = cv2.resize(binary_map.astype(float), (w * 2, h * 2))
+        binary_map = gaussian_filter((binary_map).astype(float), sigma=gaussian_sigma, truncate=3)
+        binary_map = (binary_map > 0.5).astype(np.uint8)
+        binary_map = binary_dilation(binary_map, structure=np.ones((3, 3)), iterations=dilate_iter * 2)
+        return cv2.resize(binary_map.astype(float), (w, h))
+
+    @staticmethod
     def create(map_config) -> "Map":
         """Reference map.py:121-129."""
         from . import VLMap

@@ -140,6 +140,24 @@ class VLMap(Map):
             cat_id = 0
         return max_ids == cat_id
 
+    def customize_obstacle_map(self, potential_obstacle_names: List[str], obstacle_names: List[str], vis: bool = False):
+        """Reference vlmap.py:127-156 (which reads the class lists from map_config, not from its arguments)."""
+        from ..utils.index_utils import get_dynamic_obstacles_map_3d
+
+        if self.obstacles_cropped is None and self.obstacles_map is None:
+            self.generate_obstacle_map()
+        if not hasattr(self, "clip_model"):
+            print("init_clip in customize obstacle map")
+            self._init_clip()
+        self.obstacles_new_cropped = get_dynamic_obstacles_map_3d(
+            self.clip_model, self.obstacles_cropped, cfg_get(self.map_config, "potential_obstacle_names"),
+            cfg_get(self.map_config, "obstacle_names"), self.device_map, self.grid_pos, self.rmin, self.cmin,
+            self.clip_feat_dim, vis=vis)
+        self.obstacles_new_cropped = Map._dilate_map(self.obstacles_new_cropped == 0,
+                                                     cfg_get(self.map_config, "dilate_iter"),
+                                                     cfg_get(self.map_config, "gaussian_sigma"))
+        self.obstacles_new_cropped = self.obstacles_new_cropped == 0
+
     def get_lseg_score(self, landmarks: List[str], use_multiple_templates: bool = True, add_other: bool = True):
         return get_lseg_score(self.clip_model, landmarks, self.device_map, self.clip_feat_dim,
                               use_multiple_templates=use_multiple_templates, add_other=add_other)

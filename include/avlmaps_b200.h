@@ -145,6 +145,16 @@ int avl_fuse_topk(avl_map* map_a, const float* queries_a, const float* scale_a, 
 int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mask, int64_t n, double cell_size,
                           double decay_rate, float* out_heat, int flags, void* stream);
 
+/* 2-D heat from point sources on the (rows, cols) top-down grid: replaces the per-frame / per-segment
+ * full-grid distance_transform_edt loops of AVLMap.index_area_2d (avlmaps/map/avlmap.py:78-98; mode 0:
+ * max-combine of clip(s - decay*dist, 0, 1), float64 out) and AVLMap.index_sound_2d (avlmap.py:111-133;
+ * mode 1: float32 running sum of max(con - con*dist*decay, 0) in segment order, float32 out), BEFORE the
+ * final min-max.  cells (n_src, 2) int32 (row, col) sorted by group; group_start (n_groups + 1,) int32
+ * offsets (an empty group is a frame that fell outside the grid); conf (n_groups,) fp32.  Host pointers. */
+int avl_heat2d_sources(const int32_t* cells, const int32_t* group_start, const float* conf, int32_t n_groups,
+                       int32_t rows, int32_t cols, double decay_rate, int32_t mode, void* out_heat, int flags,
+                       void* stream);
+
 /* ---- map-build path ------------------------------------------------------------------ */
 
 typedef struct avl_grid_spec {

@@ -314,3 +314,49 @@ def heatmap_from_mask_3d(grid_pos: np.ndarray, mask: np.ndarray, cell_size: floa
         d = np.sqrt(((pc[ids, None, :] - target[None, :, :]) ** 2).sum(-1)) / cell_size
         heat[ids] = np.clip(1 - d.min(1) * decay_rate, 0, 1)
     return heat
+
+
+def area_heat_2d(shape, cells, scores, decay_rate: float = 0.1):
+    """avlmaps/map/avlmap.py:78-98 restated line by line (scipy EDT per frame); cells[i] = (row, col) or None."""
+    from scipy.ndimage import distance_transform_edt
+
+    dist_map = np.zeros(shape, dtype=np.float32)
+    for i, cell in enumerate(cells):
+        tmp_dist_map = np.zeros_like(dist_map, dtype=np.float32)
+        if cell is None:
+            continue
+        row, col = cell
+        s = scores[i]
+        tmp_dist_map[row, col] = s
+        dists = distance_transform_edt(tmp_dist_map == 0)
+        tmp = np.ones_like(dists) * s - (dists * decay_rate)
+        tmp_dist_map = np.clip(tmp, 0, 1)
+        dist_map = np.where(dist_map > tmp_dist_map, dist_map, tmp_dist_map)
+    return (dist_map - np.min(dist_map)) / (np.max(dist_map) - np.min(dist_map))
+
+
+def sound_heat_2d(shape, cells_per_segment, probabilities, decay_rate: float = 0.01):
+    """avlmaps/map/avlmap.py:111-133 restated line by line."""
+    from scipy.ndimage import distance_transform_edt
+
+    dist_map = np.zeros(shape, dtype=np.float32)
+    for loc_i, cells in enumerate(cells_per_segment):
+        tmp_dist_map = np.zeros_like(dist_map, dtype=np.float32)
+        for row, col in cells:
+            tmp_dist_map[row, col] = probabilities[loc_i]
+        con = probabilities[loc_i]
+        dists = distance_transform_edt(tmp_dist_map == 0)
+        reduct = con * dists * decay_rate
+        tmp = np.ones_like(tmp_dist_map) * con - reduct
+        tmp_dist_map = np.where(tmp < 0, np.zeros_like(tmp), tmp)
+        dist_map += tmp_dist_map
+    return (dist_map - np.min(dist_map)) / (np.max(dist_map) - np.min(dist_map))
+
+
+def lift_heat_2d_to_3d(heatmap_2d, occupied_ids, n_vox):
+    """avlmaps/map/avlmap.py:100-109 / 135-144 (the Python loop over occupied cells)."""
+    heatmap_3d = np.zeros(n_vox, dtype=np.float32)
+    rows, cols, heights = np.where(occupied_ids != -1)
+    for row, col, heigh in zip(rows, cols, heights):
+        heatmap_3d[occupied_ids[row, col, heigh]] = heatmap_2d[row, col]
+    return heatmap_3d

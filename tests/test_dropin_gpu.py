@@ -105,3 +105,62 @@ def test_avlmap_index_object(lib):
     mask2 = O.index_mask(O.scores(feat, tf2), 1)
     assert np.array_equal(heat2, O.heatmap_from_mask_3d(pos, mask2, 0.05, 0.1))
     assert np.array_equal(av.get_max_pos_3d(heat2), pos[int(np.argmax(heat2))])
+
+
+def test_area_and_sound_heat_2d(lib):
+    """index_area_2d / index_sound_2d cores (avlmap.py:78-133): one kernel instead of F full-grid EDTs, same bits."""
+    from avlmaps_b200.map import AVLMap
+
+    rng = np.random.default_rng(4)
+    shape = (90, 70)
+    # area: 12 frames, two outside the grid, min-max normalised scores (one is exactly 0, one exactly 1)
+    raw = rng.standard_normal(12).astype(np.float32)
+    scores = (raw - raw.min()) / (raw.max() - raw.min())
+    cells = [None if i in (3, 8) else (int(rng.integers(0, 90)), int(rng.integers(0, 70))) for i in range(12)]
+    got = AVLMap.area_heat_2d(shape, cells, scores, decay_rate=0.1)
+    want = O.area_heat_2d(shape, cells, scores, decay_rate=0.1)
+    assert got.dtype == want.dtype == np.float64 and np.array_equal(got, want)
+    # sound: 7 segments with 1-5 locations each (one negative index that wraps like numpy)
+    probs = rng.uniform(0, 1, 7).astype(np.float32)
+    probs = (probs - probs.min()) / (probs.max() - probs.min())
+    segs = [[(int(rng.integers(0, 90)), int(rng.integers(0, 70))) for _ in range(int(rng.integers(1, 6)))] for _ in range(7)]
+    segs[2][0] = (-3, 5)
+    got = AVLMap.sound_heat_2d(shape, segs, probs, decay_rate=0.01)
+    want = O.sound_heat_2d(shape, segs, probs, decay_rate=0.01)
+    assert got.dtype == want.dtype == np.float32 and np.array_equal(got, want)
+    with pytest.raises(IndexError):
+        AVLMap.sound_heat_2d(shape, [[(95, 0)]], np.ones(1, np.float32))
+    # 2-D -> 3-D lift through grid_pos == the reference's loop over occupied cells
+    occ = -np.ones((90, 70, 4), np.int32)
+    flat = rng.choice(90 * 70 * 4, 500, replace=False)
+    occ.reshape(-1)[flat] = np.arange(500)
+    pos = np.stack(np.unravel_index(flat, occ.shape), 1).astype(np.int32)
+    cfg = {"map_config": synth.map_config(90, 0.05, 0.2, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1), "params": {"cs": 0.05}}
+    av = AVLMap(cfg)
+    av.vlmap.grid_pos, av.vlmap.occupied_ids = pos, occ
+    assert np.array_equal(av.lift_heat_2d_to_3d(want), O.lift_heat_2d_to_3d(want, occ, 500))
+
+
+def test_dynamic_obstacles_map(lib):
+    """get_dynamic_obstacles_map_3d (index_utils.py:138-184) on the fused argmax == the reference's numpy steps."""
+    from avlmaps_b200.utils.clip_utils import landmark_text_feats
+    from avlmaps_b200.utils.index_utils import get_dynamic_obstacles_map_3d
+
+    d, n = 32, 4000
+    feat, _ = synth.index_inputs(n, d, 1, seed=8)
+    rng = np.random.default_rng(1)
+    pos = np.stack([rng.integers(5, 45, n), rng.integers(10, 60, n), rng.integers(0, 8, n)], 1).astype(np.int32)
+    rmin, cmin = 5, 10
+    obstacles_cropped = rng.uniform(size=(40, 50)) > 0.5
+    potential = ["chair", "wall", "wall above the door", "table", "window", "floor", "stairs", "other"]
+    obstacle = ["wall", "chair", "table", "window", "stairs", "other"]
+    enc = fake_encoder(d)
+    got = get_dynamic_obstacles_map_3d(enc, obstacles_cropped, potential, obstacle, feat, pos, rmin, cmin, d)
+    tf, _, _ = landmark_text_feats(enc, potential, d, True, 0, True)
+    predict = O.argmax(O.scores(feat, tf))
+    inds = [i for o in obstacle for i, pn in enumerate(potential) if o == pn]
+    pts = np.isin(predict, inds)
+    want = np.zeros_like(obstacles_cropped, dtype=bool)
+    want[pos[pts, 0] - rmin, pos[pts, 1] - cmin] = 1
+    want = np.logical_not(np.logical_and(want, obstacles_cropped == 0))
+    assert np.array_equal(got, want)
