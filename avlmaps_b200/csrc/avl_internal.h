@@ -97,7 +97,8 @@ int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, 
                        int64_t out_rs, int64_t out_cs, cudaStream_t s);
 int launch_column_exact(const float* feat, int64_t n, int32_t d, const float* q, const float* scale,
                         const float* row_norm, int normalize, float* out, int num_sms, cudaStream_t s);
-int launch_argmax_rerank(const float* feat, int32_t d, const float* q, double* q64, int32_t nq, const float* scale,
+int launch_argmax_rerank(const float* feat, int32_t d, const float* q, double* q64, const float* q_bn_raw, int32_t nq,
+                         const float* scale,
                          const float* row_norm, int normalize, const uint32_t* flag_count,
                          const uint32_t* flag_rows, const uint32_t* flag_masks, uint32_t flag_cap,
                          int32_t* argmax_out, int num_sms, cudaStream_t s);

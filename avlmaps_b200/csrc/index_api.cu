@@ -541,7 +541,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
   if ((rc = run_screen(m, qs, p, s))) return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
-  if ((rc = launch_argmax_rerank(m->feat, m->d, qs.q_dev, w.q64, nq, qs.scale_dev, m->row_norm, normalize_map,
+  if ((rc = launch_argmax_rerank(m->feat, m->d, qs.q_dev, w.q64, w.q_bn, nq, qs.scale_dev, m->row_norm, normalize_map,
                                  w.flag_count, w.flag_rows, w.flag_masks, w.flag_cap, dst, m->num_sms, s)))
     return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));

@@ -196,56 +196,114 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ src, double* __restr
 
 __global__ void __launch_bounds__(256)
 argmax_rerank_kernel(const float* __restrict__ feat, int32_t d, const float* __restrict__ q,
-                     const double* __restrict__ q64, int32_t nq, const float* __restrict__ scale,
-                     const float* __restrict__ row_norm, int normalize, const uint32_t* __restrict__ flag_count,
+                     const double* __restrict__ q64, const float* __restrict__ q_bn, int32_t nq,
+                     const float* __restrict__ scale, const float* __restrict__ row_norm, int normalize,
+                     const uint32_t* __restrict__ flag_count,
                      const uint32_t* __restrict__ flag_rows, const uint32_t* __restrict__ flag_masks,
                      uint32_t flag_cap, int32_t* __restrict__ argmax_out) {
   const int lane = threadIdx.x & 31;
   const uint32_t nflag = min(*flag_count, flag_cap);
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nflag; e += nwarps) {
+  const uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (d == 512) {
+    // The fp32 rows of the flagged voxels are scattered 2 KiB reads from HBM: the rows of this warp's next
+    // two entries are prefetched into L2 (16 lanes x 128 B each, no registers held) while the candidates
+    // of the current one are scored.
+    auto prefetch_row = [&](uint32_t e) {
+      if (e < nflag && lane < 16) {
+        const float* r = feat + static_cast<int64_t>(flag_rows[e]) * 512 + lane * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+      }
+    };
+    prefetch_row(e0);
+    prefetch_row(e0 + nwarps);
+    for (uint32_t e = e0; e < nflag; e += nwarps) {
+      prefetch_row(e + 2 * nwarps);
+      const int64_t row = flag_rows[e];
+      float cur[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) cur[t] = __ldg(feat + row * 512 + t * 32 + lane);
+      const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
+      const uint4 m0 = *reinterpret_cast<const uint4*>(flag_masks + static_cast<size_t>(e) * kFlagWords);
+      const uint4 m1 = *reinterpret_cast<const uint4*>(flag_masks + static_cast<size_t>(e) * kFlagWords + 4);
+      const uint32_t masks[kFlagWords] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      // Stage 1: fp32 FMA dots with a rigorous error bound.  |fp32 dot - exact| <= (16 + 5) u sum|a_k b_k| <=
+      // 1.3e-6 ||a|| ||b||; the canonical score is within 4u of the exact one.  If the best lower bound beats
+      // every other upper bound the argmax is decided without touching fp64 (the usual case).
+      const float anorm = row_norm[row] * 1.000001f;
+      float bestL = -FLT_MAX, u1 = -FLT_MAX, u2 = -FLT_MAX;
+      int qL = -1, qU = -1;
+#pragma unroll
+      for (int w = 0; w < kFlagWords; ++w) {
+        uint32_t m = masks[w];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int qq = w * 32 + bit;
+          const float* b = q + static_cast<size_t>(qq) * 512;
+          float bf[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) bf[t] = __ldg(b + t * 32 + lane);
+          float sum = 0.f;
+#pragma unroll
+          for (int t = 0; t < 16; ++t) sum = fmaf(cur[t], bf[t], sum);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          float f = sum, g = 2e-6f * anorm * q_bn[qq];  // q_bn: norm of the scale-folded query (query_prepare)
+          if (normalize) { f *= inv; g *= inv; }
+          if (scale) f *= scale[qq];
+          const float lo = f - g, hi = f + g;
+          if (lo > bestL) { bestL = lo; qL = qq; }
+          if (hi > u1) { u2 = u1; u1 = hi; qU = qq; } else if (hi > u2) { u2 = hi; }
+        }
+      }
+      int best_q = -1;
+      if (qL >= 0 && qL == qU && u2 < bestL) {
+        best_q = qL;
+      } else {
+        // Stage 2 (rare): the fp32 bounds overlap -> canonical fp64-accumulated scores, first maximum wins
+        double ad[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) ad[t] = static_cast<double>(cur[t]);
+        float best = -FLT_MAX;
+#pragma unroll
+        for (int w = 0; w < kFlagWords; ++w) {
+          uint32_t m = masks[w];
+          while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int qq = w * 32 + bit;
+            const double* b = q64 + static_cast<size_t>(qq) * 512;
+            double bd[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) bd[t] = __ldg(b + t * 32 + lane);
+            double sum = 0.0;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) sum = fma(ad[t], bd[t], sum);  // k ascending per lane, like warp_dot
+            const float sc = canon_score(warp_sum(sum), inv, normalize, scale, qq);
+            if (best_q < 0 || sc > best) { best = sc; best_q = qq; }
+          }
+        }
+      }
+      if (lane == 0 && best_q >= 0) argmax_out[row] = best_q;
+    }
+    return;
+  }
+  for (uint32_t e = e0; e < nflag; e += nwarps) {
     const int64_t row = flag_rows[e];
     const float* a = feat + row * d;
     const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
-    const uint4 m0 = *reinterpret_cast<const uint4*>(flag_masks + static_cast<size_t>(e) * kFlagWords);
-    const uint4 m1 = *reinterpret_cast<const uint4*>(flag_masks + static_cast<size_t>(e) * kFlagWords + 4);
-    const uint32_t masks[kFlagWords] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
     float best = -FLT_MAX;
     int best_q = -1;
-    if (d == 512) {
-      double ad[16];
-#pragma unroll
-      for (int t = 0; t < 16; ++t) ad[t] = static_cast<double>(__ldg(a + t * 32 + lane));
-#pragma unroll
-      for (int w = 0; w < kFlagWords; ++w) {
-        uint32_t m = masks[w];
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int qq = w * 32 + bit;
-          const double* b = q64 + static_cast<size_t>(qq) * 512;
-          double bd[16];
-#pragma unroll
-          for (int t = 0; t < 16; ++t) bd[t] = __ldg(b + t * 32 + lane);
-          double sum = 0.0;
-#pragma unroll
-          for (int t = 0; t < 16; ++t) sum = fma(ad[t], bd[t], sum);  // k ascending per lane, like warp_dot
-          const float sc = canon_score(warp_sum(sum), inv, normalize, scale, qq);
-          if (best_q < 0 || sc > best) { best = sc; best_q = qq; }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int w = 0; w < kFlagWords; ++w) {
-        uint32_t m = masks[w];
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int qq = w * 32 + bit;
-          const double dot = warp_dot(a, q + static_cast<size_t>(qq) * d, d, lane);
-          const float sc = canon_score(dot, inv, normalize, scale, qq);
-          if (best_q < 0 || sc > best) { best = sc; best_q = qq; }
-        }
+    for (int w = 0; w < kFlagWords; ++w) {
+      uint32_t m = flag_masks[static_cast<size_t>(e) * kFlagWords + w];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int qq = w * 32 + bit;
+        const double dot = warp_dot(a, q + static_cast<size_t>(qq) * d, d, lane);
+        const float sc = canon_score(dot, inv, normalize, scale, qq);
+        if (best_q < 0 || sc > best) { best = sc; best_q = qq; }
       }
     }
     if (lane == 0 && best_q >= 0) argmax_out[row] = best_q;
@@ -617,13 +675,14 @@ int launch_column_exact(const float* feat, int64_t n, int32_t d, const float* q,
   return AVL_OK;
 }
 
-int launch_argmax_rerank(const float* feat, int32_t d, const float* q, double* q64, int32_t nq, const float* scale,
+int launch_argmax_rerank(const float* feat, int32_t d, const float* q, double* q64, const float* q_bn_raw, int32_t nq,
+                         const float* scale,
                          const float* row_norm, int normalize, const uint32_t* flag_count,
                          const uint32_t* flag_rows, const uint32_t* flag_masks, uint32_t flag_cap,
                          int32_t* argmax_out, int num_sms, cudaStream_t s) {
   const int64_t nel = static_cast<int64_t>(nq) * d;
   f32_to_f64_kernel<<<static_cast<unsigned>((nel + 255) / 256), 256, 0, s>>>(q, q64, nel);
-  argmax_rerank_kernel<<<num_sms * 8, 256, 0, s>>>(feat, d, q, q64, nq, scale, row_norm, normalize, flag_count,
+  argmax_rerank_kernel<<<num_sms * 8, 256, 0, s>>>(feat, d, q, q64, q_bn_raw, nq, scale, row_norm, normalize, flag_count,
                                                    flag_rows, flag_masks, flag_cap, argmax_out);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;

@@ -29,6 +29,7 @@ constexpr int kCtrlBytes = 1024;   // barriers + tmem slot
 constexpr int kQConstBytes = 2048; // float2[256]
 constexpr int kRingEntries = 64;   // per epilogue warp: staged candidates before a 32-entry flush
 constexpr int kRingBytes = kEpiWarps * kRingEntries * 12;
+constexpr int kXchgBytes = 4 * 32 * 8 * 4;  // argmax: the two warps of a lane quarter exchange keys / mask words
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccumStride = 256;  // columns between the two accumulator stages
 
@@ -253,6 +254,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_bfull + 1);
   float2* qc = reinterpret_cast<float2*>(ctrl + kCtrlBytes);
   uint8_t* ring_base = ctrl + kCtrlBytes + kQConstBytes;
+  uint32_t* xchg_base = reinterpret_cast<uint32_t*>(ring_base + kRingBytes);
 
   if constexpr (CG == 2) ptx::cluster_sync_all();  // both CTAs resident before the paired TMEM alloc
 
@@ -379,56 +381,79 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     uint32_t it = 0;
     for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
-      ptx::mbar_wait(ptx::smem_u32(bar_tfull + as), aphase, p.dbg, 0x50u + as);
-      ptx::tc_fence_after();
       TileCtx t;
       t.row = (static_cast<int64_t>(j) * p.tile_stride * CG + rank) * kTileRows + lane_base + lane;
       t.crow = (static_cast<int64_t>(j) * CG + rank) * kTileRows + lane_base + lane;
       t.valid = t.row < p.n_rows;
       t.taddr = tmem_base + as * kAccumStride + (lane_base << 16);
       const int n32 = p.npad & ~31;
+      // this row's statistics: issued BEFORE waiting for the accumulator so that their global-memory
+      // latency overlaps the wait instead of sitting between the MMAs and the release of the stage
+      float st_an = 0.f, st_c = 0.f, st_norm = 1.f;
+      if (t.valid) {
+        st_an = p.row_an[t.row];
+        st_c = p.row_c[t.row];
+        if (p.normalize) st_norm = p.row_norm[t.row];
+      }
+      ptx::mbar_wait(ptx::smem_u32(bar_tfull + as), aphase, p.dbg, 0x50u + as);
+      ptx::tc_fence_after();
 
       if (p.debug_flags & 4) {
         // triage: drain nothing
       } else if (p.mode == kModeDense) {
         float r_i = 0.f, w_i = 1.f;
         if (p.dense_lb && t.valid) {
-          r_i = fmaf(rho, p.row_an[t.row], p.row_c[t.row]) * 1.000001f;
-          if (p.normalize) w_i = 1.f / fmaxf(p.row_norm[t.row], 1e-30f);  // reciprocal: dense_chunk multiplies
+          r_i = fmaf(rho, st_an, st_c) * 1.000001f;
+          if (p.normalize) w_i = 1.f / fmaxf(st_norm, 1e-30f);  // reciprocal: dense_chunk multiplies
         }
         for (int c0 = half * 32; c0 < n32; c0 += 64) dense_chunk<32>(p, t, c0, qc, r_i, w_i);
         if (n32 < p.npad && ((n32 >> 5) & 1) == half) dense_chunk<16>(p, t, n32, qc, r_i, w_i);
       } else if (p.mode == kModeArgmax) {
-        if (half == 0) {  // the per-row reduction stays inside one thread: 4 of the 8 warps do it
-          uint32_t best = 0, second = 0;
-          for (int c0 = 0; c0 < n32; c0 += 32) argmax_chunk<32>(p, t, c0, best, second);
-          if (n32 < p.npad) argmax_chunk<16>(p, t, n32, best, second);
-          float r_i = 0.f, an_i = 0.f;
-          if (t.valid) {
-            an_i = p.row_an[t.row];
-            r_i = fmaf(rho, an_i, p.row_c[t.row]);
-          }
+        // The two warps of a lane quarter share the same 32 rows: warp `half` reduces the 32-column words
+        // cb = half, half + 2, ... and they meet through shared memory (named barrier 1 + quarter, 64 threads).
+        uint32_t* xq = xchg_base + (warp & 3u) * (32 * 8) + lane * 8;  // 8 words per row
+        const uint32_t bar_id = 1u + (warp & 3u);
+        uint32_t best = 0, second = 0;
+        for (int c0 = half * 32; c0 < n32; c0 += 64) argmax_chunk<32>(p, t, c0, best, second);
+        if (n32 < p.npad && ((n32 >> 5) & 1) == half) argmax_chunk<16>(p, t, n32, best, second);
+        if (half == 1) { xq[0] = best; xq[1] = second; }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        float thr = 0.f;
+        bool flagged = false;
+        if (half == 0) {
+          const uint32_t b1 = xq[0], s1k = xq[1];
+          second = max(max(second, s1k), min(best, b1));
+          best = max(best, b1);
+          const float r_i = fmaf(rho, st_an, st_c);
           // eps_i = r_i * bn_max bounds |s~ - s| for every query; 2^-15 relative is lost by the key
-          const float tol = (2.f * r_i + 6.2e-5f * an_i) * bn_max * 1.0001f;
+          const float tol = (2.f * r_i + 6.2e-5f * st_an) * bn_max * 1.0001f;
           const float s1 = ord2f(best & 0xFFFFFF00u);
           const float s2 = ord2f(second & 0xFFFFFF00u);
-          const float thr = s1 - tol;
-          const bool flagged = t.valid && second != 0u && (s2 >= thr);
+          thr = s1 - tol;
+          flagged = t.valid && second != 0u && (s2 >= thr);
           if (t.valid) p.argmax_out[t.row] = 255 - static_cast<int32_t>(best & 0xFFu);
-          const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
-          if (fl != 0u) {
-            // second pass over the accumulator: bitmask of every query inside the band
-            uint32_t m[kFlagWords];
+          xq[2] = __float_as_uint(thr);
+          xq[3] = __ballot_sync(0xffffffffu, flagged);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const uint32_t fl = xq[3];  // same word for the whole quarter: written by every lane of warp `half 0`
+        if (fl != 0u) {
+          // second pass over the accumulator: bitmask of every query inside the band
+          if (half == 1) thr = __uint_as_float(xq[2]);
+          uint32_t m[kFlagWords / 2];
 #pragma unroll
-            for (int cb = 0; cb < kFlagWords; ++cb) {
-              m[cb] = 0u;
-              const int c0 = cb * 32;
-              if (c0 + 32 <= p.npad) m[cb] = mask_chunk<32>(t, c0, thr);
-              else if (c0 < p.npad) m[cb] = mask_chunk<16>(t, c0, thr);
-              const int nv = p.nq - c0;  // valid columns in this word
-              const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv > 0 ? ((1u << nv) - 1u) : 0u);
-              m[cb] &= vm;
-            }
+          for (int i = 0; i < kFlagWords / 2; ++i) {
+            m[i] = 0u;
+            const int c0 = (2 * i + half) * 32;
+            if (c0 + 32 <= p.npad) m[i] = mask_chunk<32>(t, c0, thr);
+            else if (c0 < p.npad) m[i] = mask_chunk<16>(t, c0, thr);
+            const int nv = p.nq - c0;  // valid columns in this word
+            const uint32_t vm = nv >= 32 ? 0xffffffffu : (nv > 0 ? ((1u << nv) - 1u) : 0u);
+            m[i] &= vm;
+          }
+          if (half == 1) { xq[4] = m[0]; xq[5] = m[1]; xq[6] = m[2]; xq[7] = m[3]; }
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          if (half == 0) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(p.flag_count, static_cast<uint32_t>(__popc(fl)));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -437,19 +462,20 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
               if (slot < p.flag_cap) {
                 p.flag_rows[slot] = static_cast<uint32_t>(t.row);
                 uint4* dst = reinterpret_cast<uint4*>(p.flag_masks + static_cast<size_t>(slot) * kFlagWords);
-                dst[0] = make_uint4(m[0], m[1], m[2], m[3]);
-                dst[1] = make_uint4(m[4], m[5], m[6], m[7]);
+                dst[0] = make_uint4(m[0], xq[4], m[1], xq[5]);   // words 0..3 = (half0, half1) interleaved
+                dst[1] = make_uint4(m[2], xq[6], m[3], xq[7]);
               }
             }
           }
+          // xq is rewritten in the next tile only after both warps pass its first barrier again
         }
       } else {  // kModeThresh
         // invalid rows: ri = -inf makes every upper bound -inf (or NaN), never a candidate
         float ri = -INFINITY, iw = 1.f;
         if (t.valid) {
-          ri = fmaf(rho, p.row_an[t.row], p.row_c[t.row]);
+          ri = fmaf(rho, st_an, st_c);
           if (p.normalize) {
-            iw = 1.f / fmaxf(p.row_norm[t.row], 1e-30f);
+            iw = 1.f / fmaxf(st_norm, 1e-30f);
             ri *= iw;
           }
         }
@@ -480,7 +506,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages) {
   const size_t b_bytes = static_cast<size_t>(npad / cta_group) * 128u * kblocks;
   size_t total = ((b_bytes + 1023u) & ~size_t(1023)) + static_cast<size_t>(stages) * kStageBytes + kCtrlBytes +
-                 kQConstBytes + kRingBytes + 1024u /* alignment slack */;
+                 kQConstBytes + kRingBytes + kXchgBytes + 1024u /* alignment slack */;
   // > half of the SM's shared memory, so exactly one CTA (and one 512-column TMEM owner) per SM
   if (total < 120u * 1024u) total = 120u * 1024u;
   return total;

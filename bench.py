@@ -309,12 +309,19 @@ def run_gpu(args):
     ms_k = statistics.mean(ms_screen)
     flops = 2.0 * N_VOX * DIM * NQ
     achieved = flops / (ms_k * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+    # the kernel is timed inside a long step (hundreds of back-to-back launches under the 1 kW power cap):
+    # the sustained cuBLAS figure is the denominator the profiling recipe prescribes; the burst one is kept beside it
+    sustained = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+    long_step = args.steps >= 50
+    peak = sustained if long_step else peaks["bf16_tflops"]
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_kind": "sustained (kernel timed inside a long step)" if long_step else "burst (short run)",
+                "frac_vs_burst_peak": achieved / peaks["bf16_tflops"], "frac_vs_sustained_peak": achieved / sustained,
                 "kernel": {3: "screen_ts_kernel (tcgen05 cta_group::2, queries resident in TMEM, M=256 N=128 K=512 per tile)",
                            2: "screen_kernel<cta_group::2> (tcgen05 bf16, M=256 N=256 K=512 per tile pair)",
                            1: "screen_kernel<cta_group::1>"}.get(dmap.last_stats["cta_group"], "?"),
-                "kernel_ms": ms_k, "peak_source": peaks["source"] + ", burst figure",
+                "kernel_ms": ms_k, "peak_source": peaks["source"],
                 "algorithmic_flops": flops, "algorithmic_bytes": N_VOX * DIM * 2 + NQ * DIM * 4 + NQ * TOPK * 12,
                 "hbm_GBps": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9, "hbm_frac": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     traffic_file = ROOT / "profiles" / "traffic.json"
@@ -355,6 +362,45 @@ def run_gpu(args):
             extra["config2_error"] = repr(e)
         dmap.close()
         torch.cuda.empty_cache()
+        # BASELINE config 3: 1M-voxel LSeg-512 + AudioCLIP-1024 (unit rows, scale 100), 32 + 32 queries, min-max, product, top-16
+        try:
+            n3 = 1_000_000
+            mv = engine.DeviceMap(make_shard(torch, n3, 512, 11, dev))
+            fa = torch.randn((n3, 1024), device=dev, generator=g)
+            fa = fa / fa.norm(dim=1, keepdim=True)
+            ma = engine.DeviceMap(fa)
+            del fa
+            qv = qpool[1][:32].contiguous()
+            qa = torch.randn((32, 1024), device=dev, generator=g)
+            qa = (qa / qa.norm(dim=1, keepdim=True)).contiguous()
+            sa = torch.full((32,), 100.0, device=dev)
+            tt = []
+            for i in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                engine.fuse_topk(mv, qv, ma, qa, TOPK, scale_b=sa, combine=L.FUSE_PRODUCT)
+                b.record(stream)
+                torch.cuda.synchronize()
+                tt.append(a.elapsed_time(b))
+            extra["config3_fusion_1M_512+1024_32pairs"] = {"ms_call": min(tt[1:]), "pairs_per_s": 32 / (min(tt[1:]) * 1e-3),
+                                                           "note": "exact fp64-accumulated dense columns + min-max + product + top-16"}
+            # AVLMap.index_object heat: nearest-target distance decay over 1M voxels, 1% targets
+            pos = torch.randint(0, 1000, (n3, 3), device=dev, dtype=torch.int32, generator=g)
+            pos[:, 2] = pos[:, 2] % 30
+            mask = (torch.rand(n3, device=dev, generator=g) < 0.01)
+            tt = []
+            for i in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                engine.heat_from_mask_3d(pos, mask, 0.05, 0.1)
+                b.record(stream)
+                torch.cuda.synchronize()
+                tt.append(a.elapsed_time(b))
+            extra["heat_from_mask_3d_1M_1pct_targets"] = {"ms_call": min(tt[1:])}
+            mv.close(); ma.close()
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            extra["config3_error"] = repr(e)
         if not args.no_build:
             try:
                 extra["build"] = build_extra(torch, engine, L)
