@@ -16,6 +16,7 @@ LIB_PATH = PKG / "libavlmaps_b200.so"
 
 AVL_OK = 0
 AVL_ON_DEVICE = 1
+AVL_DEPTH_U16_MM = 2
 AVL_MAX_QUERIES = 256
 AVL_MAX_TOPK = 128
 FUSE_PRODUCT, FUSE_MAX, FUSE_SUM = 0, 1, 2
@@ -29,6 +30,9 @@ EXPORTS = [
     "avl_heat_from_mask_3d", "avl_merge_topk", "avl_heat2d_sources",
     "avl_builder_create", "avl_builder_destroy", "avl_builder_add_frame", "avl_builder_num_voxels",
     "avl_builder_num_accepted", "avl_builder_export", "avl_builder_to_map",
+    "avl_builder_create_global", "avl_builder_num_rejected_oob",
+    "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
+    "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys",
 ]
 
 
@@ -48,6 +52,11 @@ class IndexStats(C.Structure):
 class GridSpec(C.Structure):
     _fields_ = [("gs", C.c_int32), ("vh", C.c_int32), ("cs", C.c_double), ("dim", C.c_int32),
                 ("capacity", C.c_int64)]
+
+
+class GlobalGridSpec(C.Structure):
+    _fields_ = [("n_row", C.c_int32), ("n_col", C.c_int32), ("n_height", C.c_int32), ("cs", C.c_double),
+                ("pcd_min", C.c_double * 3), ("dim", C.c_int32), ("capacity", C.c_int64)]
 
 
 class Frame(C.Structure):
@@ -105,6 +114,15 @@ def load() -> C.CDLL:
         lib.avl_builder_num_accepted.argtypes = [vp, C.POINTER(i64), vp]
         lib.avl_builder_export.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
         lib.avl_builder_to_map.argtypes = [vp, vp, C.POINTER(vp)]
+        lib.avl_builder_create_global.argtypes = [C.POINTER(GlobalGridSpec), C.POINTER(vp)]
+        lib.avl_builder_num_rejected_oob.argtypes = [vp, C.POINTER(i64), vp]
+        lib.avl_bounds_create.argtypes = [C.POINTER(vp)]
+        lib.avl_bounds_destroy.argtypes = [vp]
+        lib.avl_bounds_add_frame.argtypes = [vp, C.POINTER(Frame), C.c_int, vp]
+        lib.avl_bounds_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), vp]
+        lib.avl_builder_set_slab.argtypes = [vp, i32, i32]
+        lib.avl_builder_export_keys.argtypes = [vp, vp, C.c_int, vp]
+        lib.avl_rank_keys.argtypes = [vp, vp, i32, i32, vp, C.c_int, vp]
     _lib = lib
     return lib
 

@@ -12,7 +12,7 @@
 //                    (frame, sample) order                                   -> ordered scan per frame
 //     grid_feat    = (alpha_first^2 f_first + sum_{others} alpha f) / sum alpha
 //     weight       = sum alpha
-// Kernels per frame: geometry (fp64, no FMA contraction) -> winner count -> scan -> id assignment ->
+// Kernels per frame: geometry (fp64, the reference's exact operation sequence) -> winner count -> scan -> id assignment ->
 // scatter-reduce (warp per point, float4 vector reds into the voxel row).
 #include <algorithm>
 #include <cstdio>
@@ -26,16 +26,27 @@ namespace {
 struct FrameGeom {
   double kinv[9], k[9], kfeat[9], tf[16];
   double min_depth, max_depth, cs, half_gs;
-  int32_t h, w, fh, fw, gs, vh;
+  double origin[3];      // pcd_min (global-frame grid)
+  int32_t h, w, fh, fw;
+  int32_t n0, n1, n2;    // rows, cols, heights of occupied_ids
+  int32_t mode;          // 0 = mobile-base grid (vlmap_builder.py), 1 = global-frame grid (vlmap_builder_multi_floor.py)
+  int32_t slab_lo, slab_hi;  // rows owned by this builder
+  int32_t depth_u16;     // depth is uint16 millimetres
   int32_t has_rgb;
 };
 
 constexpr int kScanBlock = 1024;
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 
+// The matrix products of the reference (cam_mat_inv @ p_2d, pose @ pc_homo, cam_mat @ p) run through
+// numpy matmul -> OpenBLAS, whose x86-64 kernels accumulate over k ascending with fused multiply-adds:
+// acc = m0*x; acc = fma(m1, y, acc); acc = fma(m2, z, acc).  This form reproduces numpy on every element
+// (tools/probe_matmul_fma.py); the element-wise operations around them round separately.
 __device__ __forceinline__ double dot3(const double* m, double x, double y, double z) {
-  // (m0*x + m1*y) + m2*z, every operation rounded separately like numpy's float64 matmul here
-  return __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), __dmul_rn(m[2], z));
+  return __fma_rn(m[2], z, __fma_rn(m[1], y, __dmul_rn(m[0], x)));
+}
+__device__ __forceinline__ double dot4h(const double* m, double x, double y, double z) {  // row . [x, y, z, 1]
+  return __fma_rn(m[3], 1.0, __fma_rn(m[2], z, __fma_rn(m[1], y, __dmul_rn(m[0], x))));
 }
 __device__ __forceinline__ long long trunc_ll(double v) {
   // python int(): toward zero; far-out values are clamped (the range tests reject them anyway)
@@ -43,40 +54,78 @@ __device__ __forceinline__ long long trunc_ll(double v) {
   if (!(v < 9.0e15)) return (1ll << 60);
   return __double2ll_rz(v);
 }
+__device__ __forceinline__ long long round_ll(double v) {
+  // np.round(...).astype(int): round half to even
+  if (!(v > -9.0e15)) return -(1ll << 60);
+  if (!(v < 9.0e15)) return (1ll << 60);
+  return __double2ll_rn(v);
+}
+__device__ __forceinline__ double load_depth(const FrameGeom& g, const float* depth, int pix) {
+  // multi-floor: load_depth_img(path) / 1000.0 -> uint16 / python float = float64 division
+  // (vlmap_builder_multi_floor.py:103,128); mobile base: float32 .npy metres widened by numpy
+  if (g.depth_u16) return __ddiv_rn(static_cast<double>(reinterpret_cast<const uint16_t*>(depth)[pix]), 1000.0);
+  return static_cast<double>(depth[pix]);
+}
 
 // ---------------------------------------------------------------- geometry + first-touch keys
 __global__ void __launch_bounds__(256)
 geom_kernel(const FrameGeom g, const float* __restrict__ depth, const int32_t* __restrict__ sample_idx,
             int32_t n_samples, uint32_t frame_seq, unsigned long long* __restrict__ first_key,
             int32_t* __restrict__ s_cell, int32_t* __restrict__ s_fpix, float* __restrict__ s_alpha,
-            int32_t* __restrict__ s_rgbpix) {
+            int32_t* __restrict__ s_rgbpix, uint8_t* __restrict__ s_wrap,
+            unsigned long long* __restrict__ n_oob) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     const int pix = sample_idx ? sample_idx[j] : j;
     const int v = pix / g.w, u = pix - v * g.w;
     const double x2 = u + 0.5, y2 = v + 0.5;
-    const double z = static_cast<double>(depth[pix]);
+    const double z = load_depth(g, depth, pix);
     // depth2pc: pc = (Kinv @ [u+.5, v+.5, 1]) * z   (mapping_utils.py:239-246)
     const double px = __dmul_rn(dot3(g.kinv + 0, x2, y2, 1.0), z);
     const double py = __dmul_rn(dot3(g.kinv + 3, x2, y2, 1.0), z);
     const double pz = __dmul_rn(dot3(g.kinv + 6, x2, y2, 1.0), z);
     int cell = -1, fpix = 0, rgbpix = -1;
+    unsigned wrap = 0;
     float alpha = 0.f;
     if (pz > g.min_depth && pz < g.max_depth) {  // mapping_utils.py:247-249
       // transform_pc: pose @ [p; 1]   (mapping_utils.py:311-315)
-      const double gx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.tf[0], px), __dmul_rn(g.tf[1], py)), __dmul_rn(g.tf[2], pz)), g.tf[3]);
-      const double gy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.tf[4], px), __dmul_rn(g.tf[5], py)), __dmul_rn(g.tf[6], pz)), g.tf[7]);
-      const double gz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.tf[8], px), __dmul_rn(g.tf[9], py)), __dmul_rn(g.tf[10], pz)), g.tf[11]);
-      // base_pos2grid_id_3d (mapping_utils.py:345-349): double truncation toward zero
-      const long long row = trunc_ll(__dsub_rn(g.half_gs, static_cast<double>(trunc_ll(__ddiv_rn(gx, g.cs)))));
-      const long long col = trunc_ll(__dsub_rn(g.half_gs, static_cast<double>(trunc_ll(__ddiv_rn(gy, g.cs)))));
-      const long long hh = trunc_ll(__ddiv_rn(gz, g.cs));
-      if (!(col >= g.gs || row >= g.gs || hh >= g.vh || col < 0 || row < 0 || hh < 0)) {  // vlmap_builder.py:283
+      const double gx = dot4h(g.tf + 0, px, py, pz);
+      const double gy = dot4h(g.tf + 4, px, py, pz);
+      const double gz = dot4h(g.tf + 8, px, py, pz);
+      long long row, col, hh;
+      bool in_grid, height_oob = false;
+      if (g.mode == 0) {
+        // base_pos2grid_id_3d (mapping_utils.py:345-349): double truncation toward zero
+        row = trunc_ll(__dsub_rn(g.half_gs, static_cast<double>(trunc_ll(__ddiv_rn(gx, g.cs)))));
+        col = trunc_ll(__dsub_rn(g.half_gs, static_cast<double>(trunc_ll(__ddiv_rn(gy, g.cs)))));
+        hh = trunc_ll(__ddiv_rn(gz, g.cs));
+        in_grid = !(col >= g.n1 || row >= g.n0 || hh >= g.n2 || col < 0 || row < 0 || hh < 0);  // vlmap_builder.py:283
+      } else {
+        // row, height, col = np.round((p - pcd_min) / cs).astype(int)   (vlmap_builder_multi_floor.py:146)
+        row = round_ll(__ddiv_rn(__dsub_rn(gx, g.origin[0]), g.cs));
+        hh = round_ll(__ddiv_rn(__dsub_rn(gy, g.origin[1]), g.cs));
+        col = round_ll(__ddiv_rn(__dsub_rn(gz, g.origin[2]), g.cs));
+        in_grid = !(row >= g.n0 || col >= g.n1);  // the only test the reference makes (:151-153)
+        if (in_grid) {
+          // negative indices wrap like numpy's; grid_pos keeps the unwrapped values (:176)
+          if (row < 0) { row += g.n0; wrap |= 1u; }
+          if (col < 0) { col += g.n1; wrap |= 2u; }
+          if (hh < 0) { hh += g.n2; wrap |= 4u; }
+          if (row < 0 || col < 0) {  // height_map[row, col] raises IndexError in the reference (:155)
+            in_grid = false;
+            atomicAdd(n_oob, 1ull);
+          }
+          height_oob = hh < 0 || hh >= g.n2;  // occupied_ids[row, col, height] would raise (:175)
+        }
+      }
+      if (in_grid && (row < g.slab_lo || row >= g.slab_hi)) in_grid = false;  // another rank's slab
+      if (in_grid) {
         // project_point with the feature camera (vlmap_builder.py:143, mapping_utils.py:599-605)
         const double f2 = dot3(g.kfeat + 6, px, py, pz);
         const long long fx = trunc_ll(__dsub_rn(__ddiv_rn(dot3(g.kfeat + 0, px, py, pz), f2), 0.5));
         const long long fy = trunc_ll(__dsub_rn(__ddiv_rn(dot3(g.kfeat + 3, px, py, pz), f2), 0.5));
-        if (!(fx < 0 || fy < 0 || fx >= g.fw || fy >= g.fh)) {  // vlmap_builder.py:161
-          cell = static_cast<int>((row * g.gs + col) * g.vh + hh);
+        if (!(fx < 0 || fy < 0 || fx >= g.fw || fy >= g.fh) && height_oob) atomicAdd(n_oob, 1ull);
+        if (!(fx < 0 || fy < 0 || fx >= g.fw || fy >= g.fh) && !height_oob) {  // vlmap_builder.py:161
+          cell = static_cast<int>((row * g.n1 + col) * g.n2 + hh);
           fpix = static_cast<int>(fy * g.fw + fx);
           // alpha = exp(-||p||^2 / (2 * 0.6))   (vlmap_builder.py:156-158)
           const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz));
@@ -98,6 +147,104 @@ geom_kernel(const FrameGeom g, const float* __restrict__ depth, const int32_t* _
     s_fpix[j] = fpix;
     s_alpha[j] = alpha;
     s_rgbpix[j] = rgbpix;
+    s_wrap[j] = static_cast<uint8_t>(wrap);
+  }
+}
+
+// ---------------------------------------------------------------- pass 1 of the global-frame build
+// min / max over the valid sampled points of transform_pc(depth2pc(depth), tf)
+// (vlmap_builder_multi_floor.py:97-118); partial[block][0..2] = min xyz, [3..5] = max xyz, [6] = count
+__global__ void __launch_bounds__(256)
+bounds_kernel(const FrameGeom g, const float* __restrict__ depth, const int32_t* __restrict__ sample_idx,
+              int32_t n_samples, double* __restrict__ partial) {
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  unsigned cnt = 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
+    const int pix = sample_idx ? sample_idx[j] : j;
+    const int v = pix / g.w, u = pix - v * g.w;
+    const double x2 = u + 0.5, y2 = v + 0.5;
+    const double z = load_depth(g, depth, pix);
+    const double px = __dmul_rn(dot3(g.kinv + 0, x2, y2, 1.0), z);
+    const double py = __dmul_rn(dot3(g.kinv + 3, x2, y2, 1.0), z);
+    const double pz = __dmul_rn(dot3(g.kinv + 6, x2, y2, 1.0), z);
+    if (pz > g.min_depth && pz < g.max_depth) {
+      const double gx = dot4h(g.tf + 0, px, py, pz);
+      const double gy = dot4h(g.tf + 4, px, py, pz);
+      const double gz = dot4h(g.tf + 8, px, py, pz);
+      mn[0] = fmin(mn[0], gx); mn[1] = fmin(mn[1], gy); mn[2] = fmin(mn[2], gz);
+      mx[0] = fmax(mx[0], gx); mx[1] = fmax(mx[1], gy); mx[2] = fmax(mx[2], gz);
+      ++cnt;
+    }
+  }
+  __shared__ double sh[8][7];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      mn[c] = fmin(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    for (int c = 0; c < 3; ++c) { sh[warp][c] = mn[c]; sh[warp][3 + c] = mx[c]; }
+    sh[warp][6] = static_cast<double>(cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    const int c = threadIdx.x;
+    double a = sh[0][c];
+    for (int w2 = 1; w2 < 8; ++w2) a = c < 3 ? fmin(a, sh[w2][c]) : (c < 6 ? fmax(a, sh[w2][c]) : a + sh[w2][c]);
+    partial[blockIdx.x * 7 + c] = a;
+  }
+}
+// one block: acc[0..5] = min/max merged with the partials, acc[6] += count
+__global__ void __launch_bounds__(32)
+bounds_merge_kernel(const double* __restrict__ partial, int32_t nblocks, double* __restrict__ acc) {
+  const int c = threadIdx.x;
+  if (c >= 7) return;
+  double a = acc[c];
+  for (int b = 0; b < nblocks; ++b) {
+    const double p = partial[b * 7 + c];
+    a = c < 3 ? fmin(a, p) : (c < 6 ? fmax(a, p) : a + p);
+  }
+  acc[c] = a;
+}
+
+// keys[id] = first-touch key of voxel id; ids are assigned in key order, so keys come out ascending
+__global__ void __launch_bounds__(256)
+export_keys_kernel(const int32_t* __restrict__ occupied_ids, const unsigned long long* __restrict__ first_key,
+                   int64_t cells, int64_t capacity, unsigned long long* __restrict__ keys) {
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < cells;
+       c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t id = occupied_ids[c];
+    if (id >= 0 && id < capacity) keys[id] = first_key[c];
+  }
+}
+
+constexpr int kMaxShards = 64;
+struct ShardOffsets { int64_t off[kMaxShards + 1]; };
+// global id = number of keys of all shards that are smaller (keys are unique: frame_seq << 32 | sample position)
+__global__ void __launch_bounds__(256)
+rank_keys_kernel(const unsigned long long* __restrict__ keys_all, const ShardOffsets so, int32_t n_shards,
+                 int32_t shard, int64_t* __restrict__ out) {
+  const int64_t n_own = so.off[shard + 1] - so.off[shard];
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < n_own;
+       j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const unsigned long long key = keys_all[so.off[shard] + j];
+    int64_t rank = j;
+    for (int s2 = 0; s2 < n_shards; ++s2) {
+      if (s2 == shard) continue;
+      int64_t lo = so.off[s2], hi = so.off[s2 + 1];
+      const int64_t base = lo;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (keys_all[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      rank += lo - base;
+    }
+    out[j] = rank;
   }
 }
 
@@ -162,8 +309,8 @@ winner_scan_kernel(uint32_t* __restrict__ block_cnt, int32_t nblocks, unsigned l
 __global__ void __launch_bounds__(kScanBlock)
 assign_ids_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_t frame_seq,
                   const unsigned long long* __restrict__ first_key, const uint32_t* __restrict__ block_base,
-                  int32_t gs, int32_t vh, int64_t capacity, int32_t* __restrict__ occupied_ids,
-                  int32_t* __restrict__ grid_pos) {
+                  int32_t n0, int32_t n1, int32_t n2, const uint8_t* __restrict__ s_wrap, int64_t capacity,
+                  int32_t* __restrict__ occupied_ids, int32_t* __restrict__ grid_pos) {
   __shared__ uint32_t warp_tot[32];
   const int j = blockIdx.x * kScanBlock + threadIdx.x;
   const int cell = j < n_samples ? s_cell[j] : -1;
@@ -187,10 +334,11 @@ assign_ids_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_
                        __popc(b & ((1u << lane) - 1u));
     if (id < capacity) {
       occupied_ids[cell] = static_cast<int32_t>(id);  // vlmap_builder.py:165
-      const int hh = cell % vh, rc = cell / vh;
-      grid_pos[id * 3 + 0] = rc / gs;                  // vlmap_builder.py:169
-      grid_pos[id * 3 + 1] = rc % gs;
-      grid_pos[id * 3 + 2] = hh;
+      const int hh = cell % n2, rc = cell / n2;
+      const unsigned wrap = s_wrap[j];                 // global-frame grid: indices that wrapped stay negative here
+      grid_pos[id * 3 + 0] = rc / n1 - ((wrap & 1u) ? n0 : 0);  // vlmap_builder.py:169, vlmap_builder_multi_floor.py:176
+      grid_pos[id * 3 + 1] = rc % n1 - ((wrap & 2u) ? n1 : 0);
+      grid_pos[id * 3 + 2] = hh - ((wrap & 4u) ? n2 : 0);
     }
   }
 }
@@ -331,7 +479,12 @@ __global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long 
 using namespace avl;
 
 struct avl_builder {
-  avl_grid_spec spec;
+  int32_t n0 = 0, n1 = 0, n2 = 0;  // occupied_ids dims: rows, cols, heights
+  int32_t dim = 0;
+  double cs = 0.0;
+  int32_t mode = 0;                // 0 mobile-base grid, 1 global-frame (multi-floor) grid
+  double origin[3] = {0.0, 0.0, 0.0};
+  int32_t slab_lo = 0, slab_hi = 0;
   int num_sms = 148;
   int64_t cells = 0;
   int64_t capacity = 0;
@@ -344,10 +497,11 @@ struct avl_builder {
   float* den = nullptr;
   float* rgb_acc = nullptr;
   int32_t* grid_pos = nullptr;
-  unsigned long long* counters = nullptr;  // [0] max_id, [1] n_accepted
+  unsigned long long* counters = nullptr;  // [0] max_id, [1] n_accepted, [2] rejected where the reference raises
   // per-frame scratch (grown on demand)
   int32_t *s_cell = nullptr, *s_fpix = nullptr, *s_rgbpix = nullptr;
   float* s_alpha = nullptr;
+  uint8_t* s_wrap = nullptr;
   uint32_t* block_cnt = nullptr;
   int64_t scratch_samples = 0;
   // staging of host inputs
@@ -372,7 +526,7 @@ int grow(T** p, size_t* have, size_t need) {
 }
 
 int alloc_rows(avl_builder* b, int64_t cap, float** num, float** den, float** rgb, int32_t** pos, cudaStream_t s) {
-  const int d = b->spec.dim;
+  const int d = b->dim;
   AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(num), static_cast<size_t>(cap) * d * sizeof(float)));
   AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(den), static_cast<size_t>(cap) * sizeof(float)));
   AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(rgb), static_cast<size_t>(cap) * 3 * sizeof(float)));
@@ -403,7 +557,7 @@ int ensure_capacity(avl_builder* b, int64_t incoming, cudaStream_t s) {
     int32_t* pos;
     int rc = alloc_rows(b, cap, &num, &den, &rgb, &pos, s);
     if (rc) return rc;
-    const size_t v = static_cast<size_t>(b->id_upper), d = b->spec.dim;
+    const size_t v = static_cast<size_t>(b->id_upper), d = b->dim;
     AVL_CUDA(cudaMemcpyAsync(num, b->num, v * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     AVL_CUDA(cudaMemcpyAsync(den, b->den, v * sizeof(float), cudaMemcpyDeviceToDevice, s));
     AVL_CUDA(cudaMemcpyAsync(rgb, b->rgb_acc, v * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -417,15 +571,33 @@ int ensure_capacity(avl_builder* b, int64_t incoming, cudaStream_t s) {
   return AVL_OK;
 }
 
+void fill_geom(FrameGeom* g, const avl_frame* f, int flags) {
+  memset(g, 0, sizeof(*g));
+  memcpy(g->kinv, f->kinv, sizeof(g->kinv));
+  memcpy(g->k, f->k, sizeof(g->k));
+  memcpy(g->kfeat, f->kfeat, sizeof(g->kfeat));
+  memcpy(g->tf, f->tf, sizeof(g->tf));
+  g->min_depth = f->min_depth;
+  g->max_depth = f->max_depth;
+  g->h = f->h; g->w = f->w; g->fh = f->fh; g->fw = f->fw;
+  g->depth_u16 = (flags & AVL_DEPTH_U16_MM) ? 1 : 0;
+}
+
 }  // namespace
+
+struct avl_bounds {
+  int num_sms = 148;
+  double* acc = nullptr;      // [7] min xyz, max xyz, count
+  double* partial = nullptr;  // [blocks][7]
+  float* d_depth = nullptr; size_t depth_elems = 0;
+  int32_t* d_sidx = nullptr; size_t sidx_elems = 0;
+};
 
 extern "C" {
 
-int avl_builder_create(const avl_grid_spec* spec, avl_builder** out) {
-  AVL_ARG(spec != nullptr && out != nullptr, "NULL argument");
-  *out = nullptr;
-  AVL_ARG(spec->gs >= 1 && spec->vh >= 1 && spec->dim >= 1 && spec->cs > 0.0, "invalid grid spec");
-  const int64_t cells = static_cast<int64_t>(spec->gs) * spec->gs * spec->vh;
+static int builder_create_common(int32_t n0, int32_t n1, int32_t n2, double cs, int32_t dim, int64_t capacity,
+                                 int32_t mode, const double* origin, avl_builder** out) {
+  const int64_t cells = static_cast<int64_t>(n0) * n1 * n2;
   AVL_ARG(cells < (int64_t(1) << 31), "grid has more than 2^31 cells");
   int dev = 0, major = 0;
   AVL_CUDA(cudaGetDevice(&dev));
@@ -435,20 +607,23 @@ int avl_builder_create(const avl_grid_spec* spec, avl_builder** out) {
     return AVL_ERR_UNSUPPORTED;
   }
   avl_builder* b = new avl_builder();
-  b->spec = *spec;
+  b->n0 = n0; b->n1 = n1; b->n2 = n2; b->cs = cs; b->dim = dim; b->mode = mode;
+  if (origin) memcpy(b->origin, origin, sizeof(b->origin));
+  b->slab_lo = 0;
+  b->slab_hi = n0;
   cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, dev);
   b->cells = cells;
-  b->capacity = spec->capacity > 0 ? std::min<int64_t>(spec->capacity, cells)
-                                   : std::min<int64_t>(static_cast<int64_t>(spec->gs) * spec->gs, cells);
+  b->capacity = capacity > 0 ? std::min<int64_t>(capacity, cells)
+                             : std::min<int64_t>(static_cast<int64_t>(n0) * n1, cells);
   int rc = AVL_OK;
   do {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->first_key), cells * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->occupied_ids), cells * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->counters), 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->counters), 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) { rc = cuda_fail(e, "builder state", __FILE__, __LINE__); break; }
     fill_u64_kernel<<<1184, 256>>>(b->first_key, cells, kNoKey);
     fill_i32_kernel<<<1184, 256>>>(b->occupied_ids, cells, -1);  // vlmap_builder.py:204
-    e = cudaMemset(b->counters, 0, 2 * sizeof(unsigned long long));
+    e = cudaMemset(b->counters, 0, 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) { rc = cuda_fail(e, "builder init", __FILE__, __LINE__); break; }
     if ((rc = alloc_rows(b, b->capacity, &b->num, &b->den, &b->rgb_acc, &b->grid_pos, nullptr))) break;
     e = cudaDeviceSynchronize();
@@ -462,11 +637,39 @@ int avl_builder_create(const avl_grid_spec* spec, avl_builder** out) {
   return AVL_OK;
 }
 
+int avl_builder_create(const avl_grid_spec* spec, avl_builder** out) {
+  AVL_ARG(spec != nullptr && out != nullptr, "NULL argument");
+  *out = nullptr;
+  AVL_ARG(spec->gs >= 1 && spec->vh >= 1 && spec->dim >= 1 && spec->cs > 0.0, "invalid grid spec");
+  return builder_create_common(spec->gs, spec->gs, spec->vh, spec->cs, spec->dim, spec->capacity, 0, nullptr, out);
+}
+
+int avl_builder_create_global(const avl_global_grid_spec* spec, avl_builder** out) {
+  AVL_ARG(spec != nullptr && out != nullptr, "NULL argument");
+  *out = nullptr;
+  AVL_ARG(spec->n_row >= 1 && spec->n_col >= 1 && spec->n_height >= 1 && spec->dim >= 1 && spec->cs > 0.0,
+          "invalid grid spec");
+  return builder_create_common(spec->n_row, spec->n_col, spec->n_height, spec->cs, spec->dim, spec->capacity, 1,
+                               spec->pcd_min, out);
+}
+
+int avl_builder_set_slab(avl_builder* b, int32_t row_lo, int32_t row_hi) {
+  AVL_ARG(b != nullptr, "builder is NULL");
+  AVL_ARG(row_lo >= 0 && row_lo <= row_hi && row_hi <= b->n0, "slab outside the grid");
+  if (b->frame_seq != 0) {
+    set_error("avl_builder_set_slab must be called before the first frame");
+    return AVL_ERR_STATE;
+  }
+  b->slab_lo = row_lo;
+  b->slab_hi = row_hi;
+  return AVL_OK;
+}
+
 int avl_builder_destroy(avl_builder* b) {
   if (!b) return AVL_OK;
   cudaFree(b->first_key); cudaFree(b->occupied_ids); cudaFree(b->num); cudaFree(b->den); cudaFree(b->rgb_acc);
   cudaFree(b->grid_pos); cudaFree(b->counters); cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix);
-  cudaFree(b->s_alpha); cudaFree(b->block_cnt); cudaFree(b->d_depth); cudaFree(b->d_feat); cudaFree(b->d_feat_t);
+  cudaFree(b->s_alpha); cudaFree(b->s_wrap); cudaFree(b->block_cnt); cudaFree(b->d_depth); cudaFree(b->d_feat); cudaFree(b->d_feat_t);
   cudaFree(b->d_rgb); cudaFree(b->d_sidx);
   delete b;
   return AVL_OK;
@@ -482,8 +685,9 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   const int32_t n_samples = f->sample_idx ? f->n_samples : static_cast<int32_t>(npix);
   AVL_ARG(n_samples >= 0 && n_samples <= npix, "n_samples out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int d = b->spec.dim;
+  const int d = b->dim;
   const size_t fpix = static_cast<size_t>(f->fh) * f->fw;
+  const size_t depth_bytes = static_cast<size_t>(npix) * ((flags & AVL_DEPTH_U16_MM) ? sizeof(uint16_t) : sizeof(float));
   int rc;
 
   // ---- inputs on the device
@@ -494,7 +698,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   if (!(flags & AVL_ON_DEVICE)) {
     if ((rc = grow(&b->d_depth, &b->depth_elems, static_cast<size_t>(npix)))) return rc;
     if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
-    AVL_CUDA(cudaMemcpyAsync(b->d_depth, f->depth, npix * sizeof(float), cudaMemcpyHostToDevice, s));
+    AVL_CUDA(cudaMemcpyAsync(b->d_depth, f->depth, depth_bytes, cudaMemcpyHostToDevice, s));
     AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * sizeof(float), cudaMemcpyHostToDevice, s));
     depth = b->d_depth;
     feat = b->d_feat;
@@ -524,39 +728,40 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
 
   // ---- scratch
   if (b->scratch_samples < n_samples) {
-    cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->block_cnt);
+    cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
+    cudaFree(b->block_cnt);
+    b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
     b->scratch_samples = 0;
     const size_t n = static_cast<size_t>(n_samples);
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_cell), n * sizeof(int32_t)));
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_fpix), n * sizeof(int32_t)));
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_rgbpix), n * sizeof(int32_t)));
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_alpha), n * sizeof(float)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_wrap), n));
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->block_cnt), ((n + kScanBlock - 1) / kScanBlock) * sizeof(uint32_t)));
     b->scratch_samples = n_samples;
   }
   if ((rc = ensure_capacity(b, n_samples, s))) return rc;
 
   FrameGeom g;
-  memcpy(g.kinv, f->kinv, sizeof(g.kinv));
-  memcpy(g.k, f->k, sizeof(g.k));
-  memcpy(g.kfeat, f->kfeat, sizeof(g.kfeat));
-  memcpy(g.tf, f->tf, sizeof(g.tf));
-  g.min_depth = f->min_depth;
-  g.max_depth = f->max_depth;
-  g.cs = b->spec.cs;
-  g.half_gs = b->spec.gs / 2.0;
-  g.h = f->h; g.w = f->w; g.fh = f->fh; g.fw = f->fw; g.gs = b->spec.gs; g.vh = b->spec.vh;
+  fill_geom(&g, f, flags);
+  g.cs = b->cs;
+  g.half_gs = b->n0 / 2.0;
+  memcpy(g.origin, b->origin, sizeof(g.origin));
+  g.n0 = b->n0; g.n1 = b->n1; g.n2 = b->n2;
+  g.mode = b->mode;
+  g.slab_lo = b->slab_lo; g.slab_hi = b->slab_hi;
   g.has_rgb = rgb != nullptr;
 
   const int nblocks = (n_samples + kScanBlock - 1) / kScanBlock;
   const int geom_blocks = std::min((n_samples + 255) / 256, b->num_sms * 8);
   geom_kernel<<<geom_blocks, 256, 0, s>>>(g, depth, sidx, n_samples, b->frame_seq, b->first_key, b->s_cell,
-                                          b->s_fpix, b->s_alpha, b->s_rgbpix);
+                                          b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap, b->counters + 2);
   winner_count_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
                                                      b->block_cnt, b->counters + 1);
   winner_scan_kernel<<<1, kScanBlock, 0, s>>>(b->block_cnt, nblocks, b->counters);
   assign_ids_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key, b->block_cnt,
-                                                   b->spec.gs, b->spec.vh, b->capacity, b->occupied_ids,
+                                                   b->n0, b->n1, b->n2, b->s_wrap, b->capacity, b->occupied_ids,
                                                    b->grid_pos);
   const int scatter_blocks = std::min((n_samples + 7) / 8, b->num_sms * 8);
   scatter_kernel<<<scatter_blocks, 256, 0, s>>>(feat, d, rgb, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix,
@@ -579,6 +784,7 @@ static int read_counter(avl_builder* b, int which, int64_t* n, void* stream) {
 }
 int avl_builder_num_voxels(avl_builder* b, int64_t* n, void* stream) { return read_counter(b, 0, n, stream); }
 int avl_builder_num_accepted(avl_builder* b, int64_t* n, void* stream) { return read_counter(b, 1, n, stream); }
+int avl_builder_num_rejected_oob(avl_builder* b, int64_t* n, void* stream) { return read_counter(b, 2, n, stream); }
 
 int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, float* weight, int32_t* occupied_ids,
                        uint8_t* grid_rgb, int flags, void* stream) {
@@ -587,7 +793,7 @@ int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, floa
   int64_t v = 0;
   int rc = read_counter(b, 0, &v, stream);
   if (rc) return rc;
-  const int d = b->spec.dim;
+  const int d = b->dim;
   const cudaMemcpyKind kind = (flags & AVL_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (grid_feat && v > 0) {
     float* dst = grid_feat;
@@ -626,11 +832,140 @@ int avl_builder_to_map(avl_builder* b, void* stream, avl_map** out) {
   int rc = read_counter(b, 0, &v, stream);
   if (rc) return rc;
   float* tmp = nullptr;
-  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), static_cast<size_t>(std::max<int64_t>(v, 1)) * b->spec.dim * sizeof(float)));
-  if (v > 0) export_feat_kernel<<<b->num_sms * 8, 256, 0, s>>>(b->num, b->den, v, b->spec.dim, tmp);
-  rc = avl_map_create(tmp, v, b->spec.dim, AVL_ON_DEVICE, stream, out);
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), static_cast<size_t>(std::max<int64_t>(v, 1)) * b->dim * sizeof(float)));
+  if (v > 0) export_feat_kernel<<<b->num_sms * 8, 256, 0, s>>>(b->num, b->den, v, b->dim, tmp);
+  rc = avl_map_create(tmp, v, b->dim, AVL_ON_DEVICE, stream, out);
   cudaFree(tmp);
   return rc;
+}
+
+int avl_builder_export_keys(avl_builder* b, uint64_t* keys, int flags, void* stream) {
+  AVL_ARG(b != nullptr && keys != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int64_t v = 0;
+  int rc = read_counter(b, 0, &v, stream);
+  if (rc) return rc;
+  if (v == 0) return AVL_OK;
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(keys);
+  if (!(flags & AVL_ON_DEVICE)) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&dst), static_cast<size_t>(v) * sizeof(unsigned long long)));
+  export_keys_kernel<<<b->num_sms * 8, 256, 0, s>>>(b->occupied_ids, b->first_key, b->cells, b->capacity, dst);
+  cudaError_t e = cudaGetLastError();
+  if (!(flags & AVL_ON_DEVICE)) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(keys, dst, static_cast<size_t>(v) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dst);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "export keys", __FILE__, __LINE__);
+  return AVL_OK;
+}
+
+int avl_rank_keys(const uint64_t* keys_all, const int64_t* offsets, int32_t n_shards, int32_t shard,
+                  int64_t* out_global_ids, int flags, void* stream) {
+  AVL_ARG(offsets != nullptr, "offsets is NULL");
+  AVL_ARG(n_shards >= 1 && n_shards <= kMaxShards && shard >= 0 && shard < n_shards, "invalid shard count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ShardOffsets so;
+  memset(&so, 0, sizeof(so));
+  for (int i = 0; i <= n_shards; ++i) {
+    so.off[i] = offsets[i];
+    AVL_ARG(i == 0 ? offsets[0] == 0 : offsets[i] >= offsets[i - 1], "offsets must start at 0 and ascend");
+  }
+  const int64_t total = so.off[n_shards], n_own = so.off[shard + 1] - so.off[shard];
+  if (n_own == 0) return AVL_OK;
+  AVL_ARG(keys_all != nullptr && out_global_ids != nullptr, "NULL argument");
+  const unsigned long long* k = reinterpret_cast<const unsigned long long*>(keys_all);
+  int64_t* o = out_global_ids;
+  unsigned long long* dk = nullptr;
+  int64_t* dout = nullptr;
+  if (!(flags & AVL_ON_DEVICE)) {
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&dk), static_cast<size_t>(total) * sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dout), static_cast<size_t>(n_own) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dk, keys_all, static_cast<size_t>(total) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { cudaFree(dk); cudaFree(dout); return cuda_fail(e, "rank keys staging", __FILE__, __LINE__); }
+    k = dk;
+    o = dout;
+  }
+  const int blocks = static_cast<int>(std::min<int64_t>((n_own + 255) / 256, 148 * 8));
+  rank_keys_kernel<<<blocks, 256, 0, s>>>(k, so, n_shards, shard, o);
+  cudaError_t e = cudaGetLastError();
+  if (!(flags & AVL_ON_DEVICE)) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_global_ids, dout, static_cast<size_t>(n_own) * sizeof(int64_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dk);
+    cudaFree(dout);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "rank keys", __FILE__, __LINE__);
+  return AVL_OK;
+}
+
+int avl_bounds_create(avl_bounds** out) {
+  AVL_ARG(out != nullptr, "NULL argument");
+  *out = nullptr;
+  int dev = 0;
+  AVL_CUDA(cudaGetDevice(&dev));
+  avl_bounds* b = new avl_bounds();
+  cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const double init[7] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0};
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->acc), sizeof(init));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&b->partial), static_cast<size_t>(b->num_sms) * 8 * 7 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(b->acc, init, sizeof(init), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    avl_bounds_destroy(b);
+    return cuda_fail(e, "bounds state", __FILE__, __LINE__);
+  }
+  *out = b;
+  return AVL_OK;
+}
+
+int avl_bounds_destroy(avl_bounds* b) {
+  if (!b) return AVL_OK;
+  cudaFree(b->acc); cudaFree(b->partial); cudaFree(b->d_depth); cudaFree(b->d_sidx);
+  delete b;
+  return AVL_OK;
+}
+
+int avl_bounds_add_frame(avl_bounds* b, const avl_frame* f, int flags, void* stream) {
+  AVL_ARG(b != nullptr && f != nullptr && f->depth != nullptr, "NULL argument");
+  AVL_ARG(f->h >= 1 && f->w >= 1, "invalid frame shape");
+  const int64_t npix = static_cast<int64_t>(f->h) * f->w;
+  AVL_ARG(npix < (int64_t(1) << 31), "frame too large");
+  const int32_t n_samples = f->sample_idx ? f->n_samples : static_cast<int32_t>(npix);
+  AVL_ARG(n_samples >= 0 && n_samples <= npix, "n_samples out of range");
+  if (n_samples == 0) return AVL_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float* depth = f->depth;
+  const int32_t* sidx = f->sample_idx;
+  int rc;
+  if (!(flags & AVL_ON_DEVICE)) {
+    const size_t depth_bytes = static_cast<size_t>(npix) * ((flags & AVL_DEPTH_U16_MM) ? sizeof(uint16_t) : sizeof(float));
+    if ((rc = grow(&b->d_depth, &b->depth_elems, static_cast<size_t>(npix)))) return rc;
+    AVL_CUDA(cudaMemcpyAsync(b->d_depth, f->depth, depth_bytes, cudaMemcpyHostToDevice, s));
+    depth = b->d_depth;
+    if (f->sample_idx) {
+      if ((rc = grow(&b->d_sidx, &b->sidx_elems, static_cast<size_t>(n_samples)))) return rc;
+      AVL_CUDA(cudaMemcpyAsync(b->d_sidx, f->sample_idx, static_cast<size_t>(n_samples) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      sidx = b->d_sidx;
+    }
+  }
+  FrameGeom g;
+  fill_geom(&g, f, flags);
+  const int blocks = std::min((n_samples + 255) / 256, b->num_sms * 8);
+  bounds_kernel<<<blocks, 256, 0, s>>>(g, depth, sidx, n_samples, b->partial);
+  bounds_merge_kernel<<<1, 32, 0, s>>>(b->partial, blocks, b->acc);
+  AVL_CUDA(cudaGetLastError());
+  if (!(flags & AVL_ON_DEVICE)) AVL_CUDA(cudaStreamSynchronize(s));
+  return AVL_OK;
+}
+
+int avl_bounds_get(avl_bounds* b, double pcd_min[3], double pcd_max[3], int64_t* n_points, void* stream) {
+  AVL_ARG(b != nullptr && pcd_min != nullptr && pcd_max != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double acc[7];
+  AVL_CUDA(cudaMemcpyAsync(acc, b->acc, sizeof(acc), cudaMemcpyDeviceToHost, s));
+  AVL_CUDA(cudaStreamSynchronize(s));
+  for (int c = 0; c < 3; ++c) { pcd_min[c] = acc[c]; pcd_max[c] = acc[3 + c]; }
+  if (n_points) *n_points = static_cast<int64_t>(acc[6]);
+  return AVL_OK;
 }
 
 }  // extern "C"

@@ -44,7 +44,8 @@ class _Arg:
         if _is_torch(x):
             import torch
 
-            want = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8}[dtype]
+            want = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8,
+                    np.uint16: torch.uint16, np.uint64: torch.uint64}[dtype]
             if x.dtype != want or not x.is_contiguous():
                 x = x.to(want).contiguous()
             if not x.is_cuda:
@@ -293,6 +294,88 @@ def heat2d_sources(shape, cells_per_group, conf, decay_rate: float, mode: str):
     return out
 
 
+def _is_u16(x) -> bool:
+    """uint16 depth = millimetres (the multi-floor builder's PNG depth, vlmap_builder_multi_floor.py:103)."""
+    if _is_torch(x):
+        import torch
+
+        return x.dtype == torch.uint16
+    return np.asarray(x).dtype == np.uint16
+
+
+def _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, min_depth, max_depth, dim=None):
+    """Build the avl_frame struct; returns (frame, flags, keep-alive args)."""
+    u16 = _is_u16(depth)
+    d_ = _Arg(depth, np.uint16 if u16 else np.float32, "depth")
+    f_ = _Arg(feat, np.float32, "feat")
+    r_ = _Arg(rgb, np.uint8, "rgb")
+    s_ = _Arg(sample_idx, np.int32, "sample_idx")
+    if len(d_.shape) != 2:
+        raise ValueError("depth must be (H, W)")
+    fh = fw = 0
+    if f_.ptr is not None:
+        if feat_layout == L.FEAT_CHW:
+            if len(f_.shape) == 4 and f_.shape[0] == 1:
+                _, dd, fh, fw = f_.shape
+            elif len(f_.shape) == 3:
+                dd, fh, fw = f_.shape
+            else:
+                raise ValueError("CHW features must be (1, D, FH, FW)")
+        else:
+            if len(f_.shape) != 3:
+                raise ValueError("HWC features must be (FH, FW, D)")
+            fh, fw, dd = f_.shape
+        if dim is not None and dd != dim:
+            raise ValueError(f"feature dim {dd} != builder dim {dim}")
+    fr = L.Frame()
+    fr.depth, fr.h, fr.w = d_.ptr, d_.shape[0], d_.shape[1]
+    fr.feat, fr.fh, fr.fw, fr.feat_layout = f_.ptr, fh, fw, feat_layout
+    fr.rgb = r_.ptr
+    fr.sample_idx = s_.ptr
+    fr.n_samples = 0 if s_.ptr is None else int(np.prod(s_.shape))
+    for name, m, n in (("kinv", kinv, 9), ("k", k, 9), ("kfeat", kfeat, 9), ("tf", tf, 16)):
+        if m is None:
+            continue
+        arr = np.ascontiguousarray(m, np.float64).reshape(-1)
+        if arr.size != n:
+            raise ValueError(f"{name} must have {n} elements")
+        getattr(fr, name)[:] = arr.tolist()
+    fr.min_depth, fr.max_depth = float(min_depth), float(max_depth)
+    flags = _flags(d_, f_, r_, s_) | (L.AVL_DEPTH_U16_MM if u16 else 0)
+    return fr, flags, (d_, f_, r_, s_)
+
+
+class FrameBounds:
+    """Pass 1 of VLMapBuilderMultiFloor.create_global_map (vlmap_builder_multi_floor.py:97-118): running
+    min / max of the back-projected, transformed, sampled points -> pcd_min / pcd_max."""
+
+    def __init__(self):
+        self._lib = L.load()
+        L.require_device()
+        self._h = C.c_void_p()
+        L.check(self._lib.avl_bounds_create(C.byref(self._h)))
+
+    def add_frame(self, depth, kinv, tf, sample_idx=None, min_depth: float = 0.1, max_depth: float = 100.0, stream=None):
+        fr, flags, keep = _fill_frame(depth, None, kinv, None, None, tf, None, sample_idx, L.FEAT_CHW, min_depth, max_depth)
+        L.check(self._lib.avl_bounds_add_frame(self._h, C.byref(fr), flags, _stream_ptr(stream)))
+
+    def get(self) -> Tuple[np.ndarray, np.ndarray, int]:
+        mn, mx, n = (C.c_double * 3)(), (C.c_double * 3)(), C.c_int64()
+        L.check(self._lib.avl_bounds_get(self._h, mn, mx, C.byref(n), None))
+        return np.array(mn[:]), np.array(mx[:]), n.value
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.avl_bounds_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class DeviceBuilder:
     """Voxel map under construction in HBM (the arrays of VLMapBuilder._init_map, vlmap_builder.py:195-224)."""
 
@@ -300,10 +383,34 @@ class DeviceBuilder:
         self._lib = L.load()
         L.require_device()
         self.gs, self.vh, self.cs, self.dim = int(gs), int(vh), float(cs), int(dim)
+        self.grid_shape = (self.gs, self.gs, self.vh)
         spec = L.GridSpec(self.gs, self.vh, self.cs, self.dim, int(capacity or 0))
         self._h = C.c_void_p()
         L.check(self._lib.avl_builder_create(C.byref(spec), C.byref(self._h)))
         self.n_frames = 0
+
+    @classmethod
+    def global_grid(cls, n_row: int, n_col: int, n_height: int, cs: float, pcd_min, dim: int,
+                    capacity: Optional[int] = None) -> "DeviceBuilder":
+        """The global-frame grid of VLMapBuilderMultiFloor._init_map (vlmap_builder_multi_floor.py:217-241):
+        cells are np.round((p - pcd_min) / cs) as (row, height, col), occupied_ids is (n_row, n_col, n_height)."""
+        self = cls.__new__(cls)
+        self._lib = L.load()
+        L.require_device()
+        self.gs, self.vh, self.cs, self.dim = int(n_row), int(n_height), float(cs), int(dim)
+        self.grid_shape = (int(n_row), int(n_col), int(n_height))
+        spec = L.GlobalGridSpec()
+        spec.n_row, spec.n_col, spec.n_height, spec.cs, spec.dim = int(n_row), int(n_col), int(n_height), float(cs), int(dim)
+        spec.pcd_min[:] = [float(v) for v in np.asarray(pcd_min, np.float64).reshape(3)]
+        spec.capacity = int(capacity or 0)
+        self._h = C.c_void_p()
+        L.check(self._lib.avl_builder_create_global(C.byref(spec), C.byref(self._h)))
+        self.n_frames = 0
+        return self
+
+    def set_slab(self, row_lo: int, row_hi: int) -> None:
+        """Own only the grid rows [row_lo, row_hi) (slab-sharded build, one process per GPU)."""
+        L.check(self._lib.avl_builder_set_slab(self._h, int(row_lo), int(row_hi)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -318,53 +425,32 @@ class DeviceBuilder:
 
     def add_frame(self, depth, feat, kinv, k, kfeat, tf, rgb=None, sample_idx=None, feat_layout: int = L.FEAT_CHW,
                   min_depth: float = 0.1, max_depth: float = 6.0, stream=None):
-        """depth (H, W) f32; feat (1, D, FH, FW) [CHW] or (FH, FW, D) [HWC] f32; rgb (H, W, 3) u8 or None;
-        sample_idx int32 pixel ids in the reference's sample order or None for every pixel."""
-        d_ = _Arg(depth, np.float32, "depth")
-        f_ = _Arg(feat, np.float32, "feat")
-        r_ = _Arg(rgb, np.uint8, "rgb")
-        s_ = _Arg(sample_idx, np.int32, "sample_idx")
-        if len(d_.shape) != 2:
-            raise ValueError("depth must be (H, W)")
-        if feat_layout == L.FEAT_CHW:
-            if len(f_.shape) == 4 and f_.shape[0] == 1:
-                _, dd, fh, fw = f_.shape
-            elif len(f_.shape) == 3:
-                dd, fh, fw = f_.shape
-            else:
-                raise ValueError("CHW features must be (1, D, FH, FW)")
-        else:
-            if len(f_.shape) != 3:
-                raise ValueError("HWC features must be (FH, FW, D)")
-            fh, fw, dd = f_.shape
-        if dd != self.dim:
-            raise ValueError(f"feature dim {dd} != builder dim {self.dim}")
-        fr = L.Frame()
-        fr.depth, fr.h, fr.w = d_.ptr, d_.shape[0], d_.shape[1]
-        fr.feat, fr.fh, fr.fw, fr.feat_layout = f_.ptr, fh, fw, feat_layout
-        fr.rgb = r_.ptr
-        fr.sample_idx = s_.ptr
-        fr.n_samples = 0 if s_.ptr is None else int(np.prod(s_.shape))
-        for name, m, n in (("kinv", kinv, 9), ("k", k, 9), ("kfeat", kfeat, 9), ("tf", tf, 16)):
-            arr = np.ascontiguousarray(m, np.float64).reshape(-1)
-            if arr.size != n:
-                raise ValueError(f"{name} must have {n} elements")
-            getattr(fr, name)[:] = arr.tolist()
-        fr.min_depth, fr.max_depth = float(min_depth), float(max_depth)
-        L.check(self._lib.avl_builder_add_frame(self._h, C.byref(fr), _flags(d_, f_, r_, s_), _stream_ptr(stream)))
+        """depth (H, W) f32 metres (or uint16 millimetres); feat (1, D, FH, FW) [CHW] or (FH, FW, D) [HWC] f32;
+        rgb (H, W, 3) u8 or None; sample_idx int32 pixel ids in the reference's sample order or None for every pixel."""
+        if feat is None:
+            raise ValueError("feat is required")
+        fr, flags, keep = _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, min_depth, max_depth,
+                                      dim=self.dim)
+        L.check(self._lib.avl_builder_add_frame(self._h, C.byref(fr), flags, _stream_ptr(stream)))
         self.n_frames += 1
+
+    def _count(self, fn) -> int:
+        n = C.c_int64()
+        L.check(fn(self._h, C.byref(n), None))
+        return n.value
 
     @property
     def num_voxels(self) -> int:
-        n = C.c_int64()
-        L.check(self._lib.avl_builder_num_voxels(self._h, C.byref(n), None))
-        return n.value
+        return self._count(self._lib.avl_builder_num_voxels)
 
     @property
     def num_accepted(self) -> int:
-        n = C.c_int64()
-        L.check(self._lib.avl_builder_num_accepted(self._h, C.byref(n), None))
-        return n.value
+        return self._count(self._lib.avl_builder_num_accepted)
+
+    @property
+    def num_rejected_oob(self) -> int:
+        """global-frame grid: points on which the reference would raise IndexError (rejected here)."""
+        return self._count(self._lib.avl_builder_num_rejected_oob)
 
     def export(self, want_rgb: bool = True):
         """numpy arrays[:max_id] + occupied_ids, like _save_3d_map (vlmap_builder.py:313-327)."""
@@ -373,7 +459,7 @@ class DeviceBuilder:
             grid_feat=np.zeros((v, self.dim), np.float32),
             grid_pos=np.zeros((v, 3), np.int32),
             weight=np.zeros((v,), np.float32),
-            occupied_ids=np.empty((self.gs, self.gs, self.vh), np.int32),
+            occupied_ids=np.empty(self.grid_shape, np.int32),
             grid_rgb=np.zeros((v, 3), np.uint8),
         )
         L.check(self._lib.avl_builder_export(self._h, L.np_ptr(out["grid_feat"]), L.np_ptr(out["grid_pos"]),
@@ -381,7 +467,27 @@ class DeviceBuilder:
                                              L.np_ptr(out["grid_rgb"]) if want_rgb else None, 0, None))
         return out
 
+    def export_keys(self) -> np.ndarray:
+        """First-touch keys (frame_seq << 32 | sample position) of the voxels, ascending: uint64 (V,)."""
+        keys = np.zeros((self.num_voxels,), np.uint64)
+        if keys.size:
+            L.check(self._lib.avl_builder_export_keys(self._h, L.np_ptr(keys), 0, None))
+        return keys
+
     def to_map(self) -> DeviceMap:
         h = C.c_void_p()
         L.check(self._lib.avl_builder_to_map(self._h, None, C.byref(h)))
         return DeviceMap(None, _handle=h)
+
+
+def rank_keys(keys_per_shard: Sequence[np.ndarray], shard: int) -> np.ndarray:
+    """Global first-touch voxel ids of shard `shard`'s voxels: the rank of each of its keys among the keys of
+    all shards (each list ascending, keys unique).  int64 (V_shard,)."""
+    lib = L.load()
+    L.require_device()
+    keys_all = np.ascontiguousarray(np.concatenate([np.asarray(k, np.uint64) for k in keys_per_shard]))
+    offsets = np.zeros(len(keys_per_shard) + 1, np.int64)
+    offsets[1:] = np.cumsum([len(k) for k in keys_per_shard])
+    out = np.zeros(int(offsets[shard + 1] - offsets[shard]), np.int64)
+    L.check(lib.avl_rank_keys(L.np_ptr(keys_all), L.np_ptr(offsets), len(keys_per_shard), int(shard), L.np_ptr(out), 0, None))
+    return out

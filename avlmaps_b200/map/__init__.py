@@ -4,6 +4,8 @@ part of the accelerated path; their similarity call sites map to engine.DeviceMa
 from .map import Map
 from .vlmap import VLMap
 from .vlmap_builder import VLMapBuilder
+from .vlmap_builder_multi_floor import VLMapBuilderMultiFloor
+from .vlmap_multi_floor import VLMapMultiFloor
 from .avlmap import AVLMap
 
-__all__ = ["Map", "VLMap", "VLMapBuilder", "AVLMap"]
+__all__ = ["Map", "VLMap", "VLMapBuilder", "VLMapMultiFloor", "VLMapBuilderMultiFloor", "AVLMap"]

@@ -111,8 +111,10 @@ class Map:
     @staticmethod
     def create(map_config) -> "Map":
         """Reference map.py:121-129."""
-        from . import VLMap
+        from . import VLMap, VLMapMultiFloor
 
         if cfg_get(map_config, "map_type") == "vlmap":
             return VLMap(map_config)
-        raise NotImplementedError("only map_type 'vlmap' is accelerated so far")
+        if cfg_get(map_config, "map_type") == "vlmap_openmap":  # reference map.py:128-129
+            return VLMapMultiFloor(map_config)
+        raise NotImplementedError("map_type must be 'vlmap' or 'vlmap_openmap'")

@@ -55,11 +55,15 @@ class ShardedMap:
     """`local` is anything with .topk(queries, k, scale=, normalize_map=) and .argmax(...) over this
     rank's slab (an engine.DeviceMap in production); `row_offset` is the slab's first global row."""
 
-    def __init__(self, local, row_offset: int, group=None):
+    def __init__(self, local, row_offset: int = 0, group=None, global_ids=None):
+        """`global_ids` (int64, one per local row, ascending) replaces `row_offset` when the slab's rows are
+        not a contiguous id range -- the case of a slab-sharded BUILD, where global voxel ids are first-touch
+        order across all slabs (ShardedBuilder.finalize)."""
         import torch.distributed as dist
 
         self.local = local
         self.row_offset = int(row_offset)
+        self.global_ids = global_ids
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -78,7 +82,11 @@ class ShardedMap:
             ti = mine[:nb_i].view(torch.int64).view(nq, k)
             tv = mine[nb_i:].view(torch.float32).view(nq, k)
             self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv))
-            if self.row_offset:
+            if self.global_ids is not None:
+                gid = self.global_ids if torch.is_tensor(self.global_ids) else torch.from_numpy(np.asarray(self.global_ids))
+                self.global_ids = gid = gid.to(queries.device)
+                ti.copy_(torch.where(ti >= 0, gid[ti.clamp(min=0)], ti))
+            elif self.row_offset:
                 ti += (ti >= 0) * self.row_offset
             gathered = torch.empty((self.world, nb_i + nb_v), dtype=torch.uint8, device=queries.device)
             dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)   # the one collective
@@ -88,12 +96,17 @@ class ShardedMap:
 
             return merge_topk_device(gi, gv, k)
         idx, val = self.local.topk(queries, k, scale=scale, normalize_map=normalize_map)
-        if self.world == 1 and self.row_offset == 0:
+        if self.world == 1 and self.row_offset == 0 and self.global_ids is None:
             return idx, val  # one slab: already global ids in final order
         as_numpy = isinstance(idx, np.ndarray)
         ti = torch.from_numpy(idx) if as_numpy else idx
         tv = torch.from_numpy(val) if as_numpy else val
-        ti = torch.where(ti >= 0, ti + self.row_offset, ti)
+        if self.global_ids is not None:
+            gid = self.global_ids if torch.is_tensor(self.global_ids) else torch.from_numpy(np.asarray(self.global_ids))
+            gid = gid.to(ti.device)
+            ti = torch.where(ti >= 0, gid[ti.clamp(min=0)], ti)
+        else:
+            ti = torch.where(ti >= 0, ti + self.row_offset, ti)
         if self.world > 1:
             gi = torch.empty((self.world,) + tuple(ti.shape), dtype=ti.dtype, device=ti.device)
             gv = torch.empty((self.world,) + tuple(tv.shape), dtype=tv.dtype, device=tv.device)
@@ -107,3 +120,78 @@ class ShardedMap:
     def argmax(self, queries, scale=None, normalize_map: bool = False):
         """Per-voxel argmax of this rank's slab; rows are independent, nothing to exchange."""
         return self.local.argmax(queries, scale=scale, normalize_map=normalize_map)
+
+
+class ShardedBuilder:
+    """Slab-sharded map BUILD: one process per GPU, rank r owns the grid rows
+    `slab_bounds(n_rows, world, r)`.  Every rank is fed every frame (depth, pose and the sample list are
+    tiny; the features come from a replicated / sharded encoder) and runs the geometry for every sample, but
+    fuses only the points that fall into its own rows -- so the frame loop has NO collective and the
+    feature scatter, the dominant HBM traffic, divides by the number of GPUs.
+
+    Voxel ids of the reference are first-touch order over the whole map.  Within a slab the local ids are
+    already in that order; `finalize()` makes them global with ONE all-gather of the per-voxel first-touch
+    keys (8 bytes per voxel) and a rank-by-binary-search kernel (avl_rank_keys), then one all-reduce(MAX)
+    of the relabelled occupied_ids grid.  Results are identical to a single-GPU build.
+
+    `local` is an engine.DeviceBuilder (anything with set_slab / add_frame / export / export_keys /
+    grid_shape); `rank_fn(keys_per_shard, shard) -> int64 ids` defaults to engine.rank_keys."""
+
+    def __init__(self, local, group=None, rank_fn=None):
+        import torch.distributed as dist
+
+        self.local = local
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.row_lo, self.row_hi = slab_bounds(int(local.grid_shape[0]), self.world, self.rank)
+        local.set_slab(self.row_lo, self.row_hi)
+        self._rank_fn = rank_fn
+
+    def add_frame(self, *args, **kwargs):
+        return self.local.add_frame(*args, **kwargs)
+
+    def _device(self):
+        import torch
+        import torch.distributed as dist
+
+        if dist.is_initialized() and dist.get_backend(self.group) == "nccl":
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
+
+    def finalize(self):
+        """-> dict(global_ids (V_local,) int64, n_voxels_total, occupied_ids (global ids, full grid),
+        grid_feat / grid_pos / weight / grid_rgb of THIS slab's voxels, rows in local (= ascending global) order)."""
+        import torch
+        import torch.distributed as dist
+
+        out = self.local.export()
+        keys = np.ascontiguousarray(self.local.export_keys(), np.uint64)
+        if self.world > 1:
+            dev = self._device()
+            counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+            mine = torch.tensor([keys.size], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts, mine, group=self.group)
+            counts = counts.cpu().numpy()
+            vmax = int(counts.max())
+            pad = torch.zeros(max(vmax, 1), dtype=torch.int64, device=dev)
+            pad[:keys.size] = torch.from_numpy(keys.view(np.int64)).to(dev)
+            gathered = torch.empty((self.world, max(vmax, 1)), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered.view(-1), pad, group=self.group)  # the one exchange of the build
+            g = gathered.cpu().numpy().view(np.uint64)
+            keys_per_shard = [g[r, :int(counts[r])] for r in range(self.world)]
+        else:
+            keys_per_shard = [keys]
+        rank_fn = self._rank_fn
+        if rank_fn is None:
+            from .engine import rank_keys as rank_fn
+        gids = np.asarray(rank_fn(keys_per_shard, self.rank), np.int64)
+        total = int(sum(len(k) for k in keys_per_shard))
+        occ = out["occupied_ids"]
+        occ_g = np.where(occ >= 0, gids[np.clip(occ, 0, max(gids.size - 1, 0))] if gids.size else -1, -1).astype(np.int32)
+        if self.world > 1:
+            t = torch.from_numpy(occ_g).to(self._device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)  # other slabs hold -1 in this rank's rows
+            occ_g = t.cpu().numpy()
+        out.update(global_ids=gids, n_voxels_total=total, occupied_ids=occ_g)
+        return out

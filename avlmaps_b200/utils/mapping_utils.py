@@ -26,6 +26,13 @@ def load_depth_npy(depth_filepath) -> np.ndarray:
         return np.load(f)
 
 
+def load_depth_img(depth_filepath):
+    """Reference mapping_utils.py:93-94 (16-bit PNG, millimetres)."""
+    import cv2
+
+    return cv2.imread(depth_filepath, cv2.IMREAD_UNCHANGED)
+
+
 def get_sim_cam_mat(h: int, w: int) -> np.ndarray:
     """Reference mapping_utils.py:591-596."""
     cam_mat = np.eye(3)
@@ -111,3 +118,39 @@ def load_3d_map(map_path) -> Tuple:
     if "init_height_id" in d:
         return out + (d["init_height_id"],)
     return out
+
+
+_FIELDS_MF = ("mapped_iter_list", "grid_feat", "grid_pos", "weight", "occupied_ids", "grid_rgb", "pcd_min", "pcd_max", "cs")
+
+
+def save_3d_map_multi_floor(save_path, grid_feat, grid_pos, weight, grid_rgb, occupied_ids, mapped_iter_set, pcd_min,
+                            pcd_max, cs) -> None:
+    """VLMapBuilderMultiFloor.save_3d_map (reference vlmap_builder_multi_floor.py:370-393): same dataset names."""
+    data = {
+        "mapped_iter_list": np.array(list(mapped_iter_set), dtype=np.int32),
+        "grid_feat": grid_feat, "grid_pos": grid_pos, "weight": weight, "occupied_ids": occupied_ids,
+        "grid_rgb": grid_rgb, "pcd_min": np.asarray(pcd_min), "pcd_max": np.asarray(pcd_max), "cs": np.asarray(cs),
+    }
+    if _have_h5py():
+        import h5py
+
+        with h5py.File(save_path, "w") as f:
+            for k, v in data.items():
+                f.create_dataset(k, data=v)
+    else:
+        with open(_npz_twin(save_path), "wb") as f:
+            np.savez(f, **data)
+
+
+def load_3d_map_multi_floor(map_path) -> Tuple:
+    """VLMapBuilderMultiFloor.load_3d_map (reference vlmap_builder_multi_floor.py:243-255): the 9-tuple."""
+    if Path(map_path).exists() and _have_h5py():
+        import h5py
+
+        with h5py.File(map_path, "r") as f:
+            d = {k: f[k][()] for k in _FIELDS_MF}
+    else:
+        with np.load(_npz_twin(map_path)) as z:
+            d = {k: z[k] for k in _FIELDS_MF}
+    return (d["mapped_iter_list"].tolist(), d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], d["grid_rgb"],
+            d["pcd_min"], d["pcd_max"], d["cs"][()])

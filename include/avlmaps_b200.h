@@ -38,6 +38,9 @@ extern "C" {
 #define AVL_ERR_STATE 4       /* call order violated (e.g. export before finalize) */
 
 #define AVL_ON_DEVICE 1 /* data pointers of this call are device pointers */
+#define AVL_DEPTH_U16_MM 2 /* avl_frame.depth points at (h, w) uint16 millimetres; the kernel evaluates
+                              float64(d) / 1000.0 like `load_depth_img(...) / 1000.0`
+                              (vlmap_builder_multi_floor.py:103,128) */
 
 #define AVL_MAX_QUERIES 256 /* per call; larger batches are chunked by the host layer */
 #define AVL_MAX_TOPK 128
@@ -53,6 +56,7 @@ extern "C" {
 
 typedef struct avl_map avl_map;         /* device-resident voxel feature map (grid_feat) */
 typedef struct avl_builder avl_builder; /* device-resident map under construction */
+typedef struct avl_bounds avl_bounds;   /* running min / max of back-projected points (multi-floor pass 1) */
 
 /* Filled by the index calls when a non-NULL pointer is passed. */
 typedef struct avl_index_stats {
@@ -166,7 +170,7 @@ typedef struct avl_grid_spec {
 } avl_grid_spec;
 
 typedef struct avl_frame {
-  const float* depth; /* (h, w) fp32 metres (mapping_utils.py:231)                              */
+  const float* depth; /* (h, w) fp32 metres (mapping_utils.py:231); uint16 mm with AVL_DEPTH_U16_MM */
   int32_t h, w;
   const float* feat; /* per-pixel features, layout below (vlmap_builder.py:123-126)             */
   int32_t fh, fw;
@@ -204,6 +208,52 @@ int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, floa
 
 /* Hand the finished map to the index path without leaving HBM. */
 int avl_builder_to_map(avl_builder* b, void* stream, avl_map** out);
+
+/* ---- multi-floor (global-frame) build: VLMapBuilderMultiFloor.create_global_map ---------
+ * (avlmaps/map/vlmap_builder_multi_floor.py:60-199).  Same fusion rule and first-touch ids as
+ * the mobile-base build; what differs is the cell function
+ *     row, height, col = np.round((p_global - pcd_min) / cs).astype(int)           (:146)
+ * (round-half-even, x -> row, y -> height, z -> col), the acceptance test (only `row >= n_row or
+ * col >= n_col` is rejected, :151-153; NEGATIVE indices wrap like numpy's, and grid_pos keeps the
+ * unwrapped values, :176), and the depth source (uint16 mm PNG / 1000.0, max_depth 100).  Where the
+ * reference would die with an IndexError (height >= n_height, any index < -size) the point is
+ * rejected and counted (avl_builder_num_rejected_oob). */
+typedef struct avl_global_grid_spec {
+  int32_t n_row, n_col, n_height; /* grid_size[[0, 2, 1]], grid_size = ceil((pcd_max - pcd_min) / cs + 1) (:222-224) */
+  double cs;
+  double pcd_min[3];              /* (x, y, z) minimum of the pass-1 cloud (:117)                   */
+  int32_t dim;
+  int64_t capacity;               /* initial voxel rows; 0 = n_row * n_col (:225)                   */
+} avl_global_grid_spec;
+
+int avl_builder_create_global(const avl_global_grid_spec* spec, avl_builder** out);
+int avl_builder_num_rejected_oob(avl_builder* b, int64_t* n, void* stream);
+
+/* Pass 1 of create_global_map (:97-118): running component-wise min / max of
+ * transform_pc(depth2pc(depth)[:, sample_idx][:, mask], tf) over the frames added.  Only depth, h, w,
+ * sample_idx, n_samples, kinv, tf, min_depth, max_depth of the frame are read.  min / max are exact
+ * (order-free), so pcd_min / pcd_max equal the reference's bit for bit.
+ * avl_bounds_get synchronises; n_points == 0 leaves +inf / -inf (the reference's np.min raises). */
+int avl_bounds_create(avl_bounds** out);
+int avl_bounds_destroy(avl_bounds* b);
+int avl_bounds_add_frame(avl_bounds* b, const avl_frame* frame, int flags, void* stream);
+int avl_bounds_get(avl_bounds* b, double pcd_min[3], double pcd_max[3], int64_t* n_points, void* stream);
+
+/* ---- slab-sharded build (one process per GPU) ----------------------
+ * A builder restricted to the grid rows [row_lo, row_hi): every rank sees every frame, runs the
+ * (cheap) geometry for every sample and keeps the points of its own slab; there is no collective in
+ * the frame loop.  Local voxel ids are first-touch order WITHIN the slab; the global first-touch id
+ * of a voxel is the rank of its first-touch key (frame_seq << 32 | sample position) among the keys
+ * of all slabs: gather avl_builder_export_keys of every rank (one all-gather at finalize) and call
+ * avl_rank_keys.  Must be set before the first frame. */
+int avl_builder_set_slab(avl_builder* b, int32_t row_lo, int32_t row_hi);
+/* keys (V,) uint64 of the builder's voxels, ascending (voxel ids are assigned in key order). */
+int avl_builder_export_keys(avl_builder* b, uint64_t* keys, int flags, void* stream);
+/* keys_all: concatenation of n_shards ascending key lists, shard s at [offsets[s], offsets[s+1]).
+ * out_global_ids[j] (offsets[shard+1]-offsets[shard] entries, int64) = number of keys of ALL shards
+ * smaller than the j-th key of `shard` = its voxel id in a single-GPU build.  offsets: host pointer. */
+int avl_rank_keys(const uint64_t* keys_all, const int64_t* offsets, int32_t n_shards, int32_t shard,
+                  int64_t* out_global_ids, int flags, void* stream);
 
 #ifdef __cplusplus
 }

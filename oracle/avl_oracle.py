@@ -54,6 +54,14 @@ def lib() -> C.CDLL:
             f.argtypes = [vp]
         L.oracle_builder_add_frame.restype = C.c_int
         L.oracle_builder_add_frame.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, dbl, dbl]
+        L.oracle_builder_add_frame_u16.restype = C.c_int
+        L.oracle_builder_add_frame_u16.argtypes = L.oracle_builder_add_frame.argtypes
+        L.oracle_builder_create_global.restype = vp
+        L.oracle_builder_create_global.argtypes = [i32, i32, i32, dbl, vp, i32, i64]
+        L.oracle_builder_num_oob.restype = i64
+        L.oracle_builder_num_oob.argtypes = [vp]
+        L.oracle_frame_bounds.restype = i64
+        L.oracle_frame_bounds.argtypes = [vp, C.c_int, i32, i32, vp, i32, vp, vp, dbl, dbl, vp]
         L.oracle_scores.argtypes = [vp, i64, i32, vp, i32, vp, C.c_int, vp]
         L.oracle_argmax.argtypes = [vp, i64, i32, vp]
         _lib = L
@@ -221,22 +229,41 @@ class BuildOracle:
 
     def __init__(self, gs: int, vh: int, cs: float, dim: int, capacity: int | None = None):
         self.gs, self.vh, self.cs, self.dim = gs, vh, cs, dim
+        self.shape = (gs, gs, vh)
         self.capacity = int(capacity if capacity is not None else gs * gs)  # vlmap_builder.py:202
         self._h = lib().oracle_builder_create(gs, vh, cs, dim, self.capacity)
         self._keep = []
 
+    @classmethod
+    def global_grid(cls, n_row: int, n_col: int, n_height: int, cs: float, pcd_min, dim: int,
+                    capacity: int | None = None):
+        """Grid of VLMapBuilderMultiFloor._init_map (vlmap_builder_multi_floor.py:217-241)."""
+        self = cls.__new__(cls)
+        self.gs, self.vh, self.cs, self.dim = n_row, n_height, cs, dim
+        self.shape = (n_row, n_col, n_height)
+        self.capacity = int(capacity if capacity is not None else n_row * n_col)  # :225
+        pm = np.ascontiguousarray(pcd_min, np.float64)
+        self._h = lib().oracle_builder_create_global(n_row, n_col, n_height, cs, _p(pm), dim, self.capacity)
+        self._keep = []
+        return self
+
+    @property
+    def num_oob(self) -> int:
+        return int(lib().oracle_builder_num_oob(self._h))
+
     def add_frame(self, depth, feat_chw, rgb, sample_idx, kinv, k, kfeat, tf, min_depth=0.1, max_depth=6.0):
-        depth = np.ascontiguousarray(depth, np.float32)
+        u16 = np.asarray(depth).dtype == np.uint16  # multi-floor: millimetres, / 1000.0 inside
+        depth = np.ascontiguousarray(depth, np.uint16 if u16 else np.float32)
         feat_chw = np.ascontiguousarray(feat_chw, np.float32)
         assert feat_chw.ndim == 4 and feat_chw.shape[0] == 1 and feat_chw.shape[1] == self.dim
         rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
         sidx = None if sample_idx is None else np.ascontiguousarray(sample_idx, np.int32)
         n = depth.size if sidx is None else sidx.size
         mats = [np.ascontiguousarray(m, np.float64) for m in (kinv, k, kfeat, tf)]
-        rc = lib().oracle_builder_add_frame(self._h, _p(depth), depth.shape[0], depth.shape[1], _p(feat_chw),
-                                            feat_chw.shape[2], feat_chw.shape[3], _p(rgb), _p(sidx), n,
-                                            _p(mats[0]), _p(mats[1]), _p(mats[2]), _p(mats[3]),
-                                            float(min_depth), float(max_depth))
+        fn = lib().oracle_builder_add_frame_u16 if u16 else lib().oracle_builder_add_frame
+        rc = fn(self._h, _p(depth), depth.shape[0], depth.shape[1], _p(feat_chw),
+                feat_chw.shape[2], feat_chw.shape[3], _p(rgb), _p(sidx), n,
+                _p(mats[0]), _p(mats[1]), _p(mats[2]), _p(mats[3]), float(min_depth), float(max_depth))
         if rc != 0:
             raise RuntimeError("oracle capacity exceeded (_reserve_map_space is not restated)")
 
@@ -262,7 +289,7 @@ class BuildOracle:
             grid_feat=view(L.oracle_builder_grid_feat(self._h), C.c_float, (v, self.dim)),
             grid_pos=view(L.oracle_builder_grid_pos(self._h), C.c_int32, (v, 3)),
             weight=view(L.oracle_builder_weight(self._h), C.c_float, (v,)),
-            occupied_ids=view(L.oracle_builder_occupied_ids(self._h), C.c_int32, (self.gs, self.gs, self.vh)),
+            occupied_ids=view(L.oracle_builder_occupied_ids(self._h), C.c_int32, self.shape),
             grid_rgb=view(L.oracle_builder_grid_rgb(self._h), C.c_uint8, (v, 3)),
         )
 
@@ -293,6 +320,57 @@ def build_map(map_config: dict, poses: np.ndarray, depths, rgbs, feats, sample_i
         b.add_frame(depths[i], feats[i], None if rgbs is None else rgbs[i], sample_idx[i], kinv, calib, kfeat, tf)
     out = b.export()
     out["num_accepted"] = b.num_accepted
+    b.close()
+    return out
+
+
+# =============================================================================== multi-floor build
+HABITAT2CAM_ROT_TF = np.diag([1.0, -1.0, -1.0, 1.0])  # vlmap_builder_multi_floor.py:77-79
+
+
+def frame_bounds(depth, sample_idx, kinv, tf, minmax=None, min_depth=0.1, max_depth=100.0):
+    """One frame of the first pass of create_global_map (vlmap_builder_multi_floor.py:97-118): merges the
+    min / max of the transformed valid sampled points into `minmax` (6 float64: min xyz, max xyz)."""
+    u16 = np.asarray(depth).dtype == np.uint16
+    depth = np.ascontiguousarray(depth, np.uint16 if u16 else np.float32)
+    if minmax is None:
+        minmax = np.array([np.inf] * 3 + [-np.inf] * 3)
+    sidx = None if sample_idx is None else np.ascontiguousarray(sample_idx, np.int32)
+    n = depth.size if sidx is None else sidx.size
+    kinv, tf = np.ascontiguousarray(kinv, np.float64), np.ascontiguousarray(tf, np.float64)
+    cnt = lib().oracle_frame_bounds(_p(depth), int(u16), depth.shape[0], depth.shape[1], _p(sidx), n, _p(kinv), _p(tf),
+                                    float(min_depth), float(max_depth), _p(minmax))
+    return minmax, int(cnt)
+
+
+def global_grid_size(pcd_min, pcd_max, cs):
+    """grid_size = ceil((pcd_max - pcd_min) / cs + 1) as (x, y, z) (vlmap_builder_multi_floor.py:222);
+    occupied_ids is grid_size[[0, 2, 1]] = (n_row, n_col, n_height) (:224)."""
+    gsz = np.ceil((np.asarray(pcd_max) - np.asarray(pcd_min)) / cs + 1).astype(int)
+    return int(gsz[0]), int(gsz[2]), int(gsz[1])
+
+
+def build_map_multi_floor(map_config: dict, cam_poses, depths_mm, rgbs, feats, sample_idx_pass1, sample_idx_pass2):
+    """Whole create_global_map (vlmap_builder_multi_floor.py:60-199) from the inputs
+    ref_shim.ref_build_multi_floor takes; sample lists are those of the frames with frame_i % skip_frame == 0."""
+    cs, skip = map_config["cell_size"], map_config["skip_frame"]
+    calib = np.array(map_config["cam_calib_mat"], dtype=np.float64).reshape((3, 3))
+    kinv = np.linalg.inv(calib)
+    used = [i for i in range(len(depths_mm)) if i % skip == 0]
+    tfs = {i: np.asarray(cam_poses[i], np.float64).reshape(4, 4) @ HABITAT2CAM_ROT_TF for i in used}  # :105,141
+    mm = None
+    for j, i in enumerate(used):
+        mm, _ = frame_bounds(depths_mm[i], sample_idx_pass1[j], kinv, tfs[i], mm)
+    pcd_min, pcd_max = mm[:3].copy(), mm[3:].copy()
+    n_row, n_col, n_height = global_grid_size(pcd_min, pcd_max, cs)
+    D = feats[0].shape[1]
+    b = BuildOracle.global_grid(n_row, n_col, n_height, cs, pcd_min, D)
+    for j, i in enumerate(used):
+        kfeat = get_sim_cam_mat(feats[i].shape[2], feats[i].shape[3])  # :135
+        b.add_frame(depths_mm[i], feats[i], None if rgbs is None else rgbs[i], sample_idx_pass2[j], kinv, calib, kfeat,
+                    tfs[i], min_depth=0.1, max_depth=100)  # :138
+    out = b.export()
+    out.update(num_accepted=b.num_accepted, num_oob=b.num_oob, pcd_min=pcd_min, pcd_max=pcd_max)
     b.close()
     return out
 

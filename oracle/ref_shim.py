@@ -175,3 +175,102 @@ def ref_build(map_config: dict, poses: np.ndarray, depths, rgbs, feats, seed: in
     rate = map_config["depth_sample_rate"]
     captured["sample_idx"] = [s[::rate].astype(np.int32) for s in sample_orders]
     return captured
+
+
+# ------------------------------------------------------------------------------------------ multi-floor build
+class _FakePointCloud:
+    """Stand-in for open3d.geometry.PointCloud: the reference only accumulates points and reads them
+    back for np.min / np.max (vlmap_builder_multi_floor.py:104-118)."""
+
+    def __init__(self):
+        self.points = np.zeros((0, 3))
+
+    def __iadd__(self, other):
+        self.points = np.concatenate([np.asarray(self.points), np.asarray(other.points)], axis=0)
+        return self
+
+
+def _install_open3d_stub():
+    _install_stubs()
+    o3d = sys.modules["open3d"]
+    geometry = types.ModuleType("open3d.geometry")
+    geometry.PointCloud = _FakePointCloud
+    utility = types.ModuleType("open3d.utility")
+    utility.Vector3dVector = lambda a: np.asarray(a)
+    o3d.geometry, o3d.utility = geometry, utility
+
+
+def ref_build_multi_floor(map_config: dict, cam_poses, depths_mm, rgbs, feats, seed: int):
+    """Run the reference's VLMapBuilderMultiFloor.create_global_map (vlmap_builder_multi_floor.py:60-199).
+    cam_poses[i] (4,4) camera pose in the global frame, depths_mm[i] (H,W) uint16 millimetres (written as
+    16-bit PNG, the reference reads them with cv2.IMREAD_UNCHANGED and divides by 1000.0), rgbs / feats as
+    ref_build.  Patched: _init_lseg, get_lseg_feat, the save_3d_map method (h5py), open3d's PointCloud.
+    Returns the saved arrays + pcd_min / pcd_max + the sample orders of both passes."""
+    import cv2
+
+    _install_open3d_stub()
+    vb = load("ref_vlmap_builder_multi_floor", "avlmaps/map/vlmap_builder_multi_floor.py")
+    cfg = AttrDict(map_config)
+    base2cam_tf, base_transform = ref_transforms(map_config)
+    D = feats[0].shape[1]
+    skip = map_config["skip_frame"]
+    used = [i for i in range(len(depths_mm)) if i % skip == 0]
+    captured = {}
+    frame_counter = {"i": 0}
+    sample_orders = []
+
+    def fake_init_lseg(self):
+        self.device = "cpu"
+        self.clip_feat_dim = D
+        return None, None, 480, 520, [0.5] * 3, [0.5] * 3
+
+    def fake_get_lseg_feat(*a, **k):
+        i = used[frame_counter["i"]]
+        frame_counter["i"] += 1
+        return feats[i]
+
+    def fake_save(self, grid_feat, grid_pos, weight, grid_rgb, occupied_ids, mapped_iter_set, max_id):
+        captured.update(grid_feat=np.array(grid_feat[:max_id]), grid_pos=np.array(grid_pos[:max_id]),
+                        weight=np.array(weight[:max_id]), grid_rgb=np.array(grid_rgb[:max_id]),
+                        occupied_ids=np.array(occupied_ids), mapped_iter_list=sorted(mapped_iter_set),
+                        pcd_min=np.array(self.pcd_min), pcd_max=np.array(self.pcd_max))
+
+    orig_shuffle = np.random.shuffle
+
+    def recording_shuffle(x):
+        orig_shuffle(x)
+        sample_orders.append(np.array(x))
+
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        for sub in ("rgb", "depth", "pose"):
+            (td / sub).mkdir()
+        rgb_paths, depth_paths, pose_paths = [], [], []
+        for i, (d, c, t) in enumerate(zip(depths_mm, rgbs, cam_poses)):
+            rp, dp, pp = td / "rgb" / f"{i:06d}.png", td / "depth" / f"{i:06d}.png", td / "pose" / f"{i:06d}.txt"
+            cv2.imwrite(str(rp), cv2.cvtColor(c, cv2.COLOR_RGB2BGR))
+            assert d.dtype == np.uint16
+            cv2.imwrite(str(dp), d)
+            np.savetxt(pp, np.asarray(t).reshape(-1))
+            rgb_paths.append(rp); depth_paths.append(dp); pose_paths.append(pp)
+        cls = vb.VLMapBuilderMultiFloor
+        saved = (cls._init_lseg, vb.get_lseg_feat, cls.save_3d_map)
+        cls._init_lseg = fake_init_lseg
+        vb.get_lseg_feat = fake_get_lseg_feat
+        cls.save_3d_map = fake_save
+        np.random.shuffle = recording_shuffle
+        try:
+            np.random.seed(seed)
+            b = cls(td, cfg, pose_paths, rgb_paths, depth_paths, base2cam_tf, base_transform)
+            b.create_global_map()
+        finally:
+            cls._init_lseg, vb.get_lseg_feat, cls.save_3d_map = saved
+            np.random.shuffle = orig_shuffle
+    rate = map_config["depth_sample_rate"]
+    orders = [s[::rate].astype(np.int32) for s in sample_orders]
+    n = len(used)
+    assert len(orders) == 2 * n
+    captured["sample_idx_pass1"] = orders[:n]
+    captured["sample_idx_pass2"] = orders[n:]
+    captured["used_frames"] = used
+    return captured

@@ -9,6 +9,7 @@ outputs of the reference's own functions:
   sound_*.npz  torch `scale * A @ T.T`, min-max, argmax (avlmaps/map/sound_map.py:108-113,151-152)
   build_*.npz  VLMapBuilder.create_mobile_base_map (avlmaps/map/vlmap_builder.py:54-185)
   heat_*.npz   get_heatmap_from_mask_3d (avlmaps/utils/visualize_utils.py:29-49)
+  mf_*.npz     VLMapBuilderMultiFloor.create_global_map (avlmaps/map/vlmap_builder_multi_floor.py:60-199)
 """
 from __future__ import annotations
 
@@ -84,6 +85,22 @@ def gen_build(name, n_frames, h, w, fh, fw, d, gs, cs, cam_h, calib, rate, seed,
           f"weight dtype {out['weight'].dtype}, rgb dtype {out['grid_rgb'].dtype}")
 
 
+def gen_multi_floor(name, n_frames, h, w, fh, fw, d, cs, calib, rate, skip, seed):
+    cfg = synth.multi_floor_config(cs, calib, rate, skip_frame=skip)
+    poses = synth.global_cam_poses(n_frames)
+    depths, rgbs, feats = synth.multi_floor_inputs(n_frames, h, w, fh, fw, d, seed=seed)
+    out = ref_shim.ref_build_multi_floor(cfg, poses, depths, rgbs, feats, seed=seed)  # raises where the reference does
+    np.savez_compressed(OUT / f"mf_{name}.npz", cfg_cs=cs, cfg_calib=np.asarray(calib, np.float64), cfg_rate=rate,
+                        cfg_skip=skip, seed=seed, n_frames=n_frames, h=h, w=w, fh=fh, fw=fw, d=d,
+                        poses=np.stack(poses), depths=np.stack(depths), rgbs=np.stack(rgbs), feats=np.stack(feats),
+                        grid_feat=out["grid_feat"], grid_pos=out["grid_pos"], weight=out["weight"],
+                        occupied_ids=out["occupied_ids"], grid_rgb=out["grid_rgb"], pcd_min=out["pcd_min"],
+                        pcd_max=out["pcd_max"], sample_idx_pass1=np.stack(out["sample_idx_pass1"]),
+                        sample_idx_pass2=np.stack(out["sample_idx_pass2"]), used_frames=np.array(out["used_frames"]))
+    print(f"mf_{name}: frames={n_frames} skip={skip} rate={rate}: {out['grid_feat'].shape[0]} voxels, grid "
+          f"{out['occupied_ids'].shape}, min grid_pos {out['grid_pos'].min(0)}")
+
+
 def gen_heat(name, n, seed):
     rng = np.random.default_rng(seed)
     pos = rng.integers(0, 40, (n, 3)).astype(np.int32)
@@ -115,6 +132,11 @@ def main():
     gen_build("revisit", 6, 60, 80, 49, 65, 12, gs=48, cs=0.1, cam_h=1.6, calib=[40, 0, 40, 0, 40, 30, 0, 0, 1],
               rate=2, seed=3, radius=0.3)
     gen_heat("n600", 600, seed=50)
+    # multi-floor builder: uint16 mm depth, global-frame grid from a first pass, np.round cells
+    gen_multi_floor("rate1", 4, 48, 64, 39, 52, 8, 0.05, k10, rate=1, skip=1, seed=0)
+    # second-pass samples fall below pcd_min in all three axes: numpy negative-index wrap-around
+    gen_multi_floor("wrap", 5, 48, 64, 39, 52, 6, 0.05, k10, rate=2, skip=1, seed=2)
+    gen_multi_floor("skip2", 5, 48, 64, 39, 52, 6, 0.05, k10, rate=4, skip=2, seed=3)
 
 
 if __name__ == "__main__":

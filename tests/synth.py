@@ -64,3 +64,39 @@ def build_inputs(n_frames: int, h: int, w: int, fh: int, fw: int, d: int, seed: 
         rgbs.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
         feats.append(fpool[i % npool])
     return depths, rgbs, feats
+
+
+def global_cam_poses(n_frames: int, radius: float = 0.5, floors: int = 2, floor_height: float = 1.2):
+    """Camera poses (4, 4) in the global habitat frame (y up, camera looks down -z) for the multi-floor
+    builder: a circle per floor, yaw tangent, a small pitch so rows of the grid are not axis-aligned."""
+    from scipy.spatial.transform import Rotation as R
+
+    out = []
+    for i in range(n_frames):
+        th = 2 * np.pi * i / max(n_frames, 1)
+        tf = np.eye(4)
+        tf[:3, :3] = (R.from_euler("y", th) * R.from_euler("x", 0.1 * np.sin(3 * th))).as_matrix()
+        tf[:3, 3] = [radius * np.cos(th), 1.5 + floor_height * (i * floors // max(n_frames, 1)), radius * np.sin(th)]
+        out.append(tf)
+    return out
+
+
+def multi_floor_config(cs: float, calib, rate: int, skip_frame: int = 1) -> dict:
+    pi = dict(DEFAULT_POSE_INFO)
+    pi["pose_type"] = "global"
+    pi["building_init_height"] = 0.0
+    return {"map_type": "vlmap_openmap", "pose_info": pi, "cam_calib_mat": [float(x) for x in np.asarray(calib).flatten()],
+            "grid_size": 1000, "cell_size": cs, "depth_sample_rate": rate, "skip_frame": skip_frame}
+
+
+def multi_floor_inputs(n_frames: int, h: int, w: int, fh: int, fw: int, d: int, seed: int = 0,
+                       depth_lo_mm: int = 50, depth_hi_mm: int = 3000):
+    """uint16 millimetre depth (some pixels below min_depth = 0.1 m), RGB, (1, D, FH, FW) features."""
+    depths, rgbs, feats = [], [], []
+    for i in range(n_frames):
+        rng = np.random.default_rng(300 + seed * 1000 + i)
+        depths.append(rng.integers(depth_lo_mm, depth_hi_mm, (h, w)).astype(np.uint16))
+        rgbs.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        f = np.random.default_rng(400 + seed * 1000 + i).standard_normal((1, d, fh, fw), dtype=np.float32)
+        feats.append(f * np.float32(14.2857 / np.sqrt(d)))
+    return depths, rgbs, feats

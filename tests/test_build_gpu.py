@@ -156,3 +156,139 @@ def test_build_then_index_without_leaving_hbm(eng):
     assert np.array_equal(idx, ri) and np.array_equal(val, rv)
     m.close()
     b.close()
+
+
+# ------------------------------------------------------------------------------------------ multi-floor
+MF_CASES = ["rate1", "wrap", "skip2"]
+
+
+def load_mf(name):
+    g = np.load(G / f"mf_{name}.npz")
+    cfg = synth.multi_floor_config(float(g["cfg_cs"]), g["cfg_calib"], int(g["cfg_rate"]), skip_frame=int(g["cfg_skip"]))
+    return g, cfg
+
+
+def gpu_build_multi_floor(eng, g, cfg, torch_inputs=False, layout=0, slab=None):
+    cs = cfg["cell_size"]
+    calib = np.array(cfg["cam_calib_mat"], np.float64).reshape(3, 3)
+    kinv = np.linalg.inv(calib)
+    used = [int(i) for i in g["used_frames"]]
+    tfs = {i: g["poses"][i] @ O.HABITAT2CAM_ROT_TF for i in used}
+    fb = eng.FrameBounds()
+    for j, i in enumerate(used):
+        d, s = g["depths"][i], g["sample_idx_pass1"][j]
+        if torch_inputs:
+            import torch
+
+            d, s = torch.from_numpy(d).cuda(), torch.from_numpy(s).cuda()
+        fb.add_frame(d, kinv, tfs[i], sample_idx=s, min_depth=0.1, max_depth=100)
+    pcd_min, pcd_max, n_points = fb.get()
+    fb.close()
+    n_row, n_col, n_height = O.global_grid_size(pcd_min, pcd_max, cs)
+    b = eng.DeviceBuilder.global_grid(n_row, n_col, n_height, cs, pcd_min, int(g["d"]))
+    if slab is not None:
+        b.set_slab(*slab(n_row))
+    for j, i in enumerate(used):
+        f = g["feats"][i]
+        kfeat = O.get_sim_cam_mat(f.shape[2], f.shape[3])
+        if layout == 1:
+            f = np.ascontiguousarray(f[0].transpose(1, 2, 0))
+        d, r, s = g["depths"][i], g["rgbs"][i], g["sample_idx_pass2"][j]
+        if torch_inputs:
+            import torch
+
+            f, d, s, r = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (f, d, s, r))
+        b.add_frame(d, f, kinv, calib, kfeat, tfs[i], rgb=r, sample_idx=s, feat_layout=layout, min_depth=0.1, max_depth=100)
+    out = b.export()
+    out.update(pcd_min=pcd_min, pcd_max=pcd_max, n_points=n_points, num_oob=b.num_rejected_oob)
+    return out, b
+
+
+@pytest.mark.parametrize("torch_inputs", [False, True])
+@pytest.mark.parametrize("name", MF_CASES)
+def test_multi_floor_golden_reference_builds(eng, name, torch_inputs):
+    """The UNMODIFIED reference's VLMapBuilderMultiFloor.create_global_map: pcd_min / pcd_max bit-exact from the
+    device bounds pass, grid_pos (negative where numpy wrapped) / occupied_ids bit-exact, features within 1e-3."""
+    g, cfg = load_mf(name)
+    out, b = gpu_build_multi_floor(eng, g, cfg, torch_inputs=torch_inputs, layout=int(torch_inputs))
+    assert np.array_equal(out["pcd_min"], g["pcd_min"]) and np.array_equal(out["pcd_max"], g["pcd_max"])
+    assert out["occupied_ids"].shape == g["occupied_ids"].shape
+    assert_build_equal(out, g)
+    assert out["num_oob"] == 0
+    b.close()
+
+
+def test_multi_floor_points_the_reference_would_crash_on_are_counted(eng):
+    """Shrink the grid by hand: second-pass points above the (fake) bounds in height raise IndexError in the
+    reference; the kernel rejects and counts them, exactly like the C oracle."""
+    g, cfg = load_mf("rate1")
+    cs = cfg["cell_size"]
+    calib = np.array(cfg["cam_calib_mat"], np.float64).reshape(3, 3)
+    kinv = np.linalg.inv(calib)
+    n_row, n_col, n_height = O.global_grid_size(g["pcd_min"], g["pcd_max"], cs)
+    n_height //= 2
+    ob = O.BuildOracle.global_grid(n_row, n_col, n_height, cs, g["pcd_min"], int(g["d"]), capacity=n_row * n_col * n_height)
+    b = eng.DeviceBuilder.global_grid(n_row, n_col, n_height, cs, g["pcd_min"], int(g["d"]))
+    for j, i in enumerate(int(x) for x in g["used_frames"]):
+        f = g["feats"][i]
+        args = (kinv, calib, O.get_sim_cam_mat(f.shape[2], f.shape[3]), g["poses"][i] @ O.HABITAT2CAM_ROT_TF)
+        ob.add_frame(g["depths"][i], f, g["rgbs"][i], g["sample_idx_pass2"][j], *args, min_depth=0.1, max_depth=100)
+        b.add_frame(g["depths"][i], f, *args, rgb=g["rgbs"][i], sample_idx=g["sample_idx_pass2"][j], min_depth=0.1,
+                    max_depth=100)
+    assert ob.num_oob > 0 and b.num_rejected_oob == ob.num_oob and b.num_accepted == ob.num_accepted
+    assert_build_equal(b.export(), ob.export())
+    b.close()
+    ob.close()
+
+
+# ------------------------------------------------------------------------------------------ slab-sharded build
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_sharded_build_equals_single_build(eng, world):
+    """Rows split into `world` slabs (here: builders side by side on one GPU; across GPUs the key exchange is
+    one all-gather, tests/test_sharded_cpu.py).  Local first-touch ids + ranked keys == the single build's ids,
+    and each slab's rows equal the single build's rows of those voxels bit for bit."""
+    from avlmaps_b200.sharded import slab_bounds
+
+    cfg, poses, depths, rgbs, feats, sidx = random_scene(5, 60, 80, 49, 65, 16, 48, 0.1, 1.6,
+                                                         [40, 0, 40, 0, 40, 30, 0, 0, 1], 1, seed=21, radius=0.3)
+    full, bf = gpu_build(eng, cfg, poses, depths, rgbs, feats, sidx)
+    cs, gs = cfg["cell_size"], cfg["grid_size"]
+    vh = int(cfg["pose_info"]["camera_height"] / cs)
+    tfs, calib, kinv = scene_mats(cfg, poses)
+    shards = []
+    for r in range(world):
+        b = eng.DeviceBuilder(gs, vh, cs, 16)
+        b.set_slab(*slab_bounds(gs, world, r))
+        for i, tf in enumerate(tfs):
+            b.add_frame(depths[i], feats[i], kinv, calib, O.get_sim_cam_mat(49, 65), tf, rgb=rgbs[i], sample_idx=sidx[i])
+        shards.append((b, b.export(), b.export_keys()))
+    keys = [k for _, _, k in shards]
+    assert all(np.all(np.diff(k.astype(np.int64)) > 0) for k in keys if k.size > 1)  # ascending = local id order
+    assert sum(k.size for k in keys) == full["grid_feat"].shape[0]
+    assert sum(b.num_accepted for b, _, _ in shards) == bf.num_accepted
+    occ = np.full_like(full["occupied_ids"], -1)
+    for r, (b, out, k) in enumerate(shards):
+        gids = eng.rank_keys(keys, r)
+        assert np.array_equal(gids, np.searchsorted(np.sort(np.concatenate(keys)), k))
+        assert np.array_equal(out["grid_pos"], full["grid_pos"][gids])
+        lo, hi = slab_bounds(gs, world, r)
+        assert np.all((out["grid_pos"][:, 0] >= lo) & (out["grid_pos"][:, 0] < hi))
+        # same points, same atomics per voxel row -> sums differ only by fp32 atomic ordering
+        assert np.allclose(out["grid_feat"], full["grid_feat"][gids], rtol=1e-4, atol=1e-6)
+        assert np.allclose(out["weight"], full["weight"][gids], rtol=1e-5)
+        m = out["occupied_ids"] >= 0
+        occ[m] = gids[out["occupied_ids"][m]]
+        b.close()
+    assert np.array_equal(occ, full["occupied_ids"])
+    bf.close()
+
+
+def test_set_slab_after_first_frame_is_a_state_error(eng):
+    from avlmaps_b200._lib import AvlError
+
+    cfg, poses, depths, rgbs, feats, sidx = random_scene(1, 30, 40, 24, 32, 4, 32, 0.1, 1.6,
+                                                         [20, 0, 20, 0, 20, 15, 0, 0, 1], 1, seed=2, radius=0.3)
+    out, b = gpu_build(eng, cfg, poses, depths, None, feats, sidx)
+    with pytest.raises(AvlError):
+        b.set_slab(0, 16)
+    b.close()

@@ -164,3 +164,44 @@ def test_dynamic_obstacles_map(lib):
     want[pos[pts, 0] - rmin, pos[pts, 1] - cmin] = 1
     want = np.logical_not(np.logical_and(want, obstacles_cropped == 0))
     assert np.array_equal(got, want)
+
+
+def test_multi_floor_create_and_load_like_the_reference(lib, tmp_path):
+    """VLMapMultiFloor.create_map / load_map on the golden scene written the way the reference's dataset is
+    laid out (rgb/*.png, depth/*.png 16-bit mm, pose/*.txt 4x4): `Map.create` dispatch on map_type
+    'vlmap_openmap' (map.py:121-129), both passes on the device, the reference's own output as the check."""
+    import cv2
+
+    from avlmaps_b200.map import Map, VLMapMultiFloor
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "mf_wrap.npz")
+    cfg = synth.multi_floor_config(float(g["cfg_cs"]), g["cfg_calib"], int(g["cfg_rate"]), skip_frame=int(g["cfg_skip"]))
+    for sub in ("rgb", "depth", "pose"):
+        (tmp_path / sub).mkdir()
+    for i in range(int(g["n_frames"])):
+        cv2.imwrite(str(tmp_path / "rgb" / f"{i:06d}.png"), cv2.cvtColor(g["rgbs"][i], cv2.COLOR_RGB2BGR))
+        cv2.imwrite(str(tmp_path / "depth" / f"{i:06d}.png"), g["depths"][i])
+        np.savetxt(tmp_path / "pose" / f"{i:06d}.txt", g["poses"][i].reshape(-1))
+    vlmap = Map.create(cfg)
+    assert isinstance(vlmap, VLMapMultiFloor)
+    feats = iter(g["feats"][int(i)] for i in g["used_frames"])
+    vlmap.feature_fn = lambda rgb: next(feats)
+    np.random.seed(int(g["seed"]))  # the reference draws both passes' sample orders from the global RNG
+    vlmap.create_map(tmp_path)
+    assert vlmap.grid_feat is None
+    assert vlmap.load_map(tmp_path) is True
+    assert np.array_equal(vlmap.pcd_min, g["pcd_min"]) and np.array_equal(vlmap.pcd_max, g["pcd_max"])
+    assert float(vlmap.cs) == float(g["cfg_cs"])
+    assert np.array_equal(vlmap.grid_pos, g["grid_pos"]) and np.array_equal(vlmap.occupied_ids, g["occupied_ids"])
+    assert np.allclose(vlmap.grid_feat, g["grid_feat"], rtol=1e-3, atol=1e-5)
+    assert np.allclose(vlmap.weight, g["weight"], rtol=1e-3)
+    assert vlmap.mapped_iter_list == [int(i) for i in g["used_frames"]]
+    assert vlmap.map_builder.device_builder.num_rejected_oob == 0
+    # the index surface is VLMap's
+    enc = fake_encoder(int(g["d"]))
+    vlmap.set_text_encoder(enc, int(g["d"]))
+    from avlmaps_b200.utils.clip_utils import landmark_text_feats
+
+    tf, _, _ = landmark_text_feats(enc, ["sofa"], int(g["d"]), True, 0, True)
+    assert np.array_equal(vlmap.index_map("sofa", with_init_cat=False), O.index_mask(O.scores(vlmap.grid_feat, tf), 0))
+    assert vlmap.map_builder.create_mobile_base_map() is NotImplementedError

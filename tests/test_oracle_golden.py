@@ -106,3 +106,53 @@ def test_fuse_topk_small():
     for j in range(3):
         heat = O.minmax(sa[:, j]) * O.minmax(sb[:, j])
         assert idx[j, 0] == int(np.argmax(heat)) and val[j, 0] == heat.max()
+
+
+MF_CASES = ["rate1", "wrap", "skip2"]
+
+
+def load_mf_case(name):
+    g = np.load(G / f"mf_{name}.npz")
+    cfg = synth.multi_floor_config(float(g["cfg_cs"]), g["cfg_calib"], int(g["cfg_rate"]), skip_frame=int(g["cfg_skip"]))
+    return g, cfg
+
+
+@pytest.mark.parametrize("name", MF_CASES)
+def test_multi_floor_oracle_reproduces_reference_bit_exact(name):
+    """VLMapBuilderMultiFloor.create_global_map: both passes (bounds, fusion), uint16 mm depth, np.round
+    cells, negative-index wrap-around ("wrap": grid_pos goes to -2 in all three axes)."""
+    g, cfg = load_mf_case(name)
+    out = O.build_map_multi_floor(cfg, list(g["poses"]), list(g["depths"]), list(g["rgbs"]), list(g["feats"]),
+                                  list(g["sample_idx_pass1"]), list(g["sample_idx_pass2"]))
+    for k in ("pcd_min", "pcd_max", "grid_pos", "occupied_ids", "weight", "grid_feat", "grid_rgb"):
+        assert np.array_equal(out[k], g[k]), k
+    assert out["num_oob"] == 0  # the reference ran through, so no point hit an IndexError
+    if name == "wrap":
+        assert g["grid_pos"].min() < 0
+
+
+@pytest.mark.parametrize("name", MF_CASES)
+def test_multi_floor_sample_orders_match_reference_rng(name):
+    """One global-RNG shuffle per used frame in pass 1, then again in pass 2 (vlmap_builder_multi_floor.py:368-370)."""
+    g, _ = load_mf_case(name)
+    np.random.seed(int(g["seed"]))
+    n = int(g["h"]) * int(g["w"])
+    for key in ("sample_idx_pass1", "sample_idx_pass2"):
+        for j in range(len(g["used_frames"])):
+            assert np.array_equal(O.sample_order(n, int(g["cfg_rate"])), g[key][j])
+
+
+def test_matmul_restatement_matches_numpy_here():
+    """The fused left-to-right form of the three small matrix products (oracle/build_oracle.c: dot3) is what
+    numpy/OpenBLAS computes on x86-64; check it on this host with full-mantissa operands, where the
+    unfused form differs on ~35 % of the elements (tools/probe_matmul_fma.py)."""
+    from fractions import Fraction as F
+
+    rng = np.random.default_rng(0)
+    a, x = rng.standard_normal((3, 3)), rng.standard_normal((3, 257))
+    y = a @ x
+    fma = lambda p, q, r: float(F(p) * F(q) + F(r))  # noqa: E731  exact, rounded once
+    got = np.array([[fma(a[i, 2], x[2, j], fma(a[i, 1], x[1, j], a[i, 0] * x[0, j])) for j in range(x.shape[1])]
+                    for i in range(3)])
+    if not np.array_equal(got, y):
+        pytest.skip("this host's BLAS does not use the FMA left-to-right kernel the goldens were produced with")

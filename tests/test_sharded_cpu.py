@@ -80,3 +80,89 @@ def test_merge_numpy_and_torch_agree_with_ties_and_padding():
         keep = flat_i >= 0
         order = np.lexsort((flat_i[keep], -flat_v[keep]))[:8]
         assert np.array_equal(mi[j], flat_i[keep][order])
+
+
+# ------------------------------------------------------------------------------------------ sharded build
+class OracleSlabBuilder:
+    """Stand-in for engine.DeviceBuilder restricted to a row slab: runs the C oracle on every frame, then keeps
+    the voxels whose row lies in the slab.  Keys: the single-build voxel id (any strictly increasing function
+    of first-touch order ranks the same as the device's frame_seq << 32 | sample position)."""
+
+    def __init__(self, cfg, d):
+        cs, gs = cfg["cell_size"], cfg["grid_size"]
+        self.vh = int(cfg["pose_info"]["camera_height"] / cs)
+        self.grid_shape = (gs, gs, self.vh)
+        self.o = O.BuildOracle(gs, self.vh, cs, d, capacity=gs * gs * self.vh)
+        self.lo, self.hi = 0, gs
+
+    def set_slab(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def add_frame(self, *a, **k):
+        self.o.add_frame(*a, **k)
+
+    def _sel(self):
+        full = self.o.export()
+        rows = full["grid_pos"][:, 0]
+        return full, np.nonzero((rows >= self.lo) & (rows < self.hi))[0]
+
+    def export(self):
+        full, sel = self._sel()
+        local = -np.ones(full["grid_feat"].shape[0], np.int32)
+        local[sel] = np.arange(sel.size)
+        occ = np.where(full["occupied_ids"] >= 0, local[np.clip(full["occupied_ids"], 0, None)], -1).astype(np.int32)
+        return dict(grid_feat=full["grid_feat"][sel], grid_pos=full["grid_pos"][sel], weight=full["weight"][sel],
+                    grid_rgb=full["grid_rgb"][sel], occupied_ids=occ)
+
+    def export_keys(self):
+        return self._sel()[1].astype(np.uint64) * np.uint64(7) + np.uint64(3)
+
+
+def _numpy_rank(keys_per_shard, shard):
+    return np.searchsorted(np.sort(np.concatenate(keys_per_shard)), keys_per_shard[shard]).astype(np.int64)
+
+
+def _build_worker(rank, world, port, out):
+    from avlmaps_b200.sharded import ShardedBuilder
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = synth.map_config(48, 0.1, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], 2)
+    poses = synth.circle_poses(3, radius=0.3)
+    depths, rgbs, feats = synth.build_inputs(3, 60, 80, 49, 65, 8, seed=4)
+    np.random.seed(11)
+    sidx = [O.sample_order(60 * 80, 2) for _ in range(3)]
+    b2c, bt = O.setup_transforms(cfg["pose_info"])
+    tfs = O.frame_transforms(poses, b2c, bt)
+    calib = np.array(cfg["cam_calib_mat"]).reshape(3, 3)
+    sb = ShardedBuilder(OracleSlabBuilder(cfg, 8), rank_fn=_numpy_rank)
+    for i in range(3):
+        sb.add_frame(depths[i], feats[i], rgbs[i], sidx[i], np.linalg.inv(calib), calib, O.get_sim_cam_mat(49, 65), tfs[i])
+    res = sb.finalize()
+    ref = O.build_map(cfg, poses, depths, rgbs, feats, sidx, capacity=48 * 48 * 16)
+    ok = (res["n_voxels_total"] == ref["grid_feat"].shape[0]
+          and np.array_equal(res["occupied_ids"], ref["occupied_ids"])          # global ids on every rank
+          and np.array_equal(res["grid_pos"], ref["grid_pos"][res["global_ids"]])
+          and np.array_equal(res["grid_feat"], ref["grid_feat"][res["global_ids"]])
+          and np.all(np.diff(res["global_ids"]) > 0)
+          and (sb.row_lo, sb.row_hi) == slab_bounds(48, world, rank))
+    # the slab-built shard answers queries with GLOBAL ids through ShardedMap(global_ids=...)
+    q = synth.index_inputs(1, 8, 3, seed=6)[1]
+    sm = ShardedMap(OracleSlab(res["grid_feat"]), global_ids=res["global_ids"])
+    idx, val = sm.topk(q, 5)
+    ri, rv = O.topk(O.scores(ref["grid_feat"], q), 5)
+    out.put(bool(ok) and np.array_equal(idx, ri) and np.array_equal(val, rv))
+    dist.destroy_process_group()
+
+
+def test_sharded_build_world2_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_build_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get() is True and out.get() is True
