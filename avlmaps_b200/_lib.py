@@ -32,7 +32,8 @@ EXPORTS = [
     "avl_builder_num_accepted", "avl_builder_export", "avl_builder_to_map",
     "avl_builder_create_global", "avl_builder_num_rejected_oob",
     "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
-    "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys",
+    "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import",
+    "avl_heat_planar",
 ]
 
 
@@ -106,6 +107,7 @@ def load() -> C.CDLL:
     lib.avl_heat2d_sources.argtypes = [vp, vp, vp, i32, i32, i32, C.c_double, i32, vp, C.c_int, vp]
     lib.avl_merge_topk.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.c_int, vp]
     lib.avl_heat_from_mask_3d.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp, C.c_int, vp]
+    lib.avl_heat_planar.argtypes = [vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp]
     if hasattr(lib, "avl_builder_create"):
         lib.avl_builder_create.argtypes = [C.POINTER(GridSpec), C.POINTER(vp)]
         lib.avl_builder_destroy.argtypes = [vp]
@@ -123,6 +125,7 @@ def load() -> C.CDLL:
         lib.avl_builder_set_slab.argtypes = [vp, i32, i32]
         lib.avl_builder_export_keys.argtypes = [vp, vp, C.c_int, vp]
         lib.avl_rank_keys.argtypes = [vp, vp, i32, i32, vp, C.c_int, vp]
+        lib.avl_builder_import.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, vp]
     _lib = lib
     return lib
 

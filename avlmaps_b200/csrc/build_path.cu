@@ -223,6 +223,39 @@ export_keys_kernel(const int32_t* __restrict__ occupied_ids, const unsigned long
   }
 }
 
+// resume: one warp per reloaded voxel -> num = grid_feat * weight, den = weight, cell -> id, key 0 (never a winner again)
+__global__ void __launch_bounds__(256)
+import_kernel(const float* __restrict__ feat, const int32_t* __restrict__ pos, const float* __restrict__ weight,
+              const uint8_t* __restrict__ rgb, int64_t v, int32_t d, int32_t n0, int32_t n1, int32_t n2,
+              float* __restrict__ num, float* __restrict__ den, float* __restrict__ rgb_acc,
+              int32_t* __restrict__ grid_pos, int32_t* __restrict__ occupied_ids,
+              unsigned long long* __restrict__ first_key, unsigned long long* __restrict__ n_bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t id = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; id < v; id += nwarps) {
+    const float w = weight[id];
+    for (int c = lane; c < d; c += 32) num[id * d + c] = feat[id * d + c] * w;
+    if (lane < 3) {
+      grid_pos[id * 3 + lane] = pos[id * 3 + lane];
+      rgb_acc[id * 3 + lane] = rgb ? static_cast<float>(rgb[id * 3 + lane]) * w : 0.f;
+    }
+    if (lane == 0) {
+      den[id] = w;
+      long long r = pos[id * 3 + 0], c = pos[id * 3 + 1], hh = pos[id * 3 + 2];
+      if (r < 0) r += n0;  // global-frame maps keep the unwrapped (negative) indices in grid_pos
+      if (c < 0) c += n1;
+      if (hh < 0) hh += n2;
+      if (r < 0 || r >= n0 || c < 0 || c >= n1 || hh < 0 || hh >= n2) {
+        atomicAdd(n_bad, 1ull);
+      } else {
+        const int64_t cell = (r * n1 + c) * n2 + hh;
+        occupied_ids[cell] = static_cast<int32_t>(id);
+        first_key[cell] = 0ull;
+      }
+    }
+  }
+}
+
 constexpr int kMaxShards = 64;
 struct ShardOffsets { int64_t off[kMaxShards + 1]; };
 // global id = number of keys of all shards that are smaller (keys are unique: frame_seq << 32 | sample position)
@@ -822,6 +855,58 @@ int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, floa
   if (occupied_ids) AVL_CUDA(cudaMemcpyAsync(occupied_ids, b->occupied_ids, static_cast<size_t>(b->cells) * sizeof(int32_t), kind, s));
   AVL_CUDA(cudaGetLastError());
   if (!(flags & AVL_ON_DEVICE)) AVL_CUDA(cudaStreamSynchronize(s));
+  return AVL_OK;
+}
+
+int avl_builder_import(avl_builder* b, const float* grid_feat, const int32_t* grid_pos, const float* weight,
+                       const uint8_t* grid_rgb, int64_t n_voxels, int flags, void* stream) {
+  AVL_ARG(b != nullptr, "builder is NULL");
+  AVL_ARG(n_voxels >= 0 && n_voxels <= b->cells, "n_voxels exceeds the number of cells");
+  if (b->frame_seq != 0 || b->id_upper != 0) {
+    set_error("avl_builder_import needs a fresh builder (no frame added yet)");
+    return AVL_ERR_STATE;
+  }
+  b->frame_seq = 1;  // keys of the frames to come are > 0 = the key of every reloaded cell
+  if (n_voxels == 0) return AVL_OK;
+  AVL_ARG(grid_feat != nullptr && grid_pos != nullptr && weight != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t v = static_cast<size_t>(n_voxels), d = b->dim;
+  if (b->capacity < n_voxels) {  // rows for the reloaded voxels (the reference's arrays are exactly this long, :221)
+    cudaFree(b->num); cudaFree(b->den); cudaFree(b->rgb_acc); cudaFree(b->grid_pos);
+    b->num = b->den = b->rgb_acc = nullptr; b->grid_pos = nullptr;
+    int rc = alloc_rows(b, n_voxels, &b->num, &b->den, &b->rgb_acc, &b->grid_pos, s);
+    if (rc) return rc;
+    b->capacity = n_voxels;
+  }
+  const float* f = grid_feat; const int32_t* p = grid_pos; const float* w = weight; const uint8_t* c = grid_rgb;
+  float *df = nullptr, *dw = nullptr; int32_t* dp = nullptr; uint8_t* dc = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (!(flags & AVL_ON_DEVICE)) {
+    e = cudaMalloc(reinterpret_cast<void**>(&df), v * d * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&dp), v * 3 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&dw), v * sizeof(float));
+    if (e == cudaSuccess && grid_rgb) e = cudaMalloc(reinterpret_cast<void**>(&dc), v * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(df, grid_feat, v * d * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dp, grid_pos, v * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dw, weight, v * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && grid_rgb) e = cudaMemcpyAsync(dc, grid_rgb, v * 3, cudaMemcpyHostToDevice, s);
+    f = df; p = dp; w = dw; c = grid_rgb ? dc : nullptr;
+  }
+  unsigned long long n_bad = 0;
+  if (e == cudaSuccess) e = cudaMemsetAsync(b->counters + 3, 0, sizeof(unsigned long long), s);
+  if (e == cudaSuccess) {
+    import_kernel<<<b->num_sms * 8, 256, 0, s>>>(f, p, w, c, n_voxels, b->dim, b->n0, b->n1, b->n2, b->num, b->den,
+                                                 b->rgb_acc, b->grid_pos, b->occupied_ids, b->first_key, b->counters + 3);
+    e = cudaGetLastError();
+  }
+  const unsigned long long vv = static_cast<unsigned long long>(n_voxels);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->counters, &vv, sizeof(vv), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_bad, b->counters + 3, sizeof(n_bad), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(df); cudaFree(dp); cudaFree(dw); cudaFree(dc);
+  if (e != cudaSuccess) return cuda_fail(e, "builder import", __FILE__, __LINE__);
+  b->id_upper = n_voxels;
+  AVL_ARG(n_bad == 0, "grid_pos of the saved map lies outside this builder's grid");
   return AVL_OK;
 }
 

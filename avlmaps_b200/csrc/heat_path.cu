@@ -231,3 +231,57 @@ extern "C" int avl_heat2d_sources(const int32_t* cells, const int32_t* group_sta
   if (e != cudaSuccess) return cuda_fail(e, "heat2d_sources", __FILE__, __LINE__);
   return AVL_OK;
 }
+
+
+// ---------------------------------------------------------------- image modality: planar distance decay
+// AVLMap.index_image after localisation (avlmaps/map/avlmap.py:156-162):
+//   dists = np.linalg.norm((grid_pos - [row, col, height])[:, :2], axis=1); sim = np.clip(con - decay * dists, 0, 1)
+// float64 throughout; sqrt(dx*dx + dy*dy) with separately rounded operations like numpy's norm.
+namespace avl {
+namespace {
+__global__ void __launch_bounds__(256)
+heat_planar_kernel(const int32_t* __restrict__ pos, int64_t n, double row, double col, double con, double decay,
+                   double* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double dx = __dsub_rn(static_cast<double>(pos[i * 3]), row);
+    const double dy = __dsub_rn(static_cast<double>(pos[i * 3 + 1]), col);
+    const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    const double v = __dsub_rn(con, __dmul_rn(decay, d));
+    out[i] = fmin(fmax(v, 0.0), 1.0);
+  }
+}
+}  // namespace
+}  // namespace avl
+
+extern "C" int avl_heat_planar(const int32_t* grid_pos, int64_t n, double row, double col, double con,
+                               double decay_rate, double* out_heat, int flags, void* stream) {
+  using namespace avl;
+  AVL_ARG(n >= 0, "n < 0");
+  if (n == 0) return AVL_OK;
+  AVL_ARG(grid_pos != nullptr && out_heat != nullptr, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int32_t* p = grid_pos;
+  double* o = out_heat;
+  int32_t* dp = nullptr;
+  double* dout = nullptr;
+  if (!(flags & AVL_ON_DEVICE)) {
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&dp), static_cast<size_t>(n) * 3 * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dout), static_cast<size_t>(n) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dp, grid_pos, static_cast<size_t>(n) * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { cudaFree(dp); cudaFree(dout); return cuda_fail(e, "heat planar staging", __FILE__, __LINE__); }
+    p = dp;
+    o = dout;
+  }
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  heat_planar_kernel<<<blocks, 256, 0, s>>>(p, n, row, col, con, decay_rate, o);
+  cudaError_t e = cudaGetLastError();
+  if (!(flags & AVL_ON_DEVICE)) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_heat, dout, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dp);
+    cudaFree(dout);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "heat planar", __FILE__, __LINE__);
+  return AVL_OK;
+}

@@ -270,6 +270,19 @@ def heat_from_mask_3d(grid_pos, mask, cell_size: float = 0.05, decay_rate: float
     return out
 
 
+def heat_planar(grid_pos, row: float, col: float, con: float = 1.0, decay_rate: float = 0.01) -> np.ndarray:
+    """Planar distance decay of AVLMap.index_image (avlmap.py:156-162): (N,) float64."""
+    lib = L.load()
+    L.require_device()
+    p = np.ascontiguousarray(grid_pos, np.int32)
+    if p.ndim != 2 or p.shape[1] != 3:
+        raise ValueError("grid_pos must be (N, 3)")
+    out = np.empty(p.shape[0], np.float64)
+    L.check(lib.avl_heat_planar(L.np_ptr(p), p.shape[0], float(row), float(col), float(con), float(decay_rate),
+                                L.np_ptr(out), 0, None))
+    return out
+
+
 def heat2d_sources(shape, cells_per_group, conf, decay_rate: float, mode: str):
     """2-D source heat before the final min-max.  mode "area": max-combine, float64 (avlmap.py:78-97);
     mode "sound": float32 running sum in group order (avlmap.py:111-131).  cells_per_group: list of (n_i, 2)
@@ -407,6 +420,17 @@ class DeviceBuilder:
         L.check(self._lib.avl_builder_create_global(C.byref(spec), C.byref(self._h)))
         self.n_frames = 0
         return self
+
+    def import_state(self, grid_feat, grid_pos, weight, grid_rgb=None) -> None:
+        """Resume from a saved map like _init_map's reload (vlmap_builder.py:212-222): frames added afterwards
+        are fused on top of it.  Fresh builder only."""
+        f = np.ascontiguousarray(grid_feat, np.float32)
+        p = np.ascontiguousarray(grid_pos, np.int32)
+        w = np.ascontiguousarray(weight, np.float32)
+        c = None if grid_rgb is None else np.ascontiguousarray(grid_rgb, np.uint8)
+        if f.ndim != 2 or f.shape[1] != self.dim or p.shape != (f.shape[0], 3) or w.shape != (f.shape[0],):
+            raise ValueError("saved map arrays do not match the builder (grid_feat (V, D), grid_pos (V, 3), weight (V,))")
+        L.check(self._lib.avl_builder_import(self._h, L.np_ptr(f), L.np_ptr(p), L.np_ptr(w), L.np_ptr(c), f.shape[0], 0, None))
 
     def set_slab(self, row_lo: int, row_hi: int) -> None:
         """Own only the grid rows [row_lo, row_hi) (slab-sharded build, one process per GPU)."""

@@ -10,7 +10,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from ..engine import heat2d_sources, heat_from_mask_3d, topk_vector
+from ..engine import heat2d_sources, heat_from_mask_3d, heat_planar, topk_vector
 from .map import cfg_get
 from .vlmap import VLMap
 
@@ -111,6 +111,20 @@ class AVLMap:
 
     def index_sound(self, sound_name: str, decay_rate: float = 0.01) -> np.ndarray:
         return self.lift_heat_2d_to_3d(self.index_sound_2d(sound_name, decay_rate))
+
+    visual_map = None
+
+    def index_image(self, image: np.ndarray, query_cam_intrinsics: np.ndarray = None, decay_rate: float = 0.01) -> np.ndarray:
+        """Reference avlmap.py:146-163.  `visual_map.localize_image` (HLoc: NetVLAD + SuperPoint/SuperGlue + PnP) is
+        outside this engine -- attach the reference's VisualMap; the per-voxel heat runs on the device."""
+        _, query_base_tf = self.visual_map.localize_image(image, query_cam_intrinsic_mat=query_cam_intrinsics)
+        self.dataloader.from_habitat_tf(query_base_tf)
+        row, col, _ = self.dataloader.to_full_map_pose()
+        return self.image_heat(row, col, decay_rate)
+
+    def image_heat(self, row: float, col: float, decay_rate: float = 0.01) -> np.ndarray:
+        """Numeric core of index_image (avlmap.py:156-162): clip(1 - decay * planar distance to (row, col), 0, 1)."""
+        return heat_planar(self.vlmap.grid_pos, row, col, 1.0, decay_rate)
 
     def get_max_pos_3d(self, heat: np.ndarray) -> np.ndarray:
         """HabitatLanguageRobot.get_max_pos_3d (habitat_lang_robot.py:427-430): grid_pos[argmax(heat)]."""

@@ -95,12 +95,13 @@ class VLMapBuilder:
         calib_inv = np.linalg.inv(calib_mat)  # depth2pc, mapping_utils.py:237
         vh = int(camera_height / cs)          # _init_map, :201
         feature_fn = self.feature_fn or _default_feature_fn
+        resume = None
         if map_file_exists(self.map_save_path):
-            # the reference reloads the saved map and then re-fuses every frame on top of it (:212-222, and
-            # the loop never consults mapped_iter_set); resuming on the device is not implemented yet
-            raise NotImplementedError(f"{self.map_save_path} exists: resume of a saved map is not supported yet")
+            # _init_map (:212-222): the saved map becomes the initial state (max_id = grid_feat.shape[0]) and the
+            # loop below fuses EVERY frame on top of it -- the reference never consults mapped_iter_set (:102-180)
+            resume = load_3d_map(self.map_save_path)
 
-        mapped_iter_set = set()
+        mapped_iter_set = set(resume[0]) if resume is not None else set()
         builder = None
         for frame_i, (rgb_path, depth_path) in enumerate(zip(self.rgb_paths, self.depth_paths)):
             rgb, depth = self._load_frame(rgb_path, depth_path)
@@ -109,6 +110,8 @@ class VLMapBuilder:
                 self.clip_feat_dim = int(pix_feats.shape[1])
                 builder = DeviceBuilder(gs, vh, cs, self.clip_feat_dim, capacity=gs * gs)  # :202
                 self.device_builder = builder
+                if resume is not None:
+                    builder.import_state(resume[1], resume[2], resume[3], resume[5])
             pix_feats_intr = get_sim_cam_mat(pix_feats.shape[2], pix_feats.shape[3])  # :126
             sample_idx = self._sample_order(depth.shape[0] * depth.shape[1], depth_sample_rate)
             on_device = type(pix_feats).__module__.startswith("torch") and pix_feats.is_cuda

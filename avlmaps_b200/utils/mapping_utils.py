@@ -154,3 +154,28 @@ def load_3d_map_multi_floor(map_path) -> Tuple:
             d = {k: z[k] for k in _FIELDS_MF}
     return (d["mapped_iter_list"].tolist(), d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], d["grid_rgb"],
             d["pcd_min"], d["pcd_max"], d["cs"][()])
+
+
+def save_clip_sparse_map(save_path, clip_sparse_map: np.ndarray, robot_pose_list) -> None:
+    """Reference mapping_utils.py:637-640."""
+    data = {"clip_sparse_map": clip_sparse_map, "robot_pose_list": np.asarray(robot_pose_list)}
+    if _have_h5py():
+        import h5py
+
+        with h5py.File(save_path, "w") as f:
+            for k, v in data.items():
+                f.create_dataset(k, data=v)
+    else:
+        with open(_npz_twin(save_path), "wb") as f:
+            np.savez(f, **data)
+
+
+def load_clip_sparse_map(load_path):
+    """Reference mapping_utils.py:643-647."""
+    if Path(load_path).exists() and _have_h5py():
+        import h5py
+
+        with h5py.File(load_path, "r") as f:
+            return f["clip_sparse_map"][:], f["robot_pose_list"][:]
+    with np.load(_npz_twin(load_path)) as z:
+        return z["clip_sparse_map"], z["robot_pose_list"]

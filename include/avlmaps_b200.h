@@ -159,6 +159,12 @@ int avl_heat2d_sources(const int32_t* cells, const int32_t* group_start, const f
                        int32_t rows, int32_t cols, double decay_rate, int32_t mode, void* out_heat, int flags,
                        void* stream);
 
+/* Image modality after localisation: out[i] = clip(con - decay_rate * ||grid_pos[i, :2] - (row, col)||, 0, 1),
+ * float64 (n,).  Replaces the numpy lines of AVLMap.index_image (avlmaps/map/avlmap.py:156-162); the
+ * localisation itself (HLoc, visual_map.py) is out of scope. */
+int avl_heat_planar(const int32_t* grid_pos, int64_t n, double row, double col, double con, double decay_rate,
+                    double* out_heat, int flags, void* stream);
+
 /* ---- map-build path ------------------------------------------------------------------ */
 
 typedef struct avl_grid_spec {
@@ -205,6 +211,15 @@ int avl_builder_num_accepted(avl_builder* b, int64_t* n, void* stream);
  * called repeatedly (the reference saves every 100 frames, :181-183). */
 int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, float* weight,
                        int32_t* occupied_ids, uint8_t* grid_rgb, int flags, void* stream);
+
+/* Resume: adopt a saved map as the builder's state, the way _init_map reloads vlmaps.h5df before the
+ * frame loop (vlmap_builder.py:212-222; max_id = grid_feat.shape[0]) -- every frame added afterwards is
+ * fused ON TOP of it, exactly like the reference (whose loop never consults mapped_iter_set, :102-180):
+ * a reloaded voxel continues its running mean from (grid_feat, weight), new cells get ids from n_voxels on.
+ * occupied_ids is rebuilt from grid_pos.  Only valid on a fresh builder (no frame added yet).
+ * grid_rgb may be NULL. */
+int avl_builder_import(avl_builder* b, const float* grid_feat, const int32_t* grid_pos, const float* weight,
+                       const uint8_t* grid_rgb, int64_t n_voxels, int flags, void* stream);
 
 /* Hand the finished map to the index path without leaving HBM. */
 int avl_builder_to_map(avl_builder* b, void* stream, avl_map** out);

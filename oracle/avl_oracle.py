@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
         L.oracle_builder_create_global.argtypes = [i32, i32, i32, dbl, vp, i32, i64]
         L.oracle_builder_num_oob.restype = i64
         L.oracle_builder_num_oob.argtypes = [vp]
+        L.oracle_builder_import.restype = C.c_int
+        L.oracle_builder_import.argtypes = [vp, vp, vp, vp, vp, vp, i64]
         L.oracle_frame_bounds.restype = i64
         L.oracle_frame_bounds.argtypes = [vp, C.c_int, i32, i32, vp, i32, vp, vp, dbl, dbl, vp]
         L.oracle_scores.argtypes = [vp, i64, i32, vp, i32, vp, C.c_int, vp]
@@ -247,6 +249,15 @@ class BuildOracle:
         self._keep = []
         return self
 
+    def import_state(self, grid_feat, grid_pos, weight, grid_rgb, occupied_ids):
+        """_init_map's reload (vlmap_builder.py:212-222)."""
+        f, p = np.ascontiguousarray(grid_feat, np.float32), np.ascontiguousarray(grid_pos, np.int32)
+        w, o = np.ascontiguousarray(weight, np.float32), np.ascontiguousarray(occupied_ids, np.int32)
+        c = None if grid_rgb is None else np.ascontiguousarray(grid_rgb, np.uint8)
+        assert o.shape == tuple(self.shape)
+        if lib().oracle_builder_import(self._h, _p(f), _p(p), _p(w), _p(c), _p(o), f.shape[0]) != 0:
+            raise RuntimeError("oracle import: capacity too small or builder not fresh")
+
     @property
     def num_oob(self) -> int:
         return int(lib().oracle_builder_num_oob(self._h))
@@ -305,8 +316,9 @@ class BuildOracle:
             pass
 
 
-def build_map(map_config: dict, poses: np.ndarray, depths, rgbs, feats, sample_idx, capacity=None):
-    """Whole build from the same inputs ref_shim.ref_build takes (vlmap_builder.py:54-185)."""
+def build_map(map_config: dict, poses: np.ndarray, depths, rgbs, feats, sample_idx, capacity=None, resume=None):
+    """Whole build from the same inputs ref_shim.ref_build takes (vlmap_builder.py:54-185).
+    `resume`: dict of a saved map (grid_feat, grid_pos, weight, grid_rgb, occupied_ids) reloaded first (:212-222)."""
     cs, gs = map_config["cell_size"], map_config["grid_size"]
     vh = int(map_config["pose_info"]["camera_height"] / cs)  # vlmap_builder.py:201
     base2cam_tf, base_transform = setup_transforms(map_config["pose_info"])
@@ -315,6 +327,8 @@ def build_map(map_config: dict, poses: np.ndarray, depths, rgbs, feats, sample_i
     kinv = np.linalg.inv(calib)  # mapping_utils.py:237
     D = feats[0].shape[1]
     b = BuildOracle(gs, vh, cs, D, capacity)
+    if resume is not None:
+        b.import_state(resume["grid_feat"], resume["grid_pos"], resume["weight"], resume.get("grid_rgb"), resume["occupied_ids"])
     for i, tf in enumerate(tfs):
         kfeat = get_sim_cam_mat(feats[i].shape[2], feats[i].shape[3])  # vlmap_builder.py:126
         b.add_frame(depths[i], feats[i], None if rgbs is None else rgbs[i], sample_idx[i], kinv, calib, kfeat, tf)

@@ -80,6 +80,21 @@ oracle_builder* oracle_builder_create_global(int32_t n_row, int32_t n_col, int32
 }
 int64_t oracle_builder_num_oob(const oracle_builder* b) { return b->n_oob; }
 
+/* _init_map's reload of a saved map (vlmap_builder.py:212-222): the arrays ARE the loaded ones and
+ * max_id = grid_feat.shape[0]; the frame loop then fuses on top.  (The reference's arrays are exactly V rows
+ * long at this point and double on the next insert; the oracle just needs capacity >= V + new voxels.) */
+int oracle_builder_import(oracle_builder* b, const float* grid_feat, const int32_t* grid_pos, const float* weight,
+                          const uint8_t* grid_rgb, const int32_t* occupied_ids, int64_t v) {
+  if (v > b->capacity || b->max_id != 0) return -1;
+  memcpy(b->grid_feat, grid_feat, (size_t)v * b->dim * sizeof(float));
+  memcpy(b->grid_pos, grid_pos, (size_t)v * 3 * sizeof(int32_t));
+  memcpy(b->weight, weight, (size_t)v * sizeof(float));
+  if (grid_rgb) memcpy(b->grid_rgb, grid_rgb, (size_t)v * 3);
+  memcpy(b->occupied_ids, occupied_ids, (size_t)b->n0 * b->n1 * b->n2 * sizeof(int32_t));
+  b->max_id = v;
+  return 0;
+}
+
 void oracle_builder_destroy(oracle_builder* b) {
   if (!b) return;
   free(b->grid_feat); free(b->grid_pos); free(b->weight); free(b->occupied_ids); free(b->grid_rgb); free(b);

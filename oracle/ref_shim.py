@@ -108,11 +108,13 @@ def ref_transforms(map_config):
     return base2cam_tf, base_transform
 
 
-def ref_build(map_config: dict, poses: np.ndarray, depths, rgbs, feats, seed: int):
+def ref_build(map_config: dict, poses: np.ndarray, depths, rgbs, feats, seed: int, resume: dict | None = None):
     """Run the reference's VLMapBuilder.create_mobile_base_map (vlmap_builder.py:54-185) on synthetic
     frames.  depths[i] (H,W) f32, rgbs[i] (H,W,3) u8 RGB, feats[i] (1,D,FH,FW) f32.
     Returns dict(grid_feat, grid_pos, weight, occupied_ids, grid_rgb, sample_idx) where sample_idx[i]
-    is the pixel order the reference's global-RNG shuffle produced for frame i."""
+    is the pixel order the reference's global-RNG shuffle produced for frame i.
+    `resume`: a previously saved map; a placeholder vlmap/vlmaps.h5df is created so that _init_map takes its
+    reload branch (:212-222) and load_3d_map (h5py) is patched to return these arrays."""
     import cv2
 
     vb = load("ref_vlmap_builder", "avlmaps/map/vlmap_builder.py")
@@ -160,17 +162,23 @@ def ref_build(map_config: dict, poses: np.ndarray, depths, rgbs, feats, seed: in
             depth_paths.append(dp)
         pose_path = td / "poses.txt"
         np.savetxt(pose_path, poses)
-        saved = (vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map)
+        saved = (vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map, vb.load_3d_map)
         vb.VLMapBuilder._init_lseg = fake_init_lseg
         vb.get_lseg_feat = fake_get_lseg_feat
         vb.save_3d_map = fake_save
+        if resume is not None:
+            (td / "vlmap").mkdir()
+            (td / "vlmap" / "vlmaps.h5df").write_bytes(b"placeholder")
+            vb.load_3d_map = lambda path: (list(resume["mapped_iter_list"]), resume["grid_feat"].copy(),
+                                           resume["grid_pos"].copy(), resume["weight"].copy(),
+                                           resume["occupied_ids"].copy(), resume["grid_rgb"].copy())
         np.random.shuffle = recording_shuffle
         try:
             np.random.seed(seed)
             b = vb.VLMapBuilder(td, cfg, pose_path, rgb_paths, depth_paths, base2cam_tf, base_transform)
             b.create_mobile_base_map()
         finally:
-            vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map = saved
+            vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map, vb.load_3d_map = saved
             np.random.shuffle = orig_shuffle
     rate = map_config["depth_sample_rate"]
     captured["sample_idx"] = [s[::rate].astype(np.int32) for s in sample_orders]

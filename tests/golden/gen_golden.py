@@ -85,6 +85,25 @@ def gen_build(name, n_frames, h, w, fh, fw, d, gs, cs, cam_h, calib, rate, seed,
           f"weight dtype {out['weight'].dtype}, rgb dtype {out['grid_rgb'].dtype}")
 
 
+def gen_build_resume(name, n_first, n_frames, h, w, fh, fw, d, gs, cs, cam_h, calib, rate, seed, radius=0.3):
+    """Run the reference twice: frames [0, n_first) from scratch, then ALL frames again with the first result
+    on disk, so that _init_map takes its reload branch (vlmap_builder.py:212-222)."""
+    cfg = synth.map_config(gs, cs, cam_h, calib, rate)
+    poses = synth.circle_poses(n_frames, radius=radius)
+    depths, rgbs, feats = synth.build_inputs(n_frames, h, w, fh, fw, d, seed=seed)
+    first = ref_shim.ref_build(cfg, poses[:n_first], depths[:n_first], rgbs[:n_first], feats[:n_first], seed=seed)
+    out = ref_shim.ref_build(cfg, poses, depths, rgbs, feats, seed=seed + 1, resume=first)
+    kw = dict(cfg_gs=gs, cfg_cs=cs, cfg_cam_h=cam_h, cfg_calib=np.asarray(calib, np.float64), cfg_rate=rate, seed=seed,
+              n_first=n_first, n_frames=n_frames, h=h, w=w, fh=fh, fw=fw, d=d, radius=radius, poses=poses,
+              sample_idx=np.stack(out["sample_idx"]).astype(np.int32), mapped_iter_list=np.array(out["mapped_iter_list"]))
+    for k in ("grid_feat", "grid_pos", "weight", "occupied_ids", "grid_rgb"):
+        kw["first_" + k] = first[k]
+        kw[k] = out[k]
+    np.savez_compressed(OUT / f"build_{name}.npz", **kw)
+    print(f"build_{name}: {first['grid_feat'].shape[0]} voxels reloaded -> {out['grid_feat'].shape[0]}; dtypes after "
+          f"the reference's capacity doubling: weight {out['weight'].dtype}, grid_rgb {out['grid_rgb'].dtype}")
+
+
 def gen_multi_floor(name, n_frames, h, w, fh, fw, d, cs, calib, rate, skip, seed):
     cfg = synth.multi_floor_config(cs, calib, rate, skip_frame=skip)
     poses = synth.global_cam_poses(n_frames)
@@ -131,6 +150,8 @@ def main():
     # larger spread: points leave the grid, several frames revisit the same cells
     gen_build("revisit", 6, 60, 80, 49, 65, 12, gs=48, cs=0.1, cam_h=1.6, calib=[40, 0, 40, 0, 40, 30, 0, 0, 1],
               rate=2, seed=3, radius=0.3)
+    gen_build_resume("resume", 2, 4, 60, 80, 49, 65, 6, gs=48, cs=0.1, cam_h=1.6, calib=[40, 0, 40, 0, 40, 30, 0, 0, 1],
+                     rate=2, seed=6)
     gen_heat("n600", 600, seed=50)
     # multi-floor builder: uint16 mm depth, global-frame grid from a first pass, np.round cells
     gen_multi_floor("rate1", 4, 48, 64, 39, 52, 8, 0.05, k10, rate=1, skip=1, seed=0)

@@ -292,3 +292,30 @@ def test_set_slab_after_first_frame_is_a_state_error(eng):
     with pytest.raises(AvlError):
         b.set_slab(0, 16)
     b.close()
+
+
+def test_resume_from_saved_map(eng):
+    """avl_builder_import + frames == the reference run on top of a saved map (vlmap_builder.py:212-222)."""
+    from avlmaps_b200._lib import AvlError
+
+    g = np.load(G / "build_resume.npz")
+    cfg = synth.map_config(int(g["cfg_gs"]), float(g["cfg_cs"]), float(g["cfg_cam_h"]), g["cfg_calib"], int(g["cfg_rate"]))
+    depths, rgbs, feats = synth.build_inputs(int(g["n_frames"]), int(g["h"]), int(g["w"]), int(g["fh"]), int(g["fw"]),
+                                             int(g["d"]), seed=int(g["seed"]))
+    cs, gs = cfg["cell_size"], cfg["grid_size"]
+    vh = int(cfg["pose_info"]["camera_height"] / cs)
+    tfs, calib, kinv = scene_mats(cfg, g["poses"])
+    b = eng.DeviceBuilder(gs, vh, cs, int(g["d"]), capacity=64)  # smaller than the saved map: rows are re-allocated
+    b.import_state(g["first_grid_feat"], g["first_grid_pos"], g["first_weight"], g["first_grid_rgb"])
+    assert b.num_voxels == g["first_grid_feat"].shape[0]
+    for i, tf in enumerate(tfs):
+        b.add_frame(depths[i], feats[i], kinv, calib, O.get_sim_cam_mat(int(g["fh"]), int(g["fw"])), tf, rgb=rgbs[i],
+                    sample_idx=g["sample_idx"][i])
+    out = b.export()
+    ref = {k: g[k] for k in ("grid_feat", "grid_pos", "occupied_ids")}
+    ref["weight"] = g["weight"].astype(np.float32)
+    ref["grid_rgb"] = np.clip(g["grid_rgb"], 0, 255).astype(np.uint8)
+    assert_build_equal(out, ref)
+    with pytest.raises(AvlError):  # only a fresh builder can adopt a saved map
+        b.import_state(g["first_grid_feat"], g["first_grid_pos"], g["first_weight"])
+    b.close()

@@ -205,3 +205,84 @@ def test_multi_floor_create_and_load_like_the_reference(lib, tmp_path):
     tf, _, _ = landmark_text_feats(enc, ["sofa"], int(g["d"]), True, 0, True)
     assert np.array_equal(vlmap.index_map("sofa", with_init_cat=False), O.index_mask(O.scores(vlmap.grid_feat, tf), 0))
     assert vlmap.map_builder.create_mobile_base_map() is NotImplementedError
+
+
+def test_create_map_twice_resumes_like_the_reference(lib, tmp_path):
+    """A second create_map over an existing vlmaps file reloads it and fuses every frame on top
+    (vlmap_builder.py:212-222, the loop never skips mapped frames): checked against the C oracle."""
+    from avlmaps_b200.map import VLMap
+
+    n_frames, h, w, fh, fw, d = 3, 60, 80, 49, 65, 8
+    cfg = synth.map_config(48, 0.1, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], 2)
+    poses = synth.circle_poses(n_frames, radius=0.3)
+    depths, rgbs, feats = synth.build_inputs(n_frames, h, w, fh, fw, d, seed=8)
+    write_scene(tmp_path, poses, depths, rgbs)
+    for seed in (5, 6):
+        it = iter(feats)
+        vlmap = VLMap(cfg, feature_fn=lambda rgb: next(it))
+        np.random.seed(seed)
+        vlmap.create_map(tmp_path)
+    assert vlmap.load_map(tmp_path) is True
+    np.random.seed(5)
+    s1 = [O.sample_order(h * w, 2) for _ in range(n_frames)]
+    first = O.build_map(cfg, poses, depths, rgbs, feats, s1, capacity=48 * 48 * 16)
+    np.random.seed(6)
+    s2 = [O.sample_order(h * w, 2) for _ in range(n_frames)]
+    ref = O.build_map(cfg, poses, depths, rgbs, feats, s2, capacity=48 * 48 * 16, resume=first)
+    assert np.array_equal(vlmap.grid_pos, ref["grid_pos"]) and np.array_equal(vlmap.occupied_ids, ref["occupied_ids"])
+    assert np.allclose(vlmap.weight, ref["weight"], rtol=1e-3)
+    assert np.allclose(vlmap.grid_feat, ref["grid_feat"], rtol=1e-3, atol=1e-5)
+
+
+def test_area_and_sound_map_similarity_call_sites(lib):
+    """AreaMap.init_categories / index_map (area_map.py:99-119) and SoundMap (sound_map.py:102-153): the golden
+    logits of the reference's torch expression, its argmax retrieval and its min-max."""
+    from avlmaps_b200.map import AreaMap, SoundMap
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "sound_m64_c12.npz")
+    a, t = g["a"], g["t"]
+    db = {i: {"audio_features": a[i], "locations": [np.array([i, 0.0, -i])]} for i in range(a.shape[0])}
+    cats = [f"sound{j}" for j in range(t.shape[0])]
+    sm = SoundMap(cats, text_encoder=lambda texts: t, logit_scale_at=np.log(1 / 0.07) + 3.0, audio_database=db,
+                  audio_encoder=lambda path, sr: a[17])
+    assert sm.scale_audio_text == float(g["scale"]) == 100.0
+    cat = int(g["cat_id"])
+    prob, locs = sm.get_distribution_and_locations(cats[cat])
+    assert np.allclose(prob, g["prob"], atol=2e-6) and len(locs) == a.shape[0]
+    assert np.array_equal(sm.get_pos(cats[cat])[0], db[int(g["retrievals"][cat])]["locations"][0])
+    assert np.array_equal(sm.get_pos_with_audio(__file__, 44100)[0], db[17]["locations"][0])   # a @ a[17] peaks at 17
+    assert sm.get_pos_with_audio("/nonexistent.wav", 44100) == ([], [])
+    # AreaMap: true cosine of unit rows; text rows are normalised by get_text_feats like the reference
+    rng = np.random.default_rng(3)
+    frames = rng.standard_normal((40, 768)).astype(np.float32)
+    frames /= np.linalg.norm(frames, axis=1, keepdims=True)
+    enc = fake_encoder(768)
+    am = AreaMap(text_encoder=enc)
+    am.set_sparse_map(frames, [np.eye(4)] * 40)
+    with pytest.raises(Exception, match="Categories are not preloaded"):
+        am.index_map("kitchen")
+    tf = enc(["kitchen", "bedroom"])
+    tf /= np.linalg.norm(tf, axis=1, keepdims=True)
+    sc = am.init_categories(["kitchen", "bedroom"])
+    assert np.array_equal(sc, O.scores(frames, tf))
+    assert np.allclose(sc, frames @ tf.T, atol=1e-6)
+    assert np.array_equal(am.index_map("bedroom"), sc[:, 1])
+    assert np.array_equal(am.index_map("kitchen", with_init_cat=False), O.scores(frames, tf[:1]).flatten())
+
+
+def test_image_heat_planar(lib):
+    """AVLMap.index_image's numeric lines (avlmap.py:156-162) as numpy executes them, bit for bit."""
+    from avlmaps_b200.map import AVLMap
+
+    rng = np.random.default_rng(9)
+    pos = rng.integers(0, 1000, (5000, 3)).astype(np.int32)
+    cfg = {"map_config": synth.map_config(1000, 0.05, 1.5, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1), "params": {"cs": 0.05}}
+    av = AVLMap(cfg)
+    av.vlmap.grid_pos = pos
+    row, col, height, decay = 417, 633, 1.5 / 0.05, 0.01
+    p = np.array([row, col, height])
+    sim_mat = np.zeros((pos.shape[0], 1))
+    sim_mat[:, 0] = np.clip(1.0 - decay * np.linalg.norm((pos - p)[:, :2], axis=1), 0, 1)
+    want = np.max(sim_mat, axis=1).flatten()
+    got = av.image_heat(row, col, decay)
+    assert got.dtype == np.float64 and np.array_equal(got, want)

@@ -156,3 +156,27 @@ def test_matmul_restatement_matches_numpy_here():
                     for i in range(3)])
     if not np.array_equal(got, y):
         pytest.skip("this host's BLAS does not use the FMA left-to-right kernel the goldens were produced with")
+
+
+def load_resume_case():
+    g = np.load(G / "build_resume.npz")
+    cfg = synth.map_config(int(g["cfg_gs"]), float(g["cfg_cs"]), float(g["cfg_cam_h"]), g["cfg_calib"], int(g["cfg_rate"]))
+    depths, rgbs, feats = synth.build_inputs(int(g["n_frames"]), int(g["h"]), int(g["w"]), int(g["fh"]), int(g["fw"]),
+                                             int(g["d"]), seed=int(g["seed"]))
+    first = {k: g["first_" + k] for k in ("grid_feat", "grid_pos", "weight", "occupied_ids", "grid_rgb")}
+    return g, cfg, depths, rgbs, feats, first
+
+
+def test_resume_from_saved_map_matches_reference():
+    """_init_map's reload branch (vlmap_builder.py:212-222): the reference re-fuses all frames on top of the saved
+    map.  ids / positions bit-exact; the floats to 1e-5 because after the reload the reference's first
+    _reserve_map_space turns `weight` into float64 and `grid_rgb` into float32 (:304-310), which is not restated."""
+    g, cfg, depths, rgbs, feats, first = load_resume_case()
+    gs, vh = int(g["cfg_gs"]), int(float(g["cfg_cam_h"]) / float(g["cfg_cs"]))
+    out = O.build_map(cfg, g["poses"], depths, rgbs, feats, list(g["sample_idx"]), capacity=gs * gs * vh, resume=first)
+    assert g["weight"].dtype == np.float64 and g["grid_rgb"].dtype == np.float32  # the drift, as executed
+    assert np.array_equal(out["grid_pos"], g["grid_pos"]) and np.array_equal(out["occupied_ids"], g["occupied_ids"])
+    assert np.array_equal(out["grid_pos"][:first["grid_pos"].shape[0]], first["grid_pos"])  # reloaded ids are kept
+    assert np.allclose(out["weight"], g["weight"], rtol=1e-5)
+    assert np.allclose(out["grid_feat"], g["grid_feat"], rtol=1e-5, atol=1e-5)
+    assert g["mapped_iter_list"].tolist() == [0, 1, 2, 3]
