@@ -122,4 +122,27 @@ int launch_fuse_heat(const float* sa, const float* sb, int64_t n, int32_t pair, 
                      const float* min_a, const float* max_a, const float* min_b, const float* max_b,
                      int32_t combine, float* heat, cudaStream_t s);
 
+
+// ---- cross-modal fusion through the screen (sim_exact.cu)
+struct FuseSideHost {
+  const float* dense;     // (pairs, n) column-major screen scores of this modality
+  const float* row_c; const float* row_an; const float* row_norm;
+  const float* q_bn; const float* q_glob; const float* scale;
+  const float* feat; const float* q;
+  int32_t d; int32_t normalize;
+};
+struct FuseScratch {
+  uint32_t* max_lb; uint32_t* min_ub;      // [2 * pairs] ordered-uint column statistics
+  uint32_t* ext_cnt; uint32_t* ext_row;    // [4 * pairs], [4 * pairs][ext_cap] candidates of the column max / min
+  uint32_t ext_cap;
+  float* mm;                               // [4][pairs]: min a, max a, min b, max b (exact)
+  float* sample_t; int32_t n_sample; int64_t sample_stride;
+  float* thr;                              // [pairs]
+  uint32_t* cand_cnt; uint32_t* cand_row; uint32_t cand_cap;
+  uint32_t* overflow;                      // [1]
+};
+int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n, int32_t pairs, int32_t combine,
+                         int32_t k, const FuseScratch& w, int64_t* out_idx, float* out_heat, int num_sms,
+                         cudaStream_t s);
+
 }  // namespace avl

@@ -16,6 +16,7 @@
 // scatter-reduce (warp per point, float4 vector reds into the voxel row).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "avl_internal.h"
@@ -73,7 +74,8 @@ geom_kernel(const FrameGeom g, const float* __restrict__ depth, const int32_t* _
             int32_t n_samples, uint32_t frame_seq, unsigned long long* __restrict__ first_key,
             int32_t* __restrict__ s_cell, int32_t* __restrict__ s_fpix, float* __restrict__ s_alpha,
             int32_t* __restrict__ s_rgbpix, uint8_t* __restrict__ s_wrap,
-            unsigned long long* __restrict__ n_oob) {
+            unsigned long long* __restrict__ n_oob, uint32_t* __restrict__ ticket) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // for the look-back scan that follows in stream order
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
     const int pix = sample_idx ? sample_idx[j] : j;
     const int v = pix / g.w, u = pix - v * g.w;
@@ -376,6 +378,99 @@ assign_ids_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_
   }
 }
 
+// ---------------------------------------------------------------- ordered id assignment, single pass
+// winner count + exclusive scan + id assignment in ONE kernel (decoupled look-back): block t (ticket order)
+// publishes its winner count, then sums the counts of its predecessors until it meets an inclusive prefix.
+// scan_state[t] = frame tag (30 bits) | status (2 bits: 1 = aggregate, 2 = inclusive prefix) | value (32 bits);
+// the tag makes entries of earlier frames read as "not yet published", so the array is never cleared.
+// *ticket is zeroed by the geometry kernel of the same frame (stream order).
+constexpr unsigned long long kStAggregate = 1ull << 32, kStInclusive = 2ull << 32;
+
+__global__ void __launch_bounds__(kScanBlock)
+assign_ids_lookback_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_t frame_seq,
+                           const unsigned long long* __restrict__ first_key, unsigned long long* __restrict__ scan_state,
+                           uint32_t* __restrict__ ticket, int32_t n0, int32_t n1, int32_t n2,
+                           const uint8_t* __restrict__ s_wrap, int64_t capacity, int32_t* __restrict__ occupied_ids,
+                           int32_t* __restrict__ grid_pos, unsigned long long* __restrict__ max_id,
+                           unsigned long long* __restrict__ n_accepted) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t s_ticket, s_base;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t t = s_ticket;
+  const int j = static_cast<int>(t) * kScanBlock + threadIdx.x;
+  const int cell = j < n_samples ? s_cell[j] : -1;
+  const bool win = is_winner(first_key, cell, frame_seq, j);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b = __ballot_sync(0xffffffffu, win);
+  const uint32_t acc_b = __ballot_sync(0xffffffffu, cell >= 0);
+  if (lane == 0) warp_tot[warp] = static_cast<uint32_t>(__popc(b)) | (static_cast<uint32_t>(__popc(acc_b)) << 16);
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t packed = warp_tot[lane];
+    uint32_t wins = packed & 0xffffu, acc = packed >> 16;
+    uint32_t incl = wins;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    warp_tot[lane] = incl;  // inclusive winner totals of the warps
+    const uint32_t agg = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned long long tag = static_cast<unsigned long long>(frame_seq & 0x3fffffffu) << 34;
+    uint32_t prefix = 0;
+    if (t == 0) {
+      prefix = static_cast<uint32_t>(*max_id);
+    } else {
+      if (lane == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(scan_state + t) = tag | kStAggregate | agg;
+        __threadfence();
+      }
+      int idx = static_cast<int>(t) - 1;
+      while (true) {
+        const int k = idx - lane;
+        unsigned long long v = 0;
+        if (k >= 0) {
+          do {
+            v = *reinterpret_cast<volatile unsigned long long*>(scan_state + k);
+          } while ((v >> 34) != (tag >> 34) || ((v >> 32) & 3ull) == 0ull);
+        } else {
+          v = tag | kStInclusive;  // before block 0: contributes nothing, terminates the walk
+        }
+        const bool inclusive = ((v >> 32) & 3ull) == 2ull;
+        const uint32_t first = __ffs(__ballot_sync(0xffffffffu, inclusive));  // nearest predecessor with a full prefix
+        uint32_t val = (first == 0 || lane < static_cast<int>(first)) ? static_cast<uint32_t>(v) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        prefix += val;
+        if (first) break;
+        idx -= 32;
+      }
+    }
+    if (lane == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(scan_state + t) = tag | kStInclusive | (prefix + agg);
+      __threadfence();
+      s_base = prefix;
+      if (acc) atomicAdd(n_accepted, static_cast<unsigned long long>(acc));
+      if (t == gridDim.x - 1) *max_id = prefix + agg;
+    }
+  }
+  __syncthreads();
+  if (win) {
+    const int64_t id = static_cast<int64_t>(s_base) + (warp ? warp_tot[warp - 1] : 0u) + __popc(b & ((1u << lane) - 1u));
+    if (id < capacity) {
+      occupied_ids[cell] = static_cast<int32_t>(id);  // vlmap_builder.py:165
+      const int hh = cell % n2, rc = cell / n2;
+      const unsigned wrap = s_wrap[j];
+      grid_pos[id * 3 + 0] = rc / n1 - ((wrap & 1u) ? n0 : 0);  // vlmap_builder.py:169, vlmap_builder_multi_floor.py:176
+      grid_pos[id * 3 + 1] = rc % n1 - ((wrap & 2u) ? n1 : 0);
+      grid_pos[id * 3 + 2] = hh - ((wrap & 4u) ? n2 : 0);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- feature layout
 // (D, P) -> (P, D), P = FH*FW pixels.  64 pixels x 64 channels per block through shared memory:
 // 256-byte contiguous reads per channel row, 256-byte contiguous writes per pixel row (float4 both
@@ -536,6 +631,8 @@ struct avl_builder {
   float* s_alpha = nullptr;
   uint8_t* s_wrap = nullptr;
   uint32_t* block_cnt = nullptr;
+  unsigned long long* scan_state = nullptr;  // per 1024-sample block: look-back scan state (tagged by frame)
+  uint32_t* ticket = nullptr;
   int64_t scratch_samples = 0;
   // staging of host inputs
   float* d_depth = nullptr; size_t depth_elems = 0;
@@ -702,7 +799,8 @@ int avl_builder_destroy(avl_builder* b) {
   if (!b) return AVL_OK;
   cudaFree(b->first_key); cudaFree(b->occupied_ids); cudaFree(b->num); cudaFree(b->den); cudaFree(b->rgb_acc);
   cudaFree(b->grid_pos); cudaFree(b->counters); cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix);
-  cudaFree(b->s_alpha); cudaFree(b->s_wrap); cudaFree(b->block_cnt); cudaFree(b->d_depth); cudaFree(b->d_feat); cudaFree(b->d_feat_t);
+  cudaFree(b->s_alpha); cudaFree(b->s_wrap); cudaFree(b->block_cnt); cudaFree(b->scan_state); cudaFree(b->ticket);
+  cudaFree(b->d_depth); cudaFree(b->d_feat); cudaFree(b->d_feat_t);
   cudaFree(b->d_rgb); cudaFree(b->d_sidx);
   delete b;
   return AVL_OK;
@@ -762,8 +860,9 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   // ---- scratch
   if (b->scratch_samples < n_samples) {
     cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
-    cudaFree(b->block_cnt);
+    cudaFree(b->block_cnt); cudaFree(b->scan_state);
     b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
+    b->scan_state = nullptr;
     b->scratch_samples = 0;
     const size_t n = static_cast<size_t>(n_samples);
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_cell), n * sizeof(int32_t)));
@@ -772,6 +871,9 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_alpha), n * sizeof(float)));
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_wrap), n));
     AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->block_cnt), ((n + kScanBlock - 1) / kScanBlock) * sizeof(uint32_t)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->scan_state), ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long)));
+    AVL_CUDA(cudaMemsetAsync(b->scan_state, 0xff, ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long), s));
+    if (!b->ticket) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->ticket), sizeof(uint32_t)));
     b->scratch_samples = n_samples;
   }
   if ((rc = ensure_capacity(b, n_samples, s))) return rc;
@@ -789,13 +891,21 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   const int nblocks = (n_samples + kScanBlock - 1) / kScanBlock;
   const int geom_blocks = std::min((n_samples + 255) / 256, b->num_sms * 8);
   geom_kernel<<<geom_blocks, 256, 0, s>>>(g, depth, sidx, n_samples, b->frame_seq, b->first_key, b->s_cell,
-                                          b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap, b->counters + 2);
-  winner_count_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
-                                                     b->block_cnt, b->counters + 1);
-  winner_scan_kernel<<<1, kScanBlock, 0, s>>>(b->block_cnt, nblocks, b->counters);
-  assign_ids_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key, b->block_cnt,
-                                                   b->n0, b->n1, b->n2, b->s_wrap, b->capacity, b->occupied_ids,
-                                                   b->grid_pos);
+                                          b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap, b->counters + 2, b->ticket);
+  static const bool three_pass = getenv("AVL_BUILD_3PASS") != nullptr;  // the original count / scan / assign kernels (A/B)
+  if (three_pass) {
+    winner_count_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
+                                                       b->block_cnt, b->counters + 1);
+    winner_scan_kernel<<<1, kScanBlock, 0, s>>>(b->block_cnt, nblocks, b->counters);
+    assign_ids_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key, b->block_cnt,
+                                                     b->n0, b->n1, b->n2, b->s_wrap, b->capacity, b->occupied_ids,
+                                                     b->grid_pos);
+  } else {
+    assign_ids_lookback_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
+                                                              b->scan_state, b->ticket, b->n0, b->n1, b->n2, b->s_wrap,
+                                                              b->capacity, b->occupied_ids, b->grid_pos, b->counters,
+                                                              b->counters + 1);
+  }
   const int scatter_blocks = std::min((n_samples + 7) / 8, b->num_sms * 8);
   scatter_kernel<<<scatter_blocks, 256, 0, s>>>(feat, d, rgb, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix,
                                                 n_samples, b->frame_seq, b->first_key, b->occupied_ids,

@@ -87,6 +87,10 @@ struct Workspace {
   uint32_t* overflow = nullptr;  // [256]
   float* sample_t = nullptr;
   size_t sample_elems = 0;
+  float* fuse_a = nullptr;       // (pairs, n) dense screen scores of the two modalities (avl_fuse_topk)
+  float* fuse_b = nullptr;
+  size_t fuse_elems = 0;
+  uint32_t* fuse_small = nullptr;  // column statistics, extreme-candidate lists, exact min / max
   int64_t* out_idx = nullptr;  // [256 x AVL_MAX_TOPK]
   float* out_score = nullptr;
   int32_t* argmax = nullptr;   // [n] (host-pointer calls)
@@ -154,6 +158,7 @@ static void ws_free(Workspace& w) {
   cudaFree(w.flag_count); cudaFree(w.flag_rows); cudaFree(w.flag_masks); cudaFree(w.cand_cnt);
   cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
+  cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
   for (int i = 0; i < 4; ++i)
     if (w.ev[i]) cudaEventDestroy(w.ev[i]);
@@ -732,9 +737,10 @@ int avl_merge_topk(const int64_t* idx, const float* val, int32_t n_shards, int32
   return launch_merge_topk(idx, val, n_shards, nq, k, out_idx, out_val, static_cast<cudaStream_t>(stream));
 }
 
-int avl_fuse_topk(avl_map* ma, const float* qa, const float* scale_a, int normalize_a, avl_map* mb,
-                  const float* qb, const float* scale_b, int normalize_b, int32_t n_pairs, int32_t combine,
-                  int32_t k, int64_t* out_idx, float* out_heat, int flags, void* stream) {
+// exact path: fp64-accumulated dense columns of both modalities, min-max, combine, vector top-k per pair
+static int fuse_topk_exact(avl_map* ma, const float* qa, const float* scale_a, int normalize_a, avl_map* mb,
+                           const float* qb, const float* scale_b, int normalize_b, int32_t n_pairs, int32_t combine,
+                           int32_t k, int64_t* out_idx, float* out_heat, int flags, void* stream) {
   AVL_ARG(ma && mb && qa && qb && out_idx && out_heat, "NULL argument");
   AVL_ARG(ma->n == mb->n, "both maps must have the same number of rows");
   AVL_ARG(n_pairs >= 1 && n_pairs <= AVL_MAX_QUERIES, "n_pairs out of range");
@@ -784,6 +790,108 @@ int avl_fuse_topk(avl_map* ma, const float* qa, const float* scale_a, int normal
   if (e != cudaSuccess && rc == AVL_OK) rc = cuda_fail(e, "fuse", __FILE__, __LINE__);
   cudaFree(da); cudaFree(db); cudaFree(mm);
   return rc;
+}
+
+// screened path: two dense tcgen05 passes + interval propagation + exact re-score of the survivors (sim_exact.cu,
+// "cross-modal fusion through the screen").  Returns 1 when the call must be redone by the exact path
+// (candidate-list overflow: massive ties, degenerate columns).
+static int fuse_topk_screened(avl_map* ma, const float* qa, const float* scale_a, int normalize_a, avl_map* mb,
+                              const float* qb, const float* scale_b, int normalize_b, int32_t n_pairs, int32_t combine,
+                              int32_t k, int64_t* out_idx, float* out_heat, int flags, cudaStream_t s) {
+  const int64_t n = ma->n;
+  QuerySetup sa, sb;
+  int rc;
+  if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, true, s, &sa))) return rc;
+  if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, true, s, &sb))) return rc;
+  if (sa.ts || sb.ts) return 1;
+  Workspace& w = ma->ws;
+  const uint32_t cand_cap = 8192, ext_cap = 2048;
+  if ((rc = ensure_cands(ma, cand_cap))) return rc;
+  // sample for the heat threshold: same sizing rule as avl_sim_topk
+  int64_t n0 = std::max<int64_t>(n / 64, static_cast<int64_t>(k) * n / 1024);
+  n0 = std::min<int64_t>(std::max<int64_t>(n0, 8192), n);
+  const int64_t stride = std::max<int64_t>(1, n / n0);
+  const int32_t n_sample = static_cast<int32_t>((n + stride - 1) / stride);
+  if ((rc = ensure_sample(ma, static_cast<size_t>(n_sample) * n_pairs))) return rc;
+  const size_t elems = static_cast<size_t>(n) * n_pairs;
+  if (w.fuse_elems < elems) {
+    cudaFree(w.fuse_a); cudaFree(w.fuse_b);
+    w.fuse_a = w.fuse_b = nullptr;
+    w.fuse_elems = 0;
+    if ((rc = dev_alloc(&w.fuse_a, elems, &ma->bytes))) return rc;
+    if ((rc = dev_alloc(&w.fuse_b, elems, &ma->bytes))) return rc;
+    w.fuse_elems = elems;
+  }
+  if (!w.fuse_small) {
+    // max_lb[512] min_ub[512] ext_cnt[1024] mm[1024 floats] overflow[1] | ext_row[1024][ext_cap]
+    if ((rc = dev_alloc(&w.fuse_small, static_cast<size_t>(3200) + static_cast<size_t>(4) * AVL_MAX_QUERIES * ext_cap, &ma->bytes)))
+      return rc;
+  }
+  for (int side = 0; side < 2; ++side) {
+    avl_map* m = side ? mb : ma;
+    const QuerySetup& qs = side ? sb : sa;
+    ScreenParams p;
+    base_params(m, qs, n_pairs, 0, &p);
+    p.mode = kModeDense;
+    p.dense_out = side ? w.fuse_b : w.fuse_a;
+    p.dense_rs = 1;
+    p.dense_cs = n;
+    p.dense_cols = n_pairs;
+    if ((rc = run_screen(m, qs, p, s))) return rc;
+  }
+  FuseSideHost ha{w.fuse_a, ma->row_c, ma->row_an, ma->row_norm, ma->ws.q_bn, ma->ws.q_glob, sa.scale_dev, ma->feat, sa.q_dev, ma->d, normalize_a};
+  FuseSideHost hb{w.fuse_b, mb->row_c, mb->row_an, mb->row_norm, mb->ws.q_bn, mb->ws.q_glob, sb.scale_dev, mb->feat, sb.q_dev, mb->d, normalize_b};
+  FuseScratch fs;
+  fs.max_lb = w.fuse_small;
+  fs.min_ub = w.fuse_small + 512;
+  fs.ext_cnt = w.fuse_small + 1024;
+  fs.mm = reinterpret_cast<float*>(w.fuse_small + 2048);
+  fs.overflow = w.fuse_small + 3072;
+  fs.ext_row = w.fuse_small + 3200;
+  fs.ext_cap = ext_cap;
+  fs.sample_t = w.sample_t;
+  fs.n_sample = n_sample;
+  fs.sample_stride = stride;
+  fs.thr = w.thr_t;
+  fs.cand_cnt = w.cand_cnt;
+  fs.cand_row = w.cand_row;
+  fs.cand_cap = cand_cap;
+  int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
+  float* d_heat = (flags & AVL_ON_DEVICE) ? out_heat : w.out_score;
+  if ((rc = launch_fuse_screened(ha, hb, n, n_pairs, combine, k, fs, d_idx, d_heat, ma->num_sms, s))) return rc;
+  uint32_t ovf = 0;
+  AVL_CUDA(cudaMemcpyAsync(&ovf, fs.overflow, sizeof(ovf), cudaMemcpyDeviceToHost, s));
+  if (!(flags & AVL_ON_DEVICE)) {
+    AVL_CUDA(cudaMemcpyAsync(out_idx, d_idx, sizeof(int64_t) * n_pairs * k, cudaMemcpyDeviceToHost, s));
+    AVL_CUDA(cudaMemcpyAsync(out_heat, d_heat, sizeof(float) * n_pairs * k, cudaMemcpyDeviceToHost, s));
+  }
+  {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return check_watchdog(ma, cuda_fail(e, "fuse (screened)", __FILE__, __LINE__));
+  }
+  return ovf ? 1 : AVL_OK;
+}
+
+int avl_fuse_topk(avl_map* ma, const float* qa, const float* scale_a, int normalize_a, avl_map* mb,
+                  const float* qb, const float* scale_b, int normalize_b, int32_t n_pairs, int32_t combine,
+                  int32_t k, int64_t* out_idx, float* out_heat, int flags, void* stream) {
+  AVL_ARG(ma && mb && qa && qb && out_idx && out_heat, "NULL argument");
+  AVL_ARG(ma->n == mb->n, "both maps must have the same number of rows");
+  AVL_ARG(n_pairs >= 1 && n_pairs <= AVL_MAX_QUERIES, "n_pairs out of range");
+  AVL_ARG(k >= 1 && k <= AVL_MAX_TOPK, "k must be in [1, AVL_MAX_TOPK]");
+  AVL_ARG(combine >= AVL_FUSE_PRODUCT && combine <= AVL_FUSE_SUM, "unknown combine rule");
+  int rc = scale_positive(scale_a, n_pairs, flags);
+  if (rc == AVL_OK) rc = scale_positive(scale_b, n_pairs, flags);
+  const bool force_exact = getenv("AVL_FUSE_EXACT") != nullptr;  // A/B and tests of the exact path
+  const bool can_screen = rc == AVL_OK && !force_exact && ma != mb && ma->n >= 1024 &&
+                          ma->n < (int64_t(1) << 32) - 1;
+  if (can_screen) {
+    rc = fuse_topk_screened(ma, qa, scale_a, normalize_a, mb, qb, scale_b, normalize_b, n_pairs, combine, k, out_idx,
+                            out_heat, flags, static_cast<cudaStream_t>(stream));
+    if (rc != 1) return rc;  // done, or a real error
+  }
+  return fuse_topk_exact(ma, qa, scale_a, normalize_a, mb, qb, scale_b, normalize_b, n_pairs, combine, k, out_idx,
+                         out_heat, flags, stream);
 }
 
 }  // extern "C"

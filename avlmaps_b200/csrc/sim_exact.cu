@@ -630,6 +630,271 @@ fuse_heat_kernel(const float* __restrict__ sa, const float* __restrict__ sb, int
   }
 }
 
+// =================================================================== cross-modal fusion through the screen
+// avl_fuse_topk without exact dense columns (BASELINE config 3).  Both modalities are screened by the
+// tcgen05 kernel in dense mode -> s~ (pairs, n) column-major, with the rigorous band
+//     |s~_ij - dot_ij| <= r_i * bn_j,   r_i = (rho * ||a~_i|| + c_i) * (1 + 1e-6)       
+// Everything the reference computes from the exact scores is monotone in them -- the column min / max
+// (sound_map.py:151-152), (s - min) / (max - min) in fp32, product | max | sum of two values in [0, 1] -- so
+// interval bounds propagate through the SAME fp32 operation sequence and decide which rows must be re-scored
+// exactly (fp64-accumulated dots, the canonical score); the returned ids / heats equal the exact path's.
+struct FuseSide {
+  const float* dense;     // (pairs, n) column-major screen scores
+  const float* row_c;
+  const float* row_an;
+  const float* row_norm;
+  const float* q_bn;
+  const float* q_glob;    // [0] = rho
+  const float* scale;     // per pair or null
+  const float* feat;      // fp32 rows for the exact re-score
+  const float* q;         // (pairs, d) fp32 queries
+  int32_t d;
+  int32_t normalize;
+};
+
+struct RowBand { float r, invw; };
+
+__device__ __forceinline__ RowBand fuse_row_band(const FuseSide& m, int64_t row) {
+  RowBand b;
+  b.r = fmaf(__ldg(m.q_glob), __ldg(m.row_an + row), __ldg(m.row_c + row)) * 1.000001f;
+  b.invw = m.normalize ? 1.f / fmaxf(__ldg(m.row_norm + row), 1e-30f) : 1.f;
+  return b;
+}
+// bounds of the canonical score fl(fl(fl(dot) * inv) * scale): the interval of the real-number value, widened by a
+// relative 4e-6 (>> the 3 fp32 roundings of the canonical sequence and the ones made here)
+__device__ __forceinline__ void fuse_bounds(const FuseSide& m, const RowBand& b, float s, int j, float& lo, float& hi) {
+  const float e = b.r * __ldg(m.q_bn + j);
+  lo = (s - e) * b.invw;
+  hi = (s + e) * b.invw;
+  if (m.scale) {
+    const float sc = __ldg(m.scale + j);  // > 0 (checked by the caller)
+    lo *= sc;
+    hi *= sc;
+  }
+  lo = fmaf(-fabsf(lo), 4e-6f, lo);
+  hi = fmaf(fabsf(hi), 4e-6f, hi);
+}
+__device__ __forceinline__ float fuse_combine(float x, float y, int combine) {
+  if (combine == AVL_FUSE_PRODUCT) return __fmul_rn(x, y);
+  if (combine == AVL_FUSE_MAX) return fmaxf(x, y);
+  return __fadd_rn(x, y);
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+constexpr int kFuseChunk = 16;  // columns per thread in the column-statistics passes
+
+// pass 1: per column max of the lower bounds and min of the upper bounds (ordered-uint atomics)
+__global__ void __launch_bounds__(256)
+fuse_colstats_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, uint32_t* __restrict__ max_lb,
+                     uint32_t* __restrict__ min_ub) {
+  const FuseSide& m = blockIdx.z ? sb : sa;
+  const int j0 = blockIdx.y * kFuseChunk;
+  uint32_t mx[kFuseChunk], mn[kFuseChunk];
+#pragma unroll
+  for (int c = 0; c < kFuseChunk; ++c) { mx[c] = 0u; mn[c] = 0xFFFFFFFFu; }
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const RowBand b = fuse_row_band(m, row);
+#pragma unroll
+    for (int c = 0; c < kFuseChunk; ++c) {
+      const int j = j0 + c;
+      if (j < pairs) {
+        float lo, hi;
+        fuse_bounds(m, b, __ldg(m.dense + static_cast<int64_t>(j) * n + row), j, lo, hi);
+        mx[c] = max(mx[c], f2ord(lo));
+        mn[c] = min(mn[c], f2ord(hi));
+      }
+    }
+  }
+  __shared__ uint32_t smx[kFuseChunk], smn[kFuseChunk];
+  if (threadIdx.x < kFuseChunk) { smx[threadIdx.x] = 0u; smn[threadIdx.x] = 0xFFFFFFFFu; }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < kFuseChunk; ++c) {
+    const uint32_t a = __reduce_max_sync(0xffffffffu, mx[c]);
+    const uint32_t i = __reduce_min_sync(0xffffffffu, mn[c]);
+    if ((threadIdx.x & 31) == 0) { atomicMax(smx + c, a); atomicMin(smn + c, i); }
+  }
+  __syncthreads();
+  if (threadIdx.x < kFuseChunk && j0 + threadIdx.x < pairs) {
+    const int o = blockIdx.z * pairs + j0 + threadIdx.x;
+    atomicMax(max_lb + o, smx[threadIdx.x]);
+    atomicMin(min_ub + o, smn[threadIdx.x]);
+  }
+}
+
+// pass 2: rows that can hold a column's exact max (ub >= max lb) or min (lb <= min ub)
+__global__ void __launch_bounds__(256)
+fuse_collect_extreme_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs,
+                            const uint32_t* __restrict__ max_lb, const uint32_t* __restrict__ min_ub,
+                            uint32_t* __restrict__ ext_cnt, uint32_t* __restrict__ ext_row, uint32_t ext_cap) {
+  const FuseSide& m = blockIdx.z ? sb : sa;
+  const int j0 = blockIdx.y * kFuseChunk;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const RowBand b = fuse_row_band(m, row);
+#pragma unroll
+    for (int c = 0; c < kFuseChunk; ++c) {
+      const int j = j0 + c;
+      if (j < pairs) {
+        float lo, hi;
+        fuse_bounds(m, b, __ldg(m.dense + static_cast<int64_t>(j) * n + row), j, lo, hi);
+        const int o = blockIdx.z * pairs + j;
+        if (f2ord(hi) >= __ldg(max_lb + o)) {
+          const uint32_t pos = atomicAdd(ext_cnt + 2 * o, 1u);
+          if (pos < ext_cap) ext_row[static_cast<size_t>(2 * o) * ext_cap + pos] = static_cast<uint32_t>(row);
+        }
+        if (f2ord(lo) <= __ldg(min_ub + o)) {
+          const uint32_t pos = atomicAdd(ext_cnt + 2 * o + 1, 1u);
+          if (pos < ext_cap) ext_row[static_cast<size_t>(2 * o + 1) * ext_cap + pos] = static_cast<uint32_t>(row);
+        }
+      }
+    }
+  }
+}
+
+// pass 3: exact column max / min from the candidates.  grid (pairs, 2 sides), one warp per candidate.
+__global__ void __launch_bounds__(256)
+fuse_exact_extreme_kernel(const FuseSide sa, const FuseSide sb, int32_t pairs, const uint32_t* __restrict__ ext_cnt,
+                          const uint32_t* __restrict__ ext_row, uint32_t ext_cap, float* __restrict__ mm,
+                          uint32_t* __restrict__ overflow) {
+  const FuseSide& m = blockIdx.y ? sb : sa;
+  const int j = blockIdx.x, o = blockIdx.y * pairs + j;
+  __shared__ uint32_t s_ext[2];
+  if (threadIdx.x == 0) { s_ext[0] = 0u; s_ext[1] = 0xFFFFFFFFu; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* b = m.q + static_cast<size_t>(j) * m.d;
+  for (int kind = 0; kind < 2; ++kind) {
+    const uint32_t cnt = ext_cnt[2 * o + kind];
+    if (cnt > ext_cap) {
+      if (threadIdx.x == 0) atomicExch(overflow, 1u);
+      continue;
+    }
+    const uint32_t* rows = ext_row + static_cast<size_t>(2 * o + kind) * ext_cap;
+    for (uint32_t c = warp; c < cnt; c += nw) {
+      const uint32_t i = rows[c];
+      const double dot = warp_dot(m.feat + static_cast<int64_t>(i) * m.d, b, m.d, lane);
+      if (lane == 0) {
+        const float inv = m.normalize ? inv_of_norm(m.row_norm[i]) : 1.f;
+        const uint32_t key = f2ord(canon_score(dot, inv, m.normalize, m.scale, j));
+        if (kind == 0) atomicMax(s_ext + 0, key); else atomicMin(s_ext + 1, key);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mm[(2 * blockIdx.y + 0) * pairs + j] = ord2f(s_ext[1]);  // exact min
+    mm[(2 * blockIdx.y + 1) * pairs + j] = ord2f(s_ext[0]);  // exact max
+  }
+}
+
+// heat bound of (row, pair): the fp32 sequence of fuse_heat_kernel applied to the clamped score bounds
+template <bool kUpper>
+__device__ __forceinline__ float fuse_heat_bound(const FuseSide& sa, const FuseSide& sb, const RowBand& ba,
+                                                 const RowBand& bb, int64_t n, int64_t row, int j, int pairs,
+                                                 const float* __restrict__ mm, int combine) {
+  float la, ha, lb, hb;
+  fuse_bounds(sa, ba, __ldg(sa.dense + static_cast<int64_t>(j) * n + row), j, la, ha);
+  fuse_bounds(sb, bb, __ldg(sb.dense + static_cast<int64_t>(j) * n + row), j, lb, hb);
+  const float mna = __ldg(mm + j), mxa = __ldg(mm + pairs + j), mnb = __ldg(mm + 2 * pairs + j), mxb = __ldg(mm + 3 * pairs + j);
+  const float x = minmax_norm(clampf(kUpper ? ha : la, mna, mxa), mna, mxa);
+  const float y = minmax_norm(clampf(kUpper ? hb : lb, mnb, mxb), mnb, mxb);
+  return fuse_combine(x, y, combine);
+}
+
+// pass 4: lower bounds of the heat on a strided row sample -> (pairs, n_sample) for select_threshold
+__global__ void __launch_bounds__(256)
+fuse_sample_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, int64_t stride, int32_t n_sample,
+                   const float* __restrict__ mm, int combine, float* __restrict__ sample_t) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_sample) return;
+  const int64_t row = static_cast<int64_t>(t) * stride;
+  if (row >= n) {
+    for (int j = 0; j < pairs; ++j) sample_t[static_cast<int64_t>(j) * n_sample + t] = -INFINITY;
+    return;
+  }
+  const RowBand ba = fuse_row_band(sa, row), bb = fuse_row_band(sb, row);
+  for (int j = 0; j < pairs; ++j) {
+    const float h = fuse_heat_bound<false>(sa, sb, ba, bb, n, row, j, pairs, mm, combine);
+    sample_t[static_cast<int64_t>(j) * n_sample + t] = h == h ? h : -INFINITY;  // NaN (max == min): no threshold
+  }
+}
+
+// pass 5: rows whose heat upper bound reaches the pair's threshold
+__global__ void __launch_bounds__(256)
+fuse_collect_heat_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, const float* __restrict__ mm,
+                         int combine, const float* __restrict__ thr, uint32_t* __restrict__ cand_cnt,
+                         uint32_t* __restrict__ cand_row, uint32_t cand_cap) {
+  const int j0 = blockIdx.y * kFuseChunk;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const RowBand ba = fuse_row_band(sa, row), bb = fuse_row_band(sb, row);
+#pragma unroll 4
+    for (int c = 0; c < kFuseChunk; ++c) {
+      const int j = j0 + c;
+      if (j >= pairs) break;
+      const float h = fuse_heat_bound<true>(sa, sb, ba, bb, n, row, j, pairs, mm, combine);
+      if (!(h < __ldg(thr + j))) {  // also true for NaN: degenerate columns go to the exact path via overflow
+        const uint32_t pos = atomicAdd(cand_cnt + j, 1u);
+        if (pos < cand_cap) cand_row[static_cast<size_t>(j) * cand_cap + pos] = static_cast<uint32_t>(row);
+      }
+    }
+  }
+}
+
+// pass 6: exact heat of the candidates, top-k by (heat desc, row asc).  One block per pair.
+__global__ void __launch_bounds__(1024)
+fuse_finalize_kernel(const FuseSide sa, const FuseSide sb, int32_t pairs, const float* __restrict__ mm, int combine,
+                     int32_t k, const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand_row,
+                     uint32_t cand_cap, int64_t* __restrict__ out_idx, float* __restrict__ out_heat,
+                     uint32_t* __restrict__ overflow) {
+  extern __shared__ uint8_t sm[];
+  unsigned long long* K64 = reinterpret_cast<unsigned long long*>(sm);
+  __shared__ int sh_cnt;
+  const int j = blockIdx.x;
+  const uint32_t cnt = cand_cnt[j];
+  if (cnt > cand_cap) {
+    if (threadIdx.x == 0) atomicExch(overflow, 1u);
+    return;
+  }
+  const int ns = static_cast<int>(cnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float mna = mm[j], mxa = mm[pairs + j], mnb = mm[2 * pairs + j], mxb = mm[3 * pairs + j];
+  const float* qa = sa.q + static_cast<size_t>(j) * sa.d;
+  const float* qb = sb.q + static_cast<size_t>(j) * sb.d;
+  for (int c = warp; c < ns; c += nw) {
+    const uint32_t i = cand_row[static_cast<size_t>(j) * cand_cap + c];
+    const double da = warp_dot(sa.feat + static_cast<int64_t>(i) * sa.d, qa, sa.d, lane);
+    const double db = warp_dot(sb.feat + static_cast<int64_t>(i) * sb.d, qb, sb.d, lane);
+    if (lane == 0) {
+      const float fa = canon_score(da, sa.normalize ? inv_of_norm(sa.row_norm[i]) : 1.f, sa.normalize, sa.scale, j);
+      const float fb = canon_score(db, sb.normalize ? inv_of_norm(sb.row_norm[i]) : 1.f, sb.normalize, sb.scale, j);
+      const float h = fuse_combine(minmax_norm(fa, mna, mxa), minmax_norm(fb, mnb, mxb), combine);
+      K64[c] = (static_cast<unsigned long long>(f2ord(h)) << 32) | (0xFFFFFFFFu - i);
+    }
+  }
+  __syncthreads();
+  const int kf = min(k, ns);
+  unsigned long long v64 = 0ull;
+  if (kf > 0 && ns > 2048) v64 = block_kth_largest<unsigned long long>([&](int t) { return K64[t]; }, ns, kf, &sh_cnt);
+  for (int c = threadIdx.x; c < ns; c += blockDim.x) {
+    const unsigned long long key = K64[c];
+    if (kf > 0 && key >= v64) {
+      int rank = 0;
+      for (int t = 0; t < ns; ++t) rank += (K64[t] > key) ? 1 : 0;
+      if (rank < kf) {
+        out_idx[static_cast<size_t>(j) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+        out_heat[static_cast<size_t>(j) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
+      }
+    }
+  }
+  for (int c = kf + threadIdx.x; c < k; c += blockDim.x) {
+    out_idx[static_cast<size_t>(j) * k + c] = -1;
+    out_heat[static_cast<size_t>(j) * k + c] = -INFINITY;
+  }
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -774,6 +1039,44 @@ int launch_fuse_heat(const float* sa, const float* sb, int64_t n, int32_t pair, 
                                           reinterpret_cast<const uint32_t*>(max_a),
                                           reinterpret_cast<const uint32_t*>(min_b),
                                           reinterpret_cast<const uint32_t*>(max_b), combine, heat);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+// ---- fusion through the screen: the passes after the two dense screens (see the kernels above)
+int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n, int32_t pairs, int32_t combine,
+                         int32_t k, const FuseScratch& w, int64_t* out_idx, float* out_heat, int num_sms,
+                         cudaStream_t s) {
+  auto side = [](const FuseSideHost& h) {
+    FuseSide m;
+    m.dense = h.dense; m.row_c = h.row_c; m.row_an = h.row_an; m.row_norm = h.row_norm; m.q_bn = h.q_bn;
+    m.q_glob = h.q_glob; m.scale = h.scale; m.feat = h.feat; m.q = h.q; m.d = h.d; m.normalize = h.normalize;
+    return m;
+  };
+  const FuseSide sa = side(a), sb = side(b);
+  const int chunks = (pairs + kFuseChunk - 1) / kFuseChunk;
+  const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(num_sms) * 8 / std::max(1, chunks) + 1));
+  AVL_CUDA(cudaMemsetAsync(w.max_lb, 0, sizeof(uint32_t) * 2 * pairs, s));
+  AVL_CUDA(cudaMemsetAsync(w.min_ub, 0xFF, sizeof(uint32_t) * 2 * pairs, s));
+  AVL_CUDA(cudaMemsetAsync(w.ext_cnt, 0, sizeof(uint32_t) * 4 * pairs, s));
+  AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * pairs, s));
+  AVL_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(uint32_t), s));
+  fuse_colstats_kernel<<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub);
+  fuse_collect_extreme_kernel<<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub, w.ext_cnt,
+                                                                   w.ext_row, w.ext_cap);
+  fuse_exact_extreme_kernel<<<dim3(pairs, 2), 256, 0, s>>>(sa, sb, pairs, w.ext_cnt, w.ext_row, w.ext_cap, w.mm,
+                                                           w.overflow);
+  fuse_sample_kernel<<<(w.n_sample + 255) / 256, 256, 0, s>>>(sa, sb, n, pairs, w.sample_stride, w.n_sample, w.mm,
+                                                              combine, w.sample_t);
+  AVL_CUDA(cudaGetLastError());
+  int rc = launch_select_threshold(w.sample_t, w.n_sample, w.n_sample, pairs, k, w.thr, s);
+  if (rc) return rc;
+  fuse_collect_heat_kernel<<<dim3(gx, chunks), 256, 0, s>>>(sa, sb, n, pairs, w.mm, combine, w.thr, w.cand_cnt,
+                                                            w.cand_row, w.cand_cap);
+  const size_t smem = static_cast<size_t>(w.cand_cap) * sizeof(unsigned long long);
+  AVL_CUDA(cudaFuncSetAttribute(fuse_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  fuse_finalize_kernel<<<pairs, 1024, smem, s>>>(sa, sb, pairs, w.mm, combine, k, w.cand_cnt, w.cand_row, w.cand_cap,
+                                                 out_idx, out_heat, w.overflow);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

@@ -161,8 +161,9 @@ def make_shard(torch, n, d, seed, device):
     return feat
 
 
-def build_extra(torch, engine, L, frames=24, reps=3):
-    """BASELINE config 4 geometry: 480x640 RGB-D -> 390x520 feature map -> 2M-cell grid, rate 1."""
+def build_scene(torch, frames):
+    """BASELINE config 4 geometry: 480x640 RGB-D -> 390x520 feature map -> 256 x 256 x 32 = 2M-cell grid, rate 1.
+    Same seeds on every rank, so every GPU holds identical inputs."""
     import synth
     from avlmaps_b200.map import Map, VLMapBuilder
     from avlmaps_b200.utils.mapping_utils import get_sim_cam_mat
@@ -178,6 +179,80 @@ def build_extra(torch, engine, L, frames=24, reps=3):
     np.random.seed(7)
     sidx = [torch.from_numpy(VLMapBuilder._sample_order(h * w, 1)).cuda() for _ in range(4)]
     depths = [torch.rand((h, w), device="cuda", generator=gen) * 5.5 + 0.5 for _ in range(4)]
+    return dict(h=h, w=w, fh=fh, fw=fw, d=d, gs=gs, cs=cs, vh=int(cam_h / cs), tfs=tfs, calib=calib, kinv=kinv,
+                kfeat=kfeat, gen=gen, sidx=sidx, depths=depths)
+
+
+def build_sharded_extra(torch, dist, engine, L, world, frames=24, reps=3):
+    """Slab-sharded build over the ranks (avlmaps_b200.sharded.ShardedBuilder): every rank sees every frame and
+    fuses the points of its own rows, no collective in the frame loop; strong scaling of ONE map build."""
+    from avlmaps_b200.sharded import ShardedBuilder
+
+    sc = build_scene(torch, frames)
+    d = sc["d"]
+    pool = [torch.randn((sc["fh"], sc["fw"], d), device="cuda", generator=sc["gen"]) * (14.2857 / d ** 0.5) for _ in range(4)]
+    stream = torch.cuda.current_stream()
+    best, acc = None, 0
+    for _ in range(reps):
+        sb = ShardedBuilder(engine.DeviceBuilder(sc["gs"], sc["vh"], sc["cs"], d, capacity=sc["gs"] * sc["gs"] * sc["vh"] // 2))
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(frames):
+            sb.add_frame(sc["depths"][i % 4], pool[i % 4], sc["kinv"], sc["calib"], sc["kfeat"], sc["tfs"][i],
+                         sample_idx=sc["sidx"][i % 4], feat_layout=L.FEAT_HWC, stream=stream)
+        e1.record(stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / frames
+        best = ms if best is None else min(best, ms)
+        acc = sb.local.num_accepted
+        sb.local.close()
+    a = torch.tensor([acc], device="cuda", dtype=torch.int64)
+    dist.all_reduce(a)
+    return {"frames_per_s": 1e3 / best, "ms_per_frame": best, "accepted_points_per_frame_all_ranks": int(a.item()) / frames,
+            "scaling": "strong (one map, rows split into slabs)", "features": "HWC, device-resident, identical on every rank"}
+
+
+def build_cpu_baseline(frames=2):
+    """The reference's sequential fusion loop (vlmap_builder.py:129-178) as the C restatement (oracle/build_oracle.c),
+    one core, on `frames` frames of the same geometry.  The reference itself runs this loop in Python at ~40 k
+    points/s; the C port is the generous baseline."""
+    import synth
+    from oracle import avl_oracle as O
+
+    h, w, fh, fw, d, gs, cs, cam_h = 480, 640, 390, 520, DIM, 256, 0.05, 1.6
+    cfg = synth.map_config(gs, cs, cam_h, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
+    poses = synth.circle_poses(frames, radius=2.0)
+    depths, _, feats = synth.build_inputs(frames, h, w, fh, fw, d, seed=4, pool=1, depth_lo=0.5, depth_hi=6.0)
+    np.random.seed(7)
+    sidx = [O.sample_order(h * w, 1) for _ in range(frames)]
+    b2c, bt = O.setup_transforms(cfg["pose_info"])
+    tfs = O.frame_transforms(poses, b2c, bt)
+    calib = np.array(cfg["cam_calib_mat"]).reshape(3, 3)
+    b = O.BuildOracle(gs, int(cam_h / cs), cs, d, capacity=1_000_000)
+    t0 = time.perf_counter()
+    for i in range(frames):
+        b.add_frame(depths[i], feats[i], None, sidx[i], np.linalg.inv(calib), calib, O.get_sim_cam_mat(fh, fw), tfs[i])
+    dt = time.perf_counter() - t0
+    acc = b.num_accepted
+    b.close()
+    return {"value": frames / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{frames} frames of 480x640 at depth_sample_rate 1 ({acc // frames} accepted points per frame), D = 512, "
+                      "C restatement of the reference's per-point loop; the reference's own Python loop does ~40 k points/s",
+            "points_per_s": acc / dt}
+
+
+def build_extra(torch, engine, L, frames=24, reps=3):
+    """Back-projection frames/s on one GPU: device-resident inputs (HWC and the reference's CHW layout) and the
+    end-to-end host-buffer call (H2D of depth, features and sample list inside the timed region)."""
+    sc = build_scene(torch, frames)
+    h, w, fh, fw, d, gs, cs = sc["h"], sc["w"], sc["fh"], sc["fw"], sc["d"], sc["gs"], sc["cs"]
+    tfs, calib, kinv, kfeat, gen, sidx, depths = (sc[k] for k in ("tfs", "calib", "kinv", "kfeat", "gen", "sidx", "depths"))
+    cam_h = sc["vh"] * cs
     out = {}
     for name, layout in (("hwc", L.FEAT_HWC), ("chw_reference_layout", L.FEAT_CHW)):
         shape = (fh, fw, d) if layout == L.FEAT_HWC else (1, d, fh, fw)
@@ -200,6 +275,31 @@ def build_extra(torch, engine, L, frames=24, reps=3):
         out[name] = {"frames_per_s": 1e3 / best, "ms_per_frame": best, "accepted_points_per_frame": pacc,
                      "algorithmic_GBps": byts / best / 1e6, "voxels": b.num_voxels}
         b.close()
+        if layout == L.FEAT_CHW:
+            # end to end through the host-pointer C-ABI call, the layout get_lseg_feat hands over: per frame the
+            # library copies depth (1.2 MB), the (1, 512, 390, 520) fp32 features (415 MB) and the sample list
+            # (1.2 MB) from pinned host memory, transposes, fuses, and synchronises
+            hp = [p_.cpu().pin_memory() for p_ in pool[:2]]
+            hd = [x.cpu().pin_memory() for x in depths[:2]]
+            hs = [x.cpu().pin_memory() for x in sidx[:2]]
+            b = engine.DeviceBuilder(gs, int(cam_h / cs), cs, d, capacity=gs * gs * int(cam_h / cs))
+            n_e2e = 6
+            for i in range(2):
+                b.add_frame(hd[i].numpy(), hp[i].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i].numpy(), feat_layout=layout)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                b.add_frame(hd[i % 2].numpy(), hp[i % 2].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i % 2].numpy(),
+                            feat_layout=layout)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_e2e
+            out["e2e_host_chw"] = {"frames_per_s": 1.0 / dt, "ms_per_frame": dt * 1e3,
+                                   "h2d_bytes_per_frame": h * w * 4 + d * fh * fw * 4 + h * w * 4,
+                                   "h2d_GBps": (h * w * 8 + d * fh * fw * 4) / dt / 1e9,
+                                   "note": "PCIe-bound: 415 MB of fp32 features per frame; a device-side encoder hand-off "
+                                           "(the hwc / chw lines above) removes it"}
+            b.close()
+            del hp
         del pool
     return out
 
@@ -250,6 +350,7 @@ def run_gpu(args):
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_screen, launches, cands = [], 0, []
+    last_cta_group = 0
     e0.record(stream)
     for i in range(args.steps):
         sm.topk(qpool[i % 8], TOPK)
@@ -257,6 +358,7 @@ def run_gpu(args):
         ms_screen.append(st["ms_screen"])
         launches += st["n_launches"]
         cands.append(st["n_candidates"])
+        last_cta_group = st["cta_group"]
     e1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -300,6 +402,14 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = NQ * world * args.steps / float(te.item())
 
+    build_sharded = None
+    if world > 1 and not args.no_build:
+        dmap.close()
+        torch.cuda.empty_cache()
+        try:
+            build_sharded = build_sharded_extra(torch, dist, engine, L, world)
+        except Exception as e:  # noqa: BLE001
+            build_sharded = {"error": repr(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -320,7 +430,7 @@ def run_gpu(args):
                 "frac_vs_burst_peak": achieved / peaks["bf16_tflops"], "frac_vs_sustained_peak": achieved / sustained,
                 "kernel": {3: "screen_ts_kernel (tcgen05 cta_group::2, queries resident in TMEM, M=256 N=128 K=512 per tile)",
                            2: "screen_kernel<cta_group::2> (tcgen05 bf16, M=256 N=256 K=512 per tile pair)",
-                           1: "screen_kernel<cta_group::1>"}.get(dmap.last_stats["cta_group"], "?"),
+                           1: "screen_kernel<cta_group::1>"}.get(last_cta_group, "?"),
                 "kernel_ms": ms_k, "peak_source": peaks["source"],
                 "algorithmic_flops": flops, "algorithmic_bytes": N_VOX * DIM * 2 + NQ * DIM * 4 + NQ * TOPK * 12,
                 "hbm_GBps": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9, "hbm_frac": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -331,7 +441,9 @@ def run_gpu(args):
         except Exception:  # noqa: BLE001
             pass
 
-    extra = {"screen_ms_mean": ms_k, "candidates_per_step": statistics.mean(cands), "cta_group": dmap.last_stats["cta_group"]}
+    extra = {"screen_ms_mean": ms_k, "candidates_per_step": statistics.mean(cands), "cta_group": last_cta_group}
+    if build_sharded is not None:
+        extra["build_slab_sharded"] = build_sharded
     cb = None
     if world == 1:
         # BASELINE config 2 (1M x 512, Q = 64): per-voxel argmax and top-16, HBM-bound
@@ -408,6 +520,11 @@ def run_gpu(args):
                 extra["build_error"] = repr(e)
         if not args.no_cpu:
             cb = cpu_baseline(steps=5, warmup=1)
+            if not args.no_build:
+                try:
+                    extra.setdefault("build", {})["cpu_baseline"] = build_cpu_baseline()
+                except Exception as e:  # noqa: BLE001
+                    extra["build_cpu_baseline_error"] = repr(e)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

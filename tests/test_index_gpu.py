@@ -284,3 +284,50 @@ def test_query_stationary_variant_matches(eng, monkeypatch):
     assert m.last_stats["cta_group"] == 3
     assert np.array_equal(idx, ref[0]) and np.array_equal(val, ref[1])
     m.close()
+
+
+def _fuse_both_paths(eng, *args, **kw):
+    import os
+
+    got = eng.fuse_topk(*args, **kw)              # tcgen05 screens + interval propagation + exact re-score
+    os.environ["AVL_FUSE_EXACT"] = "1"
+    try:
+        want = eng.fuse_topk(*args, **kw)         # exact dense columns
+    finally:
+        del os.environ["AVL_FUSE_EXACT"]
+    return got, want
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fusion_through_the_screen_equals_exact_path(eng, normalize):
+    """BASELINE config 3 shape (LSeg-512 + AudioCLIP-1024, 32 + 32 queries, scale 100, top-16), reduced to 300k rows:
+    the screened path returns the same ids and the same heat bits as the exact path, and both match the oracle."""
+    n, pairs = 300_000, 32
+    fv, qv = synth.index_inputs(n, 512, pairs, seed=40)
+    fa, qa = synth.index_inputs(n, 1024, pairs, seed=41, unit_rows=True)
+    sa = np.full(pairs, 100.0, np.float32)
+    mv_, ma_ = eng.DeviceMap(fv), eng.DeviceMap(fa)
+    for combine in (O.FUSE_PRODUCT, O.FUSE_MAX, O.FUSE_SUM):
+        (gi, gh), (wi, wh) = _fuse_both_paths(eng, mv_, qv, ma_, qa, 16, scale_b=sa, combine=combine,
+                                               normalize_a=normalize, normalize_b=False)
+        assert np.array_equal(gi, wi) and np.array_equal(gh, wh)
+    ri, rh = O.fuse_topk(O.scores(fv, qv, normalize=normalize), O.scores(fa, qa, scale=sa), O.FUSE_PRODUCT, 16)
+    (gi, gh), _ = _fuse_both_paths(eng, mv_, qv, ma_, qa, 16, scale_b=sa, combine=O.FUSE_PRODUCT, normalize_a=normalize)
+    assert np.array_equal(gi, ri) and np.allclose(gh, rh, rtol=0, atol=2e-7)
+    mv_.close()
+    ma_.close()
+
+
+def test_fusion_degenerate_and_tied_inputs_fall_back_to_the_exact_path(eng):
+    """A constant column (max == min -> NaN heat, like numpy) and massive exact ties overflow the candidate lists;
+    the call is then answered by the exact path, so both paths still agree."""
+    n, pairs = 50_000, 4
+    fv, qv = synth.index_inputs(n, 64, pairs, seed=50)
+    fa, qa = synth.index_inputs(n, 128, pairs, seed=51, unit_rows=True)
+    fv[:] = fv[0]                       # every row identical: every column of modality a is constant
+    fa[1000:] = fa[1000]                # 49k exact duplicates in modality b
+    mv_, ma_ = eng.DeviceMap(fv), eng.DeviceMap(fa)
+    (gi, gh), (wi, wh) = _fuse_both_paths(eng, mv_, qv, ma_, qa, 8, combine=O.FUSE_SUM)
+    assert np.array_equal(gi, wi) and np.array_equal(gh, wh, equal_nan=True)
+    mv_.close()
+    ma_.close()
