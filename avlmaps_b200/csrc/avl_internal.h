@@ -139,6 +139,7 @@ struct FuseScratch {
   float* sample_t; int32_t n_sample; int64_t sample_stride;
   float* thr;                              // [pairs]
   uint32_t* cand_cnt; uint32_t* cand_row; uint32_t cand_cap;
+  float* cand_lo; float* cand_hi;          // [pairs][cand_cap] heat bounds of the candidates
   uint32_t* overflow;                      // [1]
 };
 int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n, int32_t pairs, int32_t combine,

@@ -83,6 +83,7 @@ struct Workspace {
   uint32_t* cand_cnt = nullptr;  // [256] per-query candidate counters
   uint32_t* cand_row = nullptr;  // [256][cand_cap]
   float* cand_val = nullptr;
+  float* cand_val2 = nullptr;    // second per-candidate value (fusion: heat lower bounds)
   uint32_t cand_cap = 0;
   uint32_t* overflow = nullptr;  // [256]
   float* sample_t = nullptr;
@@ -158,7 +159,7 @@ static void ws_free(Workspace& w) {
   cudaFree(w.flag_count); cudaFree(w.flag_rows); cudaFree(w.flag_masks); cudaFree(w.cand_cnt);
   cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
-  cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small);
+  cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small); cudaFree(w.cand_val2);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
   for (int i = 0; i < 4; ++i)
     if (w.ev[i]) cudaEventDestroy(w.ev[i]);
@@ -178,7 +179,8 @@ static int ensure_flags(avl_map* m) {
 static int ensure_cands(avl_map* m, uint32_t cap) {
   Workspace& w = m->ws;
   if (w.cand_cap >= cap) return AVL_OK;
-  cudaFree(w.cand_row); cudaFree(w.cand_val);
+  cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.cand_val2);
+  w.cand_val2 = nullptr;
   int rc;
   if ((rc = dev_alloc(&w.cand_row, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.cand_val, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
@@ -647,19 +649,22 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
 
   ScreenParams p;
   if (m->n > 0) {
-    // phase A: screen scores of the sampled tiles, transposed so that a query's column is contiguous
+    // phase A: lower bounds of the sampled tiles.  The regular screen reduces them in its epilogue to one maximum
+    // per 32-row group and query (dense_lb = 2); the query-stationary variant stores them per row.
+    const bool grouped = !qs.ts;
+    const int64_t n_cols = grouped ? n_sample / 32 : n_sample;
     base_params(m, qs, nq, normalize_map, &p);
     p.mode = kModeDense;
     p.num_tiles = static_cast<int32_t>(sample_units);
     p.tile_stride = static_cast<int32_t>(tile_stride);
     p.dense_out = w.sample_t;
     p.dense_rs = 1;
-    p.dense_cs = n_sample;
+    p.dense_cs = n_cols;
     p.dense_cols = nq;
-    p.dense_lb = 1;
+    p.dense_lb = grouped ? 2 : 1;
     p.prefetch_tiles = 0;  // sampled tiles are strided: nothing sequential to prefetch
     if ((rc = run_screen(m, qs, p, s))) return rc;
-    if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_sample), n_sample, nq, k, w.thr_t, s)))
+    if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_cols), n_cols, nq, k, w.thr_t, s)))
       return rc;
   }
   AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
@@ -856,6 +861,9 @@ static int fuse_topk_screened(avl_map* ma, const float* qa, const float* scale_a
   fs.cand_cnt = w.cand_cnt;
   fs.cand_row = w.cand_row;
   fs.cand_cap = cand_cap;
+  fs.cand_hi = w.cand_val;
+  if (!w.cand_val2 && (rc = dev_alloc(&w.cand_val2, static_cast<size_t>(AVL_MAX_QUERIES) * w.cand_cap, &ma->bytes))) return rc;
+  fs.cand_lo = w.cand_val2;
   int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
   float* d_heat = (flags & AVL_ON_DEVICE) ? out_heat : w.out_score;
   if ((rc = launch_fuse_screened(ha, hb, n, n_pairs, combine, k, fs, d_idx, d_heat, ma->num_sms, s))) return rc;
@@ -868,6 +876,17 @@ static int fuse_topk_screened(avl_map* ma, const float* qa, const float* scale_a
   {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return check_watchdog(ma, cuda_fail(e, "fuse (screened)", __FILE__, __LINE__));
+  }
+  if (getenv("AVL_FUSE_DEBUG")) {
+    std::vector<uint32_t> cnt(n_pairs), ext(4 * n_pairs);
+    cudaMemcpy(cnt.data(), fs.cand_cnt, sizeof(uint32_t) * n_pairs, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ext.data(), fs.ext_cnt, sizeof(uint32_t) * 4 * n_pairs, cudaMemcpyDeviceToHost);
+    uint64_t tc = 0, te = 0;
+    uint32_t mc = 0, me = 0;
+    for (uint32_t c : cnt) { tc += c; mc = std::max(mc, c); }
+    for (uint32_t c : ext) { te += c; me = std::max(me, c); }
+    fprintf(stderr, "[avl fuse] heat candidates: mean %.0f max %u per pair (cap %u); extreme candidates: mean %.1f max %u (cap %u); overflow %u\n",
+            static_cast<double>(tc) / n_pairs, mc, cand_cap, static_cast<double>(te) / (4 * n_pairs), me, ext_cap, ovf);
   }
   return ovf ? 1 : AVL_OK;
 }

@@ -403,6 +403,8 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
   uint32_t* Uk = Lk + cand_cap;
   uint32_t* Ix = Uk + cand_cap;
+  // 20 bytes per candidate = 160 KiB: one block per SM.  Measured on B200: packing two blocks per SM (12 bytes per
+  // candidate + a fixed survivor array) made the 256-query finalize slower, 67 vs 57 us
   unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Ix + cand_cap);
   __shared__ int sh_cnt;
   __shared__ int sh_ns;
@@ -681,10 +683,10 @@ __device__ __forceinline__ float fuse_combine(float x, float y, int combine) {
 }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
-constexpr int kFuseChunk = 16;  // columns per thread in the column-statistics passes
+constexpr int kFuseChunk = 8;   // columns per block in the column passes (8 keeps the kernels under 64 registers)
 
 // pass 1: per column max of the lower bounds and min of the upper bounds (ordered-uint atomics)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fuse_colstats_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, uint32_t* __restrict__ max_lb,
                      uint32_t* __restrict__ min_ub) {
   const FuseSide& m = blockIdx.z ? sb : sa;
@@ -724,7 +726,7 @@ fuse_colstats_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pa
 }
 
 // pass 2: rows that can hold a column's exact max (ub >= max lb) or min (lb <= min ub)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fuse_collect_extreme_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs,
                             const uint32_t* __restrict__ max_lb, const uint32_t* __restrict__ min_ub,
                             uint32_t* __restrict__ ext_cnt, uint32_t* __restrict__ ext_row, uint32_t ext_cap) {
@@ -733,7 +735,7 @@ fuse_collect_extreme_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
        row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const RowBand b = fuse_row_band(m, row);
-#pragma unroll
+#pragma unroll 4
     for (int c = 0; c < kFuseChunk; ++c) {
       const int j = j0 + c;
       if (j < pairs) {
@@ -821,50 +823,80 @@ fuse_sample_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pair
   }
 }
 
-// pass 5: rows whose heat upper bound reaches the pair's threshold
-__global__ void __launch_bounds__(256)
+// pass 5: rows whose heat upper bound reaches the pair's threshold, with both heat bounds
+__global__ void __launch_bounds__(256, 4)
 fuse_collect_heat_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, const float* __restrict__ mm,
                          int combine, const float* __restrict__ thr, uint32_t* __restrict__ cand_cnt,
-                         uint32_t* __restrict__ cand_row, uint32_t cand_cap) {
+                         uint32_t* __restrict__ cand_row, float* __restrict__ cand_lo, float* __restrict__ cand_hi,
+                         uint32_t cand_cap) {
   const int j0 = blockIdx.y * kFuseChunk;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
        row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const RowBand ba = fuse_row_band(sa, row), bb = fuse_row_band(sb, row);
-#pragma unroll 4
+#pragma unroll 2
     for (int c = 0; c < kFuseChunk; ++c) {
       const int j = j0 + c;
       if (j >= pairs) break;
       const float h = fuse_heat_bound<true>(sa, sb, ba, bb, n, row, j, pairs, mm, combine);
       if (!(h < __ldg(thr + j))) {  // also true for NaN: degenerate columns go to the exact path via overflow
         const uint32_t pos = atomicAdd(cand_cnt + j, 1u);
-        if (pos < cand_cap) cand_row[static_cast<size_t>(j) * cand_cap + pos] = static_cast<uint32_t>(row);
+        if (pos < cand_cap) {
+          const size_t o = static_cast<size_t>(j) * cand_cap + pos;
+          cand_row[o] = static_cast<uint32_t>(row);
+          cand_hi[o] = h;
+          cand_lo[o] = fuse_heat_bound<false>(sa, sb, ba, bb, n, row, j, pairs, mm, combine);
+        }
       }
     }
   }
 }
 
-// pass 6: exact heat of the candidates, top-k by (heat desc, row asc).  One block per pair.
+// pass 6, one block per pair: k-th best LOWER bound over the candidates -> survivors (upper bound reaches it) ->
+// exact heat of the survivors (fp64-accumulated dots of both modalities) -> top-k by (heat desc, row asc).
+constexpr int kFuseSurvivors = 2048;
 __global__ void __launch_bounds__(1024)
 fuse_finalize_kernel(const FuseSide sa, const FuseSide sb, int32_t pairs, const float* __restrict__ mm, int combine,
                      int32_t k, const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand_row,
-                     uint32_t cand_cap, int64_t* __restrict__ out_idx, float* __restrict__ out_heat,
-                     uint32_t* __restrict__ overflow) {
+                     const float* __restrict__ cand_lo, const float* __restrict__ cand_hi, uint32_t cand_cap,
+                     int64_t* __restrict__ out_idx, float* __restrict__ out_heat, uint32_t* __restrict__ overflow) {
   extern __shared__ uint8_t sm[];
-  unsigned long long* K64 = reinterpret_cast<unsigned long long*>(sm);
+  uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);   // [cand_cap] ordered lower bounds
+  __shared__ unsigned long long K64[kFuseSurvivors];
+  __shared__ uint32_t S[kFuseSurvivors];            // candidate slots of the survivors
   __shared__ int sh_cnt;
+  __shared__ int sh_ns;
   const int j = blockIdx.x;
   const uint32_t cnt = cand_cnt[j];
   if (cnt > cand_cap) {
     if (threadIdx.x == 0) atomicExch(overflow, 1u);
     return;
   }
-  const int ns = static_cast<int>(cnt);
+  const int n = static_cast<int>(cnt);
+  const size_t base = static_cast<size_t>(j) * cand_cap;
+  if (threadIdx.x == 0) sh_ns = 0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) Lk[c] = max(f2ord(cand_lo[base + c]), 1u);
+  __syncthreads();
+  const int kk = min(k, n);
+  uint32_t v = 0u;
+  if (kk > 0) v = block_kth_largest<uint32_t>([&](int c) { return Lk[c]; }, n, kk, &sh_cnt);
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    if (max(f2ord(cand_hi[base + c]), 1u) >= v) {
+      const int t = atomicAdd(&sh_ns, 1);
+      if (t < kFuseSurvivors) S[t] = static_cast<uint32_t>(c);
+    }
+  }
+  __syncthreads();
+  const int ns = sh_ns;
+  if (ns > kFuseSurvivors) {  // massive ties: the exact path answers the call
+    if (threadIdx.x == 0) atomicExch(overflow, 1u);
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float mna = mm[j], mxa = mm[pairs + j], mnb = mm[2 * pairs + j], mxb = mm[3 * pairs + j];
   const float* qa = sa.q + static_cast<size_t>(j) * sa.d;
   const float* qb = sb.q + static_cast<size_t>(j) * sb.d;
   for (int c = warp; c < ns; c += nw) {
-    const uint32_t i = cand_row[static_cast<size_t>(j) * cand_cap + c];
+    const uint32_t i = cand_row[base + S[c]];
     const double da = warp_dot(sa.feat + static_cast<int64_t>(i) * sa.d, qa, sa.d, lane);
     const double db = warp_dot(sb.feat + static_cast<int64_t>(i) * sb.d, qb, sb.d, lane);
     if (lane == 0) {
@@ -876,17 +908,13 @@ fuse_finalize_kernel(const FuseSide sa, const FuseSide sb, int32_t pairs, const 
   }
   __syncthreads();
   const int kf = min(k, ns);
-  unsigned long long v64 = 0ull;
-  if (kf > 0 && ns > 2048) v64 = block_kth_largest<unsigned long long>([&](int t) { return K64[t]; }, ns, kf, &sh_cnt);
   for (int c = threadIdx.x; c < ns; c += blockDim.x) {
     const unsigned long long key = K64[c];
-    if (kf > 0 && key >= v64) {
-      int rank = 0;
-      for (int t = 0; t < ns; ++t) rank += (K64[t] > key) ? 1 : 0;
-      if (rank < kf) {
-        out_idx[static_cast<size_t>(j) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
-        out_heat[static_cast<size_t>(j) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
-      }
+    int rank = 0;
+    for (int t = 0; t < ns; ++t) rank += (K64[t] > key) ? 1 : 0;
+    if (rank < kf) {
+      out_idx[static_cast<size_t>(j) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+      out_heat[static_cast<size_t>(j) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
     }
   }
   for (int c = kf + threadIdx.x; c < k; c += blockDim.x) {
@@ -1055,7 +1083,8 @@ int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n
   };
   const FuseSide sa = side(a), sb = side(b);
   const int chunks = (pairs + kFuseChunk - 1) / kFuseChunk;
-  const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(num_sms) * 8 / std::max(1, chunks) + 1));
+  // ~8 resident blocks per SM in total, at least 2 row-blocks per (chunk, side)
+  const unsigned gx = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, std::max<int64_t>(2, static_cast<int64_t>(num_sms) * 8 / (2 * chunks))));
   AVL_CUDA(cudaMemsetAsync(w.max_lb, 0, sizeof(uint32_t) * 2 * pairs, s));
   AVL_CUDA(cudaMemsetAsync(w.min_ub, 0xFF, sizeof(uint32_t) * 2 * pairs, s));
   AVL_CUDA(cudaMemsetAsync(w.ext_cnt, 0, sizeof(uint32_t) * 4 * pairs, s));
@@ -1071,12 +1100,12 @@ int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n
   AVL_CUDA(cudaGetLastError());
   int rc = launch_select_threshold(w.sample_t, w.n_sample, w.n_sample, pairs, k, w.thr, s);
   if (rc) return rc;
-  fuse_collect_heat_kernel<<<dim3(gx, chunks), 256, 0, s>>>(sa, sb, n, pairs, w.mm, combine, w.thr, w.cand_cnt,
-                                                            w.cand_row, w.cand_cap);
-  const size_t smem = static_cast<size_t>(w.cand_cap) * sizeof(unsigned long long);
+  fuse_collect_heat_kernel<<<dim3(2 * gx, chunks), 256, 0, s>>>(sa, sb, n, pairs, w.mm, combine, w.thr, w.cand_cnt,
+                                                                w.cand_row, w.cand_lo, w.cand_hi, w.cand_cap);
+  const size_t smem = static_cast<size_t>(w.cand_cap) * sizeof(uint32_t);
   AVL_CUDA(cudaFuncSetAttribute(fuse_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  fuse_finalize_kernel<<<pairs, 1024, smem, s>>>(sa, sb, pairs, w.mm, combine, k, w.cand_cnt, w.cand_row, w.cand_cap,
-                                                 out_idx, out_heat, w.overflow);
+  fuse_finalize_kernel<<<pairs, 1024, smem, s>>>(sa, sb, pairs, w.mm, combine, k, w.cand_cnt, w.cand_row, w.cand_lo,
+                                                 w.cand_hi, w.cand_cap, out_idx, out_heat, w.overflow);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

@@ -59,7 +59,24 @@ __device__ __forceinline__ void dense_chunk(const ScreenParams& p, const TileCtx
   if constexpr (W == 32) ptx::tmem_ld32(t.taddr + c0, v); else ptx::tmem_ld16(t.taddr + c0, v);
   ptx::tmem_ld_wait();
   float* o = p.dense_out + t.crow * p.dense_rs + static_cast<int64_t>(c0) * p.dense_cs;
-  if (p.dense_lb) {
+  if (p.dense_lb == 2) {
+    // threshold sample, reduced in place: ONE value per 32-row group (this warp's rows) and query, the max of the
+    // lower bounds.  The selection only ever uses maxima of disjoint row groups (select_threshold_kernel), so the
+    // (rows x queries) sample matrix never has to exist: 32x less to write here and to read there.
+    const int lane = threadIdx.x & 31;
+    uint32_t mine = 0u;  // lane j keeps column c0 + j; 0 = no valid row in the group
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const float x = (__uint_as_float(v[j]) - r_i * qc[c0 + j].y) * w_i;
+      const float lb = fmaf(-fabsf(x), 9.5367431640625e-7f, x);
+      const uint32_t key = t.valid ? max(f2ord(__float_as_uint(lb)), 1u) : 0u;
+      const uint32_t m = __reduce_max_sync(0xffffffffu, key);
+      if (lane == j) mine = m;
+    }
+    if (lane < W && c0 + lane < p.dense_cols)
+      p.dense_out[(t.crow >> 5) * p.dense_rs + static_cast<int64_t>(c0 + lane) * p.dense_cs] =
+          mine ? ord2f(mine) : -INFINITY;
+  } else if (p.dense_lb) {
     // rows past the end of the map store -inf so that they never raise a threshold
 #pragma unroll
     for (int j = 0; j < W; ++j) {
