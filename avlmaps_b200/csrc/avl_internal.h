@@ -47,6 +47,7 @@ struct ScreenParams {
   int32_t normalize;     // divide by the fp32 row norm
   int32_t prefetch_tiles; // L2 prefetch distance of the A stream, in tiles per unit
   int32_t debug_flags;    // perf triage only (AVL_DEBUG_FLAGS): 1 = no MMA, 2 = no A loads, 4 = no epilogue work
+  int32_t op_f16;         // operands are fp16 instead of bf16 (same tcgen05 kind::f16 rate, 8x smaller rounding residual)
   // per-row statistics (map_prepare): see DESIGN.md "error band"
   const float* row_norm;   // ||a_i||  (fp32 row, fp64-accumulated)
   const float* row_c;      // >= ||a_i - bf16(a_i)|| + kappa * ||bf16(a_i)||
@@ -89,9 +90,10 @@ int screen_ts_pick_stages();
 
 // ---- exact / helper kernels (sim_exact.cu) --------------------------------
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
-                       float* row_norm, float* row_c, float* row_an, float kappa, cudaStream_t s);
+                       float* row_norm, float* row_c, float* row_an, float kappa, int f16, uint32_t* nonfinite,
+                       cudaStream_t s);
 int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, int32_t d, int32_t dpad,
-                         int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s);
+                         int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, int f16, cudaStream_t s);
 int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq,
                        const float* scale, const float* row_norm, int normalize, float* out,
                        int64_t out_rs, int64_t out_cs, cudaStream_t s);

@@ -45,7 +45,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 row-major (rows x dpad) matrix, box = 64 columns (one 128-byte swizzle row) x box_rows.
 static int encode_kmajor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t dpad,
-                             uint32_t box_rows) {
+                             uint32_t box_rows, bool f16 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -55,7 +55,8 @@ static int encode_kmajor_map(CUtensorMap* out, const void* base, uint64_t rows, 
   cuuint64_t strides[1] = {dpad * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -110,6 +111,7 @@ struct avl_map {
   int num_sms = 0;
   int64_t n = 0;
   int32_t d = 0, dpad = 0;
+  int op_f16 = 0;         // tensor-core operands are fp16 (AVL_MAP_F16) instead of bf16
   float* feat = nullptr;
   __nv_bfloat16* bf = nullptr;
   float* row_norm = nullptr;
@@ -290,7 +292,7 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
     qs->stages = screen_ts_pick_stages();
     qs->smem = screen_ts_smem_bytes(qs->stages);
     return launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
-                                w.q_bn, w.q_glob, s);
+                                w.q_bn, w.q_glob, m->op_f16, s);
   }
   qs->cg = pick_cta_group(qs->npad, kblocks, forced_cg);
   if (qs->cg == 0) {
@@ -301,10 +303,10 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
   qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks);
   qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages);
   int rc = launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
-                                w.q_bn, w.q_glob, s);
+                                w.q_bn, w.q_glob, m->op_f16, s);
   if (rc) return rc;
   return encode_kmajor_map(&qs->tmap_b, w.bq, static_cast<uint64_t>(qs->npad), static_cast<uint64_t>(m->dpad),
-                           static_cast<uint32_t>(qs->npad / qs->cg));
+                           static_cast<uint32_t>(qs->npad / qs->cg), m->op_f16 != 0);
 }
 
 static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int normalize, ScreenParams* p) {
@@ -322,6 +324,7 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->bq = m->ws.bq;
   p->q_glob = m->ws.q_glob;
   p->dbg = m->ws.dbg_dev;
+  p->op_f16 = m->op_f16;
   p->tile_stride = 1;
   {
     static int pf = -1;  // L2 prefetch distance of the A stream (tiles per unit); AVL_PREFETCH_TILES overrides
@@ -423,13 +426,25 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
     }
     // kappa: fp32 accumulation slack of the tensor core over dpad products
     const float kappa = static_cast<float>(m->dpad) * 2.4e-7f;
-    if ((rc = launch_map_prepare(m->feat, n, dim, m->dpad, m->bf, m->row_norm, m->row_c, m->row_an, kappa, s))) break;
+    m->op_f16 = (flags & AVL_MAP_F16) ? 1 : 0;
+    uint32_t* nonfinite = m->ws.flag_count;  // scratch word of the workspace
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      uint32_t bad = 0;
+      cudaError_t e = cudaMemsetAsync(nonfinite, 0, sizeof(uint32_t), s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
+      if ((rc = launch_map_prepare(m->feat, n, dim, m->dpad, m->bf, m->row_norm, m->row_c, m->row_an, kappa, m->op_f16,
+                                   nonfinite, s))) break;
+      e = cudaMemcpyAsync(&bad, nonfinite, sizeof(bad), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
+      if (!(bad && m->op_f16)) break;
+      m->op_f16 = 0;  // a value beyond the fp16 range: bf16 operands keep the fp32 range
+    }
+    if (rc) break;
     if ((rc = encode_kmajor_map(&m->tmap_a, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
-                                kTileRows))) break;
+                                kTileRows, m->op_f16 != 0))) break;
     if ((rc = encode_kmajor_map(&m->tmap_a64, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
-                                64))) break;
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
+                                64, m->op_f16 != 0))) break;
   } while (0);
   if (rc) {
     avl_map_destroy(m);
@@ -446,6 +461,8 @@ int avl_map_destroy(avl_map* m) {
   delete m;
   return AVL_OK;
 }
+
+int avl_map_operand_f16(const avl_map* m) { return m ? m->op_f16 : 0; }
 
 int avl_map_shape(const avl_map* m, int64_t* n, int32_t* dim) {
   AVL_ARG(m != nullptr, "map is NULL");

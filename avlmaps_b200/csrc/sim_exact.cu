@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cfloat>
 
+#include <cuda_fp16.h>
+
 #include "avl_internal.h"
 
 namespace avl {
@@ -40,22 +42,37 @@ __device__ __forceinline__ float canon_score(double dot, float inv_norm, int nor
 }
 __device__ __forceinline__ float inv_of_norm(float nrm) { return nrm > 0.f ? __fdiv_rn(1.0f, nrm) : 0.f; }
 
+// tensor-core operand element: bf16 (8-bit mantissa, fp32 range) or fp16 (11-bit mantissa: 8x smaller rounding
+// residual, hence an 8x tighter error band; range 65504).  Returns the 16 bits and the value they stand for.
+__device__ __forceinline__ uint16_t to_operand(float x, int f16, float* back) {
+  if (f16) {
+    const __half h = __float2half_rn(x);
+    *back = __half2float(h);
+    return __half_as_ushort(h);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  *back = __bfloat162float(h);
+  return __bfloat16_as_ushort(h);
+}
+
 // ------------------------------------------------------------------ map_prepare
 // One warp per row: bf16 copy (zero padded to dpad), fp32 norm, rounding residual norms.
 __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, int32_t d, int32_t dpad,
                                    __nv_bfloat16* __restrict__ bf, float* __restrict__ row_norm,
-                                   float* __restrict__ row_c, float* __restrict__ row_an, float kappa) {
+                                   float* __restrict__ row_c, float* __restrict__ row_an, float kappa, int f16,
+                                   uint32_t* __restrict__ nonfinite) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* a = feat + row * d;
-  __nv_bfloat16* o = bf + row * dpad;
+  uint16_t* o = reinterpret_cast<uint16_t*>(bf + row * dpad);
   double sa = 0.0, sd = 0.0, sb = 0.0;
+  bool bad = false;
   for (int k = lane; k < dpad; k += 32) {
     const float x = k < d ? a[k] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    o[k] = h;
-    const float xb = __bfloat162float(h);
+    float xb;
+    o[k] = to_operand(x, f16, &xb);
+    bad |= !isfinite(xb);    // |x| beyond the fp16 range (or a non-finite input): the caller falls back to bf16
     const float e = x - xb;  // exact
     sa += static_cast<double>(x) * x;
     sd += static_cast<double>(e) * e;
@@ -64,6 +81,7 @@ __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, in
   sa = warp_sum(sa);
   sd = warp_sum(sd);
   sb = warp_sum(sb);
+  if (__any_sync(0xffffffffu, bad) && lane == 0 && nonfinite) atomicExch(nonfinite, 1u);
   if (lane == 0) {
     const float an = __double2float_ru(sqrt(sb) * (1.0 + 1e-7));
     row_norm[row] = static_cast<float>(sqrt(sa));
@@ -77,7 +95,7 @@ __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, in
 // glob[0] = max ratio (rho), glob[1] = max ||b|| (float bits, non-negative => uint order).
 __global__ void query_prepare_kernel(const float* __restrict__ q, const float* __restrict__ fold_scale, int32_t nq,
                                      int32_t d, int32_t dpad, __nv_bfloat16* __restrict__ bq,
-                                     float* __restrict__ q_bn, uint32_t* __restrict__ glob) {
+                                     float* __restrict__ q_bn, uint32_t* __restrict__ glob, int f16) {
   const int r = blockIdx.x;
   __shared__ double red[2][32];
   double sb = 0.0, sd = 0.0;
@@ -86,9 +104,9 @@ __global__ void query_prepare_kernel(const float* __restrict__ q, const float* _
     // argmax mode compares ACROSS queries, so the per-query scale is folded into B (the bounds below
     // are then those of the scaled vector); top-k mode keeps B unscaled and divides its threshold
     if (fold_scale && r < nq) x = __fmul_rn(x, fold_scale[r]);
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    bq[static_cast<size_t>(r) * dpad + k] = h;
-    const float e = x - __bfloat162float(h);
+    float xb;
+    reinterpret_cast<uint16_t*>(bq)[static_cast<size_t>(r) * dpad + k] = to_operand(x, f16, &xb);
+    const float e = x - xb;
     sb += static_cast<double>(x) * x;
     sd += static_cast<double>(e) * e;
   }
@@ -683,10 +701,56 @@ __device__ __forceinline__ float fuse_combine(float x, float y, int combine) {
 }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
-constexpr int kFuseChunk = 8;   // columns per block in the column passes (8 keeps the kernels under 64 registers)
+constexpr int kFuseChunk = 8;   // columns per block in the column passes
+
+// V consecutive rows per thread: V = 4 turns every load of the column passes into a 16-byte one (n % 4 == 0 keeps
+// the column bases aligned), which is what lets them stream near HBM speed; V = 1 is the general fallback.
+template <int V> struct FVec { float v[V]; };
+template <int V>
+__device__ __forceinline__ FVec<V> fuse_ld(const float* __restrict__ p) {
+  FVec<V> r;
+  if constexpr (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int V> struct RowBandV { float r[V], invw[V]; };
+template <int V>
+__device__ __forceinline__ RowBandV<V> fuse_row_band_v(const FuseSide& m, int64_t row) {
+  RowBandV<V> b;
+  const float rho = __ldg(m.q_glob);
+  const FVec<V> an = fuse_ld<V>(m.row_an + row), c = fuse_ld<V>(m.row_c + row);
+  FVec<V> nr;
+  if (m.normalize) nr = fuse_ld<V>(m.row_norm + row);
+#pragma unroll
+  for (int t = 0; t < V; ++t) {
+    b.r[t] = fmaf(rho, an.v[t], c.v[t]) * 1.000001f;
+    b.invw[t] = m.normalize ? 1.f / fmaxf(nr.v[t], 1e-30f) : 1.f;
+  }
+  return b;
+}
+template <int V>
+__device__ __forceinline__ RowBand band_of(const RowBandV<V>& b, int t) {
+  RowBand o;
+  o.r = b.r[t];
+  o.invw = b.invw[t];
+  return o;
+}
+__device__ __forceinline__ void fuse_bounds_q(const FuseSide& m, const RowBand& b, float s, float bn, float sc,
+                                              float& lo, float& hi) {  // fuse_bounds with the per-query values hoisted
+  const float e = b.r * bn;
+  lo = (s - e) * b.invw * sc;
+  hi = (s + e) * b.invw * sc;
+  lo = fmaf(-fabsf(lo), 4e-6f, lo);
+  hi = fmaf(fabsf(hi), 4e-6f, hi);
+}
 
 // pass 1: per column max of the lower bounds and min of the upper bounds (ordered-uint atomics)
-__global__ void __launch_bounds__(256, 4)
+template <int V>
+__global__ void __launch_bounds__(256, 2)
 fuse_colstats_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, uint32_t* __restrict__ max_lb,
                      uint32_t* __restrict__ min_ub) {
   const FuseSide& m = blockIdx.z ? sb : sa;
@@ -694,17 +758,25 @@ fuse_colstats_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pa
   uint32_t mx[kFuseChunk], mn[kFuseChunk];
 #pragma unroll
   for (int c = 0; c < kFuseChunk; ++c) { mx[c] = 0u; mn[c] = 0xFFFFFFFFu; }
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
-       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const RowBand b = fuse_row_band(m, row);
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; row < n;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
+    const RowBandV<V> b = fuse_row_band_v<V>(m, row);
+    FVec<V> sv[kFuseChunk];
+#pragma unroll
+    for (int c = 0; c < kFuseChunk; ++c)
+      if (j0 + c < pairs) sv[c] = fuse_ld<V>(m.dense + static_cast<int64_t>(j0 + c) * n + row);
 #pragma unroll
     for (int c = 0; c < kFuseChunk; ++c) {
       const int j = j0 + c;
       if (j < pairs) {
-        float lo, hi;
-        fuse_bounds(m, b, __ldg(m.dense + static_cast<int64_t>(j) * n + row), j, lo, hi);
-        mx[c] = max(mx[c], f2ord(lo));
-        mn[c] = min(mn[c], f2ord(hi));
+        const float bn = __ldg(m.q_bn + j), sc = m.scale ? __ldg(m.scale + j) : 1.f;
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          float lo, hi;
+          fuse_bounds_q(m, band_of<V>(b, t), sv[c].v[t], bn, sc, lo, hi);
+          mx[c] = max(mx[c], f2ord(lo));
+          mn[c] = min(mn[c], f2ord(hi));
+        }
       }
     }
   }
@@ -726,29 +798,39 @@ fuse_colstats_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pa
 }
 
 // pass 2: rows that can hold a column's exact max (ub >= max lb) or min (lb <= min ub)
-__global__ void __launch_bounds__(256, 4)
+template <int V>
+__global__ void __launch_bounds__(256, 2)
 fuse_collect_extreme_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs,
                             const uint32_t* __restrict__ max_lb, const uint32_t* __restrict__ min_ub,
                             uint32_t* __restrict__ ext_cnt, uint32_t* __restrict__ ext_row, uint32_t ext_cap) {
   const FuseSide& m = blockIdx.z ? sb : sa;
   const int j0 = blockIdx.y * kFuseChunk;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
-       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const RowBand b = fuse_row_band(m, row);
-#pragma unroll 4
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; row < n;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
+    const RowBandV<V> b = fuse_row_band_v<V>(m, row);
+    FVec<V> sv[kFuseChunk];
+#pragma unroll
+    for (int c = 0; c < kFuseChunk; ++c)
+      if (j0 + c < pairs) sv[c] = fuse_ld<V>(m.dense + static_cast<int64_t>(j0 + c) * n + row);
+#pragma unroll
     for (int c = 0; c < kFuseChunk; ++c) {
       const int j = j0 + c;
       if (j < pairs) {
-        float lo, hi;
-        fuse_bounds(m, b, __ldg(m.dense + static_cast<int64_t>(j) * n + row), j, lo, hi);
         const int o = blockIdx.z * pairs + j;
-        if (f2ord(hi) >= __ldg(max_lb + o)) {
-          const uint32_t pos = atomicAdd(ext_cnt + 2 * o, 1u);
-          if (pos < ext_cap) ext_row[static_cast<size_t>(2 * o) * ext_cap + pos] = static_cast<uint32_t>(row);
-        }
-        if (f2ord(lo) <= __ldg(min_ub + o)) {
-          const uint32_t pos = atomicAdd(ext_cnt + 2 * o + 1, 1u);
-          if (pos < ext_cap) ext_row[static_cast<size_t>(2 * o + 1) * ext_cap + pos] = static_cast<uint32_t>(row);
+        const float bn = __ldg(m.q_bn + j), sc = m.scale ? __ldg(m.scale + j) : 1.f;
+        const uint32_t tmax = __ldg(max_lb + o), tmin = __ldg(min_ub + o);
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          float lo, hi;
+          fuse_bounds_q(m, band_of<V>(b, t), sv[c].v[t], bn, sc, lo, hi);
+          if (f2ord(hi) >= tmax) {
+            const uint32_t pos = atomicAdd(ext_cnt + 2 * o, 1u);
+            if (pos < ext_cap) ext_row[static_cast<size_t>(2 * o) * ext_cap + pos] = static_cast<uint32_t>(row + t);
+          }
+          if (f2ord(lo) <= tmin) {
+            const uint32_t pos = atomicAdd(ext_cnt + 2 * o + 1, 1u);
+            if (pos < ext_cap) ext_row[static_cast<size_t>(2 * o + 1) * ext_cap + pos] = static_cast<uint32_t>(row + t);
+          }
         }
       }
     }
@@ -823,28 +905,63 @@ fuse_sample_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pair
   }
 }
 
+// heat bounds of one (row, pair) from the two screen scores
+__device__ __forceinline__ void fuse_heat_bounds2(const FuseSide& sa, const FuseSide& sb, const RowBand& ba, const RowBand& bb,
+                                                  float s_a, float s_b, float bna, float sca, float bnb, float scb,
+                                                  float mna, float mxa, float mnb, float mxb, int combine, float& h_lo,
+                                                  float& h_hi) {
+  float la, ha, lb, hb;
+  fuse_bounds_q(sa, ba, s_a, bna, sca, la, ha);
+  fuse_bounds_q(sb, bb, s_b, bnb, scb, lb, hb);
+  h_hi = fuse_combine(minmax_norm(clampf(ha, mna, mxa), mna, mxa), minmax_norm(clampf(hb, mnb, mxb), mnb, mxb), combine);
+  h_lo = fuse_combine(minmax_norm(clampf(la, mna, mxa), mna, mxa), minmax_norm(clampf(lb, mnb, mxb), mnb, mxb), combine);
+}
+
 // pass 5: rows whose heat upper bound reaches the pair's threshold, with both heat bounds
-__global__ void __launch_bounds__(256, 4)
+template <int V>
+__global__ void __launch_bounds__(256, 2)
 fuse_collect_heat_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, const float* __restrict__ mm,
                          int combine, const float* __restrict__ thr, uint32_t* __restrict__ cand_cnt,
                          uint32_t* __restrict__ cand_row, float* __restrict__ cand_lo, float* __restrict__ cand_hi,
                          uint32_t cand_cap) {
+  constexpr int kC = kFuseChunk / 2;  // two modalities per pair: half the columns per step
   const int j0 = blockIdx.y * kFuseChunk;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n;
-       row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const RowBand ba = fuse_row_band(sa, row), bb = fuse_row_band(sb, row);
-#pragma unroll 2
-    for (int c = 0; c < kFuseChunk; ++c) {
-      const int j = j0 + c;
-      if (j >= pairs) break;
-      const float h = fuse_heat_bound<true>(sa, sb, ba, bb, n, row, j, pairs, mm, combine);
-      if (!(h < __ldg(thr + j))) {  // also true for NaN: degenerate columns go to the exact path via overflow
-        const uint32_t pos = atomicAdd(cand_cnt + j, 1u);
-        if (pos < cand_cap) {
-          const size_t o = static_cast<size_t>(j) * cand_cap + pos;
-          cand_row[o] = static_cast<uint32_t>(row);
-          cand_hi[o] = h;
-          cand_lo[o] = fuse_heat_bound<false>(sa, sb, ba, bb, n, row, j, pairs, mm, combine);
+  for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * V; row < n;
+       row += static_cast<int64_t>(gridDim.x) * blockDim.x * V) {
+    const RowBandV<V> ba = fuse_row_band_v<V>(sa, row), bb = fuse_row_band_v<V>(sb, row);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      FVec<V> va[kC], vb[kC];
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+        const int j = j0 + h * kC + c;
+        if (j < pairs) {
+          va[c] = fuse_ld<V>(sa.dense + static_cast<int64_t>(j) * n + row);
+          vb[c] = fuse_ld<V>(sb.dense + static_cast<int64_t>(j) * n + row);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+        const int j = j0 + h * kC + c;
+        if (j >= pairs) continue;
+        const float bna = __ldg(sa.q_bn + j), sca = sa.scale ? __ldg(sa.scale + j) : 1.f;
+        const float bnb = __ldg(sb.q_bn + j), scb = sb.scale ? __ldg(sb.scale + j) : 1.f;
+        const float mna = __ldg(mm + j), mxa = __ldg(mm + pairs + j), mnb = __ldg(mm + 2 * pairs + j), mxb = __ldg(mm + 3 * pairs + j);
+        const float tj = __ldg(thr + j);
+#pragma unroll
+        for (int t = 0; t < V; ++t) {
+          float h_lo, h_hi;
+          fuse_heat_bounds2(sa, sb, band_of<V>(ba, t), band_of<V>(bb, t), va[c].v[t], vb[c].v[t], bna, sca, bnb, scb, mna, mxa,
+                            mnb, mxb, combine, h_lo, h_hi);
+          if (!(h_hi < tj)) {  // also true for NaN: degenerate columns go to the exact path via overflow
+            const uint32_t pos = atomicAdd(cand_cnt + j, 1u);
+            if (pos < cand_cap) {
+              const size_t o = static_cast<size_t>(j) * cand_cap + pos;
+              cand_row[o] = static_cast<uint32_t>(row + t);
+              cand_hi[o] = h_hi;
+              cand_lo[o] = h_lo;
+            }
+          }
         }
       }
     }
@@ -932,20 +1049,21 @@ __global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
 
 // =================================================================== launchers
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
-                       float* row_norm, float* row_c, float* row_an, float kappa, cudaStream_t s) {
+                       float* row_norm, float* row_c, float* row_an, float kappa, int f16, uint32_t* nonfinite,
+                       cudaStream_t s) {
   if (n == 0) return AVL_OK;
   const int warps = 8;
   const unsigned blocks = static_cast<unsigned>((n + warps - 1) / warps);
-  map_prepare_kernel<<<blocks, warps * 32, 0, s>>>(feat, n, d, dpad, bf, row_norm, row_c, row_an, kappa);
+  map_prepare_kernel<<<blocks, warps * 32, 0, s>>>(feat, n, d, dpad, bf, row_norm, row_c, row_an, kappa, f16, nonfinite);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
 
 int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, int32_t d, int32_t dpad,
-                         int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, cudaStream_t s) {
+                         int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, int f16, cudaStream_t s) {
   AVL_CUDA(cudaMemsetAsync(q_glob, 0, 2 * sizeof(float), s));
   query_prepare_kernel<<<npad, 128, 0, s>>>(q, fold_scale, nq, d, dpad, bq, q_bn,
-                                            reinterpret_cast<uint32_t*>(q_glob));
+                                            reinterpret_cast<uint32_t*>(q_glob), f16);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
@@ -1090,9 +1208,16 @@ int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n
   AVL_CUDA(cudaMemsetAsync(w.ext_cnt, 0, sizeof(uint32_t) * 4 * pairs, s));
   AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * pairs, s));
   AVL_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(uint32_t), s));
-  fuse_colstats_kernel<<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub);
-  fuse_collect_extreme_kernel<<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub, w.ext_cnt,
-                                                                   w.ext_row, w.ext_cap);
+  const bool vec = (n & 3) == 0;  // column bases stay 16-byte aligned
+  if (vec) {
+    fuse_colstats_kernel<4><<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub);
+    fuse_collect_extreme_kernel<4><<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub, w.ext_cnt,
+                                                                        w.ext_row, w.ext_cap);
+  } else {
+    fuse_colstats_kernel<1><<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub);
+    fuse_collect_extreme_kernel<1><<<dim3(gx, chunks, 2), 256, 0, s>>>(sa, sb, n, pairs, w.max_lb, w.min_ub, w.ext_cnt,
+                                                                        w.ext_row, w.ext_cap);
+  }
   fuse_exact_extreme_kernel<<<dim3(pairs, 2), 256, 0, s>>>(sa, sb, pairs, w.ext_cnt, w.ext_row, w.ext_cap, w.mm,
                                                            w.overflow);
   fuse_sample_kernel<<<(w.n_sample + 255) / 256, 256, 0, s>>>(sa, sb, n, pairs, w.sample_stride, w.n_sample, w.mm,
@@ -1100,8 +1225,12 @@ int launch_fuse_screened(const FuseSideHost& a, const FuseSideHost& b, int64_t n
   AVL_CUDA(cudaGetLastError());
   int rc = launch_select_threshold(w.sample_t, w.n_sample, w.n_sample, pairs, k, w.thr, s);
   if (rc) return rc;
-  fuse_collect_heat_kernel<<<dim3(2 * gx, chunks), 256, 0, s>>>(sa, sb, n, pairs, w.mm, combine, w.thr, w.cand_cnt,
-                                                                w.cand_row, w.cand_lo, w.cand_hi, w.cand_cap);
+  if (vec)
+    fuse_collect_heat_kernel<4><<<dim3(2 * gx, chunks), 256, 0, s>>>(sa, sb, n, pairs, w.mm, combine, w.thr, w.cand_cnt,
+                                                                     w.cand_row, w.cand_lo, w.cand_hi, w.cand_cap);
+  else
+    fuse_collect_heat_kernel<1><<<dim3(2 * gx, chunks), 256, 0, s>>>(sa, sb, n, pairs, w.mm, combine, w.thr, w.cand_cnt,
+                                                                     w.cand_row, w.cand_lo, w.cand_hi, w.cand_cap);
   const size_t smem = static_cast<size_t>(w.cand_cap) * sizeof(uint32_t);
   AVL_CUDA(cudaFuncSetAttribute(fuse_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   fuse_finalize_kernel<<<pairs, 1024, smem, s>>>(sa, sb, pairs, w.mm, combine, k, w.cand_cnt, w.cand_row, w.cand_lo,

@@ -357,7 +357,8 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(kTileRows * CG, static_cast<uint32_t>(p.npad));
+      const uint32_t idesc = p.op_f16 ? ptx::make_idesc_f16(kTileRows * CG, static_cast<uint32_t>(p.npad))
+                                      : ptx::make_idesc_bf16(kTileRows * CG, static_cast<uint32_t>(p.npad));
       ptx::mbar_wait(ptx::smem_u32(bar_bfull), 0, p.dbg, 0x20u);
       ptx::tc_fence_after();
       uint32_t stage = 0, phase = 0, it = 0;

@@ -185,7 +185,7 @@ screen_ts_kernel(const __grid_constant__ CUtensorMap tmap_v, const ScreenParams 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(256, kTsTileVox);
+      const uint32_t idesc = p.op_f16 ? ptx::make_idesc_f16(256, kTsTileVox) : ptx::make_idesc_bf16(256, kTsTileVox);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;

@@ -68,20 +68,26 @@ class DeviceMap:
     """grid_feat (N, D) resident in HBM: fp32 copy (exact re-scoring), bf16 copy (tcgen05 screen),
     per-row norms and bf16 rounding residuals.  Created once per loaded map (VLMap.load_map)."""
 
-    def __init__(self, grid_feat, stream=None, _handle=None):
+    def __init__(self, grid_feat, stream=None, _handle=None, operand: str = "bf16"):
+        """operand: element type of the tensor-core copy, "bf16" or "f16" (8x tighter error band, same speed and
+        bytes; falls back to bf16 by itself if a value exceeds the fp16 range).  Results do not depend on it."""
         self._lib = L.load()
         L.require_device()
         self._h = C.c_void_p()
+        if operand not in ("bf16", "f16"):
+            raise ValueError("operand must be 'bf16' or 'f16'")
         if _handle is not None:
             self._h = _handle
         else:
             a = _Arg(grid_feat, np.float32, "grid_feat")
             if len(a.shape) != 2:
                 raise ValueError("grid_feat must be (N, D)")
-            L.check(self._lib.avl_map_create(a.ptr, a.shape[0], a.shape[1], _flags(a), _stream_ptr(stream), C.byref(self._h)))
+            flags = _flags(a) | (L.AVL_MAP_F16 if operand == "f16" else 0)
+            L.check(self._lib.avl_map_create(a.ptr, a.shape[0], a.shape[1], flags, _stream_ptr(stream), C.byref(self._h)))
         n, d = C.c_int64(), C.c_int32()
         L.check(self._lib.avl_map_shape(self._h, C.byref(n), C.byref(d)))
         self.n, self.dim = n.value, d.value
+        self.operand = "f16" if self._lib.avl_map_operand_f16(self._h) else "bf16"
         self.last_stats = None
 
     # -- lifetime

@@ -42,6 +42,11 @@ extern "C" {
                               float64(d) / 1000.0 like `load_depth_img(...) / 1000.0`
                               (vlmap_builder_multi_floor.py:103,128) */
 
+#define AVL_MAP_F16 4 /* avl_map_create: keep the tensor-core copy of the map (and of the queries) in fp16 instead of
+                         bf16.  Same tcgen05 kind::f16 rate and bytes; the rounding residual, hence the rigorous error
+                         band that decides what is re-scored exactly, is 8x smaller.  Results are identical either
+                         way.  Falls back to bf16 by itself when a value exceeds the fp16 range. */
+
 #define AVL_MAX_QUERIES 256 /* per call; larger batches are chunked by the host layer */
 #define AVL_MAX_TOPK 128
 
@@ -90,6 +95,7 @@ int avl_set_profiling(int enabled); /* record CUDA events inside index calls (ad
 int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, void* stream, avl_map** out);
 int avl_map_destroy(avl_map* map);
 int avl_map_shape(const avl_map* map, int64_t* n, int32_t* dim);
+int avl_map_operand_f16(const avl_map* map); /* 1 if the tensor-core copy is fp16, 0 if bf16 */
 int64_t avl_map_device_bytes(const avl_map* map);
 
 /* scores[i, q] = scale[q] * inv_norm[i] * <grid_feat[i], queries[q]>   (fp32, (n, nq) C-contiguous)
