@@ -948,8 +948,22 @@ fuse_collect_heat_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_
         const float bnb = __ldg(sb.q_bn + j), scb = sb.scale ? __ldg(sb.scale + j) : 1.f;
         const float mna = __ldg(mm + j), mxa = __ldg(mm + pairs + j), mnb = __ldg(mm + 2 * pairs + j), mxb = __ldg(mm + 3 * pairs + j);
         const float tj = __ldg(thr + j);
+        // division-free prefilter: (x - min) * (1 / range, rounded up) * (1 + 2^-21) >= fl((x - min) / range), so
+        // the cheap product bounds the real upper bound from above; the IEEE divisions (4 per element, which made
+        // this pass compute-bound) run only for the few rows that pass
+        const float ira = __fdiv_ru(1.0000005f, __fsub_rd(mxa, mna)), irb = __fdiv_ru(1.0000005f, __fsub_rd(mxb, mnb));
 #pragma unroll
         for (int t = 0; t < V; ++t) {
+          {
+            const RowBand ra = band_of<V>(ba, t), rb = band_of<V>(bb, t);
+            float la, ha, lb, hb;
+            fuse_bounds_q(sa, ra, va[c].v[t], bna, sca, la, ha);
+            fuse_bounds_q(sb, rb, vb[c].v[t], bnb, scb, lb, hb);
+            const float xu = fminf(__fmul_ru(__fsub_ru(clampf(ha, mna, mxa), mna), ira), 1.f);
+            const float yu = fminf(__fmul_ru(__fsub_ru(clampf(hb, mnb, mxb), mnb), irb), 1.f);
+            const float hu = combine == AVL_FUSE_PRODUCT ? __fmul_ru(xu, yu) : (combine == AVL_FUSE_MAX ? fmaxf(xu, yu) : __fadd_ru(xu, yu));
+            if (hu < tj) continue;  // NaN (degenerate column) falls through to the exact-sequence test below
+          }
           float h_lo, h_hi;
           fuse_heat_bounds2(sa, sb, band_of<V>(ba, t), band_of<V>(bb, t), va[c].v[t], vb[c].v[t], bna, sca, bnb, scb, mna, mxa,
                             mnb, mxb, combine, h_lo, h_hi);
