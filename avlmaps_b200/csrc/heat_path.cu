@@ -9,6 +9,10 @@
 // tail (sqrt, / cell_size, * decay_rate, 1 - x, clip, cast) uses the reference's operation order with
 // round-to-nearest intrinsics, so the result has the reference's bits.
 #include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
 
 #include "avl_internal.h"
 
@@ -75,6 +79,77 @@ heat_kernel(const int32_t* __restrict__ pos, const uint8_t* __restrict__ mask, i
   heat[i] = static_cast<float>(s);
 }
 
+
+// ---- windowed search -------------------------------------------------------------------------
+// The heat has finite support: beyond d = cell_size / decay_rate cells it is clipped to 0, so only targets
+// inside that ball matter.  Targets are marked in a bitmap over their bounding box; every non-target voxel walks
+// the ball's offsets in ascending squared distance and stops at the first marked cell -- its squared distance IS
+// the minimum, an integer, so the float64 tail below produces the reference's bits.  No target inside the ball:
+// the true distance exceeds the ball radius and the clip gives exactly 0.
+struct HeatBox { int lo[3]; int dim[3]; };
+
+__global__ void __launch_bounds__(256)
+target_bbox_kernel(const int4* __restrict__ targets, const uint32_t* __restrict__ count, int* __restrict__ bbox) {
+  const uint32_t nt = *count;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+    const int4 t = targets[i];
+    lo[0] = min(lo[0], t.x); lo[1] = min(lo[1], t.y); lo[2] = min(lo[2], t.z);
+    hi[0] = max(hi[0], t.x); hi[1] = max(hi[1], t.y); hi[2] = max(hi[2], t.z);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    lo[c] = __reduce_min_sync(0xffffffffu, lo[c]);
+    hi[c] = __reduce_max_sync(0xffffffffu, hi[c]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int c = 0; c < 3; ++c) { atomicMin(bbox + c, lo[c]); atomicMax(bbox + 3 + c, hi[c]); }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+target_bitmap_kernel(const int4* __restrict__ targets, uint32_t nt, const HeatBox box, uint32_t* __restrict__ bits) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+    const int4 t = targets[i];
+    const unsigned long long c = (static_cast<unsigned long long>(t.x - box.lo[0]) * box.dim[1] + (t.y - box.lo[1])) * box.dim[2] + (t.z - box.lo[2]);
+    atomicOr(bits + (c >> 5), 1u << (c & 31));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+heat_window_kernel(const int32_t* __restrict__ pos, const uint8_t* __restrict__ mask, int64_t n, const HeatBox box,
+                   const uint32_t* __restrict__ bits, const int4* __restrict__ offs, int32_t n_offs, double cell_size,
+                   double decay_rate, float* __restrict__ heat) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask[i] != 0) {
+    heat[i] = 1.0f;
+    return;
+  }
+  const int x = pos[i * 3] - box.lo[0], y = pos[i * 3 + 1] - box.lo[1], z = pos[i * 3 + 2] - box.lo[2];
+  int best = -1;
+  for (int k = 0; k < n_offs; ++k) {
+    const int4 o = __ldg(offs + k);
+    const int cx = x + o.x, cy = y + o.y, cz = z + o.z;
+    if (static_cast<unsigned>(cx) < static_cast<unsigned>(box.dim[0]) && static_cast<unsigned>(cy) < static_cast<unsigned>(box.dim[1]) &&
+        static_cast<unsigned>(cz) < static_cast<unsigned>(box.dim[2])) {
+      const unsigned long long c = (static_cast<unsigned long long>(cx) * box.dim[1] + cy) * box.dim[2] + cz;
+      if ((__ldg(bits + (c >> 5)) >> (c & 31)) & 1u) {
+        best = o.w;
+        break;
+      }
+    }
+  }
+  if (best < 0) {
+    heat[i] = 0.0f;
+    return;
+  }
+  const double dist = __ddiv_rn(__dsqrt_rn(static_cast<double>(best)), cell_size);
+  double s = __dsub_rn(1.0, __dmul_rn(dist, decay_rate));
+  s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+  heat[i] = static_cast<float>(s);
+}
+
 }  // namespace
 }  // namespace avl
 
@@ -92,6 +167,9 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
   float* d_heat = nullptr;
   int4* d_targets = nullptr;
   uint32_t* d_count = nullptr;
+  int* d_bbox = nullptr;
+  uint32_t* d_bits = nullptr;
+  int4* d_offs = nullptr;
   int rc = AVL_OK;
   cudaError_t e = cudaSuccess;
   const bool host = !(flags & AVL_ON_DEVICE);
@@ -122,13 +200,60 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
       rc = AVL_ERR_ARG;
       break;
     }
-    heat_kernel<<<blocks, 256, 0, s>>>(pos, msk, n, d_targets, d_count, cell_size, decay_rate, heat);
-    e = cudaGetLastError();
+    // window or brute force?  ball = offsets within the support radius; brute force costs nt distance evaluations per voxel
+    bool windowed = false;
+    const double support = cell_size / decay_rate;  // heat > 0 only below this many cells
+    const bool force_brute = getenv("AVL_HEAT_BRUTE") != nullptr;  // A/B and tests of the brute-force kernel
+    if (!force_brute && decay_rate > 0.0 && support < 40.0) {
+      const int rmax = static_cast<int>(std::floor(support)) + 1;
+      std::vector<int4> offs;
+      for (int dx = -rmax; dx <= rmax; ++dx)
+        for (int dy = -rmax; dy <= rmax; ++dy)
+          for (int dz = -rmax; dz <= rmax; ++dz) {
+            const int d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 <= rmax * rmax) offs.push_back(make_int4(dx, dy, dz, d2));
+          }
+      std::sort(offs.begin(), offs.end(), [](const int4& a, const int4& b) { return a.w < b.w; });
+      if (offs.size() < static_cast<size_t>(nt) * 2) {  // a bit test costs about half a distance evaluation
+        int h_bbox[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        e = cudaMalloc(reinterpret_cast<void**>(&d_bbox), sizeof(h_bbox));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_bbox, h_bbox, sizeof(h_bbox), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) break;
+        target_bbox_kernel<<<std::min((nt + 255u) / 256u, 592u), 256, 0, s>>>(d_targets, d_count, d_bbox);
+        e = cudaMemcpyAsync(h_bbox, d_bbox, sizeof(h_bbox), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) break;
+        HeatBox box;
+        double cells = 1.0;
+        for (int c = 0; c < 3; ++c) {
+          box.lo[c] = h_bbox[c];
+          box.dim[c] = h_bbox[3 + c] - h_bbox[c] + 1;
+          cells *= static_cast<double>(box.dim[c]);
+        }
+        if (cells <= 8.0e9) {  // <= 1 GB of bits
+          const size_t words = static_cast<size_t>((static_cast<unsigned long long>(cells) + 31) / 32);
+          e = cudaMalloc(reinterpret_cast<void**>(&d_bits), words * sizeof(uint32_t));
+          if (e == cudaSuccess) e = cudaMemsetAsync(d_bits, 0, words * sizeof(uint32_t), s);
+          if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_offs), offs.size() * sizeof(int4));
+          if (e == cudaSuccess) e = cudaMemcpyAsync(d_offs, offs.data(), offs.size() * sizeof(int4), cudaMemcpyHostToDevice, s);
+          if (e != cudaSuccess) break;
+          target_bitmap_kernel<<<std::min((nt + 255u) / 256u, 1184u), 256, 0, s>>>(d_targets, nt, box, d_bits);
+          heat_window_kernel<<<blocks, 256, 0, s>>>(pos, msk, n, box, d_bits, d_offs, static_cast<int32_t>(offs.size()),
+                                                    cell_size, decay_rate, heat);
+          e = cudaGetLastError();
+          if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // offs (host vector) and the scratch are released below
+          windowed = true;
+        }
+      }
+    }
+    if (!windowed) heat_kernel<<<blocks, 256, 0, s>>>(pos, msk, n, d_targets, d_count, cell_size, decay_rate, heat);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (host && e == cudaSuccess) e = cudaMemcpyAsync(out_heat, d_heat, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   } while (0);
   if (e != cudaSuccess && rc == AVL_OK) rc = cuda_fail(e, "heat_from_mask_3d", __FILE__, __LINE__);
   cudaFree(d_pos); cudaFree(d_mask); cudaFree(d_heat); cudaFree(d_targets); cudaFree(d_count);
+  cudaFree(d_bbox); cudaFree(d_bits); cudaFree(d_offs);
   return rc;
 }
 

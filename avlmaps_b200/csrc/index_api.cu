@@ -101,6 +101,7 @@ struct Workspace {
   size_t topk_scratch_bytes = 0;
   uint32_t* dbg_host = nullptr;
   uint32_t* dbg_dev = nullptr;
+  uint32_t* pin = nullptr;       // pinned host scratch for the small read-backs (pageable copies stage and stall)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -145,8 +146,10 @@ static int ws_init(avl_map* m) {
   if ((rc = dev_alloc(&w.q_glob, 2, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.thr_t, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.flag_count, 1, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.cand_cnt, AVL_MAX_QUERIES, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.overflow, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  // counters and overflow flags are adjacent: one 2 KiB read-back into pinned memory per top-k call
+  if ((rc = dev_alloc(&w.cand_cnt, 2 * AVL_MAX_QUERIES, &m->bytes))) return rc;
+  w.overflow = w.cand_cnt + AVL_MAX_QUERIES;
+  AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.pin), 2 * AVL_MAX_QUERIES * sizeof(uint32_t), cudaHostAllocDefault));
   if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
   AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.dbg_host), 64, cudaHostAllocMapped));
@@ -159,10 +162,11 @@ static int ws_init(avl_map* m) {
 static void ws_free(Workspace& w) {
   cudaFree(w.q); cudaFree(w.q64); cudaFree(w.scale); cudaFree(w.bq); cudaFree(w.q_bn); cudaFree(w.q_glob); cudaFree(w.thr_t);
   cudaFree(w.flag_count); cudaFree(w.flag_rows); cudaFree(w.flag_masks); cudaFree(w.cand_cnt);
-  cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.overflow); cudaFree(w.sample_t); cudaFree(w.out_idx);
+  cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
   cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small); cudaFree(w.cand_val2);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
+  if (w.pin) cudaFreeHost(w.pin);
   for (int i = 0; i < 4; ++i)
     if (w.ev[i]) cudaEventDestroy(w.ev[i]);
 }
@@ -684,8 +688,7 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_cols), n_cols, nq, k, w.thr_t, s)))
       return rc;
   }
-  AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
-  AVL_CUDA(cudaMemsetAsync(w.overflow, 0, sizeof(uint32_t) * AVL_MAX_QUERIES, s));
+  AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, s));  // counters + overflow flags
   if (m->n > 0) {
     // phase B: full pass, candidates = rows whose upper bound reaches the threshold
     base_params(m, qs, nq, normalize_map, &p);
@@ -707,9 +710,9 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
 
   // overflowed queries (adversarial data, massive ties): exact dense column + vector top-k
-  std::vector<uint32_t> ovf(nq), cnt(nq);
-  AVL_CUDA(cudaMemcpyAsync(ovf.data(), w.overflow, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s));
-  AVL_CUDA(cudaMemcpyAsync(cnt.data(), w.cand_cnt, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s));
+  AVL_CUDA(cudaMemcpyAsync(w.pin, w.cand_cnt, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, cudaMemcpyDeviceToHost, s));
+  const uint32_t* cnt = w.pin;
+  const uint32_t* ovf = w.pin + AVL_MAX_QUERIES;
   {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk", __FILE__, __LINE__));

@@ -8,6 +8,7 @@ the hand-written kernels in csrc/.  There is no CPU path: without a CUDA device 
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -54,7 +55,8 @@ class _Arg:
                 self.keep, self.device, self.ptr, self.shape = x, True, C.c_void_p(x.data_ptr()), tuple(x.shape)
                 return
         a = np.ascontiguousarray(x, dtype=dtype)
-        self.keep, self.ptr, self.shape = a, a.ctypes.data_as(C.c_void_p), a.shape
+        # __array_interface__ is several times cheaper than a.ctypes (this runs per frame and per query batch)
+        self.keep, self.ptr, self.shape = a, C.c_void_p(a.__array_interface__["data"][0]), a.shape
 
 
 def _flags(*args: _Arg) -> int:
@@ -313,6 +315,9 @@ def heat2d_sources(shape, cells_per_group, conf, decay_rate: float, mode: str):
     return out
 
 
+_FRAME_OFFSETS = {name: getattr(L.Frame, name).offset for name in ("kinv", "k", "kfeat", "tf")}
+
+
 def _is_u16(x) -> bool:
     """uint16 depth = millimetres (the multi-floor builder's PNG depth, vlmap_builder_multi_floor.py:103)."""
     if _is_torch(x):
@@ -351,14 +356,15 @@ def _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, m
     fr.feat, fr.fh, fr.fw, fr.feat_layout = f_.ptr, fh, fw, feat_layout
     fr.rgb = r_.ptr
     fr.sample_idx = s_.ptr
-    fr.n_samples = 0 if s_.ptr is None else int(np.prod(s_.shape))
+    fr.n_samples = 0 if s_.ptr is None else math.prod(s_.shape)
+    base = C.addressof(fr)
     for name, m, n in (("kinv", kinv, 9), ("k", k, 9), ("kfeat", kfeat, 9), ("tf", tf, 16)):
         if m is None:
             continue
-        arr = np.ascontiguousarray(m, np.float64).reshape(-1)
+        arr = np.asarray(m, np.float64)
         if arr.size != n:
             raise ValueError(f"{name} must have {n} elements")
-        getattr(fr, name)[:] = arr.tolist()
+        C.memmove(base + _FRAME_OFFSETS[name], arr.tobytes(), n * 8)  # per-frame call: keep the Python cost down
     fr.min_depth, fr.max_depth = float(min_depth), float(max_depth)
     flags = _flags(d_, f_, r_, s_) | (L.AVL_DEPTH_U16_MM if u16 else 0)
     return fr, flags, (d_, f_, r_, s_)

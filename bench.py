@@ -319,9 +319,9 @@ def run_gpu(args):
     lib = L.load()
     L.require_device()
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to STDOUT; stdout carries exactly one JSON line,
+        # so NCCL's log goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peaks = load_peaks()
@@ -344,9 +344,24 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: value
-    for i in range(args.warmup):
+    # ---- device-resident arm: value.  N = 1: the C-ABI call with DEVICE pointers (queries and outputs in HBM);
+    # N > 1: the same call per rank inside ShardedMap.topk, followed by the one NCCL all-gather + merge kernel
+    oi_dev = torch.empty((NQ, TOPK), dtype=torch.int64, device=dev)
+    os_dev = torch.empty((NQ, TOPK), dtype=torch.float32, device=dev)
+    st = L.IndexStats()
+
+    def value_step(i):
+        if world == 1:
+            L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(qpool[i % 8].data_ptr()), NQ, None, 0, TOPK,
+                                     C.c_void_p(oi_dev.data_ptr()), C.c_void_p(os_dev.data_ptr()), L.AVL_ON_DEVICE,
+                                     C.c_void_p(stream.cuda_stream), C.byref(st)))
+            return st.ms_screen, st.n_launches, st.n_candidates, st.cta_group
         sm.topk(qpool[i % 8], TOPK)
+        d = dmap.last_stats
+        return d["ms_screen"], d["n_launches"], d["n_candidates"], d["cta_group"]
+
+    for i in range(args.warmup):
+        value_step(i)
     lib.avl_set_profiling(1)
     clocks = ClockSampler(local)
     barrier()
@@ -357,12 +372,10 @@ def run_gpu(args):
     last_cta_group = 0
     e0.record(stream)
     for i in range(args.steps):
-        sm.topk(qpool[i % 8], TOPK)
-        st = dmap.last_stats
-        ms_screen.append(st["ms_screen"])
-        launches += st["n_launches"]
-        cands.append(st["n_candidates"])
-        last_cta_group = st["cta_group"]
+        a, b, c, last_cta_group = value_step(i)
+        ms_screen.append(a)
+        launches += b
+        cands.append(c)
     e1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -524,7 +537,7 @@ def run_gpu(args):
                 torch.cuda.synchronize()
                 tt.append(a.elapsed_time(b))
             extra["config3_fusion_1M_512+1024_32pairs"] = {"ms_call": min(tt[1:]), "pairs_per_s": 32 / (min(tt[1:]) * 1e-3),
-                                                           "note": "exact fp64-accumulated dense columns + min-max + product + top-16"}
+                                                           "note": "two dense tcgen05 screens + interval propagation + exact re-score of the survivors; min-max, product, top-16"}
             # AVLMap.index_object heat: nearest-target distance decay over 1M voxels, 1% targets
             pos = torch.randint(0, 1000, (n3, 3), device=dev, dtype=torch.int32, generator=g)
             pos[:, 2] = pos[:, 2] % 30

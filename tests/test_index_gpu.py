@@ -340,6 +340,28 @@ def test_heat_from_mask_bit_exact(eng):
         eng.heat_from_mask_3d(pos, np.zeros(30_000, bool))
 
 
+@pytest.mark.parametrize("decay", [0.1, 0.01, 0.004, 0.0009])
+def test_heat_windowed_search_equals_brute_force(eng, monkeypatch, decay):
+    """The heat is clipped to 0 beyond cell_size / decay cells, so the kernel only looks for targets inside that
+    ball (bitmap + offsets in ascending distance); same bits as the brute-force kernel and as the oracle.
+    decay 0.1 (AVLMap.index_object's default): radius 0.5, only the targets are hot; 0.0009: ball larger than the
+    target set, the library picks brute force by itself."""
+    rng = np.random.default_rng(7)
+    n = 200_000
+    pos = np.stack([rng.integers(-20, 400, n), rng.integers(0, 400, n), rng.integers(0, 30, n)], 1).astype(np.int32)
+    mask = rng.uniform(size=n) < 0.01
+    got = eng.heat_from_mask_3d(pos, mask, 0.05, decay)
+    monkeypatch.setenv("AVL_HEAT_BRUTE", "1")
+    brute = eng.heat_from_mask_3d(pos, mask, 0.05, decay)
+    monkeypatch.delenv("AVL_HEAT_BRUTE")
+    assert np.array_equal(got, brute)
+    sub = rng.integers(0, n, 3000)
+    want = O.heatmap_from_mask_3d(np.concatenate([pos[sub], pos[mask]]), np.concatenate([np.zeros(3000, bool) | mask[sub], np.ones(int(mask.sum()), bool)]), 0.05, decay)
+    assert np.array_equal(got[sub], want[:3000])
+    if decay >= 0.004:
+        assert (got > 0).sum() > mask.sum() or decay == 0.1
+
+
 def test_query_stationary_variant_matches(eng, monkeypatch):
     """The opt-in kernel with the queries resident in TMEM (AVL_TS=1) returns the same top-k."""
     feat, q = synth.index_inputs(40_001, 512, 200, seed=44)
