@@ -150,6 +150,48 @@ heat_window_kernel(const int32_t* __restrict__ pos, const uint8_t* __restrict__ 
   heat[i] = static_cast<float>(s);
 }
 
+// ---- scatter from the targets -----------------------------------------------------------------
+// When a dense uint32 grid over the targets' bounding box (grown by the support radius) fits, the roles flip:
+// every target writes its squared distance into the cells of its ball (atomicMin), 10 k targets x 925 offsets
+// instead of 1 M voxels x 925 offsets, and every voxel reads one cell.  Same minimum, same bits.
+__global__ void __launch_bounds__(256)
+heat_scatter_kernel(const int4* __restrict__ targets, uint32_t nt, const int4* __restrict__ offs, int32_t n_offs,
+                    const HeatBox box, uint32_t* __restrict__ best) {
+  const unsigned long long total = static_cast<unsigned long long>(nt) * n_offs;
+  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    const int4 t = targets[i / n_offs];
+    const int4 o = __ldg(offs + (i % n_offs));
+    // box is the targets' bounding box grown by the radius on every side: every ball cell is inside
+    const unsigned long long c = (static_cast<unsigned long long>(t.x + o.x - box.lo[0]) * box.dim[1] + (t.y + o.y - box.lo[1])) * box.dim[2] + (t.z + o.z - box.lo[2]);
+    atomicMin(best + c, static_cast<uint32_t>(o.w));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+heat_gather_kernel(const int32_t* __restrict__ pos, const uint8_t* __restrict__ mask, int64_t n, const HeatBox box,
+                   const uint32_t* __restrict__ best, double cell_size, double decay_rate, float* __restrict__ heat) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask[i] != 0) {
+    heat[i] = 1.0f;
+    return;
+  }
+  const int x = pos[i * 3] - box.lo[0], y = pos[i * 3 + 1] - box.lo[1], z = pos[i * 3 + 2] - box.lo[2];
+  uint32_t d2 = 0xFFFFFFFFu;
+  if (static_cast<unsigned>(x) < static_cast<unsigned>(box.dim[0]) && static_cast<unsigned>(y) < static_cast<unsigned>(box.dim[1]) &&
+      static_cast<unsigned>(z) < static_cast<unsigned>(box.dim[2]))
+    d2 = __ldg(best + (static_cast<unsigned long long>(x) * box.dim[1] + y) * box.dim[2] + z);
+  if (d2 == 0xFFFFFFFFu) {
+    heat[i] = 0.0f;
+    return;
+  }
+  const double dist = __ddiv_rn(__dsqrt_rn(static_cast<double>(d2)), cell_size);
+  double s = __dsub_rn(1.0, __dmul_rn(dist, decay_rate));
+  s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+  heat[i] = static_cast<float>(s);
+}
+
 }  // namespace
 }  // namespace avl
 
@@ -255,7 +297,11 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
             if (d2 <= rmax * rmax) offs.push_back(make_int4(dx, dy, dz, d2));
           }
       std::sort(offs.begin(), offs.end(), [](const int4& a, const int4& b) { return a.w < b.w; });
-      if (offs.size() < static_cast<size_t>(nt) * 2) {  // a bit test costs about half a distance evaluation
+      // measured on B200 (1M voxels, 10 k targets): brute force 0.66 us per target, bitmap walk 2.8 us per ball
+      // offset, scatter 0.11 us per ball offset (per 10 k targets)
+      const bool scatter_pays = static_cast<double>(offs.size()) * 20.0 < static_cast<double>(n);
+      const bool walk_pays = static_cast<double>(offs.size()) * 5.0 < static_cast<double>(nt);
+      if (scatter_pays || walk_pays) {
         int h_bbox[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
         e = hs.get(HeatScratch::kBBox, sizeof(h_bbox), reinterpret_cast<void**>(&d_bbox));
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_bbox, h_bbox, sizeof(h_bbox), cudaMemcpyHostToDevice, s);
@@ -271,7 +317,29 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
           box.dim[c] = h_bbox[3 + c] - h_bbox[c] + 1;
           cells *= static_cast<double>(box.dim[c]);
         }
-        if (cells <= 8.0e9) {  // <= 1 GB of bits
+        // preferred: scatter from the targets into a dense uint32 grid over the box grown by the radius
+        double gcells = 1.0;
+        HeatBox gbox;
+        for (int c = 0; c < 3; ++c) {
+          gbox.lo[c] = box.lo[c] - rmax;
+          gbox.dim[c] = box.dim[c] + 2 * rmax;
+          gcells *= static_cast<double>(gbox.dim[c]);
+        }
+        if (scatter_pays && gcells * 4.0 <= 2.0e9 && getenv("AVL_HEAT_BITMAP") == nullptr) {
+          const size_t gwords = static_cast<size_t>(gcells);
+          e = hs.get(HeatScratch::kBits, gwords * sizeof(uint32_t), reinterpret_cast<void**>(&d_bits));
+          if (e == cudaSuccess) e = cudaMemsetAsync(d_bits, 0xFF, gwords * sizeof(uint32_t), s);
+          if (e == cudaSuccess) e = hs.get(HeatScratch::kOffs, offs.size() * sizeof(int4), reinterpret_cast<void**>(&d_offs));
+          if (e == cudaSuccess) e = cudaMemcpyAsync(d_offs, offs.data(), offs.size() * sizeof(int4), cudaMemcpyHostToDevice, s);
+          if (e != cudaSuccess) break;
+          const unsigned long long work = static_cast<unsigned long long>(nt) * offs.size();
+          heat_scatter_kernel<<<static_cast<unsigned>(std::min<unsigned long long>((work + 255) / 256, 148ull * 32)), 256, 0, s>>>(
+              d_targets, nt, d_offs, static_cast<int32_t>(offs.size()), gbox, d_bits);
+          heat_gather_kernel<<<blocks, 256, 0, s>>>(pos, msk, n, gbox, d_bits, cell_size, decay_rate, heat);
+          e = cudaGetLastError();
+          if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // offs (host vector) is released below
+          windowed = true;
+        } else if ((walk_pays || getenv("AVL_HEAT_BITMAP") != nullptr) && cells <= 8.0e9) {  // bitmap of the targets + per-voxel walk of the ball
           const size_t words = static_cast<size_t>((static_cast<unsigned long long>(cells) + 31) / 32);
           e = hs.get(HeatScratch::kBits, words * sizeof(uint32_t), reinterpret_cast<void**>(&d_bits));
           if (e == cudaSuccess) e = cudaMemsetAsync(d_bits, 0, words * sizeof(uint32_t), s);

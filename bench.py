@@ -550,7 +550,18 @@ def run_gpu(args):
                 b.record(stream)
                 torch.cuda.synchronize()
                 tt.append(a.elapsed_time(b))
-            extra["heat_from_mask_3d_1M_1pct_targets"] = {"ms_call": min(tt[1:])}
+            extra["heat_from_mask_3d_1M_1pct_targets"] = {"ms_call": min(tt[1:]), "decay_rate": 0.1,
+                                                          "note": "AVLMap.index_object's defaults (cell 0.05, decay 0.1)"}
+            tt = []
+            for i in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                engine.heat_from_mask_3d(pos, mask, 0.05, 0.01)
+                b.record(stream)
+                torch.cuda.synchronize()
+                tt.append(a.elapsed_time(b))
+            extra["heat_from_mask_3d_1M_1pct_targets_decay0.01"] = {"ms_call": min(tt[1:]), "decay_rate": 0.01,
+                                                                    "note": "get_heatmap_from_mask_3d's own default decay"}
             mv.close(); ma.close()
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001

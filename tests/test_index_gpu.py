@@ -355,6 +355,9 @@ def test_heat_windowed_search_equals_brute_force(eng, monkeypatch, decay):
     brute = eng.heat_from_mask_3d(pos, mask, 0.05, decay)
     monkeypatch.delenv("AVL_HEAT_BRUTE")
     assert np.array_equal(got, brute)
+    monkeypatch.setenv("AVL_HEAT_BITMAP", "1")   # second strategy: target bitmap + per-voxel walk of the ball
+    assert np.array_equal(eng.heat_from_mask_3d(pos, mask, 0.05, decay), brute)
+    monkeypatch.delenv("AVL_HEAT_BITMAP")
     sub = rng.integers(0, n, 3000)
     want = O.heatmap_from_mask_3d(np.concatenate([pos[sub], pos[mask]]), np.concatenate([np.zeros(3000, bool) | mask[sub], np.ones(int(mask.sum()), bool)]), 0.05, decay)
     assert np.array_equal(got[sub], want[:3000])

@@ -19,12 +19,14 @@ pos = torch.randint(0, 1000, (n3, 3), device=dev, dtype=torch.int32, generator=g
 pos[:, 2] = pos[:, 2] % 30
 mask = (torch.rand(n3, device=dev, generator=g) < 0.01)
 stream = torch.cuda.current_stream()
-for decay in (0.1, 0.01):
-    for brute in (False, True):
-        if brute:
+for decay in (0.1, 0.01, 0.004):
+    for brute in (False, "bitmap", True):
+        os.environ.pop("AVL_HEAT_BRUTE", None)
+        os.environ.pop("AVL_HEAT_BITMAP", None)
+        if brute is True:
             os.environ["AVL_HEAT_BRUTE"] = "1"
-        else:
-            os.environ.pop("AVL_HEAT_BRUTE", None)
+        elif brute == "bitmap":
+            os.environ["AVL_HEAT_BITMAP"] = "1"
         tt = []
         for i in range(4):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,4 +35,4 @@ for decay in (0.1, 0.01):
             b.record(stream)
             torch.cuda.synchronize()
             tt.append(a.elapsed_time(b))
-        print(f"decay {decay} {'brute' if brute else 'window'}: {min(tt[1:]):.3f} ms, hot voxels {(h > 0).sum().item()}")
+        print(f"decay {decay} {'brute' if brute is True else ('bitmap walk' if brute else 'scatter')}: {min(tt[1:]):.3f} ms, hot voxels {(h > 0).sum().item()}")
