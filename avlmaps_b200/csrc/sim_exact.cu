@@ -919,7 +919,7 @@ __device__ __forceinline__ void fuse_heat_bounds2(const FuseSide& sa, const Fuse
 
 // pass 5: rows whose heat upper bound reaches the pair's threshold, with both heat bounds
 template <int V>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 fuse_collect_heat_kernel(const FuseSide sa, const FuseSide sb, int64_t n, int32_t pairs, const float* __restrict__ mm,
                          int combine, const float* __restrict__ thr, uint32_t* __restrict__ cand_cnt,
                          uint32_t* __restrict__ cand_row, float* __restrict__ cand_lo, float* __restrict__ cand_hi,
