@@ -488,17 +488,17 @@ class DeviceBuilder:
         """global-frame grid: points on which the reference would raise IndexError (rejected here)."""
         return self._count(self._lib.avl_builder_num_rejected_oob)
 
-    def export(self, want_rgb: bool = True):
+    def export(self, want_rgb: bool = True, want_feat: bool = True):
         """numpy arrays[:max_id] + occupied_ids, like _save_3d_map (vlmap_builder.py:313-327)."""
         v = self.num_voxels
         out = dict(
-            grid_feat=np.zeros((v, self.dim), np.float32),
+            grid_feat=np.zeros((v if want_feat else 0, self.dim), np.float32),
             grid_pos=np.zeros((v, 3), np.int32),
             weight=np.zeros((v,), np.float32),
             occupied_ids=np.empty(self.grid_shape, np.int32),
             grid_rgb=np.zeros((v, 3), np.uint8),
         )
-        L.check(self._lib.avl_builder_export(self._h, L.np_ptr(out["grid_feat"]), L.np_ptr(out["grid_pos"]),
+        L.check(self._lib.avl_builder_export(self._h, L.np_ptr(out["grid_feat"]) if want_feat else None, L.np_ptr(out["grid_pos"]),
                                              L.np_ptr(out["weight"]), L.np_ptr(out["occupied_ids"]),
                                              L.np_ptr(out["grid_rgb"]) if want_rgb else None, 0, None))
         return out

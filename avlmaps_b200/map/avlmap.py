@@ -1,9 +1,10 @@
-"""`AVLMap` facade (reference avlmaps/map/avlmap.py:18-163), object modality.
+"""`AVLMap` facade (reference avlmaps/map/avlmap.py:18-163).
 
-The sound / area / image modalities of the reference wrap AudioCLIP, CLIP ViT-L/14 and HLoc models
-(SoundMap, AreaMap, VisualMap) that are outside this engine; their similarity call sites are served by
-engine.DeviceMap.scores / topk and their fusion by engine.fuse_topk.  `index_object` is the modality
-whose cost sits on the accelerated path: per-voxel argmax (tcgen05) + nearest-target distance decay."""
+`index_object` is the modality whose cost sits on the accelerated path: per-voxel argmax (tcgen05) + nearest-target
+distance decay.  The sound / area / image modalities wrap AudioCLIP, CLIP ViT-L/14 and HLoc models in the reference;
+here `avlmaps_b200.map.SoundMap` / `AreaMap` take those encoders as callables (or attach the reference's own
+objects -- only the methods listed below are used), and the heat maps run on the device.  Cross-modal goal selection
+over dense per-voxel modalities is `engine.fuse_topk`."""
 from __future__ import annotations
 
 from typing import List, Optional

@@ -319,3 +319,48 @@ def test_resume_from_saved_map(eng):
     with pytest.raises(AvlError):  # only a fresh builder can adopt a saved map
         b.import_state(g["first_grid_feat"], g["first_grid_pos"], g["first_weight"])
     b.close()
+
+
+def test_full_size_c4_properties(eng):
+    """BASELINE config 4 at full size -- 2000 frames of 480x640 at depth_sample_rate 1 into a 256 x 256 x 32 grid,
+    D = 512, device-resident pixel-major features -- through size-independent properties: voxel ids are a
+    permutation of 0..V-1 in bijection with the occupied cells, grid_pos inverts occupied_ids, the accepted-point
+    count and the ids are deterministic across two builds, and every weight is positive."""
+    import torch
+
+    from avlmaps_b200 import _lib as L
+    from avlmaps_b200.map import Map, VLMapBuilder
+    from avlmaps_b200.utils.mapping_utils import get_sim_cam_mat
+
+    frames, h, w, fh, fw, d, gs, cs, cam_h = 2000, 480, 640, 390, 520, 512, 256, 0.05, 1.6
+    cfg = synth.map_config(gs, cs, cam_h, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
+    poses = synth.circle_poses(frames, radius=2.0)
+    host = Map(cfg)
+    tfs = VLMapBuilder("", cfg, None, [], [], host.base2cam_tf, host.base_transform)._frame_transforms(poses)
+    calib = np.array(cfg["cam_calib_mat"]).reshape(3, 3)
+    kinv, kfeat = np.linalg.inv(calib), get_sim_cam_mat(fh, fw)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    np.random.seed(7)
+    sidx = [torch.from_numpy(VLMapBuilder._sample_order(h * w, 1)).cuda() for _ in range(4)]
+    depths = [torch.rand((h, w), device="cuda", generator=gen) * 5.5 + 0.5 for _ in range(4)]
+    pool = [torch.randn((fh, fw, d), device="cuda", generator=gen) * (14.2857 / d ** 0.5) for _ in range(4)]
+    vh = int(cam_h / cs)
+    outs = []
+    for rep in range(2):
+        b = eng.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
+        for i in range(frames):
+            b.add_frame(depths[i % 4], pool[i % 4], kinv, calib, kfeat, tfs[i], sample_idx=sidx[i % 4], feat_layout=L.FEAT_HWC)
+        out = b.export(want_rgb=False, want_feat=False)
+        out["accepted"] = b.num_accepted
+        outs.append(out)
+        b.close()
+    a, c = outs
+    v = a["grid_pos"].shape[0]
+    occ = a["occupied_ids"]
+    assert v > 1_000_000 and a["accepted"] == c["accepted"] > 150_000_000
+    assert np.array_equal(a["grid_pos"], c["grid_pos"]) and np.array_equal(occ, c["occupied_ids"])
+    ids = occ[occ >= 0]
+    assert ids.size == v and np.array_equal(np.sort(ids), np.arange(v))            # bijection cells <-> ids
+    gp = a["grid_pos"]
+    assert np.array_equal(occ[gp[:, 0], gp[:, 1], gp[:, 2]], np.arange(v))            # grid_pos inverts occupied_ids
+    assert np.all(a["weight"] > 0) and np.allclose(a["weight"], c["weight"], rtol=1e-4)
