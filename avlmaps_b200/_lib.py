@@ -33,7 +33,7 @@ EXPORTS = [
     "avl_builder_num_accepted", "avl_builder_export", "avl_builder_to_map",
     "avl_builder_create_global", "avl_builder_num_rejected_oob",
     "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
-    "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import",
+    "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
     "avl_heat_planar",
 ]
 
@@ -114,6 +114,7 @@ def load() -> C.CDLL:
         lib.avl_builder_create.argtypes = [C.POINTER(GridSpec), C.POINTER(vp)]
         lib.avl_builder_destroy.argtypes = [vp]
         lib.avl_builder_add_frame.argtypes = [vp, C.POINTER(Frame), C.c_int, vp]
+        lib.avl_builder_add_frames.argtypes = [vp, C.POINTER(Frame), i32, C.c_int, vp]
         lib.avl_builder_num_voxels.argtypes = [vp, C.POINTER(i64), vp]
         lib.avl_builder_num_accepted.argtypes = [vp, C.POINTER(i64), vp]
         lib.avl_builder_export.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]

@@ -36,6 +36,29 @@ struct FrameGeom {
   int32_t has_rgb;
 };
 
+// Up to kMaxBatch frames per launch triple (geometry, id scan, scatter): the samples of the frames are simply
+// concatenated -- the first-touch key (frame_seq << 32 | position in the frame's sample list) already orders them.
+// Passed by value as a __grid_constant__ kernel parameter (< 4 KiB), so a batch costs no upload.
+constexpr int kMaxBatch = 8;
+struct FrameBatch {
+  FrameGeom g[kMaxBatch];
+  const float* depth[kMaxBatch];
+  const int32_t* sidx[kMaxBatch];
+  const float* feat[kMaxBatch];   // pixel-major (FH, FW, D)
+  const uint8_t* rgb[kMaxBatch];
+  int32_t off[kMaxBatch + 1];     // sample offsets of the frames inside the batch
+  int32_t nf;
+  uint32_t frame_seq0;            // frame_seq of g[0]
+};
+static_assert(sizeof(FrameBatch) <= 4000, "FrameBatch must fit the kernel parameter space");
+
+__device__ __forceinline__ int batch_frame_of(const FrameBatch& b, int gidx) {
+  int f = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxBatch; ++i) f += (i < b.nf && gidx >= b.off[i]) ? 1 : 0;
+  return f;
+}
+
 constexpr int kScanBlock = 1024;
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 
@@ -70,13 +93,19 @@ __device__ __forceinline__ double load_depth(const FrameGeom& g, const float* de
 
 // ---------------------------------------------------------------- geometry + first-touch keys
 __global__ void __launch_bounds__(256)
-geom_kernel(const FrameGeom g, const float* __restrict__ depth, const int32_t* __restrict__ sample_idx,
-            int32_t n_samples, uint32_t frame_seq, unsigned long long* __restrict__ first_key,
+geom_kernel(const __grid_constant__ FrameBatch batch, unsigned long long* __restrict__ first_key,
             int32_t* __restrict__ s_cell, int32_t* __restrict__ s_fpix, float* __restrict__ s_alpha,
             int32_t* __restrict__ s_rgbpix, uint8_t* __restrict__ s_wrap,
             unsigned long long* __restrict__ n_oob, uint32_t* __restrict__ ticket) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;  // for the look-back scan that follows in stream order
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_samples; j += gridDim.x * blockDim.x) {
+  const int n_total = batch.off[batch.nf];
+  for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < n_total; gidx += gridDim.x * blockDim.x) {
+    const int fb = batch_frame_of(batch, gidx);
+    const FrameGeom& g = batch.g[fb];
+    const float* __restrict__ depth = batch.depth[fb];
+    const int32_t* __restrict__ sample_idx = batch.sidx[fb];
+    const uint32_t frame_seq = batch.frame_seq0 + static_cast<uint32_t>(fb);
+    const int j = gidx - batch.off[fb];  // position in the frame's sample list
     const int pix = sample_idx ? sample_idx[j] : j;
     const int v = pix / g.w, u = pix - v * g.w;
     const double x2 = u + 0.5, y2 = v + 0.5;
@@ -145,11 +174,11 @@ geom_kernel(const FrameGeom g, const float* __restrict__ depth, const int32_t* _
         }
       }
     }
-    s_cell[j] = cell;
-    s_fpix[j] = fpix;
-    s_alpha[j] = alpha;
-    s_rgbpix[j] = rgbpix;
-    s_wrap[j] = static_cast<uint8_t>(wrap);
+    s_cell[gidx] = cell;
+    s_fpix[gidx] = fpix;
+    s_alpha[gidx] = alpha;
+    s_rgbpix[gidx] = rgbpix;
+    s_wrap[gidx] = static_cast<uint8_t>(wrap);
   }
 }
 
@@ -288,6 +317,13 @@ __device__ __forceinline__ bool is_winner(const unsigned long long* first_key, i
          first_key[cell] == ((static_cast<unsigned long long>(frame_seq) << 32) | static_cast<uint32_t>(j));
 }
 
+__device__ __forceinline__ bool is_winner_b(const unsigned long long* first_key, int cell, const FrameBatch& batch, int gidx) {
+  if (cell < 0) return false;
+  const int fb = batch_frame_of(batch, gidx);
+  return first_key[cell] == ((static_cast<unsigned long long>(batch.frame_seq0 + static_cast<uint32_t>(fb)) << 32) |
+                             static_cast<uint32_t>(gidx - batch.off[fb]));
+}
+
 // ---------------------------------------------------------------- ordered id assignment
 __global__ void __launch_bounds__(kScanBlock)
 winner_count_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_t frame_seq,
@@ -387,7 +423,7 @@ assign_ids_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_
 constexpr unsigned long long kStAggregate = 1ull << 32, kStInclusive = 2ull << 32;
 
 __global__ void __launch_bounds__(kScanBlock)
-assign_ids_lookback_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples, uint32_t frame_seq,
+assign_ids_lookback_kernel(const __grid_constant__ FrameBatch batch, const int32_t* __restrict__ s_cell,
                            const unsigned long long* __restrict__ first_key, unsigned long long* __restrict__ scan_state,
                            uint32_t* __restrict__ ticket, int32_t n0, int32_t n1, int32_t n2,
                            const uint8_t* __restrict__ s_wrap, int64_t capacity, int32_t* __restrict__ occupied_ids,
@@ -398,9 +434,11 @@ assign_ids_lookback_kernel(const int32_t* __restrict__ s_cell, int32_t n_samples
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t t = s_ticket;
+  const int n_samples = batch.off[batch.nf];
+  const uint32_t frame_seq = batch.frame_seq0;  // tag of this launch's scan state
   const int j = static_cast<int>(t) * kScanBlock + threadIdx.x;
   const int cell = j < n_samples ? s_cell[j] : -1;
-  const bool win = is_winner(first_key, cell, frame_seq, j);
+  const bool win = is_winner_b(first_key, cell, batch, j);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t b = __ballot_sync(0xffffffffu, win);
   const uint32_t acc_b = __ballot_sync(0xffffffffu, cell >= 0);
@@ -535,22 +573,27 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // w = alpha^2 for the point that first touched the cell (vlmap_builder.py:164-170 stores feat*alpha
 // with weight alpha), alpha otherwise (:171-178).
 __global__ void __launch_bounds__(256)
-scatter_kernel(const float* __restrict__ feat_hwc, int32_t d, const uint8_t* __restrict__ rgb,
+scatter_kernel(const __grid_constant__ FrameBatch batch, int32_t d,
                const int32_t* __restrict__ s_cell, const int32_t* __restrict__ s_fpix,
-               const float* __restrict__ s_alpha, const int32_t* __restrict__ s_rgbpix, int32_t n_samples,
-               uint32_t frame_seq, const unsigned long long* __restrict__ first_key,
+               const float* __restrict__ s_alpha, const int32_t* __restrict__ s_rgbpix,
+               const unsigned long long* __restrict__ first_key,
                const int32_t* __restrict__ occupied_ids, int64_t capacity, float* __restrict__ num,
                float* __restrict__ den, float* __restrict__ rgb_acc) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_samples = batch.off[batch.nf];
   for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n_samples; j += nwarps) {
     const int cell = s_cell[j];
     if (cell < 0) continue;
     const int64_t id = occupied_ids[cell];
     if (id < 0 || id >= capacity) continue;
     const float alpha = s_alpha[j];
-    const bool win = is_winner(first_key, cell, frame_seq, j);
+    const int fb = batch_frame_of(batch, j);
+    const bool win = first_key[cell] == ((static_cast<unsigned long long>(batch.frame_seq0 + static_cast<uint32_t>(fb)) << 32) |
+                                         static_cast<uint32_t>(j - batch.off[fb]));
     const float wgt = win ? alpha * alpha : alpha;
+    const float* __restrict__ feat_hwc = batch.feat[fb];
+    const uint8_t* __restrict__ rgb = batch.rgb[fb];
     const float* f = feat_hwc + static_cast<int64_t>(s_fpix[j]) * d;
     float* o = num + id * d;
     if ((d & 3) == 0) {
@@ -713,6 +756,97 @@ void fill_geom(FrameGeom* g, const avl_frame* f, int flags) {
   g->depth_u16 = (flags & AVL_DEPTH_U16_MM) ? 1 : 0;
 }
 
+
+struct BatchItem {
+  const avl_frame* f;
+  const float* depth; const float* feat; const uint8_t* rgb; const int32_t* sidx;  // device pointers, feat pixel-major
+  int32_t n_samples;
+};
+
+// geometry -> ordered id scan -> scatter for up to kMaxBatch frames whose inputs are on the device
+int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cudaStream_t s) {
+  FrameBatch batch;
+  memset(&batch, 0, sizeof(batch));
+  int64_t total = 0;
+  for (int i = 0; i < nf; ++i) {
+    batch.off[i] = static_cast<int32_t>(total);
+    total += items[i].n_samples;
+  }
+  if (total >= (int64_t(1) << 31)) {
+    set_error("batch has more than 2^31 samples");
+    return AVL_ERR_ARG;
+  }
+  batch.off[nf] = static_cast<int32_t>(total);
+  batch.nf = nf;
+  batch.frame_seq0 = b->frame_seq;
+  if (total == 0) {
+    b->frame_seq += static_cast<uint32_t>(nf);
+    return AVL_OK;
+  }
+  const int32_t n_samples = static_cast<int32_t>(total);
+  int rc;
+  // ---- scratch
+  if (b->scratch_samples < n_samples) {
+    cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
+    cudaFree(b->block_cnt); cudaFree(b->scan_state);
+    b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
+    b->scan_state = nullptr;
+    b->scratch_samples = 0;
+    const size_t n = static_cast<size_t>(n_samples);
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_cell), n * sizeof(int32_t)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_fpix), n * sizeof(int32_t)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_rgbpix), n * sizeof(int32_t)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_alpha), n * sizeof(float)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_wrap), n));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->block_cnt), ((n + kScanBlock - 1) / kScanBlock) * sizeof(uint32_t)));
+    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->scan_state), ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long)));
+    AVL_CUDA(cudaMemsetAsync(b->scan_state, 0xff, ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long), s));
+    if (!b->ticket) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->ticket), sizeof(uint32_t)));
+    b->scratch_samples = n_samples;
+  }
+  if ((rc = ensure_capacity(b, n_samples, s))) return rc;
+
+  for (int i = 0; i < nf; ++i) {
+    FrameGeom& g = batch.g[i];
+    fill_geom(&g, items[i].f, flags);
+    g.cs = b->cs;
+    g.half_gs = b->n0 / 2.0;
+    memcpy(g.origin, b->origin, sizeof(g.origin));
+    g.n0 = b->n0; g.n1 = b->n1; g.n2 = b->n2;
+    g.mode = b->mode;
+    g.slab_lo = b->slab_lo; g.slab_hi = b->slab_hi;
+    g.has_rgb = items[i].rgb != nullptr;
+    batch.depth[i] = items[i].depth;
+    batch.sidx[i] = items[i].sidx;
+    batch.feat[i] = items[i].feat;
+    batch.rgb[i] = items[i].rgb;
+  }
+  const int d = b->dim;
+  const int nblocks = (n_samples + kScanBlock - 1) / kScanBlock;
+  const int geom_blocks = std::min((n_samples + 255) / 256, b->num_sms * 8);
+  geom_kernel<<<geom_blocks, 256, 0, s>>>(batch, b->first_key, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap,
+                                          b->counters + 2, b->ticket);
+  static const bool three_pass = getenv("AVL_BUILD_3PASS") != nullptr;  // the original count / scan / assign kernels (A/B)
+  if (three_pass && nf == 1) {
+    winner_count_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
+                                                       b->block_cnt, b->counters + 1);
+    winner_scan_kernel<<<1, kScanBlock, 0, s>>>(b->block_cnt, nblocks, b->counters);
+    assign_ids_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key, b->block_cnt,
+                                                     b->n0, b->n1, b->n2, b->s_wrap, b->capacity, b->occupied_ids,
+                                                     b->grid_pos);
+  } else {
+    assign_ids_lookback_kernel<<<nblocks, kScanBlock, 0, s>>>(batch, b->s_cell, b->first_key, b->scan_state, b->ticket,
+                                                              b->n0, b->n1, b->n2, b->s_wrap, b->capacity,
+                                                              b->occupied_ids, b->grid_pos, b->counters, b->counters + 1);
+  }
+  const int scatter_blocks = std::min((n_samples + 7) / 8, b->num_sms * 8);
+  scatter_kernel<<<scatter_blocks, 256, 0, s>>>(batch, d, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix, b->first_key,
+                                                b->occupied_ids, b->capacity, b->num, b->den, b->rgb_acc);
+  AVL_CUDA(cudaGetLastError());
+  b->frame_seq += static_cast<uint32_t>(nf);
+  return AVL_OK;
+}
+
 }  // namespace
 
 struct avl_bounds {
@@ -857,62 +991,49 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
     feat = b->d_feat_t;
   }
 
-  // ---- scratch
-  if (b->scratch_samples < n_samples) {
-    cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
-    cudaFree(b->block_cnt); cudaFree(b->scan_state);
-    b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
-    b->scan_state = nullptr;
-    b->scratch_samples = 0;
-    const size_t n = static_cast<size_t>(n_samples);
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_cell), n * sizeof(int32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_fpix), n * sizeof(int32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_rgbpix), n * sizeof(int32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_alpha), n * sizeof(float)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_wrap), n));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->block_cnt), ((n + kScanBlock - 1) / kScanBlock) * sizeof(uint32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->scan_state), ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long)));
-    AVL_CUDA(cudaMemsetAsync(b->scan_state, 0xff, ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long), s));
-    if (!b->ticket) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->ticket), sizeof(uint32_t)));
-    b->scratch_samples = n_samples;
-  }
-  if ((rc = ensure_capacity(b, n_samples, s))) return rc;
-
-  FrameGeom g;
-  fill_geom(&g, f, flags);
-  g.cs = b->cs;
-  g.half_gs = b->n0 / 2.0;
-  memcpy(g.origin, b->origin, sizeof(g.origin));
-  g.n0 = b->n0; g.n1 = b->n1; g.n2 = b->n2;
-  g.mode = b->mode;
-  g.slab_lo = b->slab_lo; g.slab_hi = b->slab_hi;
-  g.has_rgb = rgb != nullptr;
-
-  const int nblocks = (n_samples + kScanBlock - 1) / kScanBlock;
-  const int geom_blocks = std::min((n_samples + 255) / 256, b->num_sms * 8);
-  geom_kernel<<<geom_blocks, 256, 0, s>>>(g, depth, sidx, n_samples, b->frame_seq, b->first_key, b->s_cell,
-                                          b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap, b->counters + 2, b->ticket);
-  static const bool three_pass = getenv("AVL_BUILD_3PASS") != nullptr;  // the original count / scan / assign kernels (A/B)
-  if (three_pass) {
-    winner_count_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
-                                                       b->block_cnt, b->counters + 1);
-    winner_scan_kernel<<<1, kScanBlock, 0, s>>>(b->block_cnt, nblocks, b->counters);
-    assign_ids_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key, b->block_cnt,
-                                                     b->n0, b->n1, b->n2, b->s_wrap, b->capacity, b->occupied_ids,
-                                                     b->grid_pos);
-  } else {
-    assign_ids_lookback_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
-                                                              b->scan_state, b->ticket, b->n0, b->n1, b->n2, b->s_wrap,
-                                                              b->capacity, b->occupied_ids, b->grid_pos, b->counters,
-                                                              b->counters + 1);
-  }
-  const int scatter_blocks = std::min((n_samples + 7) / 8, b->num_sms * 8);
-  scatter_kernel<<<scatter_blocks, 256, 0, s>>>(feat, d, rgb, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix,
-                                                n_samples, b->frame_seq, b->first_key, b->occupied_ids,
-                                                b->capacity, b->num, b->den, b->rgb_acc);
-  AVL_CUDA(cudaGetLastError());
-  b->frame_seq++;
+  // one frame = a batch of one (device pointers, pixel-major features by now)
+  BatchItem it;
+  it.f = f;
+  it.depth = depth; it.feat = feat; it.rgb = rgb; it.sidx = sidx;
+  it.n_samples = n_samples;
+  if ((rc = launch_batch(b, &it, 1, flags, s))) return rc;
   if (!(flags & AVL_ON_DEVICE)) AVL_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused per frame
+  return AVL_OK;
+}
+
+int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_frames, int flags, void* stream) {
+  AVL_ARG(b != nullptr && (frames != nullptr || n_frames == 0), "NULL argument");
+  AVL_ARG(n_frames >= 0, "n_frames < 0");
+  bool batchable = (flags & AVL_ON_DEVICE) != 0;
+  for (int i = 0; i < n_frames && batchable; ++i) batchable = frames[i].feat_layout == AVL_FEAT_HWC;
+  if (!batchable) {  // host pointers (staged per frame) or channel-major features (transposed per frame): one by one
+    for (int i = 0; i < n_frames; ++i) {
+      const int rc = avl_builder_add_frame(b, frames + i, flags, stream);
+      if (rc) return rc;
+    }
+    return AVL_OK;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i0 = 0; i0 < n_frames; i0 += kMaxBatch) {
+    BatchItem items[kMaxBatch];
+    const int nb = std::min(kMaxBatch, n_frames - i0);
+    int used = 0;
+    for (int i = 0; i < nb; ++i) {
+      const avl_frame* f = frames + i0 + i;
+      AVL_ARG(f->depth != nullptr && f->feat != nullptr, "depth / feat is NULL");
+      AVL_ARG(f->h >= 1 && f->w >= 1 && f->fh >= 1 && f->fw >= 1, "invalid frame shape");
+      const int64_t npix = static_cast<int64_t>(f->h) * f->w;
+      AVL_ARG(npix < (int64_t(1) << 28), "frame too large for a batch");
+      const int32_t n_samples = f->sample_idx ? f->n_samples : static_cast<int32_t>(npix);
+      AVL_ARG(n_samples >= 0 && n_samples <= npix, "n_samples out of range");
+      BatchItem& it = items[used++];
+      it.f = f;
+      it.depth = f->depth; it.feat = f->feat; it.rgb = f->rgb; it.sidx = f->sample_idx;
+      it.n_samples = n_samples;  // frames without samples stay in the batch: they still consume a frame_seq
+    }
+    const int rc = launch_batch(b, items, used, flags, s);
+    if (rc) return rc;
+  }
   return AVL_OK;
 }
 

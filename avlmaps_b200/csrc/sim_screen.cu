@@ -488,8 +488,9 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           // xq is rewritten in the next tile only after both warps pass its first barrier again
         }
       } else {  // kModeThresh
-        // invalid rows: ri = -inf makes every upper bound -inf (or NaN), never a candidate
-        float ri = -INFINITY, iw = 1.f;
+        // invalid rows (past the end of the map): ri = NaN makes every upper bound NaN, and NaN >= T is false for
+        // EVERY threshold -- -inf would pass T = -inf, which is what a tiny map (fewer sample groups than k) gets
+        float ri = __int_as_float(0x7fc00000), iw = 1.f;
         if (t.valid) {
           ri = fmaf(rho, st_an, st_c);
           if (p.normalize) {

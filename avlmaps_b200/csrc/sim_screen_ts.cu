@@ -251,7 +251,8 @@ screen_ts_kernel(const __grid_constant__ CUtensorMap tmap_v, const ScreenParams 
         }
         const float iw = 1.f / w;
         if (p.mode == kModeThresh) {
-          sr[cc] = r * iw;
+          // past the map: NaN, because NaN >= T is false for every threshold (-inf would pass T = -inf)
+          sr[cc] = (r == -INFINITY) ? __int_as_float(0x7fc00000) : r * iw;
           sw[cc] = iw;
         } else {  // dense: keep r (slightly inflated for the lower bound) and 1 / w
           sr[cc] = r * 1.000001f;

@@ -357,6 +357,10 @@ def _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, m
     fr.rgb = r_.ptr
     fr.sample_idx = s_.ptr
     fr.n_samples = 0 if s_.ptr is None else math.prod(s_.shape)
+    if sample_idx is not None and fr.n_samples == 0:
+        # an EMPTY sample list (not "every pixel", which is sample_idx=None): the C side tells the two apart by a
+        # non-NULL pointer, and an empty tensor has none -- borrow the depth pointer, it is never dereferenced
+        fr.sample_idx = d_.ptr
     base = C.addressof(fr)
     for name, m, n in (("kinv", kinv, 9), ("k", k, 9), ("kfeat", kfeat, 9), ("tf", tf, 16)):
         if m is None:
@@ -469,6 +473,29 @@ class DeviceBuilder:
                                       dim=self.dim)
         L.check(self._lib.avl_builder_add_frame(self._h, C.byref(fr), flags, _stream_ptr(stream)))
         self.n_frames += 1
+
+    def add_frames(self, frames, stream=None):
+        """Several consecutive frames in one call: `frames` is a list of dicts with add_frame's arguments
+        (depth, feat, kinv, k, kfeat, tf and optionally rgb, sample_idx, feat_layout, min_depth, max_depth).  With torch
+        CUDA tensors and pixel-major features up to 8 frames share one launch triple; same result as a loop."""
+        n = len(frames)
+        if n == 0:
+            return
+        arr = (L.Frame * n)()
+        flags, keep = None, []
+        for i, fr in enumerate(frames):
+            if fr.get("feat") is None:
+                raise ValueError("feat is required")
+            f, fl, k = _fill_frame(fr["depth"], fr["feat"], fr["kinv"], fr["k"], fr["kfeat"], fr["tf"], fr.get("rgb"),
+                                   fr.get("sample_idx"), fr.get("feat_layout", L.FEAT_CHW), fr.get("min_depth", 0.1),
+                                   fr.get("max_depth", 6.0), dim=self.dim)
+            if flags is not None and fl != flags:
+                raise ValueError("all frames of one call must be on the same side and use the same depth type")
+            flags = fl
+            C.memmove(C.addressof(arr) + i * C.sizeof(L.Frame), C.addressof(f), C.sizeof(L.Frame))
+            keep.append(k)
+        L.check(self._lib.avl_builder_add_frames(self._h, arr, n, flags, _stream_ptr(stream)))
+        self.n_frames += n
 
     def _count(self, fn) -> int:
         n = C.c_int64()

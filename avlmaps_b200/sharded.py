@@ -151,6 +151,9 @@ class ShardedBuilder:
     def add_frame(self, *args, **kwargs):
         return self.local.add_frame(*args, **kwargs)
 
+    def add_frames(self, frames, **kwargs):
+        return self.local.add_frames(frames, **kwargs)
+
     def _device(self):
         import torch
         import torch.distributed as dist

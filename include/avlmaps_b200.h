@@ -206,6 +206,12 @@ int avl_builder_destroy(avl_builder* b);
  * Frames must be added in the reference's frame order. */
 int avl_builder_add_frame(avl_builder* b, const avl_frame* frame, int flags, void* stream);
 
+/* Several consecutive frames in one call.  With device pointers and pixel-major features the samples of up to 8
+ * frames are concatenated into ONE geometry / id-scan / scatter launch triple (the first-touch key already orders
+ * them by frame, then sample), which amortises the launch and tail cost of the small kernels; the result is
+ * identical to n_frames avl_builder_add_frame calls.  Host pointers or AVL_FEAT_CHW fall back to that loop. */
+int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_frames, int flags, void* stream);
+
 /* voxels created so far (max_id, vlmap_builder.py:164-170); synchronises the stream. */
 int avl_builder_num_voxels(avl_builder* b, int64_t* n, void* stream);
 /* points that passed the depth / grid / feature-bounds tests so far (P_acc of SURVEY 8d). */

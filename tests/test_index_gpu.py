@@ -119,6 +119,27 @@ def test_f16_operand_mode(eng, cg):
     mf.close()
 
 
+def test_tiny_map_never_returns_rows_past_the_end(eng):
+    """Fewer sample groups than k gives the threshold -inf; rows of the last tile past the end of the map must
+    still be rejected (they were only harmless while freshly allocated device memory happened to be zero).
+    Dirty the allocator first, then query maps whose row count is far from a multiple of the 128-row tile."""
+    import torch
+
+    junk = torch.full((64 << 20,), 3.0e4, device="cuda")   # 256 MB of large values, freed -> recycled by cudaMalloc
+    del junk
+    torch.cuda.empty_cache()
+    for n, nq, k in ((50, 3, 16), (129, 200, 16), (5, 2, 8)):
+        feat, q = synth.index_inputs(n, 512, nq, seed=n)
+        feat -= 40.0                                        # every real score is far below 0: stale rows would win
+        m = eng.DeviceMap(feat)
+        sc = O.scores(feat, q)
+        idx, val = m.topk(q, k)
+        ri, rv = O.topk(sc, k)
+        assert idx.max() < n and np.array_equal(idx, ri) and np.array_equal(val, rv)
+        assert np.array_equal(m.argmax(q), O.argmax(sc))
+        m.close()
+
+
 def test_ties_resolve_to_lowest_index(eng):
     feat, q = synth.index_inputs(4096, 512, 4, seed=1)
     feat[100:110] = feat[7]          # ten exact copies of row 7
