@@ -713,7 +713,9 @@ int alloc_rows(avl_builder* b, int64_t cap, float** num, float** den, float** rg
 
 // capacity doubling, the analogue of _reserve_map_space (vlmap_builder.py:286-311)
 int ensure_capacity(avl_builder* b, int64_t incoming, cudaStream_t s) {
-  if (b->capacity >= b->cells) return AVL_OK;  // one row per cell already: cannot overflow
+  // a builder can only ever create voxels in the cells of its own row slab (all rows unless avl_builder_set_slab)
+  const int64_t own_cells = static_cast<int64_t>(b->slab_hi - b->slab_lo) * b->n1 * b->n2;
+  if (b->capacity >= own_cells) return AVL_OK;  // one row per own cell already: cannot overflow
   if (b->id_upper + incoming <= b->capacity) {
     b->id_upper += incoming;
     return AVL_OK;
@@ -725,7 +727,7 @@ int ensure_capacity(avl_builder* b, int64_t incoming, cudaStream_t s) {
   if (b->id_upper + incoming > b->capacity) {
     int64_t cap = b->capacity;
     while (cap < b->id_upper + incoming) cap *= 2;
-    if (cap > b->cells) cap = std::max(b->cells, b->id_upper + incoming);
+    if (cap > own_cells) cap = own_cells;  // never more rows than cells that can be occupied
     float *num, *den, *rgb;
     int32_t* pos;
     int rc = alloc_rows(b, cap, &num, &den, &rgb, &pos, s);

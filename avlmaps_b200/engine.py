@@ -478,23 +478,24 @@ class DeviceBuilder:
         """Several consecutive frames in one call: `frames` is a list of dicts with add_frame's arguments
         (depth, feat, kinv, k, kfeat, tf and optionally rgb, sample_idx, feat_layout, min_depth, max_depth).  With torch
         CUDA tensors and pixel-major features up to 8 frames share one launch triple; same result as a loop."""
-        n = len(frames)
-        if n == 0:
+        if len(frames) == 0:
             return
-        arr = (L.Frame * n)()
-        flags, keep = None, []
-        for i, fr in enumerate(frames):
-            if fr.get("feat") is None:
-                raise ValueError("feat is required")
-            f, fl, k = _fill_frame(fr["depth"], fr["feat"], fr["kinv"], fr["k"], fr["kfeat"], fr["tf"], fr.get("rgb"),
-                                   fr.get("sample_idx"), fr.get("feat_layout", L.FEAT_CHW), fr.get("min_depth", 0.1),
-                                   fr.get("max_depth", 6.0), dim=self.dim)
-            if flags is not None and fl != flags:
-                raise ValueError("all frames of one call must be on the same side and use the same depth type")
-            flags = fl
-            C.memmove(C.addressof(arr) + i * C.sizeof(L.Frame), C.addressof(f), C.sizeof(L.Frame))
-            keep.append(k)
-        L.check(self._lib.avl_builder_add_frames(self._h, arr, n, flags, _stream_ptr(stream)))
+        self.add_prepared(PreparedFrames(self, frames), stream=stream)
+
+    def prepare_frames(self, frames) -> "PreparedFrames":
+        """Marshal a list of frame dicts (see add_frames) once.  For producers that write into a fixed ring of device
+        buffers (an encoder's output slots): only the pose changes per frame -- `PreparedFrames.set_tf(i, tf)` -- and
+        `add_prepared` then costs one ctypes call instead of ~25 us of Python per frame."""
+        return PreparedFrames(self, frames)
+
+    def add_prepared(self, prepared: "PreparedFrames", start: int = 0, count: Optional[int] = None, stream=None):
+        n = prepared.n - start if count is None else count
+        if n <= 0:
+            return
+        if start < 0 or start + n > prepared.n:
+            raise IndexError("frame range outside the prepared list")
+        ptr = C.cast(C.addressof(prepared.arr) + start * C.sizeof(L.Frame), C.POINTER(L.Frame))
+        L.check(self._lib.avl_builder_add_frames(self._h, ptr, n, prepared.flags, _stream_ptr(stream)))
         self.n_frames += n
 
     def _count(self, fn) -> int:
@@ -541,6 +542,32 @@ class DeviceBuilder:
         h = C.c_void_p()
         L.check(self._lib.avl_builder_to_map(self._h, None, C.byref(h)))
         return DeviceMap(None, _handle=h)
+
+
+class PreparedFrames:
+    """avl_frame array built once from frame dicts; keeps the argument buffers alive."""
+
+    def __init__(self, builder: "DeviceBuilder", frames):
+        self.n = len(frames)
+        self.arr = (L.Frame * max(self.n, 1))()
+        self.flags, self._keep = 0, []
+        for i, fr in enumerate(frames):
+            if fr.get("feat") is None:
+                raise ValueError("feat is required")
+            f, fl, k = _fill_frame(fr["depth"], fr["feat"], fr["kinv"], fr["k"], fr["kfeat"], fr["tf"], fr.get("rgb"),
+                                   fr.get("sample_idx"), fr.get("feat_layout", L.FEAT_CHW), fr.get("min_depth", 0.1),
+                                   fr.get("max_depth", 6.0), dim=builder.dim)
+            if i and fl != self.flags:
+                raise ValueError("all frames of one call must be on the same side and use the same depth type")
+            self.flags = fl
+            C.memmove(C.addressof(self.arr) + i * C.sizeof(L.Frame), C.addressof(f), C.sizeof(L.Frame))
+            self._keep.append(k)
+
+    def set_tf(self, i: int, tf) -> None:
+        a = np.asarray(tf, np.float64)
+        if a.size != 16:
+            raise ValueError("tf must have 16 elements")
+        C.memmove(C.addressof(self.arr) + i * C.sizeof(L.Frame) + _FRAME_OFFSETS["tf"], a.tobytes(), 128)
 
 
 def rank_keys(keys_per_shard: Sequence[np.ndarray], shard: int) -> np.ndarray:

@@ -154,6 +154,12 @@ class ShardedBuilder:
     def add_frames(self, frames, **kwargs):
         return self.local.add_frames(frames, **kwargs)
 
+    def prepare_frames(self, frames):
+        return self.local.prepare_frames(frames)
+
+    def add_prepared(self, prepared, *args, **kwargs):
+        return self.local.add_prepared(prepared, *args, **kwargs)
+
     def _device(self):
         import torch
         import torch.distributed as dist

@@ -395,8 +395,15 @@ def test_batched_frames_equal_frame_by_frame(eng, n_frames):
     assert_build_equal(out, ref)
     b.close()
     b2 = eng.DeviceBuilder(gs, vh, cs, 16)
-    for fr in frames:
-        b2.add_frame(**fr)
+    prep = b2.prepare_frames(frames[:1] * n_frames)          # marshalled once, pose patched per frame ...
+    for i, fr in enumerate(frames):
+        if i % 2:
+            b2.add_frame(**fr)
+        else:                                                # ... only valid here for frames sharing frame 0's buffers
+            one = b2.prepare_frames([fr])
+            one.set_tf(0, fr["tf"])
+            b2.add_prepared(one)
+    assert prep.n == n_frames
     out2 = b2.export()
     assert np.array_equal(out["grid_pos"], out2["grid_pos"]) and np.array_equal(out["occupied_ids"], out2["occupied_ids"])
     assert np.allclose(out["grid_feat"], out2["grid_feat"], rtol=1e-4, atol=1e-6)

@@ -41,7 +41,7 @@ def main():
     L.load()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    frames = int(os.environ.get("AVL_FRAMES", "48"))
+    frames = int(os.environ.get("AVL_FRAMES", "240"))
     h, w, fh, fw, d, gs, cs, cam_h = 480, 640, 390, 520, 512, 256, 0.05, 1.6
     cfg = synth.map_config(gs, cs, cam_h, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
     poses = synth.circle_poses(frames, radius=2.0)
@@ -57,10 +57,16 @@ def main():
     vh = int(cam_h / cs)
     stream = torch.cuda.current_stream()
 
+    batch = int(os.environ.get("AVL_BATCH", "8"))
+    fr = [dict(depth=depths[i % 4], feat=pool[i % 4], kinv=kinv, k=calib, kfeat=kfeat, tf=tfs[i], sample_idx=sidx[i % 4],
+               feat_layout=L.FEAT_HWC) for i in range(frames)]
+
     def feed(b):
-        for i in range(frames):
-            b.add_frame(depths[i % 4], pool[i % 4], kinv, calib, kfeat, tfs[i], sample_idx=sidx[i % 4],
-                        feat_layout=L.FEAT_HWC, stream=stream)
+        # the 4 depth / feature / sample buffers are a fixed ring (an encoder's output slots): marshal the frame
+        # descriptors once, then up to 8 frames per launch triple (avl_builder_add_frames)
+        prep = b.prepare_frames(fr)
+        for i in range(0, frames, batch):
+            b.add_prepared(prep, i, min(batch, frames - i), stream=stream)
 
     def barrier():
         if world > 1:
@@ -94,7 +100,7 @@ def main():
     line = {"n_gpus": world, "frames": frames, "ms_per_frame": best, "frames_per_s": 1e3 / best,
             "voxels_total": res["n_voxels_total"], "voxels_rank0": int(res["global_ids"].size),
             "accepted_points_per_frame": int(acc.item()) / frames, "finalize_s": t_fin,
-            "slab_rows": [sb.row_lo, sb.row_hi]}
+            "slab_rows": [sb.row_lo, sb.row_hi], "frames_per_call": batch}
     if rank == 0:
         single = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
         feed(single)
