@@ -341,10 +341,20 @@ def run_gpu(args):
     lib = L.load()
     L.require_device()
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to STDOUT; stdout carries exactly one JSON line,
-        # so NCCL's log goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to the STDOUT file descriptor when the first
+        # communicator is created; stdout carries exactly one JSON line, so fd 1 points at stderr until that is over
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     dev = torch.device("cuda", local)
     peaks = load_peaks()
 
