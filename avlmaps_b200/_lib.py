@@ -34,7 +34,7 @@ EXPORTS = [
     "avl_builder_create_global", "avl_builder_num_rejected_oob",
     "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
     "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
-    "avl_heat_planar",
+    "avl_heat_planar", "avl_heat2d_normalize_lift",
 ]
 
 
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     lib.avl_heat2d_sources.argtypes = [vp, vp, vp, i32, i32, i32, C.c_double, i32, vp, C.c_int, vp]
     lib.avl_merge_topk.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.c_int, vp]
     lib.avl_heat_from_mask_3d.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp, C.c_int, vp]
+    lib.avl_heat2d_normalize_lift.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp, C.c_int, vp]
     lib.avl_heat_planar.argtypes = [vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp]
     if hasattr(lib, "avl_builder_create"):
         lib.avl_builder_create.argtypes = [C.POINTER(GridSpec), C.POINTER(vp)]

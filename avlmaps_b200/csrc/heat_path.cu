@@ -517,3 +517,102 @@ extern "C" int avl_heat_planar(const int32_t* grid_pos, int64_t n, double row, d
   if (e != cudaSuccess) return cuda_fail(e, "heat planar", __FILE__, __LINE__);
   return AVL_OK;
 }
+
+
+// ---------------------------------------------------------------- 2-D heat: final min-max and the 2-D -> 3-D lift
+// dist_map = (dist_map - min) / (max - min) in the map's own dtype (avlmap.py:97 float64, :131 float32), then
+// heatmap_3d[id] = heatmap_2d[row, col] for every occupied cell (avlmap.py:100-109, 135-144) = a gather through
+// grid_pos.  min / max are exact, the two IEEE operations are the reference's, so the bits match numpy's.
+namespace avl {
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(1024)
+minmax2d_kernel(const T* __restrict__ v, int64_t n, T* __restrict__ mm) {
+  T lo = v[0], hi = v[0];
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const T x = v[i];
+    lo = x < lo ? x : lo;
+    hi = x > hi ? x : hi;
+  }
+  __shared__ T slo[32], shi[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) { lo = slo[w] < lo ? slo[w] : lo; hi = shi[w] > hi ? shi[w] : hi; }
+    mm[0] = lo;
+    mm[1] = hi;
+  }
+}
+__global__ void __launch_bounds__(256) normalize2d_f64_kernel(double* __restrict__ v, int64_t n, const double* __restrict__ mm) {
+  const double lo = mm[0], range = __dsub_rn(mm[1], mm[0]);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    v[i] = __ddiv_rn(__dsub_rn(v[i], lo), range);
+}
+__global__ void __launch_bounds__(256) normalize2d_f32_kernel(float* __restrict__ v, int64_t n, const float* __restrict__ mm) {
+  const float lo = mm[0], range = __fsub_rn(mm[1], mm[0]);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    v[i] = __fdiv_rn(__fsub_rn(v[i], lo), range);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+lift2d_kernel(const T* __restrict__ heat2d, int32_t rows, int32_t cols, const int32_t* __restrict__ pos, int64_t n,
+              float* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int r = pos[i * 3], c = pos[i * 3 + 1];
+    if (r < 0) r += rows;  // multi-floor maps keep unwrapped (negative) indices in grid_pos
+    if (c < 0) c += cols;
+    out[i] = (r >= 0 && r < rows && c >= 0 && c < cols) ? static_cast<float>(heat2d[static_cast<int64_t>(r) * cols + c]) : 0.f;
+  }
+}
+}  // namespace
+}  // namespace avl
+
+extern "C" int avl_heat2d_normalize_lift(void* heat2d, int32_t is_f64, int32_t rows, int32_t cols, int32_t normalize,
+                                         const int32_t* grid_pos, int64_t n, float* out_heat3d, int flags, void* stream) {
+  using namespace avl;
+  AVL_ARG(heat2d != nullptr && rows >= 1 && cols >= 1, "invalid 2-D heat map");
+  AVL_ARG(n >= 0 && (n == 0 || (grid_pos != nullptr && out_heat3d != nullptr)), "grid_pos / out_heat3d is NULL");
+  AVL_ARG(!(flags & AVL_ON_DEVICE), "host pointers only");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t cells = static_cast<int64_t>(rows) * cols;
+  const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+  HeatScratch& hs = g_heat_scratch;
+  void *d2 = nullptr, *dmm = nullptr;
+  int32_t* dpos = nullptr;
+  float* d3 = nullptr;
+  cudaError_t e = hs.get(HeatScratch::kBits, cells * esz, &d2);
+  if (e == cudaSuccess) e = hs.get(HeatScratch::kBBox, 2 * sizeof(double), &dmm);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d2, heat2d, cells * esz, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && normalize) {
+    if (is_f64) {
+      minmax2d_kernel<double><<<1, 1024, 0, s>>>(static_cast<const double*>(d2), cells, static_cast<double*>(dmm));
+      normalize2d_f64_kernel<<<592, 256, 0, s>>>(static_cast<double*>(d2), cells, static_cast<const double*>(dmm));
+    } else {
+      minmax2d_kernel<float><<<1, 1024, 0, s>>>(static_cast<const float*>(d2), cells, static_cast<float*>(dmm));
+      normalize2d_f32_kernel<<<592, 256, 0, s>>>(static_cast<float*>(d2), cells, static_cast<const float*>(dmm));
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(heat2d, d2, cells * esz, cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess && n > 0) {
+    e = hs.get(HeatScratch::kPos, static_cast<size_t>(n) * 3 * sizeof(int32_t), reinterpret_cast<void**>(&dpos));
+    if (e == cudaSuccess) e = hs.get(HeatScratch::kHeat, static_cast<size_t>(n) * sizeof(float), reinterpret_cast<void**>(&d3));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpos, grid_pos, static_cast<size_t>(n) * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 1184));
+      if (is_f64) lift2d_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(d2), rows, cols, dpos, n, d3);
+      else lift2d_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(d2), rows, cols, dpos, n, d3);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_heat3d, d3, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return cuda_fail(e, "heat2d_normalize_lift", __FILE__, __LINE__);
+  return AVL_OK;
+}

@@ -315,6 +315,23 @@ def heat2d_sources(shape, cells_per_group, conf, decay_rate: float, mode: str):
     return out
 
 
+def heat2d_normalize_lift(heat2d, grid_pos=None, normalize: bool = True):
+    """Min-max of a 2-D heat map in its own dtype (avlmap.py:97,131) and / or its lift to the voxels through
+    grid_pos (avlmap.py:100-109,135-144), on the device.  Returns (heat2d normalised (a copy), heat3d float32 or None)."""
+    lib = L.load()
+    L.require_device()
+    h = np.array(heat2d, copy=True, order="C")
+    if h.ndim != 2 or h.dtype not in (np.float32, np.float64):
+        raise ValueError("heat2d must be a (rows, cols) float32 or float64 array")
+    pos, out3 = None, None
+    if grid_pos is not None:
+        pos = np.ascontiguousarray(grid_pos, np.int32)
+        out3 = np.empty(pos.shape[0], np.float32)
+    L.check(lib.avl_heat2d_normalize_lift(L.np_ptr(h), int(h.dtype == np.float64), h.shape[0], h.shape[1], int(normalize),
+                                          L.np_ptr(pos), 0 if pos is None else pos.shape[0], L.np_ptr(out3), 0, None))
+    return h, out3
+
+
 _FRAME_OFFSETS = {name: getattr(L.Frame, name).offset for name in ("kinv", "k", "kfeat", "tf")}
 
 

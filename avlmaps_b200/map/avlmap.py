@@ -11,7 +11,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from ..engine import heat2d_sources, heat_from_mask_3d, heat_planar, topk_vector
+from ..engine import heat2d_normalize_lift, heat2d_sources, heat_from_mask_3d, heat_planar, topk_vector
 from .map import cfg_get
 from .vlmap import VLMap
 
@@ -58,7 +58,7 @@ class AVLMap:
         it falls outside the grid; `scores` are the min-max normalised frame scores."""
         groups = [np.zeros((0, 2), np.int32) if c is None else np.asarray(c, np.int32).reshape(1, 2) for c in cells]
         dist_map = heat2d_sources(shape, groups, np.asarray(scores, np.float32), decay_rate, "area")
-        return (dist_map - np.min(dist_map)) / (np.max(dist_map) - np.min(dist_map))   # avlmap.py:97
+        return heat2d_normalize_lift(dist_map)[0]   # (dist_map - min) / (max - min), avlmap.py:97
 
     @staticmethod
     def sound_heat_2d(shape, cells_per_segment: List, probabilities: np.ndarray, decay_rate: float = 0.01) -> np.ndarray:
@@ -73,13 +73,12 @@ class AVLMap:
                 raise IndexError("sound location outside the map (the reference raises here too)")
             groups.append(seg.astype(np.int32))
         dist_map = heat2d_sources(shape, groups, np.asarray(probabilities, np.float32), decay_rate, "sound")
-        return (dist_map - np.min(dist_map)) / (np.max(dist_map) - np.min(dist_map))   # avlmap.py:131
+        return heat2d_normalize_lift(dist_map)[0]   # avlmap.py:131
 
     def lift_heat_2d_to_3d(self, heatmap_2d: np.ndarray) -> np.ndarray:
         """avlmap.py:100-109 / 135-144: heatmap_3d[id] = heatmap_2d[row, col] for every occupied cell -- the
         Python loop over np.where(occupied_ids != -1) is a gather through grid_pos."""
-        gp = self.vlmap.grid_pos
-        return heatmap_2d[gp[:, 0], gp[:, 1]].astype(np.float32)
+        return heat2d_normalize_lift(np.asarray(heatmap_2d), self.vlmap.grid_pos, normalize=False)[1]
 
     def index_area_2d(self, area_name: str, decay_rate: float = 0.1) -> np.ndarray:
         scores = self.area_map.index_map(area_name, with_init_cat=False)

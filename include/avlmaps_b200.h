@@ -165,6 +165,13 @@ int avl_heat2d_sources(const int32_t* cells, const int32_t* group_start, const f
                        int32_t rows, int32_t cols, double decay_rate, int32_t mode, void* out_heat, int flags,
                        void* stream);
 
+/* The tail of index_area(_2d) / index_sound(_2d): min-max normalise the 2-D map IN PLACE in its own dtype
+ * (`(dist_map - min) / (max - min)`, avlmaps/map/avlmap.py:97 float64, :131 float32) when `normalize`, and lift it
+ * to the voxels, heat3d[i] = float32(heat2d[grid_pos[i, 0], grid_pos[i, 1]]) (avlmap.py:100-109, 135-144: the Python
+ * loop over np.where(occupied_ids != -1)).  n == 0 skips the lift.  Host pointers. */
+int avl_heat2d_normalize_lift(void* heat2d, int32_t is_f64, int32_t rows, int32_t cols, int32_t normalize,
+                              const int32_t* grid_pos, int64_t n, float* out_heat3d, int flags, void* stream);
+
 /* Image modality after localisation: out[i] = clip(con - decay_rate * ||grid_pos[i, :2] - (row, col)||, 0, 1),
  * float64 (n,).  Replaces the numpy lines of AVLMap.index_image (avlmaps/map/avlmap.py:156-162); the
  * localisation itself (HLoc, visual_map.py) is out of scope. */
