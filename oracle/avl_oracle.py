@@ -452,3 +452,13 @@ def lift_heat_2d_to_3d(heatmap_2d, occupied_ids, n_vox):
     for row, col, heigh in zip(rows, cols, heights):
         heatmap_3d[occupied_ids[row, col, heigh]] = heatmap_2d[row, col]
     return heatmap_3d
+
+
+def image_heat(grid_pos, row, col, camera_height=1.5, cs=0.05, decay_rate=0.01):
+    """avlmaps/map/avlmap.py:156-162: planar distance decay around the localised query image."""
+    height = camera_height / cs
+    pos = np.array([row, col, height])
+    sim_mat = np.zeros((grid_pos.shape[0], 1))
+    dists = np.linalg.norm((grid_pos - pos)[:, :2], axis=1)
+    sim_mat[:, 0] = np.clip(1.0 - decay_rate * dists, 0, 1)
+    return np.max(sim_mat, axis=1).flatten()

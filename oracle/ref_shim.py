@@ -282,3 +282,56 @@ def ref_build_multi_floor(map_config: dict, cam_poses, depths_mm, rgbs, feats, s
     captured["sample_idx_pass2"] = orders[n:]
     captured["used_frames"] = used
     return captured
+
+
+# ------------------------------------------------------------------------------------------ AVLMap heat methods
+class _FakeDataloader:
+    """Stand-in for VLMapsDataloaderHabitat: the habitat pose's translation IS (row, 0, col) here, so
+    to_full_map_pose returns what the test put in (the real one converts metres to cells; scalar pose math)."""
+
+    def from_habitat_tf(self, tf):
+        self._tf = np.asarray(tf)
+
+    def to_full_map_pose(self):
+        return int(self._tf[0, 3]), int(self._tf[2, 3]), 0.0
+
+
+def ref_avlmap_heats(occupied_ids, grid_pos, frame_cells, frame_scores, sound_cells, sound_probs, image_cell,
+                     area_decay=0.1, sound_decay=0.01, image_decay=0.01, camera_height=1.5, cs=0.05):
+    """Run the reference's own AVLMap.index_area_2d / index_area / index_sound_2d / index_sound / index_image
+    (avlmaps/map/avlmap.py:78-163) on fake collaborators: avlmap.py is loaded unmodified with `avlmaps.map` and
+    `avlmaps.dataloader.habitat_dataloader` stubbed (they pull hloc / librosa / habitat), an AVLMap is created
+    without __init__ and given a vlmap (occupied_ids, grid_pos), an area_map (scores + poses), a sound_map
+    (probabilities + locations), a visual_map (a localisation result) and the dataloader above."""
+    _install_open3d_stub()
+    for name in ("avlmaps.map", "avlmaps.dataloader", "avlmaps.dataloader.habitat_dataloader"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    for cls in ("VLMap", "SoundMap", "AreaMap", "VisualMap"):
+        setattr(sys.modules["avlmaps.map"], cls, type(cls, (), {}))
+    sys.modules["avlmaps.dataloader.habitat_dataloader"].VLMapsDataloaderHabitat = _FakeDataloader
+    am = load("ref_avlmap", "avlmaps/map/avlmap.py")
+
+    def tf_of(cell):
+        tf = np.eye(4)
+        tf[0, 3], tf[2, 3] = cell[0], cell[1]
+        return tf
+
+    a = am.AVLMap.__new__(am.AVLMap)
+    a.config = AttrDict({"map_config": {"pose_info": {"camera_height": camera_height}}, "params": {"cs": cs}})
+    a.vlmap = types.SimpleNamespace(occupied_ids=occupied_ids, grid_pos=grid_pos)
+    a.dataloader = _FakeDataloader()
+    a.area_map = types.SimpleNamespace(index_map=lambda name, with_init_cat=False: np.array(frame_scores, np.float32),
+                                       robot_pose_list=[tf_of(c) for c in frame_cells])
+    locs = [[np.array([c[0], 0.0, c[1]]) for c in seg] for seg in sound_cells]
+    a.sound_map = types.SimpleNamespace(
+        get_distribution_and_locations=lambda name: (np.array(sound_probs, np.float32), locs))
+    a.visual_map = types.SimpleNamespace(localize_image=lambda image, query_cam_intrinsic_mat=None: (None, tf_of(image_cell)))
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):   # index_sound_2d prints the map shape
+        out = dict(area_2d=a.index_area_2d("kitchen", decay_rate=area_decay), area_3d=a.index_area("kitchen", decay_rate=area_decay),
+                   sound_2d=a.index_sound_2d("door", decay_rate=sound_decay), sound_3d=a.index_sound("door", decay_rate=sound_decay),
+                   image_3d=a.index_image(None, decay_rate=image_decay))
+    return out

@@ -10,6 +10,7 @@ outputs of the reference's own functions:
   build_*.npz  VLMapBuilder.create_mobile_base_map (avlmaps/map/vlmap_builder.py:54-185)
   heat_*.npz   get_heatmap_from_mask_3d (avlmaps/utils/visualize_utils.py:29-49)
   mf_*.npz     VLMapBuilderMultiFloor.create_global_map (avlmaps/map/vlmap_builder_multi_floor.py:60-199)
+  avlmap_heats.npz  AVLMap.index_area(_2d) / index_sound(_2d) / index_image (avlmaps/map/avlmap.py:78-163)
 """
 from __future__ import annotations
 
@@ -129,6 +130,32 @@ def gen_heat(name, n, seed):
     print(f"heat_{name}: n={n} targets={int(mask.sum())}")
 
 
+def gen_avlmap_heats(seed=60):
+    rng = np.random.default_rng(seed)
+    rows, cols, vh, n = 90, 70, 4, 500
+    occ = -np.ones((rows, cols, vh), np.int32)
+    flat = rng.choice(rows * cols * vh, n, replace=False)
+    occ.reshape(-1)[flat] = np.arange(n)
+    pos = np.stack(np.unravel_index(flat, occ.shape), 1).astype(np.int32)
+    # area: 12 frames, two outside the grid; raw CLIP-like scores (index_area_2d min-max normalises them itself)
+    frame_cells = [(int(rng.integers(0, rows)), int(rng.integers(0, cols))) for _ in range(12)]
+    frame_cells[3], frame_cells[8] = (-4, 10), (rows + 2, 5)
+    frame_scores = rng.standard_normal(12).astype(np.float32)
+    # sound: 7 segments with 1-5 locations each (one negative row that wraps like numpy), min-max probabilities
+    sound_cells = [[(int(rng.integers(0, rows)), int(rng.integers(0, cols))) for _ in range(int(rng.integers(1, 6)))] for _ in range(7)]
+    sound_cells[2][0] = (-3, 5)
+    probs = rng.uniform(0, 1, 7).astype(np.float32)
+    probs = (probs - probs.min()) / (probs.max() - probs.min())
+    image_cell = (41, 33)
+    out = ref_shim.ref_avlmap_heats(occ, pos, frame_cells, frame_scores, sound_cells, probs, image_cell)
+    flat_cells = np.array([c for seg in sound_cells for c in seg], np.int32)
+    seg_len = np.array([len(seg) for seg in sound_cells], np.int32)
+    np.savez_compressed(OUT / "avlmap_heats.npz", occupied_ids=occ, grid_pos=pos, frame_cells=np.array(frame_cells, np.int32),
+                        frame_scores=frame_scores, sound_cells=flat_cells, sound_seg_len=seg_len, sound_probs=probs,
+                        image_cell=np.array(image_cell, np.int32), **out)
+    print("avlmap_heats:", {k: (v.shape, str(v.dtype)) for k, v in out.items()})
+
+
 def main():
     assert ref_shim.available(), "reference tree not found"
     # index path: BASELINE config 1 exactly, then batched / other dims
@@ -153,6 +180,7 @@ def main():
     gen_build_resume("resume", 2, 4, 60, 80, 49, 65, 6, gs=48, cs=0.1, cam_h=1.6, calib=[40, 0, 40, 0, 40, 30, 0, 0, 1],
                      rate=2, seed=6)
     gen_heat("n600", 600, seed=50)
+    gen_avlmap_heats()
     # multi-floor builder: uint16 mm depth, global-frame grid from a first pass, np.round cells
     gen_multi_floor("rate1", 4, 48, 64, 39, 52, 8, 0.05, k10, rate=1, skip=1, seed=0)
     # second-pass samples fall below pcd_min in all three axes: numpy negative-index wrap-around

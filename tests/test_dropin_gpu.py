@@ -286,3 +286,44 @@ def test_image_heat_planar(lib):
     want = np.max(sim_mat, axis=1).flatten()
     got = av.image_heat(row, col, decay)
     assert got.dtype == np.float64 and np.array_equal(got, want)
+
+
+def test_avlmap_area_sound_image_against_the_reference_methods(lib):
+    """AVLMap.index_area(_2d) / index_sound(_2d) / index_image with the collaborators the reference uses (an area map with
+    frame scores and poses, a sound map with probabilities and locations, a localiser, the map-pose converter) against the
+    outputs of the reference's own methods on the same fakes (tests/golden/avlmap_heats.npz): same dtypes, same bits."""
+    import types
+
+    from avlmaps_b200.map import AVLMap
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "avlmap_heats.npz")
+    rows, cols, vh = g["occupied_ids"].shape
+
+    class Loader:  # same convention as oracle/ref_shim._FakeDataloader: translation = (row, 0, col)
+        def from_habitat_tf(self, tf):
+            self.tf = np.asarray(tf)
+
+        def to_full_map_pose(self):
+            return int(self.tf[0, 3]), int(self.tf[2, 3]), 0.0
+
+    def tf_of(cell):
+        tf = np.eye(4)
+        tf[0, 3], tf[2, 3] = cell[0], cell[1]
+        return tf
+
+    segs, o = [], 0
+    for n in g["sound_seg_len"]:
+        segs.append([np.array([r, 0.0, c]) for r, c in g["sound_cells"][o:o + n]])
+        o += n
+    cfg = {"map_config": synth.map_config(rows, 0.05, 1.5, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1), "params": {"cs": 0.05}}
+    av = AVLMap(cfg)
+    av.vlmap.grid_pos, av.vlmap.occupied_ids = g["grid_pos"], g["occupied_ids"]
+    av.dataloader = Loader()
+    av.area_map = types.SimpleNamespace(index_map=lambda name, with_init_cat=False: g["frame_scores"].copy(),
+                                        robot_pose_list=[tf_of(c) for c in g["frame_cells"]])
+    av.sound_map = types.SimpleNamespace(get_distribution_and_locations=lambda name: (g["sound_probs"].copy(), segs))
+    av.visual_map = types.SimpleNamespace(localize_image=lambda image, query_cam_intrinsic_mat=None: (None, tf_of(g["image_cell"])))
+    for got, key in ((av.index_area_2d("kitchen", decay_rate=0.1), "area_2d"), (av.index_area("kitchen", decay_rate=0.1), "area_3d"),
+                     (av.index_sound_2d("door", decay_rate=0.01), "sound_2d"), (av.index_sound("door", decay_rate=0.01), "sound_3d"),
+                     (av.index_image(None, decay_rate=0.01), "image_3d")):
+        assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key

@@ -180,3 +180,31 @@ def test_resume_from_saved_map_matches_reference():
     assert np.allclose(out["weight"], g["weight"], rtol=1e-5)
     assert np.allclose(out["grid_feat"], g["grid_feat"], rtol=1e-5, atol=1e-5)
     assert g["mapped_iter_list"].tolist() == [0, 1, 2, 3]
+
+
+def load_avlmap_heats():
+    g = np.load(G / "avlmap_heats.npz")
+    rows, cols = g["occupied_ids"].shape[:2]
+    cells = [None if (r < 0 or r >= rows or c < 0 or c >= cols) else (int(r), int(c)) for r, c in g["frame_cells"]]
+    sc = g["frame_scores"]
+    scores = (sc - np.min(sc)) / (np.max(sc) - np.min(sc))                      # avlmap.py:81
+    segs, o = [], 0
+    for n in g["sound_seg_len"]:
+        segs.append([(int(r), int(c)) for r, c in g["sound_cells"][o:o + n]])
+        o += n
+    return g, (rows, cols), cells, scores, segs
+
+
+def test_avlmap_heat_restatements_match_the_reference_methods():
+    """The reference's own AVLMap.index_area_2d / index_area / index_sound_2d / index_sound / index_image
+    (avlmap.py:78-163), executed through oracle/ref_shim.py on fake collaborators, against the oracle's restatements."""
+    g, shape, cells, scores, segs = load_avlmap_heats()
+    a2 = O.area_heat_2d(shape, cells, scores, decay_rate=0.1)
+    assert a2.dtype == g["area_2d"].dtype and np.array_equal(a2, g["area_2d"])
+    s2 = O.sound_heat_2d(shape, segs, g["sound_probs"], decay_rate=0.01)
+    assert s2.dtype == g["sound_2d"].dtype and np.array_equal(s2, g["sound_2d"])
+    n = g["grid_pos"].shape[0]
+    assert np.array_equal(O.lift_heat_2d_to_3d(a2, g["occupied_ids"], n), g["area_3d"])
+    assert np.array_equal(O.lift_heat_2d_to_3d(s2, g["occupied_ids"], n), g["sound_3d"])
+    r, c = g["image_cell"]
+    assert np.array_equal(O.image_heat(g["grid_pos"], int(r), int(c), 1.5, 0.05, 0.01), g["image_3d"])
