@@ -335,3 +335,44 @@ def ref_avlmap_heats(occupied_ids, grid_pos, frame_cells, frame_scores, sound_ce
                    sound_2d=a.index_sound_2d("door", decay_rate=sound_decay), sound_3d=a.index_sound("door", decay_rate=sound_decay),
                    image_3d=a.index_image(None, decay_rate=image_decay))
     return out
+
+
+# ------------------------------------------------------------------------------------------ template scoring, dynamic obstacles
+def _patched_text_feats(encoder):
+    """get_text_feats (clip_utils.py:133-149) with the CLIP forward replaced: encode, then the reference's own
+    normalisation line (:145) -- rows divided by their L2 norm."""
+    def f(in_text, clip_model, clip_feat_dim, batch_size=64):
+        feats = np.asarray(encoder(in_text), np.float32)
+        return feats / np.linalg.norm(feats, axis=-1, keepdims=True)
+    return f
+
+
+def ref_get_lseg_score_templates(feat, landmarks, encoder, avg_mode):
+    """The reference's get_lseg_score with use_multiple_templates=True (clip_utils.py:216-234): 63 prompts per
+    landmark (+ "other"), features (avg_mode 0) or scores (avg_mode 1) averaged over the templates."""
+    cu = load("ref_clip_utils", "avlmaps/utils/clip_utils.py")
+    saved = cu.get_text_feats
+    cu.get_text_feats = _patched_text_feats(encoder)
+    try:
+        return cu.get_lseg_score(None, list(landmarks), feat, feat.shape[-1], use_multiple_templates=True, avg_mode=avg_mode)
+    finally:
+        cu.get_text_feats = saved
+
+
+def ref_dynamic_obstacles(encoder, obstacles_cropped, potential, obstacle, grid_feat, grid_pos, rmin, cmin):
+    """The reference's get_dynamic_obstacles_map_3d (index_utils.py:138-184) with its own get_lseg_score duplicate
+    (:64-108); `openai` is stubbed (only find_similar_category_id's fallback uses it)."""
+    if "openai" not in sys.modules:
+        sys.modules["openai"] = types.ModuleType("openai")
+    iu = load("ref_index_utils", "avlmaps/utils/index_utils.py")
+    saved = iu.get_text_feats
+    iu.get_text_feats = _patched_text_feats(encoder)
+    import contextlib
+    import io
+
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            return iu.get_dynamic_obstacles_map_3d(None, obstacles_cropped, list(potential), list(obstacle), grid_feat,
+                                                   grid_pos, rmin, cmin, grid_feat.shape[-1])
+    finally:
+        iu.get_text_feats = saved

@@ -11,6 +11,8 @@ outputs of the reference's own functions:
   heat_*.npz   get_heatmap_from_mask_3d (avlmaps/utils/visualize_utils.py:29-49)
   mf_*.npz     VLMapBuilderMultiFloor.create_global_map (avlmaps/map/vlmap_builder_multi_floor.py:60-199)
   avlmap_heats.npz  AVLMap.index_area(_2d) / index_sound(_2d) / index_image (avlmaps/map/avlmap.py:78-163)
+  templates_dynobs.npz  get_lseg_score with the 63 prompt templates, avg_mode 0 / 1 (clip_utils.py:216-234), and
+                    get_dynamic_obstacles_map_3d (avlmaps/utils/index_utils.py:138-184)
 """
 from __future__ import annotations
 
@@ -156,6 +158,26 @@ def gen_avlmap_heats(seed=60):
     print("avlmap_heats:", {k: (v.shape, str(v.dtype)) for k, v in out.items()})
 
 
+POTENTIAL_OBSTACLES = ["chair", "wall", "wall above the door", "table", "window", "floor", "stairs", "other"]
+OBSTACLES = ["wall", "chair", "table", "window", "stairs", "other"]
+
+
+def gen_templates_dynobs(seed=70):
+    d, n = 64, 4000
+    feat, _ = synth.index_inputs(n, d, 1, seed=seed)
+    enc = synth.crc_text_encoder(d)
+    cats = ["chair", "table", "sofa", "potted plant"]
+    s0 = ref_shim.ref_get_lseg_score_templates(feat, cats, enc, avg_mode=0)
+    s1 = ref_shim.ref_get_lseg_score_templates(feat, cats, enc, avg_mode=1)
+    rng = np.random.default_rng(seed + 1)
+    pos = np.stack([rng.integers(5, 45, n), rng.integers(10, 60, n), rng.integers(0, 8, n)], 1).astype(np.int32)
+    obstacles_cropped = rng.uniform(size=(40, 50)) > 0.5
+    dyn = ref_shim.ref_dynamic_obstacles(enc, obstacles_cropped, POTENTIAL_OBSTACLES, OBSTACLES, feat, pos, 5, 10)
+    np.savez_compressed(OUT / "templates_dynobs.npz", n=n, d=d, seed=seed, scores_avg0=s0, scores_avg1=s1, grid_pos=pos,
+                        obstacles_cropped=obstacles_cropped, dynamic_obstacles=dyn, rmin=5, cmin=10)
+    print("templates_dynobs:", s0.shape, s1.shape, dyn.shape, int(dyn.sum()))
+
+
 def main():
     assert ref_shim.available(), "reference tree not found"
     # index path: BASELINE config 1 exactly, then batched / other dims
@@ -181,6 +203,7 @@ def main():
                      rate=2, seed=6)
     gen_heat("n600", 600, seed=50)
     gen_avlmap_heats()
+    gen_templates_dynobs()
     # multi-floor builder: uint16 mm depth, global-frame grid from a first pass, np.round cells
     gen_multi_floor("rate1", 4, 48, 64, 39, 52, 8, 0.05, k10, rate=1, skip=1, seed=0)
     # second-pass samples fall below pcd_min in all three axes: numpy negative-index wrap-around

@@ -100,3 +100,14 @@ def multi_floor_inputs(n_frames: int, h: int, w: int, fh: int, fw: int, d: int, 
         f = np.random.default_rng(400 + seed * 1000 + i).standard_normal((1, d, fh, fw), dtype=np.float32)
         feats.append(f * np.float32(14.2857 / np.sqrt(d)))
     return depths, rgbs, feats
+
+
+def crc_text_encoder(dim: int):
+    """Deterministic stand-in for a CLIP text tower: features are a function of the text's CRC32 (Python's hash() is
+    salted per process, so it cannot pin golden vectors).  Rows are NOT normalised, like encode_text's output."""
+    import zlib
+
+    def enc(texts):
+        return np.stack([np.random.default_rng(zlib.crc32(t.encode())).standard_normal(dim) for t in texts]).astype(np.float32)
+
+    return enc

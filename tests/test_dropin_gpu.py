@@ -327,3 +327,26 @@ def test_avlmap_area_sound_image_against_the_reference_methods(lib):
                      (av.index_sound_2d("door", decay_rate=0.01), "sound_2d"), (av.index_sound("door", decay_rate=0.01), "sound_3d"),
                      (av.index_image(None, decay_rate=0.01), "image_3d")):
         assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+
+
+def test_templates_and_dynamic_obstacles_against_the_reference_functions(lib):
+    """get_lseg_score with the 63 templates (both avg modes) and get_dynamic_obstacles_map_3d against the outputs of
+    the reference's own functions (tests/golden/templates_dynobs.npz, produced through oracle/ref_shim.py)."""
+    from avlmaps_b200.utils.clip_utils import get_lseg_score
+    from avlmaps_b200.utils.index_utils import get_dynamic_obstacles_map_3d
+
+    g = np.load(Path(__file__).resolve().parent / "golden" / "templates_dynobs.npz")
+    d = int(g["d"])
+    feat, _ = synth.index_inputs(int(g["n"]), d, 1, seed=int(g["seed"]))
+    enc = synth.crc_text_encoder(d)
+    cats = ["chair", "table", "sofa", "potted plant"]
+    for mode, key in ((0, "scores_avg0"), (1, "scores_avg1")):
+        sc = get_lseg_score(enc, cats, feat, d, use_multiple_templates=True, avg_mode=mode)
+        ref = g[key]
+        assert sc.dtype == np.float32 and sc.shape == ref.shape
+        assert np.max(np.abs(sc - ref)) <= 2e-6 * np.abs(ref).max()       # fp64-accumulated vs the reference's sgemm
+    potential = ["chair", "wall", "wall above the door", "table", "window", "floor", "stairs", "other"]
+    obstacle = ["wall", "chair", "table", "window", "stairs", "other"]
+    got = get_dynamic_obstacles_map_3d(enc, g["obstacles_cropped"], potential, obstacle, feat, g["grid_pos"],
+                                       int(g["rmin"]), int(g["cmin"]), d)
+    assert got.dtype == bool and np.array_equal(got, g["dynamic_obstacles"])

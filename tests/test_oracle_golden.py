@@ -208,3 +208,28 @@ def test_avlmap_heat_restatements_match_the_reference_methods():
     assert np.array_equal(O.lift_heat_2d_to_3d(s2, g["occupied_ids"], n), g["sound_3d"])
     r, c = g["image_cell"]
     assert np.array_equal(O.image_heat(g["grid_pos"], int(r), int(c), 1.5, 0.05, 0.01), g["image_3d"])
+
+
+def test_template_scoring_matches_the_reference():
+    """get_lseg_score with the 63 prompt templates (clip_utils.py:216-234) run unmodified: the host side that builds
+    the query matrix (avlmaps_b200.utils.clip_utils.landmark_text_feats) + the canonical scores reproduce the
+    reference's float32 result for both averaging modes, and its per-voxel argmax."""
+    from avlmaps_b200.utils.clip_utils import landmark_text_feats
+
+    g = np.load(G / "templates_dynobs.npz")
+    d = int(g["d"])
+    feat, _ = synth.index_inputs(int(g["n"]), d, 1, seed=int(g["seed"]))
+    enc = synth.crc_text_encoder(d)
+    cats = ["chair", "table", "sofa", "potted plant"]
+    for mode, key in ((0, "scores_avg0"), (1, "scores_avg1")):
+        tf, names, n_tmp = landmark_text_feats(enc, cats, d, True, mode, True)
+        assert names[-1] == "other" and n_tmp == 63
+        sc = O.scores(feat, tf)
+        if mode == 1:
+            sc = np.mean(sc.reshape((-1, len(names), n_tmp)), axis=2)
+        ref = g[key]
+        assert sc.shape == ref.shape == (feat.shape[0], 5)
+        assert np.max(np.abs(sc - ref)) <= 2e-6 * np.abs(ref).max()
+        part = np.partition(ref, 3, axis=1)
+        clear = (part[:, -1] - part[:, -2]) > 1e-5 * np.abs(ref).max()      # away from float32 near-ties
+        assert clear.mean() > 0.99 and np.array_equal(np.argmax(sc, 1)[clear], np.argmax(ref, 1)[clear])
