@@ -368,6 +368,54 @@ __device__ KeyT block_kth_largest(Fetch fetch, int n, int k, int* sh_cnt) {
   return v;
 }
 
+// Same result for 32-bit keys with 4 passes of an 8-bit radix histogram in shared memory instead of 32 rounds of
+// bisection (each round is a block-wide count with three barriers; the finalize kernels spend most of their
+// instructions there).  hist: 256 shared words; every thread returns the value.
+template <typename Fetch>
+__device__ uint32_t block_kth_largest_radix32(Fetch fetch, int n, int k, uint32_t* hist, int* sh_sel) {
+  uint32_t prefix = 0u, mask = 0u;
+  int kk = k;  // rank still to find among the keys that match the prefix
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const uint32_t key = fetch(j);
+      if ((key & mask) == prefix) atomicAdd(hist + ((key >> shift) & 255u), 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns digits [8l, 8l + 8); walk from the largest digit down until kk keys are covered
+      const int lane = threadIdx.x;
+      uint32_t c[8], tot = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; tot += c[i]; }
+      uint32_t suffix = tot;  // inclusive suffix sums over the lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_down_sync(0xffffffffu, suffix, o);
+        if (lane + o < 32) suffix += y;
+      }
+      const uint32_t above = suffix - tot;  // keys with a digit in a higher lane
+      if (above < static_cast<uint32_t>(kk) && static_cast<uint32_t>(kk) <= above + tot) {
+        uint32_t run = above;
+        for (int i = 7; i >= 0; --i) {
+          if (run + c[i] >= static_cast<uint32_t>(kk)) {
+            sh_sel[0] = lane * 8 + i;             // the digit of the k-th largest key
+            sh_sel[1] = kk - static_cast<int>(run);  // its rank among the keys with that digit
+            break;
+          }
+          run += c[i];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= static_cast<uint32_t>(sh_sel[0]) << shift;
+    mask |= 255u << shift;
+    kk = sh_sel[1];  // sh_sel is rewritten only after the next pass's two barriers
+  }
+  return prefix;
+}
+
 // ------------------------------------------------------------------ threshold from a sample
 // sample_lb[q][c]: LOWER bounds (s~ - eps)/w of the sampled rows, written transposed by the screen
 // kernel (dense_lb; rows past the end of the map are -inf).  Per query: T_q = k-th largest of the
@@ -453,7 +501,9 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   __syncthreads();
   const int kk = min(k, n);
   uint32_t v = 0u;
-  if (kk > 0) v = block_kth_largest<uint32_t>([&](int j) { return Lk[j]; }, n, kk, &sh_cnt);
+  __shared__ uint32_t hist[256];
+  __shared__ int sh_sel[2];
+  if (kk > 0) v = block_kth_largest_radix32([&](int j) { return Lk[j]; }, n, kk, hist, sh_sel);
   // survivors: upper bound reaches the k-th best lower bound.  Lk is dead now -> survivor list.
   __syncthreads();
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -1009,7 +1059,9 @@ fuse_finalize_kernel(const FuseSide sa, const FuseSide sb, int32_t pairs, const 
   __syncthreads();
   const int kk = min(k, n);
   uint32_t v = 0u;
-  if (kk > 0) v = block_kth_largest<uint32_t>([&](int c) { return Lk[c]; }, n, kk, &sh_cnt);
+  __shared__ uint32_t hist[256];
+  __shared__ int sh_sel[2];
+  if (kk > 0) v = block_kth_largest_radix32([&](int c) { return Lk[c]; }, n, kk, hist, sh_sel);
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     if (max(f2ord(cand_hi[base + c]), 1u) >= v) {
       const int t = atomicAdd(&sh_ns, 1);
