@@ -160,6 +160,37 @@ class VLMap(Map):
                                                      cfg_get(self.map_config, "gaussian_sigma"))
         self.obstacles_new_cropped = self.obstacles_new_cropped == 0
 
+    def get_pos(self, name: str):
+        """Reference vlmap.py:158-187: contours, centres and bounding boxes (full-map coordinates) of the islands of a
+        category.  The mask comes from the device (`index_map`); what follows is the reference's host-side 2-D
+        morphology on the small cropped top-down map (scipy / cv2), with the per-voxel Python loop of
+        `pool_3d_label_to_2d` (visualize_utils.py:77-83) as one vectorised assignment."""
+        import cv2
+        from scipy.ndimage import binary_closing, binary_dilation, gaussian_filter
+
+        assert self.categories
+        pc_mask = self.index_map(name, with_init_cat=True)
+        if self.obstacles_cropped is None:
+            self.generate_obstacle_map()                      # sets rmin / rmax / cmin / cmax like the reference's callers
+        mask_2d = np.zeros((self.gs, self.gs), dtype=bool)
+        hit = self.grid_pos[pc_mask]
+        mask_2d[hit[:, 0], hit[:, 1]] = True
+        mask_2d = mask_2d[self.rmin:self.rmax + 1, self.cmin:self.cmax + 1]
+        foreground = binary_closing(mask_2d, iterations=3)
+        foreground = gaussian_filter(foreground.astype(float), sigma=0.8, truncate=3) > 0.5
+        foreground = binary_dilation(foreground)
+        # get_segment_islands_pos (index_utils.py:34-62): external contours in (row, col) order, bbox and centre each
+        found, _ = cv2.findContours(foreground.astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        contours, centers, bbox_list = [], [], []
+        for contour in found:
+            xy = contour.reshape((-1, 2))
+            rc = np.stack([xy[:, 1] + self.rmin, xy[:, 0] + self.cmin], axis=1)
+            rmin_, rmax_, cmin_, cmax_ = rc[:, 0].min(), rc[:, 0].max(), rc[:, 1].min(), rc[:, 1].max()
+            contours.append(rc)
+            centers.append([(rmin_ + rmax_) / 2, (cmin_ + cmax_) / 2])
+            bbox_list.append([rmin_, rmax_, cmin_, cmax_])
+        return contours, centers, bbox_list
+
     def get_lseg_score(self, landmarks: List[str], use_multiple_templates: bool = True, add_other: bool = True):
         return get_lseg_score(self.clip_model, landmarks, self.device_map, self.clip_feat_dim,
                               use_multiple_templates=use_multiple_templates, add_other=add_other)

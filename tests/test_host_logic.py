@@ -90,3 +90,40 @@ def test_generate_obstacle_map_quirk():
     obs = m.generate_obstacle_map()
     assert obs[1, 1] and not obs[2, 2]
     assert (m.rmin, m.rmax, m.cmin, m.cmax) == (2, 2, 2, 2)
+
+
+def test_get_pos_matches_the_reference_helpers():
+    """VLMap.get_pos (vlmap.py:158-187): the mask comes from index_map (stubbed here, no GPU); pooling, morphology and
+    island extraction must equal the reference's helpers, restated in the test: pool_3d_label_to_2d
+    (visualize_utils.py:77-83, a per-voxel loop) and get_segment_islands_pos (index_utils.py:34-62)."""
+    import cv2
+    from scipy.ndimage import binary_closing, binary_dilation, gaussian_filter
+
+    rng = np.random.default_rng(3)
+    gs = 64
+    v = VLMap(cfg())
+    n = 3000
+    pos = np.stack([rng.integers(8, 56, n), rng.integers(10, 50, n), rng.integers(0, 8, n)], 1).astype(np.int32)
+    occ = -np.ones((gs, gs, 32), np.int32)
+    occ[pos[:, 0], pos[:, 1], pos[:, 2]] = np.arange(n)
+    v.grid_pos, v.occupied_ids, v.categories = pos, occ, ["chair"]
+    blob = ((pos[:, 0] - 20) ** 2 + (pos[:, 1] - 22) ** 2 < 30) | ((pos[:, 0] - 44) ** 2 + (pos[:, 1] - 40) ** 2 < 16)
+    v.index_map = lambda name, with_init_cat=True: blob
+    contours, centers, bboxes = v.get_pos("chair")
+    # reference arithmetic, loop form
+    mask_2d = np.zeros((gs, gs), dtype=bool)
+    for i, (row, col, _) in enumerate(pos):
+        mask_2d[row, col] = blob[i] or mask_2d[row, col]
+    m = Map(cfg())
+    m.occupied_ids = occ
+    m.generate_obstacle_map()
+    crop = mask_2d[m.rmin:m.rmax + 1, m.cmin:m.cmax + 1]
+    fg = binary_dilation(gaussian_filter(binary_closing(crop, iterations=3).astype(float), sigma=0.8, truncate=3) > 0.5)
+    found, _ = cv2.findContours((fg == 1).astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    assert len(contours) == len(found) == 2
+    for got, c, ctr, bb in zip(contours, found, centers, bboxes):
+        t = c.reshape((-1, 2))
+        want = np.stack([t[:, 1] + m.rmin, t[:, 0] + m.cmin], axis=1)
+        assert np.array_equal(got, want)
+        assert bb == [want[:, 0].min(), want[:, 0].max(), want[:, 1].min(), want[:, 1].max()]
+        assert ctr == [(bb[0] + bb[1]) / 2, (bb[2] + bb[3]) / 2]
