@@ -22,11 +22,25 @@ class AVLMap:
         self.vlmap = VLMap(cfg_get(config, "map_config"), data_dir=data_dir, feature_fn=feature_fn)
 
     def create_map(self, data_dir) -> bool:
+        """Reference avlmap.py:38-47; the area / visual / sound maps are built too when such objects are attached."""
         self.vlmap.create_map(data_dir)   # avlmap.py:39
+        if self.area_map is not None:
+            self.area_map.create_map(data_dir)
+        if self.visual_map is not None:
+            self.visual_map.create_and_load_map(data_dir)
+        if self.sound_map is not None and hasattr(self.sound_map, "create_sound_map"):
+            self.sound_map.create_sound_map(data_dir)
         return True
 
     def load_map(self, data_dir: str) -> bool:
+        """Reference avlmap.py:49-55."""
         self.vlmap.load_map(data_dir)     # avlmap.py:50
+        if self.area_map is not None:
+            self.area_map.load_map(data_dir)
+        if self.visual_map is not None:
+            self.visual_map.create_and_load_map(data_dir)
+        if self.sound_map is not None:
+            self.sound_map.load_sound_map(data_dir)
         return True
 
     def index_object(self, object_name: str, init_categories: Optional[List[str]] = None, decay_rate: float = 0.1) -> np.ndarray:

@@ -95,6 +95,15 @@ class Map:
         self.obstacles_cropped = obstacle_map[self.rmin:self.rmax + 1, self.cmin:self.cmax + 1]
         return self.obstacles_cropped
 
+    def generate_rgb_topdown_map(self) -> np.ndarray:
+        """Reference map.py:106-113 (a per-voxel loop: later voxels overwrite earlier ones of the same column)."""
+        assert self.grid_rgb is not None, "map not loaded"
+        assert self.grid_pos is not None
+        rgb_topdown = np.zeros((self.gs, self.gs, 3))
+        # numpy's fancy assignment keeps the LAST value written for repeated indices, like the loop
+        rgb_topdown[self.grid_pos[:, 0], self.grid_pos[:, 1], :] = np.asarray(self.grid_rgb).reshape(-1, 3)
+        return rgb_topdown.astype(np.uint8)
+
     @staticmethod
     def _dilate_map(binary_map: np.ndarray, dilate_iter: int = 0, gaussian_sigma: float = 1.0):
         """Reference map.py:170-181 (host-side 2-D morphology on the small cropped obstacle map)."""
