@@ -127,3 +127,71 @@ def test_get_pos_matches_the_reference_helpers():
         assert np.array_equal(got, want)
         assert bb == [want[:, 0].min(), want[:, 0].max(), want[:, 1].min(), want[:, 1].max()]
         assert ctr == [(bb[0] + bb[1]) / 2, (bb[2] + bb[3]) / 2]
+
+
+def test_frame_marshalling_without_a_device():
+    """avl_frame structs as the ctypes layer fills them (no GPU needed): pointers, shapes, the four matrices as
+    row-major float64, uint16 depth flag, an empty sample list told apart from 'every pixel', set_tf patching one frame."""
+    import ctypes as C
+    import types
+
+    from avlmaps_b200 import _lib as L
+    from avlmaps_b200 import engine
+
+    depth = np.arange(12, dtype=np.float32).reshape(3, 4)
+    feat = np.zeros((1, 5, 2, 3), np.float32)
+    k = np.arange(9.0).reshape(3, 3)
+    tf = np.arange(16.0).reshape(4, 4).T                    # non-contiguous on purpose
+    sidx = np.array([5, 1, 7], np.int32)
+    fr, flags, keep = engine._fill_frame(depth, feat, np.linalg.inv(k + np.eye(3)), k, k * 2, tf, None, sidx, L.FEAT_CHW, 0.1, 6.0, dim=5)
+    assert (fr.h, fr.w, fr.fh, fr.fw, fr.feat_layout, fr.n_samples) == (3, 4, 2, 3, L.FEAT_CHW, 3)
+    assert fr.depth == keep[0].keep.ctypes.data and fr.rgb is None and flags == 0
+    assert list(fr.k) == k.ravel().tolist() and list(fr.kfeat) == (k * 2).ravel().tolist()
+    assert list(fr.tf) == np.ascontiguousarray(tf).ravel().tolist()
+    assert (fr.min_depth, fr.max_depth) == (0.1, 6.0)
+    with pytest.raises(ValueError):
+        engine._fill_frame(depth, feat, k, k, k, tf, None, sidx, L.FEAT_CHW, 0.1, 6.0, dim=4)   # feature dim mismatch
+    # uint16 depth = millimetres -> flag for the kernel's / 1000.0
+    _, flags16, _ = engine._fill_frame(depth.astype(np.uint16), feat, k, k, k, tf, None, None, L.FEAT_CHW, 0.1, 100.0, dim=5)
+    assert flags16 == L.AVL_DEPTH_U16_MM
+    # sample_idx=None means every pixel (NULL pointer); an EMPTY list must stay distinguishable (non-NULL, 0 samples)
+    fr_all, _, _ = engine._fill_frame(depth, feat, k, k, k, tf, None, None, L.FEAT_CHW, 0.1, 6.0, dim=5)
+    fr_none, _, _ = engine._fill_frame(depth, feat, k, k, k, tf, None, sidx[:0], L.FEAT_CHW, 0.1, 6.0, dim=5)
+    assert fr_all.sample_idx is None and fr_all.n_samples == 0
+    assert fr_none.sample_idx is not None and fr_none.n_samples == 0
+    # PreparedFrames: marshalled once, pose patched per frame
+    frames = [dict(depth=depth, feat=feat, kinv=k, k=k, kfeat=k, tf=np.eye(4) * (i + 1), sample_idx=sidx) for i in range(3)]
+    prep = engine.PreparedFrames(types.SimpleNamespace(dim=5), frames)
+    assert prep.n == 3 and [prep.arr[i].tf[0] for i in range(3)] == [1.0, 2.0, 3.0]
+    prep.set_tf(1, tf)
+    assert list(prep.arr[1].tf) == np.ascontiguousarray(tf).ravel().tolist() and prep.arr[2].tf[0] == 3.0
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct in include/avlmaps_b200.h, as gcc lays them out, against the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+
+    from avlmaps_b200 import _lib as L
+
+    root = Path(__file__).resolve().parents[1]
+    mirrors = {"avl_frame": L.Frame, "avl_grid_spec": L.GridSpec, "avl_global_grid_spec": L.GlobalGridSpec,
+               "avl_index_stats": L.IndexStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "avlmaps_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {field}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(root / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        cls = mirrors[name]
+        assert C.sizeof(cls) == int(size), name
+        assert [getattr(cls, f).offset for f, _ in cls._fields_] == [int(o) for o in offs], name
