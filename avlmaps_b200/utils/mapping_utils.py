@@ -58,9 +58,12 @@ def grid_id2base_pos_3d(row, col, height, cs, gs):
 
 
 # ---------------------------------------------------------------------------------------------- map files
-# The reference writes HDF5 through h5py (mapping_utils.py:469-505).  h5py is used when it is
-# importable (same dataset names and dtypes, so files interchange with the reference); otherwise the
-# same arrays go to an .npz twin next to the requested path (`<path>.npz`).
+# The reference writes HDF5 through h5py (mapping_utils.py:469-505).  h5py is used when it is importable;
+# otherwise `h5lite` (this package's dependency-free reader / writer of the same file structure) reads and writes
+# the very same datasets, so `vlmaps.h5df` files interchange with the reference either way.  Maps saved by earlier
+# versions of this package as an `.npz` twin (`<path>.npz`) still load.
+from . import h5lite
+
 _FIELDS = ("mapped_iter_list", "grid_feat", "grid_pos", "weight", "occupied_ids", "grid_rgb", "init_height_id")
 
 
@@ -81,6 +84,33 @@ def map_file_exists(path) -> bool:
     return Path(path).exists() or _npz_twin(path).exists()
 
 
+def _write_datasets(save_path, data: dict) -> None:
+    if _have_h5py():
+        import h5py
+
+        with h5py.File(save_path, "w") as f:
+            for k, v in data.items():
+                f.create_dataset(k, data=v)
+    else:
+        h5lite.write_file(save_path, data)
+
+
+def _read_datasets(map_path, fields) -> dict:
+    """{name: array} of the datasets of `fields` present in the file (scalars as 0-d arrays)."""
+    if Path(map_path).exists():
+        if _have_h5py():
+            import h5py
+
+            with h5py.File(map_path, "r") as f:
+                return {k: np.asarray(f[k][()]) for k in fields if k in f}
+        return h5lite.read_file(map_path, list(fields))
+    twin = _npz_twin(map_path)
+    if not twin.exists():
+        raise FileNotFoundError(f"{map_path} does not exist")
+    with np.load(twin) as z:
+        return {k: z[k] for k in fields if k in z.files}
+
+
 def save_3d_map(save_path, grid_feat: np.ndarray, grid_pos: np.ndarray, weight: np.ndarray, occupied_ids: np.ndarray,
                 mapped_iter_list: Set[int], grid_rgb: Optional[np.ndarray] = None, init_height_id: Optional[int] = None) -> None:
     """Reference mapping_utils.py:469-505: same arguments, same dataset names."""
@@ -92,27 +122,12 @@ def save_3d_map(save_path, grid_feat: np.ndarray, grid_pos: np.ndarray, weight: 
         data["init_height_id"] = np.array(init_height_id, dtype=np.int32)
     if grid_rgb is not None:
         data["grid_rgb"] = grid_rgb
-    if _have_h5py():
-        import h5py
-
-        with h5py.File(save_path, "w") as f:
-            for k, v in data.items():
-                f.create_dataset(k, data=v)
-    else:
-        with open(_npz_twin(save_path), "wb") as f:
-            np.savez(f, **data)
+    _write_datasets(save_path, data)
 
 
 def load_3d_map(map_path) -> Tuple:
     """Reference mapping_utils.py:508-541: returns the 6-tuple (7 with init_height_id)."""
-    if Path(map_path).exists() and _have_h5py():
-        import h5py
-
-        with h5py.File(map_path, "r") as f:
-            d = {k: f[k][()] for k in _FIELDS if k in f}
-    else:
-        with np.load(_npz_twin(map_path)) as z:
-            d = {k: z[k] for k in _FIELDS if k in z.files}
+    d = _read_datasets(map_path, _FIELDS)
     mapped_iter_list = d["mapped_iter_list"].tolist()
     out = (mapped_iter_list, d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], d.get("grid_rgb"))
     if "init_height_id" in d:
@@ -126,56 +141,29 @@ _FIELDS_MF = ("mapped_iter_list", "grid_feat", "grid_pos", "weight", "occupied_i
 def save_3d_map_multi_floor(save_path, grid_feat, grid_pos, weight, grid_rgb, occupied_ids, mapped_iter_set, pcd_min,
                             pcd_max, cs) -> None:
     """VLMapBuilderMultiFloor.save_3d_map (reference vlmap_builder_multi_floor.py:370-393): same dataset names."""
-    data = {
+    _write_datasets(save_path, {
         "mapped_iter_list": np.array(list(mapped_iter_set), dtype=np.int32),
         "grid_feat": grid_feat, "grid_pos": grid_pos, "weight": weight, "occupied_ids": occupied_ids,
         "grid_rgb": grid_rgb, "pcd_min": np.asarray(pcd_min), "pcd_max": np.asarray(pcd_max), "cs": np.asarray(cs),
-    }
-    if _have_h5py():
-        import h5py
-
-        with h5py.File(save_path, "w") as f:
-            for k, v in data.items():
-                f.create_dataset(k, data=v)
-    else:
-        with open(_npz_twin(save_path), "wb") as f:
-            np.savez(f, **data)
+    })
 
 
 def load_3d_map_multi_floor(map_path) -> Tuple:
     """VLMapBuilderMultiFloor.load_3d_map (reference vlmap_builder_multi_floor.py:243-255): the 9-tuple."""
-    if Path(map_path).exists() and _have_h5py():
-        import h5py
-
-        with h5py.File(map_path, "r") as f:
-            d = {k: f[k][()] for k in _FIELDS_MF}
-    else:
-        with np.load(_npz_twin(map_path)) as z:
-            d = {k: z[k] for k in _FIELDS_MF}
+    d = _read_datasets(map_path, _FIELDS_MF)
+    missing = [k for k in _FIELDS_MF if k not in d]
+    if missing:
+        raise KeyError(f"{map_path} lacks the multi-floor datasets {missing}")
     return (d["mapped_iter_list"].tolist(), d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], d["grid_rgb"],
             d["pcd_min"], d["pcd_max"], d["cs"][()])
 
 
 def save_clip_sparse_map(save_path, clip_sparse_map: np.ndarray, robot_pose_list) -> None:
     """Reference mapping_utils.py:637-640."""
-    data = {"clip_sparse_map": clip_sparse_map, "robot_pose_list": np.asarray(robot_pose_list)}
-    if _have_h5py():
-        import h5py
-
-        with h5py.File(save_path, "w") as f:
-            for k, v in data.items():
-                f.create_dataset(k, data=v)
-    else:
-        with open(_npz_twin(save_path), "wb") as f:
-            np.savez(f, **data)
+    _write_datasets(save_path, {"clip_sparse_map": np.asarray(clip_sparse_map), "robot_pose_list": np.asarray(robot_pose_list)})
 
 
 def load_clip_sparse_map(load_path):
     """Reference mapping_utils.py:643-647."""
-    if Path(load_path).exists() and _have_h5py():
-        import h5py
-
-        with h5py.File(load_path, "r") as f:
-            return f["clip_sparse_map"][:], f["robot_pose_list"][:]
-    with np.load(_npz_twin(load_path)) as z:
-        return z["clip_sparse_map"], z["robot_pose_list"]
+    d = _read_datasets(load_path, ("clip_sparse_map", "robot_pose_list"))
+    return d["clip_sparse_map"], d["robot_pose_list"]
