@@ -401,16 +401,17 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
   AVL_ARG(dim >= 1 && dim <= 4096, "dim must be in [1, 4096]");
   AVL_ARG(n == 0 || grid_feat != nullptr, "grid_feat is NULL");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  avl_map* m = new avl_map();
-  AVL_CUDA(cudaGetDevice(&m->device));
-  AVL_CUDA(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device));
-  int major = 0;
-  AVL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, m->device));
+  int device = 0, num_sms = 0, major = 0;  // queried before the handle exists: a box without a GPU fails here
+  AVL_CUDA(cudaGetDevice(&device));
+  AVL_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  AVL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   if (major != 10) {
-    delete m;
     set_error("avlmaps_b200 needs an sm_100a (B200) device");
     return AVL_ERR_UNSUPPORTED;
   }
+  avl_map* m = new avl_map();
+  m->device = device;
+  m->num_sms = num_sms;
   m->n = n;
   m->d = dim;
   m->dpad = (dim + kBlockK - 1) / kBlockK * kBlockK;
