@@ -7,6 +7,7 @@ that `index_map` needs, without materialising the (N, C) score matrix.  `scores_
 available (computed exactly, on demand) because callers of the reference read it."""
 from __future__ import annotations
 
+import os
 from pathlib import Path
 from typing import List, Optional, Union
 
@@ -60,8 +61,10 @@ class VLMap(Map):
         if not map_file_exists(self.map_save_path):
             print("Loading VLMap failed because the file doesn't exist.")
             return False
+        # `self.mmap_load = True` (or AVL_MMAP_LOAD=1) maps grid_feat from the file instead of copying it to host RAM
+        mmap_feat = bool(getattr(self, "mmap_load", os.environ.get("AVL_MMAP_LOAD", "0") == "1"))
         (self.mapped_iter_list, self.grid_feat, self.grid_pos, self.weight, self.occupied_ids,
-         self.grid_rgb) = load_3d_map(self.map_save_path)[:6]
+         self.grid_rgb) = load_3d_map(self.map_save_path, mmap_feat=mmap_feat)[:6]
         self.set_map_arrays(self.grid_feat)
         return True
 

@@ -68,6 +68,38 @@ class ShardedMap:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    @classmethod
+    def from_file(cls, map_path, group=None, local_factory=None, operand: str = "bf16") -> "ShardedMap":
+        """Open a saved map (`vlmaps.h5df`, reference mapping_utils.py:469-505) slab-wise: every rank memory-maps
+        `grid_feat` in place and uploads ONLY its own row slab, so a 16 M x 512 map (34 GB) costs each of 8 ranks
+        4.3 GB of page-cache reads instead of the whole file in host RAM.  `grid_pos` (N x 3 int32, small) is kept
+        whole on every rank as `.grid_pos` for the goal lookup `grid_pos[idx]` (habitat_lang_robot.py:427-430).
+        `local_factory(slab_array) -> local map` defaults to engine.DeviceMap."""
+        import torch.distributed as dist
+
+        from .utils import h5lite
+
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        with h5lite.File(map_path) as f:
+            ds = f["grid_feat"]
+            if len(ds.shape) != 2:
+                raise ValueError(f"{map_path}: grid_feat must be (N, D), found {ds.shape}")
+            lo, hi = slab_bounds(ds.shape[0], world, rank)
+            if ds.offset is not None and ds.size and ds.dtype == np.dtype("<f4"):
+                slab = ds.memmap()[lo:hi]          # a view: pages are read as the upload touches them
+            else:
+                slab = np.ascontiguousarray(ds.read()[lo:hi], dtype=np.float32)   # chunked / converted storage
+            grid_pos = f["grid_pos"].read() if "grid_pos" in f else None
+        if local_factory is None:
+            from .engine import DeviceMap
+
+            def local_factory(a):
+                return DeviceMap(a, operand=operand)
+        sm = cls(local_factory(slab), row_offset=lo, group=group)
+        sm.n_total, sm.row_lo, sm.row_hi, sm.grid_pos = int(ds.shape[0]), lo, hi, grid_pos
+        return sm
+
     def topk(self, queries, k: int, scale=None, normalize_map: bool = False):
         import torch
         import torch.distributed as dist

@@ -125,9 +125,22 @@ def save_3d_map(save_path, grid_feat: np.ndarray, grid_pos: np.ndarray, weight: 
     _write_datasets(save_path, data)
 
 
-def load_3d_map(map_path) -> Tuple:
-    """Reference mapping_utils.py:508-541: returns the 6-tuple (7 with init_height_id)."""
-    d = _read_datasets(map_path, _FIELDS)
+def load_3d_map(map_path, mmap_feat: bool = False) -> Tuple:
+    """Reference mapping_utils.py:508-541: returns the 6-tuple (7 with init_height_id).
+
+    mmap_feat=True returns `grid_feat` as a read-only memory map of the file instead of a copy (contiguous float32
+    storage only, which is what the reference and this package write): the device upload then reads the page cache
+    directly and host RAM holds no second copy of a multi-GB map.  The map file must not be rewritten in place while
+    the array is alive (this package's writer renames a temporary, which is safe; h5py's "w" mode truncates)."""
+    d = _read_datasets(map_path, _FIELDS if not mmap_feat else tuple(k for k in _FIELDS if k != "grid_feat"))
+    if mmap_feat:
+        feat = None
+        if Path(map_path).exists():
+            with h5lite.File(map_path) as f:
+                ds = f["grid_feat"]
+                if ds.offset is not None and ds.size and ds.dtype == np.dtype("<f4"):
+                    feat = ds.memmap()
+        d["grid_feat"] = feat if feat is not None else _read_datasets(map_path, ("grid_feat",))["grid_feat"]
     mapped_iter_list = d["mapped_iter_list"].tolist()
     out = (mapped_iter_list, d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], d.get("grid_rgb"))
     if "init_height_id" in d:

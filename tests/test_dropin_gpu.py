@@ -350,3 +350,30 @@ def test_templates_and_dynamic_obstacles_against_the_reference_functions(lib):
     got = get_dynamic_obstacles_map_3d(enc, g["obstacles_cropped"], potential, obstacle, feat, g["grid_pos"],
                                        int(g["rmin"]), int(g["cmin"]), d)
     assert got.dtype == bool and np.array_equal(got, g["dynamic_obstacles"])
+
+
+def test_load_map_from_a_memory_mapped_file_and_slab_wise(lib, tmp_path):
+    """grid_feat goes from the page cache to the device without a host copy (`mmap_load`), and
+    ShardedMap.from_file uploads only this rank's row slab: same answers as the copying load."""
+    from avlmaps_b200.map import VLMap
+    from avlmaps_b200.sharded import ShardedMap
+    from avlmaps_b200.utils import mapping_utils
+
+    feat, q = synth.index_inputs(6000, 64, 9, seed=12)
+    gp = np.random.default_rng(0).integers(0, 48, (6000, 3)).astype(np.int32)
+    (tmp_path / "vlmap").mkdir()
+    mapping_utils.save_3d_map(tmp_path / "vlmap" / "vlmaps.h5df", feat, gp, np.ones(6000, np.float32),
+                              -np.ones((48, 48, 16), np.int32), [0], np.zeros((6000, 3), np.uint8))
+    cfg = synth.map_config(48, 0.1, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1)
+    a, b = VLMap(cfg), VLMap(cfg)
+    b.mmap_load = True
+    assert a.load_map(tmp_path) and b.load_map(tmp_path)
+    assert isinstance(b.grid_feat, np.memmap) and not isinstance(a.grid_feat, np.memmap)
+    assert np.array_equal(a.grid_feat, b.grid_feat)
+    want = O.argmax(O.scores(feat, q))
+    assert np.array_equal(a.device_map.argmax(q), want) and np.array_equal(b.device_map.argmax(q), want)
+    sm = ShardedMap.from_file(tmp_path / "vlmap" / "vlmaps.h5df")           # world of one: the slab is the whole map
+    idx, val = sm.topk(q, 8)
+    ri, rv = O.topk(O.scores(feat, q), 8)
+    assert (sm.row_lo, sm.row_hi, sm.n_total) == (0, 6000, 6000) and np.array_equal(sm.grid_pos, gp)
+    assert np.array_equal(idx, ri) and np.array_equal(val, rv)

@@ -185,6 +185,23 @@ def test_mapping_utils_write_real_hdf5_without_h5py(tmp_path, monkeypatch):
         mapping_utils.load_3d_map(tmp_path / "missing.h5df")
 
 
+def test_load_3d_map_memory_maps_grid_feat_on_request(tmp_path, monkeypatch):
+    monkeypatch.setattr(mapping_utils, "_have_h5py", lambda: False)
+    rng = np.random.default_rng(4)
+    d = _map_fields(rng)
+    p = tmp_path / "vlmaps.h5df"
+    mapping_utils.save_3d_map(p, d["grid_feat"], d["grid_pos"], d["weight"], d["occupied_ids"], [1, 2], d["grid_rgb"])
+    it, gf, gp, w, occ, rgb = mapping_utils.load_3d_map(p, mmap_feat=True)
+    assert isinstance(gf, np.memmap) and not gf.flags.writeable and gf.flags.c_contiguous
+    assert np.array_equal(gf, d["grid_feat"]) and it == [1, 2] and np.array_equal(gp, d["grid_pos"])
+    assert not isinstance(gp, np.memmap)
+    # a legacy .npz twin has nothing to map: the copy comes back instead
+    q = tmp_path / "old.h5df"
+    np.savez(str(q) + ".npz", **d)
+    gf2 = mapping_utils.load_3d_map(q, mmap_feat=True)[1]
+    assert not isinstance(gf2, np.memmap) and np.array_equal(gf2, d["grid_feat"])
+
+
 def test_legacy_npz_twin_still_loads(tmp_path):
     rng = np.random.default_rng(2)
     d = _map_fields(rng)

@@ -59,6 +59,59 @@ def test_sharded_topk_world2_gloo():
     assert out.get() == (True, True)
 
 
+def _file_worker(rank, world, port, path, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seen = {}
+
+    def factory(slab):
+        seen["slab"] = slab
+        return OracleSlab(np.asarray(slab))
+
+    sm = ShardedMap.from_file(path, local_factory=factory)
+    feat, q = synth.index_inputs(5001, 64, 7, seed=3)
+    lo, hi = slab_bounds(5001, world, rank)
+    idx, val = sm.topk(q, 16)
+    ri, rv = O.topk(O.scores(feat, q), 16)
+    ok = (isinstance(seen["slab"], np.memmap) and seen["slab"].shape == (hi - lo, 64) and not seen["slab"].flags.writeable
+          and np.array_equal(seen["slab"], feat[lo:hi]) and (sm.row_lo, sm.row_hi, sm.n_total) == (lo, hi, 5001)
+          and sm.grid_pos.shape == (5001, 3) and np.array_equal(idx, ri) and np.array_equal(val, rv))
+    out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_map_from_file_world2_gloo(tmp_path):
+    """Every rank memory-maps the saved map and hands ONLY its row slab to its local map; results carry global ids."""
+    from avlmaps_b200.utils import h5lite
+
+    feat, _ = synth.index_inputs(5001, 64, 7, seed=3)
+    path = tmp_path / "vlmaps.h5df"
+    h5lite.write_file(path, {"grid_feat": feat, "grid_pos": np.zeros((5001, 3), np.int32), "weight": np.ones(5001, np.float32)})
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_file_worker, args=(r, 2, port, str(path), out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() is True and out.get() is True
+
+
+def test_sharded_map_from_file_single_process_and_chunked_fallback(tmp_path):
+    from avlmaps_b200.utils import h5lite
+
+    feat, q = synth.index_inputs(700, 32, 3, seed=5)
+    path = tmp_path / "m.h5df"
+    h5lite.write_file(path, {"grid_feat": feat.astype(np.float64), "grid_pos": np.zeros((700, 3), np.int32)})
+    sm = ShardedMap.from_file(path, local_factory=lambda a: OracleSlab(np.asarray(a)))   # float64 storage: converted copy
+    assert sm.local.feat.dtype == np.float32 and not isinstance(sm.local.feat, np.memmap)
+    idx, val = sm.topk(q, 4)
+    ri, rv = O.topk(O.scores(feat, q), 4)
+    assert np.array_equal(idx, ri) and np.array_equal(val, rv)
+
+
 def test_slab_bounds_cover_all_rows():
     for n, w in ((10, 3), (16_777_216, 8), (5, 8), (0, 2)):
         spans = [slab_bounds(n, w, r) for r in range(w)]
