@@ -414,3 +414,33 @@ def test_batched_frames_equal_frame_by_frame(eng, n_frames):
                         rgb=rgbs[i], sample_idx=sidx[i]) for i in range(n_frames)])
     assert_build_equal(b3.export(), ref)
     b3.close()
+
+
+def test_frames_without_valid_depth_and_non_finite_depths(eng):
+    """Edge cases of `_backproject_depth`'s mask (`min_depth < z < max_depth`, vlmap_builder.py:266-281): a first
+    frame with no valid pixel at all (the map stays empty, export of zero voxels works), then frames with NaN / inf /
+    negative / too-far patches, which the mask drops."""
+    cfg, poses, depths, rgbs, feats, sidx = random_scene(4, 60, 80, 49, 65, 16, 48, 0.1, 1.6,
+                                                         [40, 0, 40, 0, 40, 30, 0, 0, 1], 1, seed=31, radius=0.3)
+    depths = [d.copy() for d in depths]
+    depths[0][:] = 0.0                                  # below min_depth everywhere
+    depths[1][:20] = np.nan
+    depths[1][20:30] = np.inf
+    depths[2][:, :30] = -1.0
+    depths[2][:, 30:40] = 50.0                          # beyond max_depth
+    depths[3][::2] = 0.0999                             # just below min_depth (float32(0.1) itself is > 0.1 and passes)
+    tfs, calib, kinv = scene_mats(cfg, poses)
+    kfeat = O.get_sim_cam_mat(49, 65)
+    b = eng.DeviceBuilder(48, 16, 0.1, 16)
+    b.add_frame(depths[0], feats[0], kinv, calib, kfeat, tfs[0], rgb=rgbs[0], sample_idx=sidx[0])
+    empty = b.export()
+    assert b.num_voxels == 0 and b.num_accepted == 0 and empty["grid_feat"].shape == (0, 16)
+    assert empty["grid_pos"].shape == (0, 3) and np.all(empty["occupied_ids"] == -1)
+    for i in range(1, 4):
+        b.add_frame(depths[i], feats[i], kinv, calib, kfeat, tfs[i], rgb=rgbs[i], sample_idx=sidx[i])
+    out = b.export()
+    ref = O.build_map(cfg, poses, depths, rgbs, feats, sidx, capacity=48 * 48 * 16)
+    assert ref["grid_feat"].shape[0] > 100              # the scene is not degenerate
+    assert_build_equal(out, ref)
+    assert b.num_accepted == ref["num_accepted"]
+    b.close()
