@@ -111,25 +111,24 @@ def load() -> C.CDLL:
     lib.avl_heat_from_mask_3d.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp, C.c_int, vp]
     lib.avl_heat2d_normalize_lift.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp, C.c_int, vp]
     lib.avl_heat_planar.argtypes = [vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, vp, C.c_int, vp]
-    if hasattr(lib, "avl_builder_create"):
-        lib.avl_builder_create.argtypes = [C.POINTER(GridSpec), C.POINTER(vp)]
-        lib.avl_builder_destroy.argtypes = [vp]
-        lib.avl_builder_add_frame.argtypes = [vp, C.POINTER(Frame), C.c_int, vp]
-        lib.avl_builder_add_frames.argtypes = [vp, C.POINTER(Frame), i32, C.c_int, vp]
-        lib.avl_builder_num_voxels.argtypes = [vp, C.POINTER(i64), vp]
-        lib.avl_builder_num_accepted.argtypes = [vp, C.POINTER(i64), vp]
-        lib.avl_builder_export.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
-        lib.avl_builder_to_map.argtypes = [vp, vp, C.POINTER(vp)]
-        lib.avl_builder_create_global.argtypes = [C.POINTER(GlobalGridSpec), C.POINTER(vp)]
-        lib.avl_builder_num_rejected_oob.argtypes = [vp, C.POINTER(i64), vp]
-        lib.avl_bounds_create.argtypes = [C.POINTER(vp)]
-        lib.avl_bounds_destroy.argtypes = [vp]
-        lib.avl_bounds_add_frame.argtypes = [vp, C.POINTER(Frame), C.c_int, vp]
-        lib.avl_bounds_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), vp]
-        lib.avl_builder_set_slab.argtypes = [vp, i32, i32]
-        lib.avl_builder_export_keys.argtypes = [vp, vp, C.c_int, vp]
-        lib.avl_rank_keys.argtypes = [vp, vp, i32, i32, vp, C.c_int, vp]
-        lib.avl_builder_import.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, vp]
+    lib.avl_builder_create.argtypes = [C.POINTER(GridSpec), C.POINTER(vp)]
+    lib.avl_builder_destroy.argtypes = [vp]
+    lib.avl_builder_add_frame.argtypes = [vp, C.POINTER(Frame), C.c_int, vp]
+    lib.avl_builder_add_frames.argtypes = [vp, C.POINTER(Frame), i32, C.c_int, vp]
+    lib.avl_builder_num_voxels.argtypes = [vp, C.POINTER(i64), vp]
+    lib.avl_builder_num_accepted.argtypes = [vp, C.POINTER(i64), vp]
+    lib.avl_builder_export.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    lib.avl_builder_to_map.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.avl_builder_create_global.argtypes = [C.POINTER(GlobalGridSpec), C.POINTER(vp)]
+    lib.avl_builder_num_rejected_oob.argtypes = [vp, C.POINTER(i64), vp]
+    lib.avl_bounds_create.argtypes = [C.POINTER(vp)]
+    lib.avl_bounds_destroy.argtypes = [vp]
+    lib.avl_bounds_add_frame.argtypes = [vp, C.POINTER(Frame), C.c_int, vp]
+    lib.avl_bounds_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), vp]
+    lib.avl_builder_set_slab.argtypes = [vp, i32, i32]
+    lib.avl_builder_export_keys.argtypes = [vp, vp, C.c_int, vp]
+    lib.avl_rank_keys.argtypes = [vp, vp, i32, i32, vp, C.c_int, vp]
+    lib.avl_builder_import.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, vp]
     _lib = lib
     return lib
 

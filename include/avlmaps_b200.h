@@ -19,6 +19,9 @@
  *     back, which is documented per call).
  *   - inputs are borrowed for the duration of the call; handles own their
  *     device memory; outputs are caller-allocated.
+ *   - threading: a handle (avl_map / avl_builder / avl_bounds) owns a per-handle
+ *     workspace and must not be used from two threads at once; different handles
+ *     may be used concurrently.  The reference is single-threaded and synchronous.
  *   - there is NO CPU implementation behind any entry point: without a
  *     CUDA device every compute call fails with AVL_ERR_CUDA.
  */
