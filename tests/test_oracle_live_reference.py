@@ -1,0 +1,105 @@
+"""The oracle against the UNMODIFIED reference executed live (oracle/ref_shim.py), on randomised scenes beyond the
+committed golden vectors.  CPU only; skipped where the reference tree does not exist (the GPU box), so nothing that
+runs there reads /root/reference.  What is pinned here and not by tests/golden: depth-mask edge cases (NaN / inf /
+negative / too-far / no valid pixel), several sampling rates and seeds, the heat function on random masks, and the
+scoring function on random shapes."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import avl_oracle as O
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (it never travels to the GPU box)")
+
+
+def _assert_same_map(out, ref):
+    for k in ("grid_pos", "occupied_ids", "weight", "grid_feat", "grid_rgb"):
+        assert np.array_equal(out[k], ref[k]), k
+
+
+@pytest.mark.parametrize("seed,rate,radius", [(41, 1, 0.3), (42, 3, 0.5), (43, 7, 0.2)])
+def test_build_oracle_equals_reference_on_random_scenes(seed, rate, radius):
+    cfg = synth.map_config(64, 0.1, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], rate)   # 64^2 rows: no capacity doubling (dtype drift)
+    poses = synth.circle_poses(3, radius=radius)
+    depths, rgbs, feats = synth.build_inputs(3, 60, 80, 49, 65, 8, seed=seed)
+    ref = ref_shim.ref_build(cfg, poses, depths, rgbs, feats, seed=seed)
+    out = O.build_map(cfg, poses, depths, rgbs, feats, ref["sample_idx"])
+    assert 50 < ref["grid_feat"].shape[0] < 64 * 64
+    _assert_same_map(out, ref)
+    # the sampling order itself: the reference's global-RNG shuffle (vlmap_builder.py:275-277)
+    np.random.seed(seed)
+    for s in ref["sample_idx"]:
+        assert np.array_equal(O.sample_order(60 * 80, rate), s)
+
+
+def test_build_oracle_equals_reference_on_depth_mask_edge_cases():
+    """`min_depth < z < max_depth` (mapping_utils.py:246-248) is strict and false for NaN; float32(0.1) is above the
+    float64 0.1 and passes; a frame without any valid pixel leaves the map empty."""
+    cfg = synth.map_config(64, 0.1, 1.6, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1)
+    poses = synth.circle_poses(4, radius=0.3)
+    depths, rgbs, feats = synth.build_inputs(4, 60, 80, 49, 65, 8, seed=31)
+    depths = [d.copy() for d in depths]
+    depths[0][:] = 0.0
+    depths[1][:20] = np.nan
+    depths[1][20:30] = np.inf
+    depths[2][:, :30] = -1.0
+    depths[2][:, 30:40] = 50.0
+    depths[3][::2] = np.float32(0.1)            # > 0.1 as a double: accepted, hundreds of points in a few cells
+    depths[3][1::4] = 0.0999
+    depths[3][3::4, :40] = 6.0                  # exactly max_depth: rejected
+    ref = ref_shim.ref_build(cfg, poses, depths, rgbs, feats, seed=5)
+    out = O.build_map(cfg, poses, depths, rgbs, feats, ref["sample_idx"])
+    assert 100 < ref["grid_feat"].shape[0] < 64 * 64
+    _assert_same_map(out, ref)
+    # two frames, neither with a valid pixel (a one-line poses.txt makes np.loadtxt return a 1-D array and the
+    # reference itself fails on it, vlmap_builder.py:64-67, so the smallest scene has two frames)
+    e_d, e_r, e_f = [depths[0], depths[0]], rgbs[:2], feats[:2]
+    only_empty = ref_shim.ref_build(cfg, poses[:2], e_d, e_r, e_f, seed=5)
+    assert only_empty["grid_feat"].shape[0] == 0 and np.all(only_empty["occupied_ids"] == -1)
+    o2 = O.build_map(cfg, poses[:2], e_d, e_r, e_f, only_empty["sample_idx"])
+    assert o2["grid_feat"].shape == (0, 8) and o2["num_accepted"] == 0
+
+
+@pytest.mark.parametrize("n,d,nq,seed", [(777, 48, 5, 1), (2048, 512, 33, 2), (129, 1024, 2, 3)])
+def test_scores_and_mask_equal_reference_on_random_shapes(n, d, nq, seed):
+    feat, q = synth.index_inputs(n, d, nq, seed)
+    ref = ref_shim.ref_get_lseg_score(feat, q)                       # the reference's float32 `@`
+    s = O.scores(feat, q)
+    floor = (np.linalg.norm(feat, axis=1)[:, None] * np.linalg.norm(q, axis=1)[None, :]) / np.sqrt(d)
+    assert ref.dtype == np.float32 and np.all(np.abs(s - ref) <= 1e-3 * np.maximum(np.abs(ref), floor))
+    assert np.array_equal(O.argmax(s), np.argmax(ref, axis=1))
+    for c in range(min(nq, 3)):
+        assert np.array_equal(O.index_mask(s, c), ref_shim.ref_index_mask(ref, c))
+    assert np.array_equal(O.ref_scores_fp32(feat, q), ref)           # the literal restatement: same bits
+
+
+@pytest.mark.parametrize("seed,frac,decay", [(0, 0.02, 0.1), (1, 0.3, 0.01), (2, 0.002, 0.05)])
+def test_heat_equals_reference_on_random_masks(seed, frac, decay):
+    rng = np.random.default_rng(seed)
+    pos = np.unique(rng.integers(0, 30, (500, 3)).astype(np.int32), axis=0)
+    mask = rng.random(pos.shape[0]) < frac
+    mask[int(rng.integers(0, pos.shape[0]))] = True                 # the reference's argmin needs one target
+    ref = ref_shim.ref_heatmap_from_mask_3d(pos, mask, cell_size=0.05, decay_rate=decay)
+    out = O.heatmap_from_mask_3d(pos, mask, 0.05, decay)
+    assert np.array_equal(out, ref) and out.dtype == ref.dtype
+
+
+@pytest.mark.parametrize("seed,rate,skip,n_frames", [(11, 1, 1, 3), (12, 3, 2, 6)])
+def test_multi_floor_oracle_equals_reference_on_random_scenes(seed, rate, skip, n_frames):
+    """VLMapBuilderMultiFloor.create_global_map (vlmap_builder_multi_floor.py:60-199) run live: both passes, uint16-mm
+    depth, np.round cells, numpy negative-index wrap."""
+    k10 = [40, 0, 32, 0, 40, 24, 0, 0, 1]
+    cfg = synth.multi_floor_config(0.05, k10, rate, skip_frame=skip)
+    poses = synth.global_cam_poses(n_frames)
+    depths, rgbs, feats = synth.multi_floor_inputs(n_frames, 48, 64, 39, 52, 6, seed=seed)
+    try:
+        ref = ref_shim.ref_build_multi_floor(cfg, poses, depths, rgbs, feats, seed=seed)
+    except IndexError:
+        pytest.skip("the reference itself raises IndexError on this random scene (height >= n_height)")
+    assert ref["used_frames"] == list(range(0, n_frames, skip))      # the oracle applies skip_frame itself
+    out = O.build_map_multi_floor(cfg, poses, depths, rgbs, feats, ref["sample_idx_pass1"], ref["sample_idx_pass2"])
+    assert np.array_equal(out["pcd_min"], ref["pcd_min"]) and np.array_equal(out["pcd_max"], ref["pcd_max"])
+    _assert_same_map(out, ref)
