@@ -23,8 +23,8 @@ def load_callable(spec: Optional[str]) -> Optional[Callable]:
     return obj
 
 
-def base_parser(prog: str, config_name: str) -> argparse.ArgumentParser:
-    ap = argparse.ArgumentParser(prog=prog, description=__doc__)
+def base_parser(prog: str, config_name: str, description: str = "") -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog=prog, description=description, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--config-dir", default=os.environ.get("AVL_CONFIG_DIR", "config"),
                     help="the reference's config/ directory (default: $AVL_CONFIG_DIR or ./config)")
     ap.add_argument("--config-name", default=config_name)

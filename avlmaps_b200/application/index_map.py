@@ -33,7 +33,7 @@ def _report(avlmap: AVLMap, name: str, heat: np.ndarray, out_dir: Optional[Path]
 
 
 def main(argv: Optional[List[str]] = None, input_fn=input) -> int:
-    ap = base_parser("avlmaps_b200.application.index_map", "map_indexing_cfg.yaml")
+    ap = base_parser("avlmaps_b200.application.index_map", "map_indexing_cfg.yaml", __doc__)
     ap.add_argument("--object", action="append", default=[], help="object name to index (repeatable); none = prompt loop")
     ap.add_argument("--text-encoder", default=None, help="module:function, list[str] -> (len, D) array")
     ap.add_argument("--clip-dim", type=int, default=512)
