@@ -203,3 +203,35 @@ def test_index_map_application_flow(tmp_path, monkeypatch, capsys):
     a = FakeAVLMap.last
     assert rc == 0 and a.calls == [("chair", 0.05)] and a.vlmap.clip_inited
     assert "needs the reference's SoundMap" in capsys.readouterr().out
+
+
+def test_generate_obstacle_map_application_flow(tmp_path, monkeypatch, capsys):
+    """generate_obstacle_map.py:19-33 -> Map.create / load_map / generate_obstacle_map on a map file written here
+    (the device upload of load_map is stubbed: no GPU in this suite)."""
+    import avlmaps_b200.map.vlmap as vlmap_mod
+    from avlmaps_b200.application import generate_obstacle_map
+    from avlmaps_b200.utils import mapping_utils
+
+    root = write_tree(tmp_path / "config")
+    scene = tmp_path / "data" / "vlmaps_dataset" / "scene0"
+    (scene / "vlmap").mkdir(parents=True)
+    gs, vh = 1000, 30
+    occ = -np.ones((gs, gs, vh), np.int32)
+    occ[500:510, 400:420, 3] = np.arange(200, dtype=np.int32).reshape(10, 20) + 1
+    occ[505, 405, 3] = 0                      # voxel id 0 counts as free (map.py:93 tests `> 0`)
+    occ[600, 600, 0] = 7                      # height 0 is outside (h_min, h_max): ignored
+    pos = np.argwhere(occ >= 0).astype(np.int32)
+    mapping_utils.save_3d_map(scene / "vlmap" / "vlmaps.h5df", np.zeros((pos.shape[0], 4), np.float32), pos,
+                              np.ones(pos.shape[0], np.float32), occ, [0], np.zeros((pos.shape[0], 3), np.uint8))
+    monkeypatch.setattr(vlmap_mod, "DeviceMap", lambda feat, operand="f16": None)
+    out = tmp_path / "obs"
+    rc = generate_obstacle_map.main(["--config-dir", str(root), "--config-name", "main.yaml", "--out", str(out),
+                                     f"data_paths.avlmaps_data_dir={tmp_path / 'data'}"])
+    assert rc == 0
+    obs = np.load(out / "obstacles.npy")
+    assert obs.shape == (10, 20) and obs.dtype == bool and int((obs == 0).sum()) == 199 and obs[5, 5]
+    assert (out / "obstacles.png").exists()
+    assert "rows 500..509, cols 400..419, 199 occupied cells" in capsys.readouterr().out
+    with pytest.raises(SystemExit, match="not a directory"):
+        generate_obstacle_map.main(["--config-dir", str(root), "--config-name", "main", "--dataset-dir-name", "nope",
+                                    f"data_paths.avlmaps_data_dir={tmp_path / 'data'}"])
