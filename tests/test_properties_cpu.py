@@ -65,3 +65,62 @@ def test_closed_form_fusion_matches_sequential_update(n_obs, d, seed):
         w = np.float32(np.float64(w) + a[i])
     closed = (a[0] ** 2 * f[0].astype(np.float64) + (a[1:, None] * f[1:].astype(np.float64)).sum(0)) / a.sum()
     assert np.allclose(g, closed, rtol=2e-4, atol=1e-6) and np.isclose(w, a.sum(), rtol=1e-5)
+
+
+_DTYPES = ["<f4", "<f8", "<f2", "<i4", "<i8", "<u1", "<u2", ">i4", ">f8", "<i1", "<u8"]
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from(_DTYPES), st.lists(st.integers(0, 7), min_size=0, max_size=3)), min_size=1, max_size=9),
+       st.integers(0, 2 ** 31 - 1))
+def test_h5lite_roundtrip_of_arbitrary_datasets(specs, seed):
+    """Any set of numeric datasets -- scalars, empty dimensions, either byte order -- comes back with the same bytes,
+    shape and dtype; names are found whatever their sort order in the symbol table."""
+    import tempfile
+    from pathlib import Path
+
+    from avlmaps_b200.utils import h5lite
+
+    rng = np.random.default_rng(seed)
+    data = {}
+    for i, (dt, shape) in enumerate(specs):
+        a = (rng.standard_normal(shape) * 100).astype(np.dtype(dt)) if np.dtype(dt).kind == "f" else \
+            rng.integers(0, 100, shape).astype(np.dtype(dt))
+        data[f"{'zyxab'[i % 5]}_{i}_{'grid_feat' if i % 2 else 'w'}"] = a
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "m.h5df"
+        h5lite.write_file(p, data)
+        with h5lite.File(p) as f:
+            assert sorted(f.keys()) == sorted(data)
+            for k, v in data.items():
+                got = f[k].read()
+                assert got.shape == v.shape and got.dtype == v.dtype and got.tobytes() == v.tobytes(), k
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.dictionaries(st.sampled_from(["a", "b", "c", "d"]), st.one_of(st.integers(-5, 5), st.booleans(), st.floats(-2, 2, allow_nan=False),
+                                                                        st.sampled_from(["x", "y z", ""])), min_size=1),
+       st.sampled_from(["a", "b", "c", "d"]))
+def test_config_interpolation_returns_the_target_value_and_type(values, ref_key):
+    """`${group.key}` as a whole value yields the referenced value with its type; embedded in text it is formatted."""
+    import tempfile
+    from pathlib import Path
+
+    import yaml
+
+    from avlmaps_b200.config import ConfigError, compose
+
+    with tempfile.TemporaryDirectory() as td:
+        root = Path(td)
+        (root / "g").mkdir()
+        (root / "g" / "v.yaml").write_text(yaml.safe_dump(values))
+        (root / "main.yaml").write_text("defaults:\n  - g: v\n  - _self_\nwhole: ${g." + ref_key + "}\ntext: \"<${g." + ref_key + "}>\"\n")
+        if ref_key not in values:
+            try:
+                compose(root, "main")
+                raise AssertionError("a dangling interpolation must fail at compose time")
+            except ConfigError:
+                return
+        c = compose(root, "main")
+        assert c.whole == values[ref_key] and type(c.whole) is type(values[ref_key])
+        assert c.text == f"<{values[ref_key]}>"
