@@ -6,7 +6,12 @@ TAG=${1:-r1c}
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 python __graft_entry__.py smoke 2>&1 | tail -1
 python bench.py --steps 200 --warmup 5 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; tail -c 300 gpurun_out/${TAG}_bench_n1.err
-python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_reference_arm.json 2>&1
+python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_reference_arm.json 2>&1
+# sanitizers on tiny shapes (every kernel family; results still checked against the oracle)
+for tool in memcheck racecheck synccheck; do
+  timeout 600 compute-sanitizer --tool $tool --log-file gpurun_out/${TAG}_${tool}.log python tools/sanitize_small.py > gpurun_out/${TAG}_${tool}.out 2>&1
+  echo "$tool: $(tail -n 1 gpurun_out/${TAG}_${tool}.log)"
+done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_build.csv python tools/perf_build.py > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches_fuse.csv python tools/perf_fuse.py > /dev/null 2>&1
