@@ -35,6 +35,8 @@ EXPORTS = [
     "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
     "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
     "avl_heat_planar", "avl_heat2d_normalize_lift",
+    "avl_p2p_create", "avl_p2p_handle_bytes", "avl_p2p_local_handle", "avl_p2p_connect", "avl_p2p_exchange_merge",
+    "avl_p2p_status", "avl_p2p_destroy",
 ]
 
 
@@ -129,6 +131,13 @@ def load() -> C.CDLL:
     lib.avl_builder_export_keys.argtypes = [vp, vp, C.c_int, vp]
     lib.avl_rank_keys.argtypes = [vp, vp, i32, i32, vp, C.c_int, vp]
     lib.avl_builder_import.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, vp]
+    lib.avl_p2p_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+    lib.avl_p2p_handle_bytes.argtypes = []
+    lib.avl_p2p_local_handle.argtypes = [vp, vp]
+    lib.avl_p2p_connect.argtypes = [vp, vp]
+    lib.avl_p2p_exchange_merge.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.c_int, vp]
+    lib.avl_p2p_status.argtypes = [vp, C.POINTER(i32), vp]
+    lib.avl_p2p_destroy.argtypes = [vp]
     _lib = lib
     return lib
 

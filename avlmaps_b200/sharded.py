@@ -6,6 +6,7 @@ locally.  The per-voxel argmax needs no exchange at all (
 torch.distributed is plumbing only; scoring runs in the C-ABI library."""
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -67,6 +68,7 @@ class ShardedMap:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._p2p = None
 
     @classmethod
     def from_file(cls, map_path, group=None, local_factory=None, operand: str = "bf16") -> "ShardedMap":
@@ -120,6 +122,13 @@ class ShardedMap:
                 ti.copy_(torch.where(ti >= 0, gid[ti.clamp(min=0)], ti))
             elif self.row_offset:
                 ti += (ti >= 0) * self.row_offset
+            if os.environ.get("AVL_P2P_EXCHANGE", "0") == "1" and k * self.world <= 1024:
+                # opt-in: exchange + merge fused in one kernel over NVLink peer memory (csrc/p2p_exchange.cu)
+                if self._p2p is None:
+                    from .engine import P2PExchange
+
+                    self._p2p = P2PExchange(self.group)
+                return self._p2p.exchange_merge(ti, tv)
             gathered = torch.empty((self.world, nb_i + nb_v), dtype=torch.uint8, device=queries.device)
             dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)   # the one collective
             gi = gathered[:, :nb_i].contiguous().view(torch.int64).view(self.world, nq, k)

@@ -44,6 +44,10 @@ def test_argument_errors_need_no_device():
     assert lib.avl_map_create(L.np_ptr(feat), 4, 0, 0, None, C.byref(out)) == 2
     assert b"dim" in lib.avl_last_error()
     assert lib.avl_builder_create(None, C.byref(out)) == 2
+    # the peer-memory exchange: shape checks come before any CUDA call
+    assert lib.avl_p2p_create(0, 0, 256, 16, C.byref(out)) == 2 and lib.avl_p2p_create(3, 2, 256, 16, C.byref(out)) == 2
+    assert lib.avl_p2p_create(0, 16, 256, 128, C.byref(out)) == 2 and b"1024" in lib.avl_last_error()
+    assert lib.avl_p2p_handle_bytes() == 64 and lib.avl_p2p_destroy(None) == 0
 
 
 def test_no_cpu_fallback_without_device():
@@ -55,6 +59,8 @@ def test_no_cpu_fallback_without_device():
         DeviceMap(np.zeros((4, 8), np.float32))
     with pytest.raises(L.AvlError):
         DeviceBuilder(8, 4, 0.05, 8)
+    out = C.c_void_p()
+    assert L.load().avl_p2p_create(0, 1, 256, 16, C.byref(out)) == 1 and not out.value      # AVL_ERR_CUDA, no handle
 
 
 def test_product_never_imports_oracle():
