@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "avl_internal.h"
 
 namespace avl {
@@ -563,6 +565,61 @@ chw_to_hwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int32_
   }
 }
 
+// Same transposition for fp16 features (AVL_FEAT_F16): (D, P) __half -> (P, D) float.  LSeg emits
+// `logit_scale * normalize(feat).half()` (lseg_net.py:318-321), so the fp32 array get_lseg_feat hands over holds
+// fp16-exact values: taking the halves directly halves the hand-off bytes (PCIe or HBM) and changes no result.
+__global__ void __launch_bounds__(256)
+chw16_to_hwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int32_t d, int64_t p) {
+  __shared__ float tile[64][65];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int c0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+  const bool vec_in = (p & 3) == 0, vec_out = (d & 3) == 0;
+  {
+    const int q4 = (t & 15) * 4, r0 = t >> 4;
+#pragma unroll
+    for (int rr = 0; rr < 64; rr += 16) {
+      const int c = c0 + r0 + rr;
+      const int64_t pp = p0 + q4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        const __half* s = src + static_cast<int64_t>(c) * p + pp;
+        if (vec_in && pp + 3 < p) {  // 4 halves = one 8-byte load (c * p + pp is a multiple of 4)
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(s));
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          v = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          if (pp < p) v.x = __half2float(s[0]);
+          if (pp + 1 < p) v.y = __half2float(s[1]);
+          if (pp + 2 < p) v.z = __half2float(s[2]);
+          if (pp + 3 < p) v.w = __half2float(s[3]);
+        }
+      }
+      tile[r0 + rr][q4] = v.x; tile[r0 + rr][q4 + 1] = v.y; tile[r0 + rr][q4 + 2] = v.z; tile[r0 + rr][q4 + 3] = v.w;
+    }
+  }
+  __syncthreads();
+  {
+    const int c4 = (t & 15) * 4, r0 = t >> 4;
+#pragma unroll
+    for (int rr = 0; rr < 64; rr += 16) {
+      const int64_t pp = p0 + r0 + rr;
+      const int c = c0 + c4;
+      if (pp >= p) continue;
+      const float4 v = make_float4(tile[c4][r0 + rr], tile[c4 + 1][r0 + rr], tile[c4 + 2][r0 + rr], tile[c4 + 3][r0 + rr]);
+      float* o = dst + pp * d + c;
+      if (vec_out && c + 3 < d) *reinterpret_cast<float4*>(o) = v;
+      else {
+        if (c < d) o[0] = v.x;
+        if (c + 1 < d) o[1] = v.y;
+        if (c + 2 < d) o[2] = v.z;
+        if (c + 3 < d) o[3] = v.w;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- scatter-reduce
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -948,6 +1005,11 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   AVL_ARG(f->h >= 1 && f->w >= 1 && f->fh >= 1 && f->fw >= 1, "invalid frame shape");
   AVL_ARG(static_cast<int64_t>(f->h) * f->w < (int64_t(1) << 31), "frame too large");
   AVL_ARG(f->feat_layout == AVL_FEAT_CHW || f->feat_layout == AVL_FEAT_HWC, "unknown feat_layout");
+  const bool feat_f16 = (flags & AVL_FEAT_F16) != 0;
+  if (feat_f16 && f->feat_layout != AVL_FEAT_CHW) {
+    set_error("AVL_FEAT_F16 features are accepted in the AVL_FEAT_CHW layout only");
+    return AVL_ERR_UNSUPPORTED;
+  }
   const int64_t npix = static_cast<int64_t>(f->h) * f->w;
   const int32_t n_samples = f->sample_idx ? f->n_samples : static_cast<int32_t>(npix);
   AVL_ARG(n_samples >= 0 && n_samples <= npix, "n_samples out of range");
@@ -966,7 +1028,8 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
     if ((rc = grow(&b->d_depth, &b->depth_elems, static_cast<size_t>(npix)))) return rc;
     if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
     AVL_CUDA(cudaMemcpyAsync(b->d_depth, f->depth, depth_bytes, cudaMemcpyHostToDevice, s));
-    AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * sizeof(float), cudaMemcpyHostToDevice, s));
+    AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float)),
+                             cudaMemcpyHostToDevice, s));
     depth = b->d_depth;
     feat = b->d_feat;
     if (f->rgb) {
@@ -988,7 +1051,10 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   if (f->feat_layout == AVL_FEAT_CHW) {  // (1, D, FH, FW) -> pixel-major rows for the coalesced gather
     if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, fpix * d))) return rc;
     dim3 grid(static_cast<unsigned>((fpix + 63) / 64), static_cast<unsigned>((d + 63) / 64));
-    chw_to_hwc_kernel<<<grid, 256, 0, s>>>(feat, b->d_feat_t, d, static_cast<int64_t>(fpix));
+    if (feat_f16)
+      chw16_to_hwc_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(feat), b->d_feat_t, d, static_cast<int64_t>(fpix));
+    else
+      chw_to_hwc_kernel<<<grid, 256, 0, s>>>(feat, b->d_feat_t, d, static_cast<int64_t>(fpix));
     AVL_CUDA(cudaGetLastError());
     feat = b->d_feat_t;
   }
@@ -1006,7 +1072,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
 int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_frames, int flags, void* stream) {
   AVL_ARG(b != nullptr && (frames != nullptr || n_frames == 0), "NULL argument");
   AVL_ARG(n_frames >= 0, "n_frames < 0");
-  bool batchable = (flags & AVL_ON_DEVICE) != 0;
+  bool batchable = (flags & AVL_ON_DEVICE) != 0 && !(flags & AVL_FEAT_F16);  // fp16 features: transposed per frame
   for (int i = 0; i < n_frames && batchable; ++i) batchable = frames[i].feat_layout == AVL_FEAT_HWC;
   if (!batchable) {  // host pointers (staged per frame) or channel-major features (transposed per frame): one by one
     for (int i = 0; i < n_frames; ++i) {

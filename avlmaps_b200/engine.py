@@ -46,7 +46,7 @@ class _Arg:
             import torch
 
             want = {np.float32: torch.float32, np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8,
-                    np.uint16: torch.uint16, np.uint64: torch.uint64}[dtype]
+                    np.uint16: torch.uint16, np.uint64: torch.uint64, np.float16: torch.float16}[dtype]
             if x.dtype != want or not x.is_contiguous():
                 x = x.to(want).contiguous()
             if not x.is_cuda:
@@ -405,11 +405,25 @@ def _is_u16(x) -> bool:
     return np.asarray(x).dtype == np.uint16
 
 
+def _is_f16(x) -> bool:
+    """float16 features are handed over as they are (AVL_FEAT_F16): LSeg's output is fp16-exact (lseg_net.py:318-321)."""
+    if x is None:
+        return False
+    if _is_torch(x):
+        import torch
+
+        return x.dtype == torch.float16
+    return getattr(x, "dtype", None) == np.float16
+
+
 def _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, min_depth, max_depth, dim=None):
     """Build the avl_frame struct; returns (frame, flags, keep-alive args)."""
     u16 = _is_u16(depth)
+    f16 = _is_f16(feat)
+    if f16 and feat_layout != L.FEAT_CHW:
+        raise ValueError("float16 features are accepted in the CHW layout only (cast to float32 for HWC)")
     d_ = _Arg(depth, np.uint16 if u16 else np.float32, "depth")
-    f_ = _Arg(feat, np.float32, "feat")
+    f_ = _Arg(feat, np.float16 if f16 else np.float32, "feat")
     r_ = _Arg(rgb, np.uint8, "rgb")
     s_ = _Arg(sample_idx, np.int32, "sample_idx")
     if len(d_.shape) != 2:
@@ -448,7 +462,7 @@ def _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, m
             raise ValueError(f"{name} must have {n} elements")
         C.memmove(base + _FRAME_OFFSETS[name], arr.tobytes(), n * 8)  # per-frame call: keep the Python cost down
     fr.min_depth, fr.max_depth = float(min_depth), float(max_depth)
-    flags = _flags(d_, f_, r_, s_) | (L.AVL_DEPTH_U16_MM if u16 else 0)
+    flags = _flags(d_, f_, r_, s_) | (L.AVL_DEPTH_U16_MM if u16 else 0) | (L.AVL_FEAT_F16 if f16 else 0)
     return fr, flags, (d_, f_, r_, s_)
 
 
