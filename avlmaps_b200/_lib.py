@@ -136,7 +136,7 @@ def load() -> C.CDLL:
     lib.avl_p2p_handle_bytes.argtypes = []
     lib.avl_p2p_local_handle.argtypes = [vp, vp]
     lib.avl_p2p_connect.argtypes = [vp, vp]
-    lib.avl_p2p_exchange_merge.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.c_int, vp]
+    lib.avl_p2p_exchange_merge.argtypes = [vp, vp, vp, i32, i32, i64, vp, vp, C.c_int, vp]
     lib.avl_p2p_status.argtypes = [vp, C.POINTER(i32), vp]
     lib.avl_p2p_destroy.argtypes = [vp]
     _lib = lib

@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 __global__ void __launch_bounds__(128)
 p2p_exchange_merge_kernel(const __grid_constant__ P2PView v, const int64_t* __restrict__ idx,
-                          const float* __restrict__ val, int32_t nq, int32_t k, uint32_t epoch,
+                          const float* __restrict__ val, int32_t nq, int32_t k, uint32_t epoch, int64_t row_offset,
                           int64_t* __restrict__ out_idx, float* __restrict__ out_val, uint32_t* __restrict__ status) {
   __shared__ int64_t si[1024];
   __shared__ float sv[1024];
@@ -54,7 +54,8 @@ p2p_exchange_merge_kernel(const __grid_constant__ P2PView v, const int64_t* __re
   for (int e = threadIdx.x; e < v.world * k; e += blockDim.x) {
     const int dst = e / k, j = e - dst * k;
     uint8_t* slot = v.peer[dst] + (static_cast<uint64_t>(parity) * v.world + v.rank) * v.slot_bytes;
-    reinterpret_cast<int64_t*>(slot)[static_cast<size_t>(q) * k + j] = idx[static_cast<size_t>(q) * k + j];
+    const int64_t id = idx[static_cast<size_t>(q) * k + j];   // slab-local row -> global row (empty slots stay -1)
+    reinterpret_cast<int64_t*>(slot)[static_cast<size_t>(q) * k + j] = id >= 0 ? id + row_offset : id;
     reinterpret_cast<float*>(slot + ids_bytes)[static_cast<size_t>(q) * k + j] = val[static_cast<size_t>(q) * k + j];
   }
   __threadfence_system();
@@ -182,8 +183,8 @@ int avl_p2p_connect(avl_p2p* p, const uint8_t* handles) {
   return AVL_OK;
 }
 
-int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int32_t nq, int32_t k, int64_t* out_idx,
-                           float* out_val, int flags, void* stream) {
+int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int32_t nq, int32_t k, int64_t row_offset,
+                           int64_t* out_idx, float* out_val, int flags, void* stream) {
   AVL_ARG(p != nullptr && idx && val && out_idx && out_val, "NULL argument");
   AVL_ARG(nq >= 1 && nq <= p->view.nq_max && k >= 1 && k <= p->view.k_max, "nq / k exceed what the exchange was created for");
   if (!(flags & AVL_ON_DEVICE)) {
@@ -195,8 +196,8 @@ int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int
     return AVL_ERR_STATE;
   }
   p->epoch += 1;
-  p2p_exchange_merge_kernel<<<nq, 128, 0, static_cast<cudaStream_t>(stream)>>>(p->view, idx, val, nq, k, p->epoch, out_idx,
-                                                                              out_val, p->status);
+  p2p_exchange_merge_kernel<<<nq, 128, 0, static_cast<cudaStream_t>(stream)>>>(p->view, idx, val, nq, k, p->epoch, row_offset,
+                                                                              out_idx, out_val, p->status);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

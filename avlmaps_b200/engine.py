@@ -243,9 +243,10 @@ class P2PExchange:
             L.check(self._lib.avl_p2p_connect(self._h, buf))
             dist.barrier(group=group)   # nobody stores into a peer before every peer has mapped every buffer
 
-    def exchange_merge(self, idx, val, stream=None):
-        """idx (nq, k) int64 GLOBAL row ids (-1 = empty), val (nq, k) float32, both torch.cuda tensors of this rank's
-        slab -> (idx, val) of the global top-k, identical on every rank.  Enqueues one kernel, no synchronisation."""
+    def exchange_merge(self, idx, val, row_offset: int = 0, stream=None):
+        """idx (nq, k) int64 row ids (-1 = empty; `row_offset` is added to the others, making slab-local rows global),
+        val (nq, k) float32, both torch.cuda tensors of this rank's slab -> (idx, val) of the global top-k, identical on
+        every rank.  Enqueues one kernel, no synchronisation."""
         import torch
 
         nq, k = idx.shape
@@ -254,7 +255,7 @@ class P2PExchange:
         out_v = torch.empty((nq, k), dtype=torch.float32, device=idx.device)
         sp = _stream_ptr(stream) if stream is not None else _current_torch_stream()
         L.check(self._lib.avl_p2p_exchange_merge(self._h, C.c_void_p(idx.data_ptr()), C.c_void_p(val.data_ptr()), nq, k,
-                                                 C.c_void_p(out_i.data_ptr()), C.c_void_p(out_v.data_ptr()),
+                                                 int(row_offset), C.c_void_p(out_i.data_ptr()), C.c_void_p(out_v.data_ptr()),
                                                  L.AVL_ON_DEVICE, sp))
         return out_i, out_v
 

@@ -116,19 +116,21 @@ class ShardedMap:
             ti = mine[:nb_i].view(torch.int64).view(nq, k)
             tv = mine[nb_i:].view(torch.float32).view(nq, k)
             self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv))
+            # opt-in: exchange + merge fused in one kernel over NVLink peer memory (csrc/p2p_exchange.cu)
+            use_p2p = os.environ.get("AVL_P2P_EXCHANGE", "0") == "1" and k * self.world <= 1024
             if self.global_ids is not None:
                 gid = self.global_ids if torch.is_tensor(self.global_ids) else torch.from_numpy(np.asarray(self.global_ids))
                 self.global_ids = gid = gid.to(queries.device)
                 ti.copy_(torch.where(ti >= 0, gid[ti.clamp(min=0)], ti))
-            elif self.row_offset:
+            elif self.row_offset and not use_p2p:
                 ti += (ti >= 0) * self.row_offset
-            if os.environ.get("AVL_P2P_EXCHANGE", "0") == "1" and k * self.world <= 1024:
-                # opt-in: exchange + merge fused in one kernel over NVLink peer memory (csrc/p2p_exchange.cu)
+            if use_p2p:
                 if self._p2p is None:
                     from .engine import P2PExchange
 
                     self._p2p = P2PExchange(self.group)
-                return self._p2p.exchange_merge(ti, tv)
+                # the kernel adds the slab's row offset itself (ids from a slab-sharded build are global already)
+                return self._p2p.exchange_merge(ti, tv, row_offset=0 if self.global_ids is not None else self.row_offset)
             gathered = torch.empty((self.world, nb_i + nb_v), dtype=torch.uint8, device=queries.device)
             dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)   # the one collective
             gi = gathered[:, :nb_i].contiguous().view(torch.int64).view(self.world, nq, k)

@@ -301,8 +301,8 @@ int avl_rank_keys(const uint64_t* keys_all, const int64_t* offsets, int32_t n_sh
  * One object per rank (one process per GPU).  Every rank creates it, publishes the CUDA-IPC handle of its receive
  * buffer (avl_p2p_local_handle, avl_p2p_handle_bytes() bytes), gathers the handles of all ranks through any host
  * channel (torch.distributed.all_gather_object in avlmaps_b200/sharded.py) and maps them (avl_p2p_connect).
- * avl_p2p_exchange_merge then takes this slab's (nq, k) result with GLOBAL row ids (device pointers, as
- * avl_sim_topk left it in HBM), stores it into every peer's buffer with plain peer stores, and merges what the peers
+ * avl_p2p_exchange_merge then takes this slab's (nq, k) result (device pointers, as avl_sim_topk left it in HBM;
+ * ids are made global by adding row_offset, or are global already with row_offset = 0), stores it into every peer's buffer with plain peer stores, and merges what the peers
  * delivered -- ONE kernel per query batch, no host round trip, no NCCL call; every rank must call it for every
  * batch with the same nq and k.  out_idx / out_val (nq, k): the global top-k, (score desc, row asc), on every rank.
  * A peer that never delivers trips a ~2 s watchdog instead of hanging the GPU (avl_p2p_status: source rank or -1).
@@ -314,6 +314,7 @@ int avl_p2p_handle_bytes(void);
 int avl_p2p_local_handle(avl_p2p* p, uint8_t* handle);
 int avl_p2p_connect(avl_p2p* p, const uint8_t* handles /* world * avl_p2p_handle_bytes() */);
 int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int32_t nq, int32_t k,
+                           int64_t row_offset /* added to every id >= 0: slab-local -> global rows */,
                            int64_t* out_idx, float* out_val, int flags, void* stream);
 int avl_p2p_status(avl_p2p* p, int32_t* timed_out_source, void* stream);
 int avl_p2p_destroy(avl_p2p* p);

@@ -70,8 +70,10 @@ def test_p2p_exchange_with_a_world_of_one(lib):
         val = rng.integers(0, 6, (nq, k)).astype(np.float32)          # many ties
         idx[:, k // 2:] = np.where(rng.random((nq, k - k // 2)) < 0.3, -1, idx[:, k // 2:])
         val[idx < 0] = -np.inf
-        oi, ov = ex.exchange_merge(torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda())
+        off = 1_000_000 * nq                                           # slab-local rows -> global rows inside the kernel
+        oi, ov = ex.exchange_merge(torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda(), row_offset=off)
         oi, ov = oi.cpu().numpy(), ov.cpu().numpy()
+        idx = np.where(idx >= 0, idx + off, idx)
         assert ex.timed_out_source() == -1
         for q in range(nq):
             keep = idx[q] >= 0
