@@ -94,7 +94,17 @@ class AVLMap:
         Python loop over np.where(occupied_ids != -1) is a gather through grid_pos."""
         return heat2d_normalize_lift(np.asarray(heatmap_2d), self.vlmap.grid_pos, normalize=False)[1]
 
+    def _ensure_dataloader(self):
+        """The reference builds its pose converter in load_map (avlmap.py:54); here it is made on first use, so that
+        maps without a poses.txt (or with an attached converter) keep working."""
+        if self.dataloader is None:
+            from ..dataloader import VLMapsDataloaderHabitat
+
+            self.dataloader = VLMapsDataloaderHabitat(self.vlmap.data_dir, cfg_get(self.config, "map_config"), self.vlmap)
+        return self.dataloader
+
     def index_area_2d(self, area_name: str, decay_rate: float = 0.1) -> np.ndarray:
+        self._ensure_dataloader()
         scores = self.area_map.index_map(area_name, with_init_cat=False)
         scores = (scores - np.min(scores)) / (np.max(scores) - np.min(scores))          # avlmap.py:81
         shape = self.vlmap.occupied_ids.shape[:2]
@@ -109,6 +119,7 @@ class AVLMap:
         return self.lift_heat_2d_to_3d(self.index_area_2d(area_name, decay_rate))
 
     def index_sound_2d(self, sound_name: str, decay_rate: float = 0.01) -> np.ndarray:
+        self._ensure_dataloader()
         probabilities, locations_list = self.sound_map.get_distribution_and_locations(sound_name)
         shape = self.vlmap.occupied_ids.shape[:2]
         segs = []
@@ -131,6 +142,7 @@ class AVLMap:
     def index_image(self, image: np.ndarray, query_cam_intrinsics: np.ndarray = None, decay_rate: float = 0.01) -> np.ndarray:
         """Reference avlmap.py:146-163.  `visual_map.localize_image` (HLoc: NetVLAD + SuperPoint/SuperGlue + PnP) is
         outside this engine -- attach the reference's VisualMap; the per-voxel heat runs on the device."""
+        self._ensure_dataloader()
         _, query_base_tf = self.visual_map.localize_image(image, query_cam_intrinsic_mat=query_cam_intrinsics)
         self.dataloader.from_habitat_tf(query_base_tf)
         row, col, _ = self.dataloader.to_full_map_pose()

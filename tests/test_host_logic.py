@@ -202,3 +202,36 @@ def test_ctypes_structs_match_the_header(tmp_path):
         cls = mirrors[name]
         assert C.sizeof(cls) == int(size), name
         assert [getattr(cls, f).offset for f, _ in cls._fields_] == [int(o) for o in offs], name
+
+
+def test_avlmap_builds_its_pose_converter_on_first_use(tmp_path):
+    """AVLMap.load_map creates a VLMapsDataloaderHabitat in the reference (avlmap.py:54); here it appears when a
+    modality first needs it, unless the caller attached one.  The round trip pose -> cell -> pose stays within a cell."""
+    import synth
+    from avlmaps_b200.dataloader import VLMapsDataloaderHabitat
+    from avlmaps_b200.map import AVLMap
+    from avlmaps_b200.utils.mapping_utils import cvt_pose_vec2tf
+
+    map_config = synth.map_config(100, 0.05, 1.5, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1)
+    map_config["map_type"] = "vlmap"
+    poses = synth.circle_poses(5, radius=1.0)
+    np.savetxt(tmp_path / "poses.txt", poses)
+    av = AVLMap({"map_config": map_config, "params": {"cs": 0.05}}, data_dir=str(tmp_path))
+    occ = -np.ones((100, 100, 30), np.int32)
+    occ[20:80, 30:70, 4] = 5
+    av.vlmap.occupied_ids = occ
+    assert av.dataloader is None
+    dl = av._ensure_dataloader()
+    assert isinstance(dl, VLMapsDataloaderHabitat) and av._ensure_dataloader() is dl
+    assert (dl.rmin, dl.rmax, dl.cmin, dl.cmax) == (20, 79, 30, 69)
+    dl.from_habitat_tf(cvt_pose_vec2tf(poses[0]))
+    assert dl.to_full_map_pose()[:2] == [50, 50]                 # the first pose is the map origin = the grid centre
+    for p in poses:
+        tf = cvt_pose_vec2tf(p)
+        dl.from_habitat_tf(tf)
+        back = dl.to_habitat_tf()
+        assert np.linalg.norm(back[:3, 3] - tf[:3, 3]) < 0.05 * 2 ** 0.5 + 1e-9
+    sentinel = object()
+    av2 = AVLMap({"map_config": map_config, "params": {"cs": 0.05}})
+    av2.dataloader = sentinel
+    assert av2._ensure_dataloader() is sentinel

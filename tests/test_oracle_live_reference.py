@@ -103,3 +103,53 @@ def test_multi_floor_oracle_equals_reference_on_random_scenes(seed, rate, skip, 
     out = O.build_map_multi_floor(cfg, poses, depths, rgbs, feats, ref["sample_idx_pass1"], ref["sample_idx_pass2"])
     assert np.array_equal(out["pcd_min"], ref["pcd_min"]) and np.array_equal(out["pcd_max"], ref["pcd_max"])
     _assert_same_map(out, ref)
+
+
+def test_pose_converter_equals_the_reference_class(tmp_path):
+    """avlmaps_b200.dataloader.VLMapsDataloaderHabitat against the reference's class (habitat_dataloader.py:21-148)
+    loaded unmodified (hydra / avlmaps.map stubbed: they pull the simulator stack), on random base poses: same
+    (row, col, angle), same cropped pose, same habitat transform back, and the reference's own round-trip check."""
+    import sys
+    import types
+
+    from avlmaps_b200.dataloader import VLMapsDataloaderHabitat
+    from avlmaps_b200.map.map import Map
+
+    ref_shim._install_stubs()
+    hydra = types.ModuleType("hydra")
+    hydra.main = lambda **kw: (lambda fn: fn)
+    sys.modules.setdefault("hydra", hydra)
+    for name in ("avlmaps.map", "avlmaps.map.map"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["avlmaps.map.map"].Map = object
+    ref = ref_shim.load("ref_habitat_dataloader", "avlmaps/dataloader/habitat_dataloader.py")
+
+    cfg = synth.map_config(200, 0.05, 1.5, [40, 0, 40, 0, 40, 30, 0, 0, 1], 1)
+    cfg["map_type"] = "vlmap"
+    poses = synth.circle_poses(12, radius=1.7)
+    np.savetxt(tmp_path / "poses.txt", poses)
+    m = Map(cfg, data_dir=str(tmp_path))
+    occ = -np.ones((200, 200, 30), np.int32)
+    occ[60:140, 70:150, 5] = 1 + np.arange(80 * 80, dtype=np.int32).reshape(80, 80)
+    m.occupied_ids = occ
+    ours = VLMapsDataloaderHabitat(tmp_path, cfg, m)
+    theirs = ref.VLMapsDataloaderHabitat(tmp_path, ref_shim.AttrDict(cfg), m)
+    assert (ours.rmin, ours.rmax, ours.cmin, ours.cmax) == (60, 139, 70, 149) == (theirs.rmin, theirs.rmax, theirs.cmin, theirs.cmax)
+    rng = np.random.default_rng(0)
+    for i in range(12):
+        tf = O.cvt_pose_vec2tf(poses[i])
+        tf[:3, 3] += rng.uniform(-1.5, 1.5, 3) * [1, 0, 1]
+        ours.from_habitat_tf(tf)
+        theirs.from_habitat_tf(tf)
+        assert ours.to_full_map_pose() == theirs.to_full_map_pose()
+        assert ours.to_cropped_map_pose() == theirs.to_cropped_map_pose()
+        assert np.array_equal(ours.to_habitat_tf(), theirs.to_habitat_tf())
+        assert np.linalg.norm(tf - ours.to_habitat_tf()) < 1            # the reference's own self-check (:170-172)
+        cam = np.linalg.inv(ours.base2cam_tf) @ tf
+        ours.from_camera_tf(cam)
+        theirs.from_camera_tf(cam)
+        assert ours.to_full_map_pose() == theirs.to_full_map_pose()
+    ours.from_cropped_map_pose(3, 4, 90.0)
+    theirs.from_cropped_map_pose(3, 4, 90.0)
+    assert ours.to_full_map_pose() == theirs.to_full_map_pose() == [63, 74, 90.0]
+    assert np.array_equal(ours.to_habitat_tf(), theirs.to_habitat_tf())
