@@ -458,7 +458,7 @@ class File(Group):
                 return {"class": 1, "address": None if addr == buf.undef else addr, "size": UNDEF}
             size = buf.uint(body, p, 4)
             return {"class": 0, "data": body[p + 4:p + 4 + size]}
-        if version == 3:
+        if version in (3, 4):                                   # v4 (libver >= v110) encodes compact / contiguous like v3
             cls = body[1]
             if cls == 0:
                 size = buf.uint(body, 2, 2)
@@ -466,6 +466,9 @@ class File(Group):
             if cls == 1:
                 addr, size = buf.uint(body, 2, buf.so), buf.uint(body, 2 + buf.so, buf.sl)
                 return {"class": 1, "address": None if addr == buf.undef else addr, "size": size}
+            if cls == 2 and version == 4:
+                raise H5Error(f"dataset {name!r}: chunked layout message v4 (single-chunk / array / B-tree v2 indexes, "
+                              "libver >= v110) is not supported; contiguous and v1-B-tree chunked datasets are")
             if cls == 2:
                 rank = body[2]
                 addr = buf.uint(body, 3, buf.so)

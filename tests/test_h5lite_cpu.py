@@ -332,17 +332,32 @@ def test_superblock_v2_and_v2_object_headers_with_link_messages(tmp_path):
     dtype = h5lite._datatype_message(arr.dtype)
     layout = struct.pack("<BBH", 3, 0, arr.nbytes) + arr.tobytes()
     ds = ohdr2([(1, space), (3, dtype), (8, layout)])
+    big = np.arange(40, dtype="<f4")
     sb_size = 48
     ds_addr = sb_size
-    root_addr = ds_addr + len(ds)
+    # a second dataset with a layout message v4, contiguous (what libver >= v110 writes), raw data after the headers
+    ds2_addr = ds_addr + len(ds)
+    space2 = struct.pack("<BBBB", 2, 1, 0, 1) + struct.pack("<Q", 40)
+    probe = ohdr2([(1, space2), (3, h5lite._datatype_message(big.dtype)), (8, struct.pack("<BBQQ", 4, 1, 0, big.nbytes))])
     link = struct.pack("<BB", 1, 0) + struct.pack("<B", 4) + b"tiny" + struct.pack("<Q", ds_addr)
+    link2 = struct.pack("<BB", 1, 0) + struct.pack("<B", 3) + b"big" + struct.pack("<Q", ds2_addr)
     link_info = struct.pack("<BB", 0, 0) + struct.pack("<QQ", h5lite.UNDEF, h5lite.UNDEF)
-    root = ohdr2([(2, link_info), (6, link)])
-    eof = root_addr + len(root)
+    root = ohdr2([(2, link_info), (6, link), (6, link2)])
+    root_addr = ds2_addr + len(probe)
+    data_addr = root_addr + len(root)
+    ds2 = ohdr2([(1, space2), (3, h5lite._datatype_message(big.dtype)), (8, struct.pack("<BBQQ", 4, 1, data_addr, big.nbytes))])
+    assert len(ds2) == len(probe)
+    eof = data_addr + big.nbytes
     sb = h5lite.SIGNATURE + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", 0, h5lite.UNDEF, eof, root_addr) + b"\0" * 4
     assert len(sb) == sb_size
     p = tmp_path / "v2.h5"
-    p.write_bytes(sb + ds + root)
+    p.write_bytes(sb + ds + ds2 + root + big.tobytes())
     with h5lite.File(p) as f:
-        assert f.superblock_version == 2 and f.keys() == ["tiny"]
+        assert f.superblock_version == 2 and f.keys() == ["tiny", "big"]
         assert np.array_equal(f["tiny"][:], arr) and f["tiny"].dtype == np.dtype("<i2")
+        assert np.array_equal(f["big"][:], big) and f["big"].offset == data_addr and np.array_equal(f["big"].memmap(), big)
+    # a chunked layout v4 is named as unsupported instead of being misread
+    bad = ohdr2([(1, space2), (3, h5lite._datatype_message(big.dtype)), (8, struct.pack("<BBQQ", 4, 2, data_addr, big.nbytes))])
+    p.write_bytes(sb + ds + bad + root + big.tobytes())
+    with h5lite.File(p) as f, pytest.raises(h5lite.H5Error, match="layout message v4"):
+        f["big"]
