@@ -7,7 +7,7 @@ torch.distributed is plumbing only; scoring runs in the C-ABI library."""
 from __future__ import annotations
 
 import os
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 

@@ -5,7 +5,7 @@ the reference computes it (numpy + scipy), because the kernels take these matric
 from __future__ import annotations
 
 from pathlib import Path
-from typing import List, Optional, Set, Tuple
+from typing import Optional, Set, Tuple
 
 import numpy as np
 
