@@ -352,6 +352,28 @@ def build_extra(torch, engine, L, frames=24, reps=3):
                                    "note": "PCIe-bound: 415 MB of fp32 features per frame; a device-side encoder hand-off "
                                            "(the hwc / chw lines above) removes it"}
             b.close()
+            if os.environ.get("AVL_BENCH_F16") == "1":
+                # same end-to-end call with the features handed over as float16 (AVL_FEAT_F16: LSeg's output is
+                # fp16-exact, so the map is identical): half the PCIe bytes.  Opt-in until its first GPU run.
+                try:
+                    hp16 = [p_.cpu().to(torch.float16).pin_memory() for p_ in pool[:2]]
+                    b = engine.DeviceBuilder(gs, int(cam_h / cs), cs, d, capacity=gs * gs * int(cam_h / cs))
+                    for i in range(2):
+                        b.add_frame(hd[i].numpy(), hp16[i].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i].numpy(), feat_layout=layout)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for i in range(n_e2e):
+                        b.add_frame(hd[i % 2].numpy(), hp16[i % 2].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i % 2].numpy(),
+                                    feat_layout=layout)
+                    torch.cuda.synchronize()
+                    dt16 = (time.perf_counter() - t0) / n_e2e
+                    out["e2e_host_chw_f16"] = {"frames_per_s": 1.0 / dt16, "ms_per_frame": dt16 * 1e3,
+                                               "h2d_bytes_per_frame": h * w * 4 + d * fh * fw * 2 + h * w * 4,
+                                               "h2d_GBps": (h * w * 8 + d * fh * fw * 2) / dt16 / 1e9}
+                    b.close()
+                    del hp16
+                except Exception as e:  # noqa: BLE001
+                    out["e2e_host_chw_f16_error"] = repr(e)
             del hp
         del pool
     return out
