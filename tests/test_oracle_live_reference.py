@@ -153,3 +153,29 @@ def test_pose_converter_equals_the_reference_class(tmp_path):
     theirs.from_cropped_map_pose(3, 4, 90.0)
     assert ours.to_full_map_pose() == theirs.to_full_map_pose() == [63, 74, 90.0]
     assert np.array_equal(ours.to_habitat_tf(), theirs.to_habitat_tf())
+
+
+def test_committed_golden_vectors_are_reproducible(tmp_path, monkeypatch):
+    """tests/golden/gen_golden.py, run again against the reference tree, reproduces every committed .npz array for
+    array: the fixtures are what the committed script makes from the unmodified reference, nothing hand-edited."""
+    import importlib.util
+    from pathlib import Path
+
+    gdir = Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("gen_golden_live", gdir / "gen_golden.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    monkeypatch.setattr(gen, "OUT", tmp_path)
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        gen.main()
+    made = sorted(p.name for p in tmp_path.glob("*.npz"))
+    committed = sorted(p.name for p in gdir.glob("*.npz"))
+    assert made == committed and len(made) == 16
+    for name in made:
+        with np.load(tmp_path / name) as a, np.load(gdir / name) as b:
+            assert sorted(a.files) == sorted(b.files), name
+            for k in a.files:
+                assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f"), (name, k)
