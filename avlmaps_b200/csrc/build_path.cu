@@ -574,7 +574,7 @@ chw16_to_hwc_kernel(const __half* __restrict__ src, float* __restrict__ dst, int
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * 64;
   const int c0 = blockIdx.y * 64;
   const int t = threadIdx.x;
-  const bool vec_in = (p & 3) == 0, vec_out = (d & 3) == 0;
+  const bool vec_in = (p & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0, vec_out = (d & 3) == 0;
   {
     const int q4 = (t & 15) * 4, r0 = t >> 4;
 #pragma unroll

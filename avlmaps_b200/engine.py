@@ -52,6 +52,10 @@ class _Arg:
             if not x.is_cuda:
                 x = x.numpy()
             else:
+                if x.data_ptr() & 15:
+                    # a view that starts off a 16-byte boundary (t[1:], an odd offset into a packed buffer): the
+                    # kernels read their inputs with 8 / 16-byte vector loads, so hand them an aligned copy
+                    x = x.clone()
                 self.keep, self.device, self.ptr, self.shape = x, True, C.c_void_p(x.data_ptr()), tuple(x.shape)
                 return
         a = np.ascontiguousarray(x, dtype=dtype)
