@@ -17,7 +17,7 @@ from ._common import base_parser, compose_from_args, load_callable
 def main(argv: Optional[List[str]] = None) -> int:
     ap = base_parser("avlmaps_b200.application.create_map", "map_creation_cfg.yaml", __doc__)
     ap.add_argument("--feature-fn", default=None, help="module:function of the pixel encoder")
-    args = ap.parse_args(argv)
+    args = ap.parse_intermixed_args(argv)
     config, scene = compose_from_args(args)
     avlmap = AVLMap(config, feature_fn=load_callable(args.feature_fn))   # create_map.py:13
     avlmap.create_map(scene)                                             # create_map.py:17

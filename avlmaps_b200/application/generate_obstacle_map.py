@@ -29,7 +29,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--clip-dim", type=int, default=512)
     ap.add_argument("--dataset-dir-name", default="vlmaps_dataset", help="generate_obstacle_map.py:20 reads vlmaps_dataset")
     ap.add_argument("--out", default=None, help="directory for obstacles.png / obstacles_custom.png (+ .npy)")
-    args = ap.parse_args(argv)
+    args = ap.parse_intermixed_args(argv)
     config = compose(args.config_dir, args.config_name, args.overrides)
     data_dir = Path(config.data_paths.avlmaps_data_dir) / args.dataset_dir_name
     if not data_dir.is_dir():

@@ -166,11 +166,22 @@ class FakeAVLMap:
         self.config, self.vlmap, self.calls = config, FakeVLMap(), []
         FakeAVLMap.last = self
 
+    area_map = None
+    sound_map = None
+
     def index_object(self, name, decay_rate=0.1):
         self.calls.append((name, decay_rate))
         heat = np.zeros(10, np.float32)
         heat[len(name) % 10] = 1.0
         return heat
+
+    def index_area(self, name, decay_rate=0.1):
+        self.calls.append(("area:" + name, decay_rate))
+        return np.linspace(0, 1, 10, dtype=np.float32)
+
+    def index_sound(self, name, decay_rate=0.01):
+        self.calls.append(("sound:" + name, decay_rate))
+        return np.linspace(1, 0, 10, dtype=np.float32)
 
     def get_max_pos_3d(self, heat):
         return self.vlmap.grid_pos[int(np.argmax(heat))]
@@ -202,7 +213,39 @@ def test_index_map_application_flow(tmp_path, monkeypatch, capsys):
     rc = index_map.main(common + ["decay_rate=0.05"], input_fn=lambda prompt: next(answers))
     a = FakeAVLMap.last
     assert rc == 0 and a.calls == [("chair", 0.05)] and a.vlmap.clip_inited
-    assert "needs the reference's SoundMap" in capsys.readouterr().out
+    out_text = capsys.readouterr().out
+    assert "needs --sound-text-encoder" in out_text
+    # area and sound modalities once their encoders are named on the command line
+    made = {}
+
+    class FakeArea:
+        def __init__(self, data_dir, text_encoder=None, clip_feat_dim=768):
+            made["area"] = (Path(data_dir).name, text_encoder, clip_feat_dim)
+
+        def load_map(self, d):
+            made["area_loaded"] = Path(d).name
+
+    class FakeSound:
+        def __init__(self, cats, text_encoder, logit_scale_at, difficulty_level=1):
+            made["sound"] = (cats, text_encoder, round(float(logit_scale_at), 3), difficulty_level)
+
+        def load_sound_map(self, d):
+            made["sound_loaded"] = Path(d).name
+
+    monkeypatch.setattr(index_map, "AreaMap", FakeArea)
+    monkeypatch.setattr(index_map, "SoundMap", FakeSound)
+    rc = index_map.main(common + ["--area", "kitchen", "--sound", "door knock", "--object", "sofa",
+                                  "--area-text-encoder", "test_config_apps_cpu:fake_text_encoder",
+                                  "--sound-text-encoder", "test_config_apps_cpu:fake_text_encoder",
+                                  "--sound-categories", "door knock, dog ,", "+sound_data_collect_params.difficulty=2"])
+    a = FakeAVLMap.last
+    assert rc == 0 and a.calls == [("sofa", 0.01), ("area:kitchen", 0.01), ("sound:door knock", 0.01)]
+    assert (made["area"][0], made["area"][1].__name__, made["area"][2]) == ("a_scene", "fake_text_encoder", 768)
+    assert made["area_loaded"] == "a_scene" and made["sound_loaded"] == "a_scene"
+    assert (made["sound"][0], made["sound"][1].__name__) + made["sound"][2:] == (["door knock", "dog"], "fake_text_encoder", 4.605, 2)
+    answers = iter(["3", "kitchen", "4", "6"])
+    assert index_map.main(common, input_fn=lambda prompt: next(answers)) == 0
+    assert "needs --area-text-encoder" in capsys.readouterr().out
 
 
 def test_generate_obstacle_map_application_flow(tmp_path, monkeypatch, capsys):
