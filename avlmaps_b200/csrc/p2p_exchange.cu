@@ -23,7 +23,7 @@ namespace avl {
 namespace {
 
 constexpr int kMaxWorld = 16;
-constexpr unsigned long long kSpinTimeoutCycles = 4000000000ull;  // ~2 s: a missing peer must not hang the GPU
+constexpr unsigned long long kSpinTimeoutCycles = 20000000000ull;  // ~10 s: a missing peer must not hang the GPU
 
 struct P2PView {
   uint8_t* peer[kMaxWorld];  // base of every rank's receive buffer, as mapped into THIS process
@@ -71,7 +71,8 @@ p2p_exchange_merge_kernel(const __grid_constant__ P2PView v, const int64_t* __re
     const unsigned long long t0 = clock64();
     while (ld_acquire_sys(mine) != epoch) {
       if (clock64() - t0 > kSpinTimeoutCycles) {
-        atomicExch(status, 1u + threadIdx.x);  // which source never arrived
+        *reinterpret_cast<volatile uint32_t*>(status) = 1u + threadIdx.x;  // which source never arrived (host-mapped word)
+        __threadfence_system();
         break;
       }
       __nanosleep(64);
@@ -118,7 +119,8 @@ struct avl_p2p {
   P2PView view;
   uint8_t* local = nullptr;
   size_t total_bytes = 0;
-  uint32_t* status = nullptr;  // device word: 0 = fine, 1 + source = that source timed out
+  uint32_t* status_host = nullptr;  // pinned, device-mapped word: 0 = fine, 1 + source = that source timed out
+  uint32_t* status = nullptr;       // its device address (the kernel's atomicExch lands in host memory)
   uint32_t epoch = 0;
   bool connected = false;
   bool opened[kMaxWorld] = {};
@@ -143,11 +145,15 @@ int avl_p2p_create(int32_t rank, int32_t world, int32_t nq_max, int32_t k_max, a
   p->total_bytes = p->view.data_bytes + 2ull * world * nq_max * sizeof(uint32_t);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p->local), p->total_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->local, 0, p->total_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&p->status), sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(p->status, 0, sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&p->status_host), sizeof(uint32_t), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *p->status_host = 0u;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&p->status), p->status_host, 0);
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
-    cudaFree(p->local); cudaFree(p->status);
+    cudaFree(p->local);
+    if (p->status_host) cudaFreeHost(p->status_host);
     delete p;
     return cuda_fail(e, "p2p buffers", __FILE__, __LINE__);
   }
@@ -195,6 +201,13 @@ int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int
     set_error("avl_p2p_connect has not been called");
     return AVL_ERR_STATE;
   }
+  if (const uint32_t st = *static_cast<volatile uint32_t*>(p->status_host)) {
+    // an earlier exchange gave up on a peer (its result was merged from stale data): refuse to go on silently
+    char buf[160];
+    snprintf(buf, sizeof(buf), "an earlier peer exchange timed out waiting for rank %u; the exchange object is unusable", st - 1u);
+    set_error(buf);
+    return AVL_ERR_STATE;
+  }
   p->epoch += 1;
   p2p_exchange_merge_kernel<<<nq, 128, 0, static_cast<cudaStream_t>(stream)>>>(p->view, idx, val, nq, k, p->epoch, row_offset,
                                                                               out_idx, out_val, p->status);
@@ -204,9 +217,8 @@ int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int
 
 int avl_p2p_status(avl_p2p* p, int32_t* timed_out_source, void* stream) {
   AVL_ARG(p != nullptr && timed_out_source != nullptr, "NULL argument");
-  uint32_t s = 0;
-  AVL_CUDA(cudaMemcpyAsync(&s, p->status, sizeof(s), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
   AVL_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  const uint32_t s = *static_cast<volatile uint32_t*>(p->status_host);
   *timed_out_source = s ? static_cast<int32_t>(s) - 1 : -1;
   return AVL_OK;
 }
@@ -215,7 +227,8 @@ int avl_p2p_destroy(avl_p2p* p) {
   if (!p) return AVL_OK;
   for (int r = 0; r < p->view.world; ++r)
     if (p->opened[r]) cudaIpcCloseMemHandle(p->view.peer[r]);
-  cudaFree(p->local); cudaFree(p->status);
+  cudaFree(p->local);
+  if (p->status_host) cudaFreeHost(p->status_host);
   delete p;
   return AVL_OK;
 }

@@ -264,7 +264,7 @@ class P2PExchange:
         return out_i, out_v
 
     def timed_out_source(self) -> int:
-        """-1, or the rank whose data never arrived within the kernel's ~2 s watchdog (synchronises)."""
+        """-1, or the rank whose data never arrived within the kernel's ~10 s watchdog (synchronises)."""
         s = C.c_int32(-1)
         L.check(self._lib.avl_p2p_status(self._h, C.byref(s), None))
         return int(s.value)

@@ -305,7 +305,8 @@ int avl_rank_keys(const uint64_t* keys_all, const int64_t* offsets, int32_t n_sh
  * ids are made global by adding row_offset, or are global already with row_offset = 0), stores it into every peer's buffer with plain peer stores, and merges what the peers
  * delivered -- ONE kernel per query batch, no host round trip, no NCCL call; every rank must call it for every
  * batch with the same nq and k.  out_idx / out_val (nq, k): the global top-k, (score desc, row asc), on every rank.
- * A peer that never delivers trips a ~2 s watchdog instead of hanging the GPU (avl_p2p_status: source rank or -1).
+ * A peer that never delivers trips a ~10 s in-kernel watchdog instead of hanging the GPU; the next call on the object
+ * then fails with AVL_ERR_STATE (avl_p2p_status: the source rank that never arrived, or -1).
  * The NCCL all-gather + avl_merge_topk form stays the default; this one is opt-in (AVL_P2P_EXCHANGE=1) until it has
  * been measured on 2 / 8 GPUs. */
 typedef struct avl_p2p avl_p2p;
