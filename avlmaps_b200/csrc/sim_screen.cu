@@ -15,6 +15,8 @@
 // rows and HALF of B, so a 256-query x 512-d B (256 KiB) is resident across the pair.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "avl_internal.h"
 #include "ptx_sm100.cuh"
 
@@ -252,7 +254,11 @@ __device__ __forceinline__ uint32_t thresh_tile(const ScreenParams& p, const Til
   return pend;
 }
 
-template <int CG>
+// SB ("streamed B", opt-in AVL_STREAM_B=1, not yet measured): B is not resident; its k-block travels with A's in every
+// pipeline stage (re-read from L2, where EVICT_LAST keeps it), which frees the 128 KiB B took per CTA at 256 queries
+// for a deeper ring -- more voxel bytes in flight per SM.  SB = false is the measured kernel, instruction for
+// instruction (tools/sass_diff.py).
+template <int CG, bool SB>
 __global__ void __launch_bounds__(kThreads, 1)
 screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
               const ScreenParams p) {
@@ -270,9 +276,10 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   const uint32_t b_rows = static_cast<uint32_t>(p.npad) / CG;
   const uint32_t bblk = b_rows * 128u;                       // bytes of one resident k-block of B
   const uint32_t b_bytes = bblk * static_cast<uint32_t>(p.kblocks);
+  const uint32_t stage_bytes = SB ? kStageBytes + bblk : static_cast<uint32_t>(kStageBytes);  // SB: A tile, then B k-block
   uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + ((b_bytes + 1023u) & ~1023u);
-  uint8_t* ctrl = smem_a + static_cast<uint32_t>(p.stages) * kStageBytes;
+  uint8_t* smem_a = smem + (SB ? 0u : ((b_bytes + 1023u) & ~1023u));
+  uint8_t* ctrl = smem_a + static_cast<uint32_t>(p.stages) * stage_bytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(ctrl);    // [kMaxStages]
   uint64_t* bar_empty = bar_full + kMaxStages;               // [kMaxStages]
   uint64_t* bar_tfull = bar_empty + kMaxStages;              // [2]
@@ -337,11 +344,13 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < p.kblocks; ++kb)
-        ptx::tma_load_2d<CG>(ptx::smem_u32(smem_b + kb * bblk), &tmap_b, ptx::smem_u32(bar_bfull),
-                             kb * kBlockK, static_cast<int32_t>(rank * b_rows), ptx::kEvictLast);
-      if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_bfull), b_bytes * CG);
-      else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_bfull), 0);
+      if constexpr (!SB) {
+        for (int kb = 0; kb < p.kblocks; ++kb)
+          ptx::tma_load_2d<CG>(ptx::smem_u32(smem_b + kb * bblk), &tmap_b, ptx::smem_u32(bar_bfull),
+                               kb * kBlockK, static_cast<int32_t>(rank * b_rows), ptx::kEvictLast);
+        if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_bfull), b_bytes * CG);
+        else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_bfull), 0);
+      }
 
       uint32_t stage = 0, phase = 0;
       // The ring holds `stages` x 16 KiB per CTA, not enough bytes in flight to cover HBM latency at
@@ -363,10 +372,14 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
           if (do_pf) ptx::tma_prefetch_2d(&tmap_a, kb * kBlockK, static_cast<int32_t>(rowp));
           ptx::mbar_wait(ptx::smem_u32(bar_empty + stage), phase ^ 1u, p.dbg, 0x10u + stage);
           if (!(p.debug_flags & 2)) {
-            ptx::tma_load_2d<CG>(ptx::smem_u32(smem_a + stage * kStageBytes), &tmap_a,
+            ptx::tma_load_2d<CG>(ptx::smem_u32(smem_a + stage * stage_bytes), &tmap_a,
                                  ptx::smem_u32(bar_full + stage), kb * kBlockK,
                                  static_cast<int32_t>(row0), ptx::kEvictFirst);
-            if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_full + stage), kStageBytes * CG);
+            if constexpr (SB)
+              ptx::tma_load_2d<CG>(ptx::smem_u32(smem_a + stage * stage_bytes + kStageBytes), &tmap_b,
+                                   ptx::smem_u32(bar_full + stage), kb * kBlockK,
+                                   static_cast<int32_t>(rank * b_rows), ptx::kEvictLast);
+            if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_full + stage), stage_bytes * CG);
             else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_full + stage), 0);
           } else {  // triage: barrier protocol only
             if (leader) ptx::mbar_arrive(ptx::smem_u32(bar_full + stage));
@@ -382,8 +395,10 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     if (leader && lane == 0) {
       const uint32_t idesc = p.op_f16 ? ptx::make_idesc_f16(kTileRows * CG, static_cast<uint32_t>(p.npad))
                                       : ptx::make_idesc_bf16(kTileRows * CG, static_cast<uint32_t>(p.npad));
-      ptx::mbar_wait(ptx::smem_u32(bar_bfull), 0, p.dbg, 0x20u);
-      ptx::tc_fence_after();
+      if constexpr (!SB) {
+        ptx::mbar_wait(ptx::smem_u32(bar_bfull), 0, p.dbg, 0x20u);
+        ptx::tc_fence_after();
+      }
       uint32_t stage = 0, phase = 0, it = 0;
       for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
@@ -393,8 +408,9 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         for (int kb = 0; kb < p.kblocks; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(bar_full + stage), phase, p.dbg, 0x40u + stage);
           ptx::tc_fence_after();
-          const uint64_t a0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_a + stage * kStageBytes));
-          const uint64_t b0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_b + kb * bblk));
+          const uint64_t a0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_a + stage * stage_bytes));
+          const uint64_t b0 = ptx::make_kmajor_sw128_desc(
+              ptx::smem_u32(SB ? smem_a + stage * stage_bytes + kStageBytes : smem_b + kb * bblk));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes inside the swizzle row
             if (!(p.debug_flags & 1))
@@ -545,10 +561,17 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 
 }  // namespace
 
+static bool stream_b() {  // opt-in variant: B's k-blocks travel with A's instead of staying resident (see the kernel)
+  static const bool on = [] { const char* e = getenv("AVL_STREAM_B"); return e && e[0] == '1'; }();
+  return on;
+}
+
 size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages) {
-  const size_t b_bytes = static_cast<size_t>(npad / cta_group) * 128u * kblocks;
-  size_t total = ((b_bytes + 1023u) & ~size_t(1023)) + static_cast<size_t>(stages) * kStageBytes + kCtrlBytes +
-                 kQConstBytes + kRingBytes + kXchgBytes + 1024u /* alignment slack */;
+  const size_t bblk = static_cast<size_t>(npad / cta_group) * 128u;
+  const size_t b_bytes = bblk * kblocks;
+  size_t total = stream_b() ? static_cast<size_t>(stages) * (kStageBytes + bblk)
+                            : ((b_bytes + 1023u) & ~size_t(1023)) + static_cast<size_t>(stages) * kStageBytes;
+  total += kCtrlBytes + kQConstBytes + kRingBytes + kXchgBytes + 1024u /* alignment slack */;
   // > half of the SM's shared memory, so exactly one CTA (and one 512-column TMEM owner) per SM
   if (total < 120u * 1024u) total = 120u * 1024u;
   return total;
@@ -580,15 +603,10 @@ int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const S
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cta_group == 2) {
-    AVL_CUDA(cudaFuncSetAttribute(screen_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
-    AVL_CUDA(cudaLaunchKernelEx(&cfg, screen_kernel<2>, ta, tb, p));
-  } else {
-    AVL_CUDA(cudaFuncSetAttribute(screen_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem_bytes)));
-    AVL_CUDA(cudaLaunchKernelEx(&cfg, screen_kernel<1>, ta, tb, p));
-  }
+  auto kernel = cta_group == 2 ? (stream_b() ? screen_kernel<2, true> : screen_kernel<2, false>)
+                               : (stream_b() ? screen_kernel<1, true> : screen_kernel<1, false>);
+  AVL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  AVL_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
   return AVL_OK;
 }
 

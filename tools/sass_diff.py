@@ -26,7 +26,8 @@ def sass_of(cu: Path, include_root: Path, out: Path):
     mangled = re.findall(r"Function : (\S+)", txt)
     pretty = subprocess.run(["cu++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.splitlines()
     # the anonymous-namespace hash in the mangled name depends on the file path: compare by the demangled signature
-    names = {m: re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", p) for m, p in zip(mangled, pretty)}
+    names = {m: re.sub(r"\((int|bool)\)", "", re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", p))
+             for m, p in zip(mangled, pretty)}
     funcs, cur = {}, None
     for line in txt.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -56,12 +57,18 @@ def main():
         old = sass_of(old_root / "avlmaps_b200" / "csrc" / name, old_root, td / "old.o")
         new = sass_of(_build.CSRC / name, ROOT, td / "new.o")
     differ = 0
+    short_of = lambda k: re.sub(r"^void ", "", k).split("(")[0][-70:]  # noqa: E731
     for k in sorted(set(old) | set(new)):
-        short = re.sub(r"^void ", "", k).split("(")[0][-70:]
+        short = short_of(k)
         if k not in old:
-            print(f"NEW    {short}  ({len(new[k])} instructions)")
+            twins = [short_of(o) for o in old if o not in new and old[o] == new[k]]
+            if twins:
+                print(f"same   {short}  ({len(new[k])}; was {twins[0]}: renamed, instructions identical)")
+            else:
+                print(f"NEW    {short}  ({len(new[k])} instructions)")
         elif k not in new:
-            print(f"GONE   {short}")
+            if not any(new[n] == old[k] for n in new if n not in old):
+                print(f"GONE   {short}")
         elif old[k] == new[k]:
             print(f"same   {short}  ({len(new[k])})")
         else:
