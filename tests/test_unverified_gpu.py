@@ -96,7 +96,9 @@ def test_streamed_b_screen_variant_matches_the_oracle(lib, extra_env):
 
     root = Path(__file__).resolve().parents[1]
     env = dict(os.environ, AVL_STREAM_B="1", **extra_env)
-    cmd = [sys.executable, str(root / "__graft_entry__.py"), "smoke"] if extra_env else [sys.executable, str(root / "tools" / "sanitize_small.py")]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    # smoke() only (not the script's main, which would rebuild the library this process has loaded)
+    cmd = ([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"] if extra_env
+           else [sys.executable, str(root / "tools" / "sanitize_small.py")])
+    r = subprocess.run(cmd, env=env, cwd=str(root), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert ("smoke ok" in r.stdout) if extra_env else ("build ok" in r.stdout)
