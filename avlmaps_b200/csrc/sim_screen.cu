@@ -603,10 +603,19 @@ int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const S
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  auto kernel = cta_group == 2 ? (stream_b() ? screen_kernel<2, true> : screen_kernel<2, false>)
-                               : (stream_b() ? screen_kernel<1, true> : screen_kernel<1, false>);
-  AVL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  AVL_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
+  if (stream_b()) {  // opt-in variant
+    auto kernel = cta_group == 2 ? screen_kernel<2, true> : screen_kernel<1, true>;
+    AVL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+    AVL_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
+  } else if (cta_group == 2) {
+    AVL_CUDA(cudaFuncSetAttribute(screen_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes)));
+    AVL_CUDA(cudaLaunchKernelEx(&cfg, screen_kernel<2, false>, ta, tb, p));
+  } else {
+    AVL_CUDA(cudaFuncSetAttribute(screen_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem_bytes)));
+    AVL_CUDA(cudaLaunchKernelEx(&cfg, screen_kernel<1, false>, ta, tb, p));
+  }
   return AVL_OK;
 }
 
