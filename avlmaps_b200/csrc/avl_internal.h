@@ -45,8 +45,10 @@ struct ScreenParams {
   int32_t stages;        // A pipeline depth
   int32_t mode;          // ScreenMode
   int32_t normalize;     // divide by the fp32 row norm
-  int32_t prefetch_tiles; // L2 prefetch distance of the A stream, in tiles per unit
-  int32_t debug_flags;    // perf triage only (AVL_DEBUG_FLAGS): 1 = no MMA, 2 = no A loads, 4 = no epilogue work
+  int32_t prefetch_tiles; // L2 prefetch distance of the A stream, in tiles per unit (tiled layout: the prefetch warp)
+  int32_t a_tiled;        // operand copy of the map is tile-major ([tile][k-block][128 rows][64]), see map_prepare
+  int32_t debug_flags;    // perf triage only (AVL_DEBUG_FLAGS): 1 = no MMA, 2 = no A loads, 4 = no epilogue work,
+                          // 8 = pre-test always passes, 16 = thresholds +inf (nothing emitted), 32 = TMEM loads only
   int32_t op_f16;         // operands are fp16 instead of bf16 (same tcgen05 kind::f16 rate, 8x smaller rounding residual)
   // per-row statistics (map_prepare): see DESIGN.md "error band"
   const float* row_norm;   // ||a_i||  (fp32 row, fp64-accumulated)
@@ -54,6 +56,7 @@ struct ScreenParams {
   const float* row_an;     // >= ||bf16(a_i)||
   // per-query statistics (query_prepare)
   const float* q_bn;       // >= ||b_q||
+  const __nv_bfloat16* a_base; // operand copy of the map (tile-major: the L2 prefetch addresses it directly)
   const __nv_bfloat16* bq; // bf16 queries (256 zero-padded rows x dpad), read by the query-stationary kernel
   const float* q_glob;     // [0] rho >= max_q ||b_q - bf16(b_q)|| / ||b_q|| (+slack), [1] max_q q_bn
   // kModeDense
@@ -80,8 +83,8 @@ struct ScreenParams {
 // Launch the tcgen05 screen.  tmap_a / tmap_b are CUtensorMap (128 bytes each).
 int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const ScreenParams& p,
                   int num_sms, size_t smem_bytes, cudaStream_t stream);
-size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages);
-int screen_pick_stages(int cta_group, int npad, int kblocks);  // <=0: does not fit
+size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages, int mode);
+int screen_pick_stages(int cta_group, int npad, int kblocks, int mode);  // <=0: does not fit
 // query-stationary variant (sim_screen_ts.cu): queries in TMEM, 128-voxel tiles, cta_group::2 only
 int launch_screen_ts(const void* tmap_v64, const ScreenParams& p, int num_sms, size_t smem_bytes,
                      cudaStream_t stream);
@@ -91,7 +94,7 @@ int screen_ts_pick_stages();
 // ---- exact / helper kernels (sim_exact.cu) --------------------------------
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
                        float* row_norm, float* row_c, float* row_an, float kappa, int f16, uint32_t* nonfinite,
-                       cudaStream_t s);
+                       int tiled, cudaStream_t s);
 int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, int32_t d, int32_t dpad,
                          int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, int f16, cudaStream_t s);
 int launch_dense_exact(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq,

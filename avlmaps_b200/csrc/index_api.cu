@@ -44,6 +44,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 row-major (rows x dpad) matrix, box = 64 columns (one 128-byte swizzle row) x box_rows.
+// The tile-major operand copy of a map is described as (tiles * kblocks * 128) rows of 64 elements: a box is then
+// one contiguous run of memory (see map_prepare_kernel).
 static int encode_kmajor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t dpad,
                              uint32_t box_rows, bool f16 = false) {
   EncodeTiledFn fn = get_encode_fn();
@@ -113,6 +115,7 @@ struct avl_map {
   int64_t n = 0;
   int32_t d = 0, dpad = 0;
   int op_f16 = 0;         // tensor-core operands are fp16 (AVL_MAP_F16) instead of bf16
+  int tiled = 0;          // operand copy is tile-major (map_prepare_kernel)
   float* feat = nullptr;
   __nv_bfloat16* bf = nullptr;
   float* row_norm = nullptr;
@@ -152,8 +155,8 @@ static int ws_init(avl_map* m) {
   AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.pin), 2 * AVL_MAX_QUERIES * sizeof(uint32_t), cudaHostAllocDefault));
   if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
-  AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.dbg_host), 64, cudaHostAllocMapped));
-  memset(w.dbg_host, 0, 64);
+  AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.dbg_host), 4096, cudaHostAllocMapped));
+  memset(w.dbg_host, 0, 4096);
   AVL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.dbg_dev), w.dbg_host, 0));
   for (int i = 0; i < 4; ++i) AVL_CUDA(cudaEventCreate(&w.ev[i]));
   return AVL_OK;
@@ -228,16 +231,16 @@ static int check_watchdog(avl_map* m, int rc) {
 }
 
 // which tcgen05 variant: 2 when B only fits the shared memory of an SM pair (or forced by env)
-static int pick_cta_group(int npad, int kblocks, int forced) {
-  if (forced == 1 || forced == 2) return screen_pick_stages(forced, npad, kblocks) >= 2 ? forced : 0;
+static int pick_cta_group(int npad, int kblocks, int forced, int mode) {
+  if (forced == 1 || forced == 2) return screen_pick_stages(forced, npad, kblocks, mode) >= 2 ? forced : 0;
   const char* env = getenv("AVL_CTA_GROUP");
   if (env && (env[0] == '1' || env[0] == '2')) {
     const int f = env[0] - '0';
-    if (screen_pick_stages(f, npad, kblocks) >= 2) return f;
+    if (screen_pick_stages(f, npad, kblocks, mode) >= 2) return f;
   }
-  if (screen_pick_stages(1, npad, kblocks) >= 4) return 1;
-  if (screen_pick_stages(2, npad, kblocks) >= 2) return 2;
-  if (screen_pick_stages(1, npad, kblocks) >= 2) return 1;
+  if (screen_pick_stages(1, npad, kblocks, mode) >= 4) return 1;
+  if (screen_pick_stages(2, npad, kblocks, mode) >= 2) return 2;
+  if (screen_pick_stages(1, npad, kblocks, mode) >= 2) return 1;
   return 0;
 }
 
@@ -267,8 +270,8 @@ struct QuerySetup {
 
 // stage queries, build bf16 B + norms, pick the kernel variant
 static int setup_queries(avl_map* m, const float* queries, int32_t nq, const float* scale, int flags,
-                         int forced_cg, bool need_screen, cudaStream_t s, QuerySetup* qs,
-                         bool fold_scale = false, bool allow_ts = false) {
+                         int forced_cg, int screen_mode /* ScreenMode of the pass that follows, -1: no screen */,
+                         cudaStream_t s, QuerySetup* qs, bool fold_scale = false, bool allow_ts = false) {
   Workspace& w = m->ws;
   AVL_ARG(queries != nullptr, "queries is NULL");
   AVL_ARG(nq >= 1 && nq <= AVL_MAX_QUERIES, "nq must be in [1, AVL_MAX_QUERIES]");
@@ -284,7 +287,7 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
       qs->scale_dev = w.scale;
     }
   }
-  if (!need_screen) return AVL_OK;
+  if (screen_mode < 0) return AVL_OK;
   qs->npad = (nq + 15) & ~15;
   const int kblocks = m->dpad / kBlockK;
   if (want_ts(nq, m->dpad, forced_cg, allow_ts)) {
@@ -298,14 +301,14 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
     return launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
                                 w.q_bn, w.q_glob, m->op_f16, s);
   }
-  qs->cg = pick_cta_group(qs->npad, kblocks, forced_cg);
+  qs->cg = pick_cta_group(qs->npad, kblocks, forced_cg, screen_mode);
   if (qs->cg == 0) {
     set_error("query batch does not fit the shared memory of an SM pair (nq * dim too large); split the batch");
     return AVL_ERR_UNSUPPORTED;
   }
   qs->unit_rows = kTileRows * qs->cg;
-  qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks);
-  qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages);
+  qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks, screen_mode);
+  qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages, screen_mode);
   int rc = launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
                                 w.q_bn, w.q_glob, m->op_f16, s);
   if (rc) return rc;
@@ -329,12 +332,14 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->q_glob = m->ws.q_glob;
   p->dbg = m->ws.dbg_dev;
   p->op_f16 = m->op_f16;
+  p->a_tiled = m->tiled;
+  p->a_base = m->bf;
   p->tile_stride = 1;
   {
     static int pf = -1;  // L2 prefetch distance of the A stream (tiles per unit); AVL_PREFETCH_TILES overrides
     if (pf < 0) {
       const char* e = getenv("AVL_PREFETCH_TILES");
-      pf = e ? atoi(e) : 0;  // measured on B200: 0.90 ms without, 1.02-1.31 ms with 1-8 tiles of prefetch
+      pf = e ? atoi(e) : 0;  // round 1 (row-major copy, prefetch issued by the producer): 0.90 ms without, 1.02-1.31 ms with
       if (pf < 0 || pf > 16) pf = 0;
     }
     p->prefetch_tiles = pf;
@@ -419,7 +424,18 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
   const size_t rows = static_cast<size_t>(std::max<int64_t>(n, 1));
   do {
     if ((rc = dev_alloc(&m->feat, rows * dim, &m->bytes))) break;
-    if ((rc = dev_alloc(&m->bf, rows * m->dpad, &m->bytes))) break;
+    // operand copy: whole 128-row tiles (the tile-major layout addresses by tile; the tail rows are zero)
+    const size_t tile_rows_total = (rows + kTileRows - 1) / kTileRows * kTileRows;
+    {
+      const char* e = getenv("AVL_TILED");
+      m->tiled = !(e && e[0] == '0');
+    }
+    if ((rc = dev_alloc(&m->bf, tile_rows_total * m->dpad, &m->bytes))) break;
+    {
+      const size_t tail = static_cast<size_t>(kTileRows) * m->dpad;  // last tile: rows past n stay zero
+      cudaError_t e = cudaMemsetAsync(m->bf + (tile_rows_total * m->dpad - tail), 0, tail * sizeof(__nv_bfloat16), s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "clear operand tail", __FILE__, __LINE__); break; }
+    }
     if ((rc = dev_alloc(&m->row_norm, rows, &m->bytes))) break;
     if ((rc = dev_alloc(&m->row_c, rows, &m->bytes))) break;
     if ((rc = dev_alloc(&m->row_an, rows, &m->bytes))) break;
@@ -438,7 +454,7 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
       cudaError_t e = cudaMemsetAsync(nonfinite, 0, sizeof(uint32_t), s);
       if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
       if ((rc = launch_map_prepare(m->feat, n, dim, m->dpad, m->bf, m->row_norm, m->row_c, m->row_an, kappa, m->op_f16,
-                                   nonfinite, s))) break;
+                                   nonfinite, m->tiled, s))) break;
       e = cudaMemcpyAsync(&bad, nonfinite, sizeof(bad), cudaMemcpyDeviceToHost, s);
       if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) { rc = cuda_fail(e, "map_prepare", __FILE__, __LINE__); break; }
@@ -446,10 +462,10 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
       m->op_f16 = 0;  // a value beyond the fp16 range: bf16 operands keep the fp32 range
     }
     if (rc) break;
-    if ((rc = encode_kmajor_map(&m->tmap_a, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
-                                kTileRows, m->op_f16 != 0))) break;
-    if ((rc = encode_kmajor_map(&m->tmap_a64, m->bf, static_cast<uint64_t>(rows), static_cast<uint64_t>(m->dpad),
-                                64, m->op_f16 != 0))) break;
+    const uint64_t map_rows = m->tiled ? static_cast<uint64_t>(tile_rows_total) * (m->dpad / kBlockK) : rows;
+    const uint64_t map_cols = m->tiled ? static_cast<uint64_t>(kBlockK) : static_cast<uint64_t>(m->dpad);
+    if ((rc = encode_kmajor_map(&m->tmap_a, m->bf, map_rows, map_cols, kTileRows, m->op_f16 != 0))) break;
+    if ((rc = encode_kmajor_map(&m->tmap_a64, m->bf, map_rows, map_cols, 64, m->op_f16 != 0))) break;
   } while (0);
   if (rc) {
     avl_map_destroy(m);
@@ -482,7 +498,7 @@ int avl_sim_dense(avl_map* m, const float* queries, int32_t nq, const float* sca
   AVL_ARG(m != nullptr && out_scores != nullptr, "NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   QuerySetup qs;
-  int rc = setup_queries(m, queries, nq, scale, flags, 0, false, s, &qs);
+  int rc = setup_queries(m, queries, nq, scale, flags, 0, -1, s, &qs);
   if (rc) return rc;
   if (m->n == 0) return AVL_OK;
   if (flags & AVL_ON_DEVICE)
@@ -511,7 +527,7 @@ int avl_sim_screen_dense(avl_map* m, const float* queries, int32_t nq, int32_t c
   AVL_ARG(m != nullptr && out_scores != nullptr, "NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   QuerySetup qs;
-  int rc = setup_queries(m, queries, nq, nullptr, flags, cta_group, true, s, &qs);
+  int rc = setup_queries(m, queries, nq, nullptr, flags, cta_group, kModeDense, s, &qs);
   if (rc) return rc;
   if (m->n == 0) return AVL_OK;
   float* dst = out_scores;
@@ -551,7 +567,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
   if (m->n == 0) return AVL_OK;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
   QuerySetup qs;
-  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs, /*fold_scale=*/true))) return rc;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeArgmax, s, &qs, /*fold_scale=*/true))) return rc;
   if ((rc = ensure_flags(m))) return rc;
   int32_t* dst = out_argmax;
   if (!(flags & AVL_ON_DEVICE)) {
@@ -652,7 +668,7 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   }
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
   QuerySetup qs;
-  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, true, s, &qs, false, /*allow_ts=*/true))) return rc;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeThresh, s, &qs, false, /*allow_ts=*/true))) return rc;
   int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
   float* d_score = (flags & AVL_ON_DEVICE) ? out_score : w.out_score;
 
@@ -718,6 +734,19 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk", __FILE__, __LINE__));
   }
+  if (p.debug_flags & 64)  // triage: true SM clock of the main screen launch (cycles / nanoseconds of block 0)
+    fprintf(stderr, "[avl clock] screen: %llu cycles in %u ns = %.0f MHz\n",
+            static_cast<unsigned long long>(w.dbg_host[8]) | (static_cast<unsigned long long>(w.dbg_host[9]) << 32),
+            w.dbg_host[10], w.dbg_host[10] ? 1e3 * (static_cast<double>(w.dbg_host[8]) + 4294967296.0 * w.dbg_host[9]) / w.dbg_host[10] : 0.0);
+  if (p.debug_flags & 64) {  // per-CTA spans of the main screen launch: start offset, duration, MHz, SM
+    uint32_t t0 = 0xFFFFFFFFu;
+    for (int b = 0; b < m->num_sms && b < 160; ++b) t0 = std::min(t0, w.dbg_host[16 + 4 * b]);
+    for (int b = 0; b < m->num_sms && b < 160; ++b) {
+      const uint32_t* r = w.dbg_host + 16 + 4 * b;
+      fprintf(stderr, "[avl cta] %3d sm %3u start %6u ns dur %7u ns end %7u ns %5.0f MHz\n", b, r[3], r[0] - t0, r[1],
+              r[0] - t0 + r[1], r[1] ? 1e3 * r[2] / r[1] : 0.0);
+    }
+  }
   int n_fallback = 0;
   int64_t n_cand = 0;
   for (int q = 0; q < nq; ++q) {
@@ -776,8 +805,8 @@ static int fuse_topk_exact(avl_map* ma, const float* qa, const float* scale_a, i
   const int64_t n = ma->n;
   QuerySetup sa, sb;
   int rc;
-  if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, false, s, &sa))) return rc;
-  if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, false, s, &sb))) return rc;
+  if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, -1, s, &sa))) return rc;
+  if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, -1, s, &sb))) return rc;
   if ((rc = ensure_column(ma))) return rc;
   float *da = nullptr, *db = nullptr, *mm = nullptr;
   const size_t elems = static_cast<size_t>(std::max<int64_t>(n, 1)) * n_pairs;
@@ -827,8 +856,8 @@ static int fuse_topk_screened(avl_map* ma, const float* qa, const float* scale_a
   const int64_t n = ma->n;
   QuerySetup sa, sb;
   int rc;
-  if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, true, s, &sa))) return rc;
-  if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, true, s, &sb))) return rc;
+  if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, kModeDense, s, &sa))) return rc;
+  if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, kModeDense, s, &sb))) return rc;
   if (sa.ts || sb.ts) return 1;
   Workspace& w = ma->ws;
   const uint32_t cand_cap = 8192, ext_cap = 2048;

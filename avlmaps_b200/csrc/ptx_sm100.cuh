@@ -136,6 +136,12 @@ __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, in
                : "memory");
 }
 
+// L2 prefetch of a contiguous run of global memory (size a multiple of 16 bytes)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -57,21 +57,30 @@ __device__ __forceinline__ uint16_t to_operand(float x, int f16, float* back) {
 
 // ------------------------------------------------------------------ map_prepare
 // One warp per row: bf16 copy (zero padded to dpad), fp32 norm, rounding residual norms.
+// tiled: the operand copy is stored tile-major -- [tile of 128 rows][k-block of 64][row][64 elements] -- so that the
+// 16 KiB box one TMA load of the screen kernel fetches (128 rows x 128 bytes) is ONE contiguous 16 KiB run of HBM
+// and a whole 128-row tile is one contiguous 128 * dpad * 2 bytes (what its L2 prefetch names with one instruction),
+// instead of 128 separate 128-byte pieces 2 * dpad bytes apart.
 __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, int32_t d, int32_t dpad,
                                    __nv_bfloat16* __restrict__ bf, float* __restrict__ row_norm,
                                    float* __restrict__ row_c, float* __restrict__ row_an, float kappa, int f16,
-                                   uint32_t* __restrict__ nonfinite) {
+                                   uint32_t* __restrict__ nonfinite, int tiled) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* a = feat + row * d;
   uint16_t* o = reinterpret_cast<uint16_t*>(bf + row * dpad);
+  const int64_t tile_base = (row / kTileRows) * kTileRows * dpad + (row % kTileRows) * kBlockK;
   double sa = 0.0, sd = 0.0, sb = 0.0;
   bool bad = false;
   for (int k = lane; k < dpad; k += 32) {
     const float x = k < d ? a[k] : 0.f;
     float xb;
-    o[k] = to_operand(x, f16, &xb);
+    const uint16_t ob = to_operand(x, f16, &xb);
+    if (tiled)
+      reinterpret_cast<uint16_t*>(bf)[tile_base + static_cast<int64_t>(k / kBlockK) * (kTileRows * kBlockK) + (k % kBlockK)] = ob;
+    else
+      o[k] = ob;
     bad |= !isfinite(xb);    // |x| beyond the fp16 range (or a non-finite input): the caller falls back to bf16
     const float e = x - xb;  // exact
     sa += static_cast<double>(x) * x;
@@ -1116,11 +1125,11 @@ __global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
 // =================================================================== launchers
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
                        float* row_norm, float* row_c, float* row_an, float kappa, int f16, uint32_t* nonfinite,
-                       cudaStream_t s) {
+                       int tiled, cudaStream_t s) {
   if (n == 0) return AVL_OK;
   const int warps = 8;
   const unsigned blocks = static_cast<unsigned>((n + warps - 1) / warps);
-  map_prepare_kernel<<<blocks, warps * 32, 0, s>>>(feat, n, d, dpad, bf, row_norm, row_c, row_an, kappa, f16, nonfinite);
+  map_prepare_kernel<<<blocks, warps * 32, 0, s>>>(feat, n, d, dpad, bf, row_norm, row_c, row_an, kappa, f16, nonfinite, tiled);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

@@ -167,10 +167,14 @@ screen_ts_kernel(const __grid_constant__ CUtensorMap tmap_v, const ScreenParams 
           const int na = min(kAtomsPerStage, p.kblocks - kb);
           ptx::mbar_wait(ptx::smem_u32(bar_empty + stage), phase ^ 1u, p.dbg, 0x110u + stage);
           if (!(p.debug_flags & 2)) {
-            for (int a = 0; a < na; ++a)
+            for (int a = 0; a < na; ++a) {
+              // tile-major copy (map_prepare_kernel): the 64-row half of tile row0 / 128, k-block kb + a
+              const int32_t c0 = p.a_tiled ? 0 : (kb + a) * kBlockK;
+              const int32_t c1 = p.a_tiled ? static_cast<int32_t>((((row0 >> 7) * p.kblocks + kb + a) << 7) + (row0 & 127))
+                                           : static_cast<int32_t>(row0);
               ptx::tma_load_2d<CG>(ptx::smem_u32(smem_v + stage * kTsStageBytes + a * kTsAtomBytes), &tmap_v,
-                                   ptx::smem_u32(bar_full + stage), (kb + a) * kBlockK, static_cast<int32_t>(row0),
-                                   ptx::kEvictFirst);
+                                   ptx::smem_u32(bar_full + stage), c0, c1, ptx::kEvictFirst);
+            }
             if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bar_full + stage), kTsAtomBytes * na * CG);
             else ptx::mbar_arrive_cluster(ptx::smem_u32(bar_full + stage), 0);
           } else {  // triage: barrier protocol only

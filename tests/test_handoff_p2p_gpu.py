@@ -1,11 +1,6 @@
-"""GPU tests of code written AFTER the GPU budget of round 1 was spent: they have compiled and passed their CPU-side
-checks, but have not run on a B200 yet, so they are opt-in (`AVL_UNVERIFIED=1 pytest -m gpu tests/test_unverified_gpu.py`)
-instead of silently joining the suite the driver runs.  Once they pass on the GPU they move to the regular files.
-
-  * fp16 feature hand-off (AVL_FEAT_F16, csrc/build_path.cu chw16_to_hwc_kernel)
-  * the fused peer-memory exchange with a world of one (csrc/p2p_exchange.cu); N > 1: tools/p2p_check.py under torchrun
-  * the streamed-B variant of the screen kernel (AVL_STREAM_B=1, csrc/sim_screen.cu screen_kernel<CG, true>)
-"""
+"""fp16 feature hand-off (AVL_FEAT_F16, csrc/build_path.cu chw16_to_hwc_kernel) and the fused peer-memory exchange with a
+world of one (csrc/p2p_exchange.cu; N > 1: tools/p2p_check.py and tools/sharded_index_check.py under torchrun).
+Written at the end of round 1 without GPU time; first run on a B200 in round 2 (gpurun_out/r2a_call.log: 4 passed)."""
 import os
 
 import numpy as np
@@ -14,8 +9,7 @@ import pytest
 import synth
 from oracle import avl_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AVL_UNVERIFIED") != "1", reason="not yet run on a GPU: set AVL_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_fp16_features_give_the_same_map_as_their_float32_values(lib):
@@ -83,22 +77,3 @@ def test_p2p_exchange_with_a_world_of_one(lib):
             assert np.array_equal(oi[q, :n], idx[q][keep][order]) and np.array_equal(ov[q, :n], val[q][keep][order])
             assert np.all(oi[q, n:] == -1) and np.all(np.isneginf(ov[q, n:]))
     ex.close()
-
-
-@pytest.mark.parametrize("extra_env", [{"AVL_CTA_GROUP": "2"}, {}])
-def test_streamed_b_screen_variant_matches_the_oracle(lib, extra_env):
-    """screen_kernel<CG, SB = true> (AVL_STREAM_B=1: B's k-blocks travel with A's instead of staying resident).  The
-    switch is read once per process, so the checks run in child processes: the smoke test (20 k x 512 map, 64 and 256
-    queries, argmax + top-k) with the 2-CTA kernel forced, and the small every-kernel driver with the engine's choice."""
-    import subprocess
-    import sys
-    from pathlib import Path
-
-    root = Path(__file__).resolve().parents[1]
-    env = dict(os.environ, AVL_STREAM_B="1", **extra_env)
-    # smoke() only (not the script's main, which would rebuild the library this process has loaded)
-    cmd = ([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"] if extra_env
-           else [sys.executable, str(root / "tools" / "sanitize_small.py")])
-    r = subprocess.run(cmd, env=env, cwd=str(root), capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert ("smoke ok" in r.stdout) if extra_env else ("build ok" in r.stdout)
