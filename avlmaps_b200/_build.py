@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG.parent / "build" / "obj"
 LIB = PKG / "libavlmaps_b200.so"
 
-SOURCES = ["sim_screen.cu", "sim_screen_ts.cu", "sim_exact.cu", "index_api.cu", "build_path.cu", "heat_path.cu", "p2p_exchange.cu"]
+SOURCES = ["sim_screen.cu", "sim_exact.cu", "index_api.cu", "build_path.cu", "heat_path.cu", "p2p_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

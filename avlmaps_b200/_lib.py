@@ -28,6 +28,7 @@ FEAT_CHW, FEAT_HWC = 0, 1
 EXPORTS = [
     "avl_version", "avl_last_error", "avl_device_count", "avl_set_device", "avl_set_profiling",
     "avl_map_create", "avl_map_destroy", "avl_map_shape", "avl_map_device_bytes", "avl_map_operand_f16",
+    "avl_map_screen_times",
     "avl_sim_dense", "avl_sim_argmax", "avl_sim_topk", "avl_sim_screen_dense", "avl_topk_f32", "avl_fuse_topk",
     "avl_heat_from_mask_3d", "avl_merge_topk", "avl_heat2d_sources",
     "avl_builder_create", "avl_builder_destroy", "avl_builder_add_frame", "avl_builder_num_voxels",
@@ -102,6 +103,7 @@ def load() -> C.CDLL:
     lib.avl_map_destroy.argtypes = [vp]
     lib.avl_map_operand_f16.argtypes = [vp]
     lib.avl_map_shape.argtypes = [vp, C.POINTER(i64), C.POINTER(i32)]
+    lib.avl_map_screen_times.argtypes = [vp, C.POINTER(C.c_float), i32, C.POINTER(i32)]
     lib.avl_sim_dense.argtypes = [vp, f32p, i32, f32p, C.c_int, f32p, C.c_int, vp]
     lib.avl_sim_argmax.argtypes = [vp, f32p, i32, f32p, C.c_int, vp, C.c_int, vp, C.POINTER(IndexStats)]
     lib.avl_sim_topk.argtypes = [vp, f32p, i32, f32p, C.c_int, i32, vp, vp, C.c_int, vp, C.POINTER(IndexStats)]
@@ -136,7 +138,7 @@ def load() -> C.CDLL:
     lib.avl_p2p_handle_bytes.argtypes = []
     lib.avl_p2p_local_handle.argtypes = [vp, vp]
     lib.avl_p2p_connect.argtypes = [vp, vp]
-    lib.avl_p2p_exchange_merge.argtypes = [vp, vp, vp, i32, i32, i64, vp, vp, C.c_int, vp]
+    lib.avl_p2p_exchange_merge.argtypes = [vp, vp, vp, i32, i32, i64, vp, vp, vp, C.c_int, vp]
     lib.avl_p2p_status.argtypes = [vp, C.POINTER(i32), vp]
     lib.avl_p2p_destroy.argtypes = [vp]
     _lib = lib

@@ -57,7 +57,7 @@ struct ScreenParams {
   // per-query statistics (query_prepare)
   const float* q_bn;       // >= ||b_q||
   const __nv_bfloat16* a_base; // operand copy of the map (tile-major: the L2 prefetch addresses it directly)
-  const __nv_bfloat16* bq; // bf16 queries (256 zero-padded rows x dpad), read by the query-stationary kernel
+  const __nv_bfloat16* bq; // bf16 queries (256 zero-padded rows x dpad)
   const float* q_glob;     // [0] rho >= max_q ||b_q - bf16(b_q)|| / ||b_q|| (+slack), [1] max_q q_bn
   // kModeDense
   float* dense_out;        // element (r, q) at r * dense_rs + q * dense_cs, r = compact row
@@ -72,10 +72,10 @@ struct ScreenParams {
   uint32_t flag_cap;
   // kModeThresh
   const float* thr_t;      // per query tau_q / scale_q  (+inf disables a query)
-  uint32_t* cand_cnt;      // [nq] entries appended per query (may exceed cand_cap)
-  uint32_t* cand_row;      // [nq][cand_cap] map row
-  float* cand_val;         // [nq][cand_cap] screen score s~
-  uint32_t cand_cap;
+  uint32_t* cand_cnt;      // [grid][AVL_MAX_QUERIES] fill count of bucket (query, CTA); may exceed cand_bucket
+  uint32_t* cand_row;      // [nq][grid][cand_bucket] map row
+  float* cand_val;         // [nq][grid][cand_bucket] screen score s~
+  uint32_t cand_bucket;    // entries per (query, CTA) bucket
   // watchdog record (host-mapped), may be null
   uint32_t* dbg;
 };
@@ -85,11 +85,7 @@ int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const S
                   int num_sms, size_t smem_bytes, cudaStream_t stream);
 size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages, int mode);
 int screen_pick_stages(int cta_group, int npad, int kblocks, int mode);  // <=0: does not fit
-// query-stationary variant (sim_screen_ts.cu): queries in TMEM, 128-voxel tiles, cta_group::2 only
-int launch_screen_ts(const void* tmap_v64, const ScreenParams& p, int num_sms, size_t smem_bytes,
-                     cudaStream_t stream);
-size_t screen_ts_smem_bytes(int stages);
-int screen_ts_pick_stages();
+int screen_grid(int cta_group, int num_sms, int num_tiles);  // CTAs launch_screen starts
 
 // ---- exact / helper kernels (sim_exact.cu) --------------------------------
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
@@ -112,9 +108,15 @@ int launch_select_threshold(const float* sample_lb, int32_t n_sample_rows, int64
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c,
                          const float* row_an, const float* q_bn, const float* q_glob, int normalize,
-                         int32_t k, const uint32_t* cand_cnt, const uint32_t* cand_row, const float* cand_val,
-                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
+                         int32_t k, const uint32_t* bucket_cnt, int32_t grid, uint32_t cand_bucket,
+                         const uint32_t* cand_row, const float* cand_val, uint32_t fin_cap, int64_t* out_idx,
+                         float* out_score, uint32_t* cand_total, uint32_t* overflow_flags, cudaStream_t s);
+// exact re-score of the queries whose overflow flag is set, decided on the device (no host round trip)
+int launch_topk_fallback(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq, const float* scale,
+                         const float* row_norm, int normalize, int32_t k, const uint32_t* overflow_flags,
+                         void* scratch, uint32_t* tickets, int64_t* out_idx, float* out_score, int num_sms,
                          cudaStream_t s);
+size_t topk_fallback_scratch_bytes(int num_sms);
 int launch_topk_vector(const float* values, int64_t n, int32_t k, int64_t* out_idx, float* out_val,
                        void* scratch, size_t scratch_bytes, cudaStream_t s);
 size_t topk_vector_scratch_bytes(int64_t n);

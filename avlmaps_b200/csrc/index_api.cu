@@ -89,6 +89,10 @@ struct Workspace {
   float* cand_val2 = nullptr;    // second per-candidate value (fusion: heat lower bounds)
   uint32_t cand_cap = 0;
   uint32_t* overflow = nullptr;  // [256]
+  uint32_t* bucket_cnt = nullptr;  // [num_sms][256] fill counts of the per-CTA candidate buckets (top-k screen)
+  void* fb_scratch = nullptr;    // per-block top-k keys of the exact fallback
+  size_t fb_scratch_bytes = 0;
+  uint32_t* fb_tickets = nullptr;  // [256]
   float* sample_t = nullptr;
   size_t sample_elems = 0;
   float* fuse_a = nullptr;       // (pairs, n) dense screen scores of the two modalities (avl_fuse_topk)
@@ -105,6 +109,8 @@ struct Workspace {
   uint32_t* dbg_dev = nullptr;
   uint32_t* pin = nullptr;       // pinned host scratch for the small read-backs (pageable copies stage and stall)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ring_ev[2 * 256] = {};  // event pairs around the main screen launch of the last 256 profiled top-k calls
+  int ring_n = 0;                      // pairs recorded since the last avl_map_screen_times
 };
 
 }  // namespace avl
@@ -122,7 +128,6 @@ struct avl_map {
   float* row_c = nullptr;
   float* row_an = nullptr;
   CUtensorMap tmap_a;     // box 64 x 128 rows (sim_screen.cu)
-  CUtensorMap tmap_a64;   // box 64 x 64 rows  (sim_screen_ts.cu)
   int64_t bytes = 0;
   avl::Workspace ws;
 };
@@ -152,6 +157,10 @@ static int ws_init(avl_map* m) {
   // counters and overflow flags are adjacent: one 2 KiB read-back into pinned memory per top-k call
   if ((rc = dev_alloc(&w.cand_cnt, 2 * AVL_MAX_QUERIES, &m->bytes))) return rc;
   w.overflow = w.cand_cnt + AVL_MAX_QUERIES;
+  AVL_CUDA(cudaMemset(w.cand_cnt, 0, 2 * AVL_MAX_QUERIES * sizeof(uint32_t)));
+  if ((rc = dev_alloc(&w.bucket_cnt, static_cast<size_t>(256) * AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.fb_tickets, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  AVL_CUDA(cudaMemset(w.fb_tickets, 0, AVL_MAX_QUERIES * sizeof(uint32_t)));
   AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.pin), 2 * AVL_MAX_QUERIES * sizeof(uint32_t), cudaHostAllocDefault));
   if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
@@ -159,6 +168,7 @@ static int ws_init(avl_map* m) {
   memset(w.dbg_host, 0, 4096);
   AVL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.dbg_dev), w.dbg_host, 0));
   for (int i = 0; i < 4; ++i) AVL_CUDA(cudaEventCreate(&w.ev[i]));
+  for (int i = 0; i < 2 * 256; ++i) AVL_CUDA(cudaEventCreate(&w.ring_ev[i]));
   return AVL_OK;
 }
 
@@ -168,10 +178,13 @@ static void ws_free(Workspace& w) {
   cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
   cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small); cudaFree(w.cand_val2);
+  cudaFree(w.bucket_cnt); cudaFree(w.fb_scratch); cudaFree(w.fb_tickets);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
   if (w.pin) cudaFreeHost(w.pin);
   for (int i = 0; i < 4; ++i)
     if (w.ev[i]) cudaEventDestroy(w.ev[i]);
+  for (int i = 0; i < 2 * 256; ++i)
+    if (w.ring_ev[i]) cudaEventDestroy(w.ring_ev[i]);
 }
 
 static int ensure_flags(avl_map* m) {
@@ -194,6 +207,18 @@ static int ensure_cands(avl_map* m, uint32_t cap) {
   if ((rc = dev_alloc(&w.cand_row, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.cand_val, static_cast<size_t>(AVL_MAX_QUERIES) * cap, &m->bytes))) return rc;
   w.cand_cap = cap;
+  return AVL_OK;
+}
+static int ensure_fallback(avl_map* m, int32_t k) {
+  Workspace& w = m->ws;
+  const size_t need = static_cast<size_t>(AVL_MAX_QUERIES) * (2 * m->num_sms) * k * sizeof(unsigned long long);
+  if (w.fb_scratch_bytes >= need) return AVL_OK;
+  cudaFree(w.fb_scratch);
+  w.fb_scratch = nullptr;
+  w.fb_scratch_bytes = 0;
+  AVL_CUDA(cudaMalloc(&w.fb_scratch, need));
+  w.fb_scratch_bytes = need;
+  m->bytes += static_cast<int64_t>(need);
   return AVL_OK;
 }
 static int ensure_sample(avl_map* m, size_t elems) {
@@ -244,24 +269,11 @@ static int pick_cta_group(int npad, int kblocks, int forced, int mode) {
   return 0;
 }
 
-// query-stationary kernel: 128 < nq <= 256 and D <= 512 (AVL_TS=0 disables, AVL_TS=1 forces for any nq)
-static bool want_ts(int nq, int dpad, int forced_cg, bool allow_ts) {
-  if (forced_cg == 3) return dpad <= 512;
-  if (!allow_ts || forced_cg != 0 || dpad > 512) return false;
-  const char* e = getenv("AVL_TS");
-  // Measured on B200 (4M x 512 x 256): 1.15 ms vs 0.90 ms for the shared-memory-operand kernel -- the
-  // M=256 x N=128 A-from-TMEM MMAs retire at ~106 cycles instead of the 64 the tile shape suggests, so the
-  // deeper ring does not pay.  Kept as an opt-in variant (AVL_TS=1), parity-tested like the default.
-  (void)nq;
-  return e && e[0] == '1';
-}
-
 struct QuerySetup {
   const float* q_dev = nullptr;      // fp32 queries on device
   const float* scale_dev = nullptr;  // or null
   int npad = 0;
   int cg = 0;
-  bool ts = false;                   // query-stationary kernel (queries in TMEM)
   int unit_rows = 0;                 // voxel rows per tile unit of the chosen kernel
   int stages = 0;
   size_t smem = 0;
@@ -271,7 +283,7 @@ struct QuerySetup {
 // stage queries, build bf16 B + norms, pick the kernel variant
 static int setup_queries(avl_map* m, const float* queries, int32_t nq, const float* scale, int flags,
                          int forced_cg, int screen_mode /* ScreenMode of the pass that follows, -1: no screen */,
-                         cudaStream_t s, QuerySetup* qs, bool fold_scale = false, bool allow_ts = false) {
+                         cudaStream_t s, QuerySetup* qs, bool fold_scale = false) {
   Workspace& w = m->ws;
   AVL_ARG(queries != nullptr, "queries is NULL");
   AVL_ARG(nq >= 1 && nq <= AVL_MAX_QUERIES, "nq must be in [1, AVL_MAX_QUERIES]");
@@ -290,17 +302,6 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
   if (screen_mode < 0) return AVL_OK;
   qs->npad = (nq + 15) & ~15;
   const int kblocks = m->dpad / kBlockK;
-  if (want_ts(nq, m->dpad, forced_cg, allow_ts)) {
-    // large batches: queries live in TMEM, all of shared memory streams voxel tiles
-    qs->ts = true;
-    qs->cg = 2;
-    qs->npad = AVL_MAX_QUERIES;
-    qs->unit_rows = 128;
-    qs->stages = screen_ts_pick_stages();
-    qs->smem = screen_ts_smem_bytes(qs->stages);
-    return launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
-                                w.q_bn, w.q_glob, m->op_f16, s);
-  }
   qs->cg = pick_cta_group(qs->npad, kblocks, forced_cg, screen_mode);
   if (qs->cg == 0) {
     set_error("query batch does not fit the shared memory of an SM pair (nq * dim too large); split the batch");
@@ -355,7 +356,6 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
 }
 
 static int run_screen(avl_map* m, const QuerySetup& qs, const ScreenParams& p, cudaStream_t s) {
-  if (qs.ts) return launch_screen_ts(&m->tmap_a64, p, m->num_sms, qs.smem, s);
   return launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s);
 }
 
@@ -465,7 +465,6 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
     const uint64_t map_rows = m->tiled ? static_cast<uint64_t>(tile_rows_total) * (m->dpad / kBlockK) : rows;
     const uint64_t map_cols = m->tiled ? static_cast<uint64_t>(kBlockK) : static_cast<uint64_t>(m->dpad);
     if ((rc = encode_kmajor_map(&m->tmap_a, m->bf, map_rows, map_cols, kTileRows, m->op_f16 != 0))) break;
-    if ((rc = encode_kmajor_map(&m->tmap_a64, m->bf, map_rows, map_cols, 64, m->op_f16 != 0))) break;
   } while (0);
   if (rc) {
     avl_map_destroy(m);
@@ -668,29 +667,32 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   }
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
   QuerySetup qs;
-  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeThresh, s, &qs, false, /*allow_ts=*/true))) return rc;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeThresh, s, &qs))) return rc;
   int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
   float* d_score = (flags & AVL_ON_DEVICE) ? out_score : w.out_score;
 
   const int64_t unit = qs.unit_rows;
   const int64_t total_units = (m->n + unit - 1) / unit;
-  // rows sampled for the threshold: ~n/64, enough that ~k*n/n0 candidates per query stay << cand_cap
+  // rows sampled for the threshold: ~n/64, enough that ~k*n/n0 candidates per query stay << the finalize capacity
   int64_t n0 = std::max<int64_t>(m->n / 64, static_cast<int64_t>(k) * m->n / 1024);
   n0 = std::min<int64_t>(std::max<int64_t>(n0, 8192), std::max<int64_t>(m->n, 1));
   int64_t sample_units = std::min<int64_t>(total_units, (n0 + unit - 1) / unit);
   int64_t tile_stride = sample_units > 0 ? std::max<int64_t>(1, total_units / sample_units) : 1;
   if (sample_units > 0) sample_units = std::min<int64_t>(sample_units, (total_units + tile_stride - 1) / tile_stride);
   const int64_t n_sample = sample_units * unit;
-  const uint32_t cand_cap = 8192;            // per-query entries the finalize block can hold (~4x the expected load)
-  if ((rc = ensure_cands(m, cand_cap))) return rc;
+  // candidates: one bucket per (query, CTA of the screen launch); the finalize block of a query holds fin_cap of them
+  const uint32_t fin_cap = 8192;
+  const int grid = screen_grid(qs.cg, m->num_sms, static_cast<int>(std::min<int64_t>(total_units, 1 << 30)));
+  const uint32_t bucket = std::min<uint32_t>(fin_cap, std::max<uint32_t>(128u, 4u * fin_cap / static_cast<uint32_t>(std::max(grid, 1))));
+  if ((rc = ensure_cands(m, static_cast<uint32_t>(std::max(grid, 1)) * bucket))) return rc;
   if ((rc = ensure_sample(m, static_cast<size_t>(std::max<int64_t>(n_sample, 1)) * nq))) return rc;
+  if ((rc = ensure_fallback(m, k))) return rc;
 
   ScreenParams p;
   if (m->n > 0) {
-    // phase A: lower bounds of the sampled tiles.  The regular screen reduces them in its epilogue to one maximum
-    // per 32-row group and query (dense_lb = 2); the query-stationary variant stores them per row.
-    const bool grouped = !qs.ts;
-    const int64_t n_cols = grouped ? n_sample / 32 : n_sample;
+    // phase A: lower bounds of the sampled tiles, reduced in the screen's epilogue to one maximum per 32-row group
+    // and query (dense_lb = 2)
+    const int64_t n_cols = n_sample / 32;
     base_params(m, qs, nq, normalize_map, &p);
     p.mode = kModeDense;
     p.num_tiles = static_cast<int32_t>(sample_units);
@@ -699,77 +701,76 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     p.dense_rs = 1;
     p.dense_cs = n_cols;
     p.dense_cols = nq;
-    p.dense_lb = grouped ? 2 : 1;
+    p.dense_lb = 2;
     p.prefetch_tiles = 0;  // sampled tiles are strided: nothing sequential to prefetch
     if ((rc = run_screen(m, qs, p, s))) return rc;
     if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_cols), n_cols, nq, k, w.thr_t, s)))
       return rc;
-  }
-  AVL_CUDA(cudaMemsetAsync(w.cand_cnt, 0, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, s));  // counters + overflow flags
-  if (m->n > 0) {
     // phase B: full pass, candidates = rows whose upper bound reaches the threshold
     base_params(m, qs, nq, normalize_map, &p);
     p.mode = kModeThresh;
     p.thr_t = w.thr_t;
-    p.cand_cnt = w.cand_cnt;
+    p.cand_cnt = w.bucket_cnt;
     p.cand_row = w.cand_row;
     p.cand_val = w.cand_val;
-    p.cand_cap = cand_cap;
-    if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[1], s));
+    p.cand_bucket = bucket;
+    const int slot = w.ring_n % 256;
+    if (g_profiling) {
+      AVL_CUDA(cudaEventRecord(w.ev[1], s));
+      AVL_CUDA(cudaEventRecord(w.ring_ev[2 * slot], s));
+    }
     if ((rc = run_screen(m, qs, p, s))) return rc;
-    if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[2], s));
-  }
-  // phase C: exact re-score of the survivors, final order
-  if ((rc = launch_topk_finalize(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, m->row_c,
-                                 m->row_an, w.q_bn, w.q_glob, normalize_map, k, w.cand_cnt, w.cand_row,
-                                 w.cand_val, cand_cap, d_idx, d_score, w.overflow, s)))
-    return rc;
-  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
-
-  // overflowed queries (adversarial data, massive ties): exact dense column + vector top-k
-  AVL_CUDA(cudaMemcpyAsync(w.pin, w.cand_cnt, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, cudaMemcpyDeviceToHost, s));
-  const uint32_t* cnt = w.pin;
-  const uint32_t* ovf = w.pin + AVL_MAX_QUERIES;
-  {
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk", __FILE__, __LINE__));
-  }
-  if (p.debug_flags & 64)  // triage: true SM clock of the main screen launch (cycles / nanoseconds of block 0)
-    fprintf(stderr, "[avl clock] screen: %llu cycles in %u ns = %.0f MHz\n",
-            static_cast<unsigned long long>(w.dbg_host[8]) | (static_cast<unsigned long long>(w.dbg_host[9]) << 32),
-            w.dbg_host[10], w.dbg_host[10] ? 1e3 * (static_cast<double>(w.dbg_host[8]) + 4294967296.0 * w.dbg_host[9]) / w.dbg_host[10] : 0.0);
-  if (p.debug_flags & 64) {  // per-CTA spans of the main screen launch: start offset, duration, MHz, SM
-    uint32_t t0 = 0xFFFFFFFFu;
-    for (int b = 0; b < m->num_sms && b < 160; ++b) t0 = std::min(t0, w.dbg_host[16 + 4 * b]);
-    for (int b = 0; b < m->num_sms && b < 160; ++b) {
-      const uint32_t* r = w.dbg_host + 16 + 4 * b;
-      fprintf(stderr, "[avl cta] %3d sm %3u start %6u ns dur %7u ns end %7u ns %5.0f MHz\n", b, r[3], r[0] - t0, r[1],
-              r[0] - t0 + r[1], r[1] ? 1e3 * r[2] / r[1] : 0.0);
+    if (g_profiling) {
+      AVL_CUDA(cudaEventRecord(w.ev[2], s));
+      AVL_CUDA(cudaEventRecord(w.ring_ev[2 * slot + 1], s));
+      ++w.ring_n;
     }
   }
-  int n_fallback = 0;
-  int64_t n_cand = 0;
-  for (int q = 0; q < nq; ++q) {
-    n_cand += cnt[q];
-    if (!ovf[q]) continue;
-    ++n_fallback;
-    if ((rc = ensure_column(m))) return rc;
-    if ((rc = launch_column_exact(m->feat, m->n, m->d, qs.q_dev + static_cast<size_t>(q) * m->d,
-                                  qs.scale_dev ? qs.scale_dev + q : nullptr, m->row_norm, normalize_map, w.column,
-                                  m->num_sms, s)))
-      return rc;
-    if ((rc = launch_topk_vector(w.column, m->n, k, d_idx + static_cast<size_t>(q) * k,
-                                 d_score + static_cast<size_t>(q) * k, w.topk_scratch, w.topk_scratch_bytes, s)))
-      return rc;
-  }
+  // phase C: exact re-score of the survivors, final order; totals and overflow flags per query
+  if ((rc = launch_topk_finalize(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, m->row_c,
+                                 m->row_an, w.q_bn, w.q_glob, normalize_map, k, w.bucket_cnt, m->n > 0 ? grid : 0,
+                                 bucket, w.cand_row, w.cand_val, fin_cap, d_idx, d_score, w.cand_cnt, w.overflow, s)))
+    return rc;
+  // phase D: queries whose buckets overflowed (adversarial data, massive ties) are re-scored exactly -- decided on
+  // the device: the kernel leaves at once when no flag is set, so the call needs no host round trip
+  if ((rc = launch_topk_fallback(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map, k,
+                                 w.overflow, w.fb_scratch, w.fb_tickets, d_idx, d_score, m->num_sms, s)))
+    return rc;
+  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
   if (!(flags & AVL_ON_DEVICE)) {
     AVL_CUDA(cudaMemcpyAsync(out_idx, d_idx, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, s));
     AVL_CUDA(cudaMemcpyAsync(out_score, d_score, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, s));
-    AVL_CUDA(cudaStreamSynchronize(s));
+  }
+  const bool triage = m->n > 0 && (p.debug_flags & 64);
+  if (stats || triage) AVL_CUDA(cudaMemcpyAsync(w.pin, w.cand_cnt, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, cudaMemcpyDeviceToHost, s));
+  // device-pointer calls without stats return here, asynchronously: results are ordered on `stream` like any kernel's
+  if (!(flags & AVL_ON_DEVICE) || stats || triage) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk", __FILE__, __LINE__));
+  }
+  if (triage) {  // true SM clock of the main screen launch (cycles / nanoseconds of block 0) and per-CTA spans
+    fprintf(stderr, "[avl clock] screen: %llu cycles in %u ns = %.0f MHz\n",
+            static_cast<unsigned long long>(w.dbg_host[8]) | (static_cast<unsigned long long>(w.dbg_host[9]) << 32),
+            w.dbg_host[10], w.dbg_host[10] ? 1e3 * (static_cast<double>(w.dbg_host[8]) + 4294967296.0 * w.dbg_host[9]) / w.dbg_host[10] : 0.0);
+    uint32_t t0 = 0xFFFFFFFFu;
+    for (int b = 0; b < grid && b < 160; ++b) t0 = std::min(t0, w.dbg_host[16 + 4 * b]);
+    for (int b = 0; b < grid && b < 160; ++b) {
+      const uint32_t* r = w.dbg_host + 16 + 4 * b;
+      fprintf(stderr, "[avl cta] %3d sm %3u start %6u ns dur %7u ns end %7u ns %5.0f MHz tiles %u\n", b, r[3], r[0] - t0, r[1],
+              r[0] - t0 + r[1], r[1] ? 1e3 * r[2] / r[1] : 0.0, w.dbg_host[16 + 4 * 160 + b]);
+    }
   }
   if (stats) {
-    stats->cta_group = qs.ts ? 3 : qs.cg;
-    stats->n_launches = 5 + 3 * n_fallback;  // query_prepare, sample screen, select, screen, finalize
+    const uint32_t* cnt = w.pin;
+    const uint32_t* ovf = w.pin + AVL_MAX_QUERIES;
+    int n_fallback = 0;
+    int64_t n_cand = 0;
+    for (int q = 0; q < nq; ++q) {
+      n_cand += cnt[q];
+      n_fallback += ovf[q] ? 1 : 0;
+    }
+    stats->cta_group = qs.cg;
+    stats->n_launches = 6;  // query_prepare, sample screen, select, screen, finalize, fallback
     stats->n_candidates = n_cand;
     stats->n_fallback_queries = n_fallback;
     stats->sample_rows = static_cast<int32_t>(std::min<int64_t>(n_sample, m->n));
@@ -778,6 +779,22 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
       cudaEventElapsedTime(&stats->ms_total, w.ev[0], w.ev[3]);
     }
   }
+  return AVL_OK;
+}
+
+int avl_map_screen_times(avl_map* m, float* out_ms, int32_t cap, int32_t* n_out) {
+  AVL_ARG(m != nullptr && out_ms != nullptr && n_out != nullptr && cap >= 0, "invalid argument");
+  Workspace& w = m->ws;
+  const int have = std::min(w.ring_n, 256);
+  const int n = std::min<int>(have, cap);
+  *n_out = 0;
+  if (have > 0) AVL_CUDA(cudaEventSynchronize(w.ring_ev[2 * ((w.ring_n - 1) % 256) + 1]));
+  for (int i = 0; i < n; ++i) {
+    const int slot = (w.ring_n - n + i) % 256;
+    AVL_CUDA(cudaEventElapsedTime(out_ms + i, w.ring_ev[2 * slot], w.ring_ev[2 * slot + 1]));
+  }
+  *n_out = n;
+  w.ring_n = 0;
   return AVL_OK;
 }
 
@@ -858,7 +875,6 @@ static int fuse_topk_screened(avl_map* ma, const float* qa, const float* scale_a
   int rc;
   if ((rc = setup_queries(ma, qa, n_pairs, scale_a, flags, 0, kModeDense, s, &sa))) return rc;
   if ((rc = setup_queries(mb, qb, n_pairs, scale_b, flags, 0, kModeDense, s, &sb))) return rc;
-  if (sa.ts || sb.ts) return 1;
   Workspace& w = ma->ws;
   const uint32_t cand_cap = 8192, ext_cap = 2048;
   if ((rc = ensure_cands(ma, cand_cap))) return rc;

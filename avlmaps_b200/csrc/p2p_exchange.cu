@@ -44,9 +44,13 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(128)
 p2p_exchange_merge_kernel(const __grid_constant__ P2PView v, const int64_t* __restrict__ idx,
                           const float* __restrict__ val, int32_t nq, int32_t k, uint32_t epoch, int64_t row_offset,
-                          int64_t* __restrict__ out_idx, float* __restrict__ out_val, uint32_t* __restrict__ status) {
+                          const int64_t* __restrict__ global_ids, int64_t* __restrict__ out_idx,
+                          float* __restrict__ out_val, uint32_t* __restrict__ status) {
   __shared__ int64_t si[1024];
   __shared__ float sv[1024];
+  __shared__ uint32_t sh_timeout;
+  if (threadIdx.x == 0) sh_timeout = 0u;
+  __syncthreads();
   const int q = blockIdx.x;
   const uint32_t parity = epoch & 1u;
   const uint64_t ids_bytes = static_cast<uint64_t>(v.nq_max) * v.k_max * sizeof(int64_t);
@@ -54,8 +58,11 @@ p2p_exchange_merge_kernel(const __grid_constant__ P2PView v, const int64_t* __re
   for (int e = threadIdx.x; e < v.world * k; e += blockDim.x) {
     const int dst = e / k, j = e - dst * k;
     uint8_t* slot = v.peer[dst] + (static_cast<uint64_t>(parity) * v.world + v.rank) * v.slot_bytes;
-    const int64_t id = idx[static_cast<size_t>(q) * k + j];   // slab-local row -> global row (empty slots stay -1)
-    reinterpret_cast<int64_t*>(slot)[static_cast<size_t>(q) * k + j] = id >= 0 ? id + row_offset : id;
+    // slab-local row -> global row (empty slots stay -1): a contiguous slab adds its first row; the slab of a sharded
+    // BUILD looks its rows up in the first-touch id table (ShardedBuilder.finalize)
+    const int64_t id = idx[static_cast<size_t>(q) * k + j];
+    reinterpret_cast<int64_t*>(slot)[static_cast<size_t>(q) * k + j] =
+        id < 0 ? id : (global_ids ? global_ids[id] : id + row_offset);
     reinterpret_cast<float*>(slot + ids_bytes)[static_cast<size_t>(q) * k + j] = val[static_cast<size_t>(q) * k + j];
   }
   __threadfence_system();
@@ -73,12 +80,22 @@ p2p_exchange_merge_kernel(const __grid_constant__ P2PView v, const int64_t* __re
       if (clock64() - t0 > kSpinTimeoutCycles) {
         *reinterpret_cast<volatile uint32_t*>(status) = 1u + threadIdx.x;  // which source never arrived (host-mapped word)
         __threadfence_system();
+        sh_timeout = 1u;
         break;
       }
       __nanosleep(64);
     }
   }
   __syncthreads();
+  if (sh_timeout) {
+    // a source never delivered this query: stale bytes must not pass for a result.  The query comes back EMPTY
+    // (-1 / -inf) and the status word makes every later call on this exchange fail with AVL_ERR_STATE.
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      out_idx[static_cast<size_t>(q) * k + j] = -1;
+      out_val[static_cast<size_t>(q) * k + j] = -INFINITY;
+    }
+    return;
+  }
   // ---- 3. merge world * k entries: (score desc, global id asc), -1 = empty slot
   const int m = v.world * k;
   const uint8_t* base = v.peer[v.rank] + static_cast<uint64_t>(parity) * v.world * v.slot_bytes;
@@ -190,7 +207,7 @@ int avl_p2p_connect(avl_p2p* p, const uint8_t* handles) {
 }
 
 int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int32_t nq, int32_t k, int64_t row_offset,
-                           int64_t* out_idx, float* out_val, int flags, void* stream) {
+                           const int64_t* global_ids, int64_t* out_idx, float* out_val, int flags, void* stream) {
   AVL_ARG(p != nullptr && idx && val && out_idx && out_val, "NULL argument");
   AVL_ARG(nq >= 1 && nq <= p->view.nq_max && k >= 1 && k <= p->view.k_max, "nq / k exceed what the exchange was created for");
   if (!(flags & AVL_ON_DEVICE)) {
@@ -210,7 +227,7 @@ int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int
   }
   p->epoch += 1;
   p2p_exchange_merge_kernel<<<nq, 128, 0, static_cast<cudaStream_t>(stream)>>>(p->view, idx, val, nq, k, p->epoch, row_offset,
-                                                                              out_idx, out_val, p->status);
+                                                                              global_ids, out_idx, out_val, p->status);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

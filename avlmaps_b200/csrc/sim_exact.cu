@@ -466,14 +466,16 @@ select_threshold_kernel(const float* __restrict__ sample_lb, int32_t n_sample, i
 // LOWER bound, keeps the entries whose UPPER bound reaches it, re-scores those exactly (fp64) and
 // orders them by (score desc, row asc).
 constexpr int kFinThreads = 1024;
+constexpr int kFinMaxGrid = 256;   // CTAs of one screen launch (one per SM)
 __global__ void __launch_bounds__(kFinThreads)
 topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, const float* __restrict__ q,
                      const float* __restrict__ scale, const float* __restrict__ row_norm,
                      const float* __restrict__ row_c, const float* __restrict__ row_an,
                      const float* __restrict__ q_bn, const uint32_t* __restrict__ glob, int normalize,
-                     int32_t k, const uint32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ cand_row,
-                     const float* __restrict__ cand_val, uint32_t cand_cap, int64_t* __restrict__ out_idx,
-                     float* __restrict__ out_score, uint32_t* __restrict__ overflow_flags) {
+                     int32_t k, const uint32_t* __restrict__ bucket_cnt, int32_t grid, uint32_t cand_bucket,
+                     const uint32_t* __restrict__ cand_row, const float* __restrict__ cand_val, uint32_t cand_cap,
+                     int64_t* __restrict__ out_idx, float* __restrict__ out_score,
+                     uint32_t* __restrict__ cand_total, uint32_t* __restrict__ overflow_flags) {
   extern __shared__ uint8_t sm[];
   uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
   uint32_t* Uk = Lk + cand_cap;
@@ -483,16 +485,49 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Ix + cand_cap);
   __shared__ int sh_cnt;
   __shared__ int sh_ns;
+  __shared__ uint32_t sh_off[kFinMaxGrid + 1];
+  __shared__ uint32_t sh_bad;
   const int qq = blockIdx.x;
-  const uint32_t cnt = cand_cnt[qq];
-  if (cnt > cand_cap) {  // list overflow (adversarial data, massive ties): exact fallback on the host side
+  // The screen left this query's candidates in one bucket per CTA (sim_screen.cu): exclusive scan of the fill counts,
+  // then every warp copies whole buckets.  A bucket that overflowed, or more candidates than this block can hold,
+  // flags the query for the exact fallback (adversarial data, massive ties).
+  if (threadIdx.x == 0) { sh_ns = 0; sh_bad = 0u; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t run = 0u;
+    for (int c0 = 0; c0 < grid; c0 += 32) {
+      const int c = c0 + static_cast<int>(threadIdx.x);
+      const uint32_t v = c < grid ? bucket_cnt[static_cast<size_t>(c) * AVL_MAX_QUERIES + qq] : 0u;
+      if (v > cand_bucket) sh_bad = 1u;
+      uint32_t x = v;  // inclusive warp scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (static_cast<int>(threadIdx.x) >= o) x += y;
+      }
+      if (c < grid) sh_off[c] = run + x - v;
+      run += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (threadIdx.x == 0) sh_off[grid] = run;
+  }
+  __syncthreads();
+  const uint32_t cnt = sh_off[grid];
+  if (threadIdx.x == 0) cand_total[qq] = cnt;
+  if (sh_bad || cnt > cand_cap) {
     if (threadIdx.x == 0) overflow_flags[qq] = 1u;
     return;
   }
-  if (threadIdx.x == 0) sh_ns = 0;
-  for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-    Ix[j] = cand_row[static_cast<size_t>(qq) * cand_cap + j];
-    Lk[j] = __float_as_uint(cand_val[static_cast<size_t>(qq) * cand_cap + j]);
+  if (threadIdx.x == 0) overflow_flags[qq] = 0u;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int c = warp; c < grid; c += nw) {
+      const uint32_t o = sh_off[c], m = sh_off[c + 1] - o;
+      const size_t src = (static_cast<size_t>(qq) * grid + c) * cand_bucket;
+      for (uint32_t j = lane; j < m; j += 32) {
+        Ix[o + j] = cand_row[src + j];
+        Lk[o + j] = __float_as_uint(cand_val[src + j]);
+      }
+    }
   }
   __syncthreads();
   const int n = static_cast<int>(cnt);
@@ -617,6 +652,100 @@ topk_vec_l2_kernel(const unsigned long long* __restrict__ keys, int m, int32_t k
   for (int s = ns + threadIdx.x; s < k; s += blockDim.x) {
     out_idx[s] = -1;
     out_val[s] = -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------ exact fallback, decided on the device
+// Always launched after topk_finalize; every block walks the overflow flags and leaves at once when none is set (the
+// normal case: one short launch, no host round trip -- the call stays asynchronous).  For a flagged query (its
+// candidate buckets overflowed: adversarial data, massive ties) the whole column is re-scored exactly: every warp
+// keeps the top-k keys of its rows in shared memory, the block merges its warps' lists, the LAST block to finish
+// (ticket) merges the blocks' lists.  keys = (ordered score bits << 32) | ~row: unique, so (score desc, row asc).
+constexpr int kFbThreads = 256;
+__global__ void __launch_bounds__(kFbThreads)
+topk_fallback_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const float* __restrict__ q, int32_t nq,
+                     const float* __restrict__ scale, const float* __restrict__ row_norm, int normalize, int32_t k,
+                     const uint32_t* __restrict__ overflow_flags, unsigned long long* __restrict__ scratch,
+                     uint32_t* __restrict__ tickets, int64_t* __restrict__ out_idx, float* __restrict__ out_score) {
+  constexpr int kWarps = kFbThreads / 32;
+  __shared__ unsigned long long wl[kWarps][AVL_MAX_TOPK];
+  __shared__ int wcnt[kWarps];
+  __shared__ int sh_cnt;
+  __shared__ uint32_t sh_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * kWarps + warp, nwarps = static_cast<int64_t>(gridDim.x) * kWarps;
+  // the normal case first: one flag per thread, one barrier, gone (walking the 256 flags one dependent load after the
+  // other cost 24 us per call on B200)
+  static_assert(kFbThreads >= AVL_MAX_QUERIES, "one flag per thread");
+  if (!__syncthreads_or(static_cast<int>(threadIdx.x) < nq && overflow_flags[threadIdx.x] != 0u)) return;
+  for (int qq = 0; qq < nq; ++qq) {
+    if (!overflow_flags[qq]) continue;  // read-only during this launch: uniform over the grid
+    // ---- phase 1: per-warp top-k of its rows (sorted descending, insertion by lane 0)
+    int cnt = 0;
+    unsigned long long kmin = 0ull;  // smallest kept key once the list is full
+    const float* b = q + static_cast<size_t>(qq) * d;
+    for (int64_t row = gw; row < n; row += nwarps) {
+      const double dot = warp_dot(feat + row * d, b, d, lane);
+      if (lane == 0) {
+        const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
+        const unsigned long long key = vec_key(canon_score(dot, inv, normalize, scale, qq), row);
+        if (cnt < k || key > kmin) {
+          int pos = cnt < k ? cnt : k - 1;
+          while (pos > 0 && wl[warp][pos - 1] < key) { wl[warp][pos] = wl[warp][pos - 1]; --pos; }
+          wl[warp][pos] = key;
+          if (cnt < k) ++cnt;
+          if (cnt == k) kmin = wl[warp][k - 1];
+        }
+      }
+    }
+    if (lane == 0) wcnt[warp] = cnt;
+    __syncthreads();
+    // ---- phase 2: block merge by rank counting (<= 8 * 128 keys), block list -> scratch[qq][block][k] (0 = nothing)
+    unsigned long long* mine = scratch + (static_cast<size_t>(qq) * gridDim.x + blockIdx.x) * k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) mine[j] = 0ull;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kWarps * k; e += blockDim.x) {
+      const int w = e / k, j = e - w * k;
+      if (j >= wcnt[w]) continue;
+      const unsigned long long key = wl[w][j];
+      int rank = 0;
+      for (int w2 = 0; w2 < kWarps; ++w2)
+        for (int j2 = 0; j2 < wcnt[w2]; ++j2) rank += (wl[w2][j2] > key) ? 1 : 0;
+      if (rank < k) mine[rank] = key;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sh_last = (atomicAdd(tickets + qq, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (sh_last) {
+      // ---- phase 3 (last block): top-k of the gridDim.x * k block keys
+      __threadfence();
+      const unsigned long long* all = scratch + static_cast<size_t>(qq) * gridDim.x * k;
+      const int m = static_cast<int>(gridDim.x) * k;
+      const int kk = static_cast<int>(min(static_cast<int64_t>(k), n));
+      const unsigned long long t =
+          block_kth_largest<unsigned long long>([&](int j) { return __ldcg(all + j); }, m, kk, &sh_cnt);
+      for (int s = threadIdx.x; s < k; s += blockDim.x) {
+        out_idx[static_cast<size_t>(qq) * k + s] = -1;
+        out_score[static_cast<size_t>(qq) * k + s] = -INFINITY;
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const unsigned long long key = __ldcg(all + j);
+        if (key == 0ull || key < t) continue;
+        int rank = 0;
+        for (int u = 0; u < m; ++u) {
+          const unsigned long long o = __ldcg(all + u);
+          rank += (o > key) ? 1 : 0;
+        }
+        if (rank < kk) {
+          out_idx[static_cast<size_t>(qq) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+          out_score[static_cast<size_t>(qq) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
+        }
+      }
+      if (threadIdx.x == 0) tickets[qq] = 0u;  // ready for the next call
+    }
+    __syncthreads();
   }
 }
 
@@ -1190,16 +1319,35 @@ size_t topk_finalize_smem(uint32_t cand_cap) { return static_cast<size_t>(cand_c
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c, const float* row_an,
                          const float* q_bn, const float* q_glob, int normalize, int32_t k,
-                         const uint32_t* cand_cnt, const uint32_t* cand_row, const float* cand_val,
-                         uint32_t cand_cap, int64_t* out_idx, float* out_score, uint32_t* overflow_flags,
-                         cudaStream_t s) {
+                         const uint32_t* bucket_cnt, int32_t grid, uint32_t cand_bucket, const uint32_t* cand_row,
+                         const float* cand_val, uint32_t cand_cap, int64_t* out_idx, float* out_score,
+                         uint32_t* cand_total, uint32_t* overflow_flags, cudaStream_t s) {
+  if (grid > kFinMaxGrid) {
+    set_error("topk_finalize: screen grid larger than kFinMaxGrid");
+    return AVL_ERR_UNSUPPORTED;
+  }
   const size_t smem = topk_finalize_smem(cand_cap);
   AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   topk_finalize_kernel<<<nq, kFinThreads, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
                                                      reinterpret_cast<const uint32_t*>(q_glob), normalize, k,
-                                                     cand_cnt, cand_row, cand_val, cand_cap, out_idx, out_score,
-                                                     overflow_flags);
+                                                     bucket_cnt, grid, cand_bucket, cand_row, cand_val, cand_cap,
+                                                     out_idx, out_score, cand_total, overflow_flags);
+  AVL_CUDA(cudaGetLastError());
+  return AVL_OK;
+}
+
+size_t topk_fallback_scratch_bytes(int num_sms) {
+  return static_cast<size_t>(AVL_MAX_QUERIES) * (2 * num_sms) * AVL_MAX_TOPK * sizeof(unsigned long long);
+}
+
+int launch_topk_fallback(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq, const float* scale,
+                         const float* row_norm, int normalize, int32_t k, const uint32_t* overflow_flags,
+                         void* scratch, uint32_t* tickets, int64_t* out_idx, float* out_score, int num_sms,
+                         cudaStream_t s) {
+  topk_fallback_kernel<<<2 * num_sms, kFbThreads, 0, s>>>(feat, n, d, q, nq, scale, row_norm, normalize, k, overflow_flags,
+                                                         static_cast<unsigned long long*>(scratch), tickets, out_idx,
+                                                         out_score);
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

@@ -34,7 +34,7 @@ constexpr int kMaxStages = 12;
 constexpr int kCtrlBytes = 512;    // barriers + tmem slot + producer progress word, chunk summaries at +256
 constexpr int kQConstBytes = 2048; // float2[256]
 constexpr int kXchgBytes = 4 * 32 * 8 * 4;  // argmax only: the two warps of a lane quarter exchange keys / mask words
-constexpr int kPendDepth = 4;      // emitted candidate columns a warp keeps in registers before their slots are needed
+constexpr int kBucketCntBytes = AVL_MAX_QUERIES * 4;  // threshold mode only: per-query fill counts of this CTA's buckets
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccumStride = 256;  // columns between the two accumulator stages
 
@@ -176,50 +176,17 @@ __device__ __forceinline__ uint32_t thresh_mask_chunk(const TileCtx& t, int c0, 
 }
 
 // Slow path (~2 marked columns per warp and tile).  Kept tiny on purpose: an unrolled per-bit version thrashed the
-// instruction cache.  Every marked column costs ONE atomicAdd (lane 0 reserves popc(ballot) slots of the query's
-// list), and the slot base is NOT consumed where the atomic is issued: the column -- (query, per-lane row / score /
-// rank) -- waits in a register queue of kPendDepth columns and is stored when it is pushed out, one to two tiles
-// later, or at the end of the kernel.  History, all measured on B200: consuming the slot at once cost ~2000 cycles per
-// candidate column between the accumulator and its release (epilogue 3x slower than the MMAs); staging the candidates
-// in a per-warp shared-memory ring and flushing 32 at a time hid most of that but took 6 KiB of shared memory -- the
-// difference between 5 and 6 pipeline stages of A when 256 queries are resident -- and every flush still waited.
-struct Pending {
-  uint32_t q;      // warp-uniform query of the column; 0xFFFFFFFF = empty slot
-  uint32_t base;   // lane 0: slot base returned by the atomicAdd
-  uint32_t row;    // this lane's map row
-  uint32_t rank;   // this lane's position among the marked lanes; 0xFFFFFFFF = this lane's score was not marked
-  float val;       // this lane's screen score
-};
-
-__device__ __forceinline__ void pend_commit(const ScreenParams& p, Pending& e) {
-  if (e.q != 0xFFFFFFFFu) {  // warp-uniform
-    const uint32_t base = __shfl_sync(0xffffffffu, e.base, 0);  // first use of the atomic's result
-    const uint32_t slot = base + e.rank;
-    if (e.rank != 0xFFFFFFFFu && slot < p.cand_cap) {
-      p.cand_row[static_cast<size_t>(e.q) * p.cand_cap + slot] = e.row;
-      p.cand_val[static_cast<size_t>(e.q) * p.cand_cap + slot] = e.val;
-    }
-    e.q = 0xFFFFFFFFu;
-  }
-}
-
-// Replace the queue entry `e` (the oldest: its slot base has had kPendDepth columns' time to arrive) by a new column.
-// The queue is a circular buffer with STATIC register indices (the switch in thresh_emit_word): shifting entries
-// along would copy `base` while its atomic is still in flight -- a register read that waits for the round trip.
-__device__ __forceinline__ void pend_replace(const ScreenParams& p, Pending& e, uint32_t q, uint32_t row, float val,
-                                             bool mine, uint32_t b, uint32_t lane) {
-  pend_commit(p, e);
-  e.q = q;
-  e.row = row;
-  e.val = val;
-  e.rank = mine ? __popc(b & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
-  e.base = 0u;
-  if (lane == 0) e.base = atomicAdd(p.cand_cnt + q, static_cast<uint32_t>(__popc(b)));
-}
-
-__device__ __forceinline__ uint32_t thresh_emit_word(const ScreenParams& p, uint32_t taddr, int64_t row, int c0,
-                                                     uint32_t m, Pending (&pq)[kPendDepth], uint32_t head,
-                                                     uint32_t lane) {
+// instruction cache.  Candidates go to PER-CTA buckets: bucket (query q, CTA c) is `cand_bucket` entries at
+// cand_row / cand_val[(q * gridDim.x + c) * cand_bucket], its fill count lives in this CTA's shared memory (one ATOMS
+// by lane 0 per marked column, ~60 cycles) and is written to cand_cnt[c][q] once, when the CTA is done.  No global
+// atomic is left in the epilogue.  History, all measured on B200: a global atomicAdd per candidate column cost ~2000
+// cycles between the accumulator and its release (epilogue 3x slower than the MMAs); staging in a per-warp ring and
+// appending 32 at a time hid most of it, but with 16 epilogue warps per CTA pair more than half of the tiles still had
+// one warp waiting on a burst, and the accumulator is only released when ALL of them are done; deferring the use of
+// the returned slot through registers did not help either (ptxas puts the atomics on one scoreboard, so waiting for the
+// oldest waits for the newest).  The finalize kernel gathers a query's buckets (sim_exact.cu).
+__device__ __forceinline__ void thresh_emit_word(const ScreenParams& p, uint32_t taddr, int64_t row, int c0,
+                                                 uint32_t m, uint32_t* bucket_cnt, uint32_t lane) {
   uint32_t u = __reduce_or_sync(0xffffffffu, m);
   while (u) {  // warp-uniform loop over the columns any lane marked
     const int j = __ffs(u) - 1;
@@ -229,24 +196,24 @@ __device__ __forceinline__ uint32_t thresh_emit_word(const ScreenParams& p, uint
     ptx::tmem_ld_wait();
     const bool mine = (m >> j) & 1u;
     const uint32_t b = __ballot_sync(0xffffffffu, mine);
-    const uint32_t q = static_cast<uint32_t>(c0 + j), r32 = static_cast<uint32_t>(row);
-    static_assert(kPendDepth == 4, "the switch below enumerates the queue slots");
-    switch (head) {
-      case 0: pend_replace(p, pq[0], q, r32, __uint_as_float(v), mine, b, lane); break;
-      case 1: pend_replace(p, pq[1], q, r32, __uint_as_float(v), mine, b, lane); break;
-      case 2: pend_replace(p, pq[2], q, r32, __uint_as_float(v), mine, b, lane); break;
-      default: pend_replace(p, pq[3], q, r32, __uint_as_float(v), mine, b, lane); break;
+    const uint32_t q = static_cast<uint32_t>(c0 + j);
+    uint32_t base = 0u;
+    if (lane == 0) base = atomicAdd(bucket_cnt + q, static_cast<uint32_t>(__popc(b)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t slot = base + __popc(b & ((1u << lane) - 1u));
+    if (mine && slot < p.cand_bucket) {
+      const size_t o = (static_cast<size_t>(q) * gridDim.x + blockIdx.x) * p.cand_bucket + slot;
+      p.cand_row[o] = static_cast<uint32_t>(row);
+      p.cand_val[o] = __uint_as_float(v);
     }
-    head = (head + 1u) & (kPendDepth - 1);
   }
-  return head;
 }
 
 // One epilogue warp handles the 32-column words cb = half, half + 2, ... of its 32 rows.
 template <bool kNorm>
-__device__ __forceinline__ uint32_t thresh_tile(const ScreenParams& p, const TileCtx& t, const float2* qc,
-                                                const float2* qchunk, float iw, float ri, int half,
-                                                Pending (&pq)[kPendDepth], uint32_t head, uint32_t lane) {
+__device__ __forceinline__ void thresh_tile(const ScreenParams& p, const TileCtx& t, const float2* qc,
+                                            const float2* qchunk, float iw, float ri, int half,
+                                            uint32_t* bucket_cnt, uint32_t lane) {
   uint32_t m[kFlagWords / 2];
   uint32_t any = 0;
 #pragma unroll
@@ -264,10 +231,9 @@ __device__ __forceinline__ uint32_t thresh_tile(const ScreenParams& p, const Til
     for (int i = 0; i < kFlagWords / 2; ++i) {
       const int c0 = (2 * i + half) * 32;
       const uint32_t mi = i == 0 ? m[0] : (i == 1 ? m[1] : (i == 2 ? m[2] : m[3]));
-      if (c0 < p.npad) head = thresh_emit_word(p, t.taddr, t.row, c0, mi, pq, head, lane);
+      if (c0 < p.npad) thresh_emit_word(p, t.taddr, t.row, c0, mi, bucket_cnt, lane);
     }
   }
-  return head;
 }
 
 template <int CG>
@@ -301,7 +267,9 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   uint32_t* prod_it = tmem_slot + 1;                         // tile iteration the producer is loading
   float2* qchunk = reinterpret_cast<float2*>(ctrl + 256);    // [8] per 32-query chunk: (min threshold, max ||b||)
   float2* qc = reinterpret_cast<float2*>(ctrl + kCtrlBytes);
-  uint32_t* xchg_base = reinterpret_cast<uint32_t*>(ctrl + kCtrlBytes + kQConstBytes);  // argmax mode only
+  // argmax mode: exchange words of the two warps of a lane quarter; threshold mode: this CTA's bucket fill counts
+  uint32_t* xchg_base = reinterpret_cast<uint32_t*>(ctrl + kCtrlBytes + kQConstBytes);
+  uint32_t* bucket_cnt = xchg_base;                          // [AVL_MAX_QUERIES]
 
   if ((ptx::smem_u32(smem) & 1023u) != 0u) {
     if (threadIdx.x == 0 && p.dbg) {
@@ -343,6 +311,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       c.y = p.q_bn[q];
     }
     qc[q] = c;
+    if (p.mode == kModeThresh) bucket_cnt[q] = 0u;
   } else if (threadIdx.x < 264) {
     // chunk summaries for the pre-test of the threshold epilogue, straight from global memory (qc is not visible yet)
     const int c0 = (static_cast<int>(threadIdx.x) - 256) * 32;
@@ -460,14 +429,7 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     const uint32_t lane_base = quarter * 32u;
     const int half = static_cast<int>(warp >> 2);         // which interleaved set of 32-column words
     const float rho = p.q_glob[0], bn_max = p.q_glob[1];
-    Pending pq[kPendDepth];
-#pragma unroll
-    for (int i = 0; i < kPendDepth; ++i) {
-      pq[i].q = 0xFFFFFFFFu;
-      pq[i].base = pq[i].row = pq[i].rank = 0u;
-      pq[i].val = 0.f;
-    }
-    uint32_t it = 0, head = 0;
+    uint32_t it = 0;
     for (int j = unit; j < p.num_tiles; j += num_units, ++it) {
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       TileCtx t;
@@ -577,12 +539,12 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
             ri *= iw;
           }
         }
-        if (p.normalize) head = thresh_tile<true>(p, t, qc, qchunk, iw, ri, half, pq, head, lane);
-        else head = thresh_tile<false>(p, t, qc, qchunk, iw, ri, half, pq, head, lane);
+        if (p.normalize) thresh_tile<true>(p, t, qc, qchunk, iw, ri, half, bucket_cnt, lane);
+        else thresh_tile<false>(p, t, qc, qchunk, iw, ri, half, bucket_cnt, lane);
       }
 
       // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier); one arrive
-      // per warp -- per-thread remote arrives serialise on the barrier (see sim_screen_ts.cu)
+      // per warp -- per-thread remote arrives serialise on the barrier
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -590,14 +552,13 @@ screen_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         else ptx::mbar_arrive(ptx::smem_u32(bar_tempty + as));
       }
     }
-    if (p.mode == kModeThresh) {
-#pragma unroll
-      for (int i = kPendDepth - 1; i >= 0; --i) pend_commit(p, pq[i]);
-    }
   }
 
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all(); else __syncthreads();
+  // bucket fill counts of this CTA (may exceed cand_bucket: the finalize kernel flags that query as overflowed)
+  if (p.mode == kModeThresh && threadIdx.x < static_cast<uint32_t>(p.nq))
+    p.cand_cnt[static_cast<size_t>(blockIdx.x) * AVL_MAX_QUERIES + threadIdx.x] = bucket_cnt[threadIdx.x];
   if (warp == kWarpAlloc) ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
   if ((p.debug_flags & 64) && threadIdx.x == 0 && p.dbg) {
     unsigned long long ns1;
@@ -629,7 +590,7 @@ size_t screen_smem_bytes(int cta_group, int npad, int kblocks, int stages, int m
   const size_t bblk = static_cast<size_t>(npad / cta_group) * 128u;
   const size_t b_bytes = bblk * kblocks;
   size_t total = ((b_bytes + 1023u) & ~size_t(1023)) + static_cast<size_t>(stages) * kStageBytes;
-  total += kCtrlBytes + kQConstBytes + (mode == kModeArgmax ? kXchgBytes : 0);
+  total += kCtrlBytes + kQConstBytes + (mode == kModeArgmax ? kXchgBytes : (mode == kModeThresh ? kBucketCntBytes : 0));
   // > half of the SM's shared memory, so exactly one CTA (and one 512-column TMEM owner) per SM
   if (total < 120u * 1024u) total = 120u * 1024u;
   return total;
@@ -647,13 +608,18 @@ int screen_pick_stages(int cta_group, int npad, int kblocks, int mode) {
   return 0;
 }
 
+int screen_grid(int cta_group, int num_sms, int num_tiles) {
+  int units = num_sms / cta_group;
+  if (units > num_tiles) units = num_tiles;
+  return units * cta_group;
+}
+
 int launch_screen(int cta_group, const void* tmap_a, const void* tmap_b, const ScreenParams& p,
                   int num_sms, size_t smem_bytes, cudaStream_t stream) {
   if (p.num_tiles <= 0) return AVL_OK;
   const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(tmap_a);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(tmap_b);
-  int units = num_sms / cta_group;
-  if (units > p.num_tiles) units = p.num_tiles;
+  const int units = screen_grid(cta_group, num_sms, p.num_tiles) / cta_group;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(units * cta_group));
   cfg.blockDim = dim3(kThreads);

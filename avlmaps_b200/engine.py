@@ -171,17 +171,20 @@ class DeviceMap:
         return o
 
     # -- per-query top-k rows
-    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None, out=None):
-        """out=(idx int64 (Q, k), score float32 (Q, k)) torch CUDA tensors: write there (device path, Q <= 256)."""
+    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None, out=None, stats: bool = True):
+        """out=(idx int64 (Q, k), score float32 (Q, k)) torch CUDA tensors: write there (device path, Q <= 256).
+        With out= and stats=False the call is asynchronous: it only enqueues work on `stream` (no host round trip --
+        the exact fallback for overflowed queries is decided on the device) and `last_stats` is not updated."""
         q, s = self._queries(queries, scale)
         if out is not None:
             if not q.device or q.shape[0] > L.AVL_MAX_QUERIES:
                 raise ValueError("out= needs CUDA queries and at most 256 of them")
-            st = L.IndexStats()
+            st = L.IndexStats() if stats else None
             L.check(self._lib.avl_sim_topk(self._h, q.ptr, q.shape[0], s.ptr, int(normalize_map), k,
                                            C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
-                                           _flags(q, s), _stream_ptr(stream), C.byref(st)))
-            self.last_stats = st.as_dict()
+                                           _flags(q, s), _stream_ptr(stream), C.byref(st) if stats else None))
+            if stats:
+                self.last_stats = st.as_dict()
             return out
         outs_i, outs_s = [], []
         stats = None
@@ -222,8 +225,7 @@ def merge_topk_device(gathered_idx, gathered_val, k: int, stream=None):
 class P2PExchange:
     """Fused exchange + merge of per-slab top-k results over NVLink peer memory (csrc/p2p_exchange.cu): one kernel
     per query batch instead of an NCCL all-gather plus a merge kernel.  One object per rank; the CUDA-IPC handles of
-    the receive buffers travel once through `torch.distributed.all_gather_object`.  Opt-in (AVL_P2P_EXCHANGE=1 in
-    ShardedMap) until measured on 2 / 8 GPUs."""
+    the receive buffers travel once through `torch.distributed.all_gather_object`.  ShardedMap's default exchange."""
 
     def __init__(self, group=None, nq_max: int = L.AVL_MAX_QUERIES, k_max: Optional[int] = None):
         import torch.distributed as dist
@@ -247,21 +249,26 @@ class P2PExchange:
             L.check(self._lib.avl_p2p_connect(self._h, buf))
             dist.barrier(group=group)   # nobody stores into a peer before every peer has mapped every buffer
 
-    def exchange_merge(self, idx, val, row_offset: int = 0, stream=None):
-        """idx (nq, k) int64 row ids (-1 = empty; `row_offset` is added to the others, making slab-local rows global),
-        val (nq, k) float32, both torch.cuda tensors of this rank's slab -> (idx, val) of the global top-k, identical on
-        every rank.  Enqueues one kernel, no synchronisation."""
+    def exchange_merge(self, idx, val, row_offset: int = 0, stream=None, global_ids=None, out=None):
+        """idx (nq, k) int64 row ids (-1 = empty; the others are made global inside the kernel: + `row_offset`, or a
+        lookup in `global_ids`, an int64 CUDA tensor with one entry per slab row), val (nq, k) float32, both torch.cuda
+        tensors of this rank's slab -> (idx, val) of the global top-k, identical on every rank.  Enqueues one kernel on
+        `stream` (default: torch's current stream), no synchronisation.  Every rank issues the same sequence of calls;
+        calls on one object go to one stream at a time."""
         import torch
 
         nq, k = idx.shape
-        idx, val = idx.contiguous(), val.contiguous()
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=idx.device)
-        out_v = torch.empty((nq, k), dtype=torch.float32, device=idx.device)
+        if not (idx.is_contiguous() and val.is_contiguous()):
+            idx, val = idx.contiguous(), val.contiguous()
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.int64, device=idx.device),
+                   torch.empty((nq, k), dtype=torch.float32, device=idx.device))
         sp = _stream_ptr(stream) if stream is not None else _current_torch_stream()
+        gid = C.c_void_p(global_ids.data_ptr()) if global_ids is not None else None
         L.check(self._lib.avl_p2p_exchange_merge(self._h, C.c_void_p(idx.data_ptr()), C.c_void_p(val.data_ptr()), nq, k,
-                                                 int(row_offset), C.c_void_p(out_i.data_ptr()), C.c_void_p(out_v.data_ptr()),
-                                                 L.AVL_ON_DEVICE, sp))
-        return out_i, out_v
+                                                 int(row_offset), gid, C.c_void_p(out[0].data_ptr()),
+                                                 C.c_void_p(out[1].data_ptr()), L.AVL_ON_DEVICE, sp))
+        return out
 
     def timed_out_source(self) -> int:
         """-1, or the rank whose data never arrived within the kernel's ~10 s watchdog (synchronises)."""

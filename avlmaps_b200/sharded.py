@@ -1,7 +1,8 @@
 """Slab-sharded map over the GPUs of one box: one process per GPU (torchrun), each rank owns a
 contiguous slab of voxel rows; a query batch is scored against every slab independently and the
-per-slab top-k are exchanged with ONE small NCCL all-gather (world * Q * k * 12 bytes) and merged
-locally.  The per-voxel argmax needs no exchange at all (it stays sharded).
+per-slab top-k (world * Q * k * 12 bytes) are exchanged and merged by ONE kernel over NVLink peer memory
+(csrc/p2p_exchange.cu; AVL_P2P_EXCHANGE=0: one NCCL all-gather + a merge kernel).
+The per-voxel argmax needs no exchange at all (it stays sharded).
 
 torch.distributed is plumbing only; scoring runs in the C-ABI library."""
 from __future__ import annotations
@@ -50,6 +51,22 @@ def slab_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     base, rem = divmod(n_total, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class PendingTopK:
+    """Result of ShardedMap.topk_async: (idx, val) CUDA tensors that become valid on a side stream."""
+
+    def __init__(self, tensors, event):
+        self._tensors, self._event = tensors, event
+
+    def result(self):
+        """Make torch's current stream wait for the exchange, return (idx int64 (Q, k), val float32 (Q, k)).  The
+        tensors belong to a ring of 3 batches: copy them if they must outlive two more topk_async calls."""
+        if self._event is not None:
+            import torch
+
+            torch.cuda.current_stream().wait_event(self._event)
+        return self._tensors
 
 
 class ShardedMap:
@@ -102,35 +119,103 @@ class ShardedMap:
         sm.n_total, sm.row_lo, sm.row_hi, sm.grid_pos = int(ds.shape[0]), lo, hi, grid_pos
         return sm
 
+    # ---- device path -----------------------------------------------------------------------------------------
+    _RING = 3   # per-slab result buffers in flight: the exchange of step i reads what the screen of step i wrote
+
+    def _use_p2p(self, k: int) -> bool:
+        # default: exchange + merge fused in ONE kernel over NVLink peer memory (csrc/p2p_exchange.cu);
+        # AVL_P2P_EXCHANGE=0 selects the NCCL all-gather + merge kernel
+        return os.environ.get("AVL_P2P_EXCHANGE", "1") != "0" and k * self.world <= 1024
+
+    def _device_state(self, device, nq: int, k: int):
+        import torch
+
+        st = getattr(self, "_dev", None)
+        if st is None or st["nq"] != nq or st["k"] != k:
+            st = {"nq": nq, "k": k, "slot": 0,
+                  "mine": [(torch.empty((nq, k), dtype=torch.int64, device=device),
+                            torch.empty((nq, k), dtype=torch.float32, device=device)) for _ in range(self._RING)],
+                  "out": [(torch.empty((nq, k), dtype=torch.int64, device=device),
+                           torch.empty((nq, k), dtype=torch.float32, device=device)) for _ in range(self._RING)],
+                  "scored": [torch.cuda.Event() for _ in range(self._RING)],
+                  "merged": [None] * self._RING,
+                  "side": torch.cuda.Stream(device=device)}
+            if self.global_ids is not None:
+                gid = self.global_ids if torch.is_tensor(self.global_ids) else torch.from_numpy(np.asarray(self.global_ids))
+                self.global_ids = gid.to(device=device, dtype=torch.int64).contiguous()
+            self._dev = st
+        return st
+
+    def topk_async(self, queries, k: int, scale=None, normalize_map: bool = False):
+        """Device path (CUDA queries, at most 256): enqueue the slab's screen on the CURRENT stream and the peer exchange
+        + merge on a side stream, return a `PendingTopK`; `.result()` makes the current stream wait for the merged
+        (idx, val).  Nothing here synchronises the host, and the next batch's screen does not wait for this batch's
+        exchange -- a slower peer delays the side stream only, until the ring of result buffers is used up (3 batches).
+        No eager tensor ops: the slab's result lands in a ring buffer, the exchange kernel makes the ids global."""
+        import torch
+
+        nq = queries.shape[0]
+        st = self._device_state(queries.device, nq, k)
+        i = st["slot"]
+        st["slot"] = (i + 1) % self._RING
+        cur = torch.cuda.current_stream(queries.device)
+        if st["merged"][i] is not None:
+            cur.wait_event(st["merged"][i])        # the exchange that last read this ring slot (3 batches ago)
+        ti, tv = st["mine"][i]
+        self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv), stats=False)
+        if self.world == 1:
+            return PendingTopK(self._globalize_single(ti, tv), None)
+        st["scored"][i].record(cur)
+        side = st["side"]
+        side.wait_event(st["scored"][i])
+        if self._p2p is None:
+            from .engine import P2PExchange
+
+            self._p2p = P2PExchange(self.group)
+        gid = self.global_ids if self.global_ids is not None else None
+        self._p2p.exchange_merge(ti, tv, row_offset=0 if gid is not None else self.row_offset, global_ids=gid,
+                                 out=st["out"][i], stream=side.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        st["merged"][i] = ev
+        return PendingTopK(st["out"][i], ev)
+
+    def _globalize_single(self, ti, tv):
+        import torch
+
+        if self.global_ids is not None:
+            return torch.where(ti >= 0, self.global_ids[ti.clamp(min=0)], ti), tv
+        if self.row_offset:
+            return torch.where(ti >= 0, ti + self.row_offset, ti), tv
+        return ti, tv
+
     def topk(self, queries, k: int, scale=None, normalize_map: bool = False):
         import torch
         import torch.distributed as dist
 
         on_device = type(queries).__module__.startswith("torch") and queries.is_cuda
+        if on_device and self.world > 1 and queries.shape[0] <= 256 and self._use_p2p(k):
+            res = self.topk_async(queries, k, scale=scale, normalize_map=normalize_map).result()
+            if self._p2p is not None and getattr(self, "check_exchange", False):
+                src = self._p2p.timed_out_source()   # synchronises: opt-in (tools / tests)
+                if src >= 0:
+                    raise RuntimeError(f"peer exchange timed out waiting for rank {src}")
+            return res
         if on_device and self.world > 1 and queries.shape[0] <= 256:
-            # device path: the slab's result is written straight into a packed (ids | scores) buffer, ONE
-            # NCCL all-gather moves world * Q * k * 12 bytes, one kernel of the library merges.
+            # NCCL form (AVL_P2P_EXCHANGE=0): the slab's result goes into a packed (ids | scores) buffer, ONE all-gather
+            # moves world * Q * k * 12 bytes, one kernel of the library merges
             nq = queries.shape[0]
             nb_i, nb_v = nq * k * 8, nq * k * 4
             mine = torch.empty(nb_i + nb_v, dtype=torch.uint8, device=queries.device)
             ti = mine[:nb_i].view(torch.int64).view(nq, k)
             tv = mine[nb_i:].view(torch.float32).view(nq, k)
-            self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv))
-            # opt-in: exchange + merge fused in one kernel over NVLink peer memory (csrc/p2p_exchange.cu)
-            use_p2p = os.environ.get("AVL_P2P_EXCHANGE", "0") == "1" and k * self.world <= 1024
+            self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv), stats=False)
             if self.global_ids is not None:
                 gid = self.global_ids if torch.is_tensor(self.global_ids) else torch.from_numpy(np.asarray(self.global_ids))
                 self.global_ids = gid = gid.to(queries.device)
                 ti.copy_(torch.where(ti >= 0, gid[ti.clamp(min=0)], ti))
-            elif self.row_offset and not use_p2p:
+            elif self.row_offset:
                 ti += (ti >= 0) * self.row_offset
-            if use_p2p:
-                if self._p2p is None:
-                    from .engine import P2PExchange
-
-                    self._p2p = P2PExchange(self.group)
-                # the kernel adds the slab's row offset itself (ids from a slab-sharded build are global already)
-                return self._p2p.exchange_merge(ti, tv, row_offset=0 if self.global_ids is not None else self.row_offset)
             gathered = torch.empty((self.world, nb_i + nb_v), dtype=torch.uint8, device=queries.device)
             dist.all_gather_into_tensor(gathered.view(-1), mine, group=self.group)   # the one collective
             gi = gathered[:, :nb_i].contiguous().view(torch.int64).view(self.world, nq, k)

@@ -106,76 +106,168 @@ class ClockSampler:
 _CPU_POOL = None
 
 
-def cpu_topk_step(feat_s: np.ndarray, q: np.ndarray, k: int):
-    """The reference's operation on the host: the float32 product of `map_feats` and `text_feats`
-    (clip_utils.py:229, numpy -> OpenBLAS sgemm with every core), then the k best rows per query (np.argmax
-    generalised).  The product is taken as (Q, N) = `text_feats @ map_feats.T` -- the same sgemm with the operands
-    swapped -- so that each query's scores are contiguous for np.argpartition, which runs on one thread per block of
-    queries (numpy releases the GIL inside partition): 6x faster than partitioning the reference's (N, Q) layout
-    column-wise, i.e. the generous form of the baseline."""
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def blas_threads(n: int):
+    """Pin the BLAS pool explicitly: torchrun exports OMP_NUM_THREADS=1 when it is unset, which silently turned the
+    round-1 reference arm into a single-threaded sgemm at N > 1.  Returns (context manager, description)."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+
+    ctx = threadpool_limits(limits=n, user_api="blas")
+    info = [f"{d.get('internal_api')} {d.get('version')} threads={d.get('num_threads')}" for d in threadpool_info()
+            if d.get("user_api") == "blas"]
+    return ctx, "; ".join(info)
+
+
+def make_host_slab(n: int, d: int, seed: int) -> np.ndarray:
+    """LSeg-like rows (norm ~14.29 * alpha, un-normalised), float32, generated on every host thread (one seeded
+    generator per 128 Ki-row block, so the array does not depend on the thread count)."""
     global _CPU_POOL
     from concurrent.futures import ThreadPoolExecutor
 
-    ncpu = os.cpu_count() or 1
+    if _CPU_POOL is None:
+        _CPU_POOL = ThreadPoolExecutor(host_threads())
+    out = np.empty((n, d), np.float32)
+    blk = 1 << 17
+
+    def fill(b):
+        r0, r1 = b * blk, min(n, (b + 1) * blk)
+        g = np.random.default_rng([seed, b])
+        g.standard_normal(out=out[r0:r1], dtype=np.float32)
+        out[r0:r1] *= (14.2857 / d ** 0.5) * g.uniform(0.05, 1.0, (r1 - r0, 1)).astype(np.float32)
+
+    list(_CPU_POOL.map(fill, range((n + blk - 1) // blk)))
+    return out
+
+
+def cpu_topk_step(feat_s: np.ndarray, q: np.ndarray, k: int, chunk: int = 1 << 19):
+    """The reference's operation on the host: the float32 product of `map_feats` and `text_feats`
+    (clip_utils.py:229, numpy -> OpenBLAS sgemm with every core), then the k best rows per query (np.argmax
+    generalised).  The product is taken as (Q, rows) = `text_feats @ map_feats.T` -- the same sgemm with the operands
+    swapped -- so that each query's scores are contiguous for np.argpartition, which runs on one thread per block of
+    queries (numpy releases the GIL inside partition): 6x faster than partitioning the reference's (N, Q) layout
+    column-wise, i.e. the generous form of the baseline.  Rows go through in chunks of 512 Ki (a (256, 4M) float32
+    score matrix would be 4.3 GB); the per-chunk winners are merged at the end."""
+    global _CPU_POOL
+    from concurrent.futures import ThreadPoolExecutor
+
+    ncpu = host_threads()
     if _CPU_POOL is None:
         _CPU_POOL = ThreadPoolExecutor(ncpu)
-    s = q @ feat_s.T
-    n = s.shape[1]
-    kk = min(k, n)
-    bounds = np.linspace(0, s.shape[0], ncpu + 1).astype(int)
+    nq = q.shape[0]
+    bounds = np.linspace(0, nq, min(ncpu, nq) + 1).astype(int)
+    best_i, best_v = [], []
+    for r0 in range(0, feat_s.shape[0], chunk):
+        blk = feat_s[r0:r0 + chunk]
+        s = q @ blk.T
+        n = s.shape[1]
+        kk = min(k, n)
 
-    def part(i):
-        return np.argpartition(s[bounds[i]:bounds[i + 1]], n - kk, axis=1)[:, n - kk:]
+        def part(i):
+            sub = s[bounds[i]:bounds[i + 1]]
+            idx = np.argpartition(sub, n - kk, axis=1)[:, n - kk:]
+            return idx, np.take_along_axis(sub, idx, axis=1)
 
-    return np.concatenate(list(_CPU_POOL.map(part, range(ncpu))))
+        res = list(_CPU_POOL.map(part, range(len(bounds) - 1)))
+        best_i.append(np.concatenate([r[0] for r in res]) + r0)
+        best_v.append(np.concatenate([r[1] for r in res]))
+    ci, cv = np.concatenate(best_i, axis=1), np.concatenate(best_v, axis=1)
+    order = np.argsort(-cv, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(ci, order, axis=1), np.take_along_axis(cv, order, axis=1)
 
 
-def cpu_baseline(steps: int, warmup: int, sample_rows: int = 262_144, budget_s: float = None):
-    """`steps` timed steps of the CPU arm on a bounded row sample.  With `budget_s` the sample is sized (a power of
-    two between 16 Ki and 256 Ki rows) from one probe step so that the `steps` timed steps fit the budget."""
+def cpu_baseline(steps: int = 5, sample_rows: int = 1 << 20):
+    """The CPU leg beside our own line: the same operation on a bounded row sample (1 Mi of the 4 Mi rows x all 256
+    queries per step), every host thread, scaled to the full map by the row ratio; what the sample was is stated."""
     import synth
 
-    qs = [synth.index_inputs(1, DIM, NQ, seed=100 + i)[1] for i in range(2)]
-    if budget_s is not None:
-        probe, _ = synth.index_inputs(65_536, DIM, 1, seed=0)
-        cpu_topk_step(probe, qs[0], TOPK)                       # first call: thread pool start-up, page faults
-        t0 = time.perf_counter()
-        cpu_topk_step(probe, qs[1], TOPK)
-        per_row = (time.perf_counter() - t0) / probe.shape[0]
-        sample_rows = 262_144
-        while sample_rows > 16_384 and per_row * sample_rows * (steps + warmup) > budget_s:
-            sample_rows //= 2
-        del probe
-    feat_s, _ = synth.index_inputs(sample_rows, DIM, 1, seed=0)
-    for i in range(warmup):
-        cpu_topk_step(feat_s, qs[i % 2], TOPK)
-    t = []
-    for i in range(steps):
-        t0 = time.perf_counter()
-        cpu_topk_step(feat_s, qs[i % 2], TOPK)
-        t.append(time.perf_counter() - t0)
-    per_step = statistics.median(t) * (N_VOX / sample_rows)  # extrapolated to the 4M-voxel map
-    return {"value": NQ / per_step, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{sample_rows} of {N_VOX} rows x all {NQ} queries per step (numpy float32 `@` through OpenBLAS with "
-                      f"all threads + np.argpartition top-{TOPK} on {os.cpu_count()} threads), time scaled "
-                      f"x{N_VOX // sample_rows}; median of {steps} steps",
+    nthreads = host_threads()
+    ctx, blas = blas_threads(nthreads)
+    with ctx:
+        qs = [synth.index_inputs(1, DIM, NQ, seed=100 + i)[1] for i in range(2)]
+        feat_s = make_host_slab(sample_rows, DIM, 0)
+        cpu_topk_step(feat_s, qs[0], TOPK)                      # first call: thread pool start-up, page faults
+        t = []
+        for i in range(steps):
+            t0 = time.perf_counter()
+            cpu_topk_step(feat_s, qs[i % 2], TOPK)
+            t.append(time.perf_counter() - t0)
+    per_step = statistics.median(t) * (N_VOX / sample_rows)
+    return {"value": NQ / per_step, "unit": UNIT, "cores": nthreads, "kind": "port", "blas": blas,
+            "sample": f"{sample_rows} of {N_VOX} rows x all {NQ} queries per step (numpy float32 `@` through OpenBLAS, "
+                      f"{nthreads} threads, + np.argpartition top-{TOPK} on {nthreads} threads), time scaled "
+                      f"x{N_VOX // sample_rows}; median of {steps} steps; the full-size run is `--impl reference`",
             "ms_per_step_extrapolated": per_step * 1e3}
 
 
 def run_reference(args):
-    """The reference's own operation on the host cores: W warm-up steps, then exactly K timed steps, each over a
-    bounded row sample sized so that the whole run stays within ~2 minutes.  Rank 0 only under torchrun."""
+    """The reference's own operation (numpy float32 `@` = OpenBLAS sgemm, clip_utils.py:229, + the k best rows per
+    query) on the host cores, on OUR arm's config: every step scores all 256 queries against `--gpus` slabs of
+    4 194 304 x 512 float32 rows (the host holds ONE slab and scores it once per slab: identical work, 8.6 GB instead of
+    N x 8.6 GB of host RAM).  W warm-up steps, then exactly K timed steps; `ms_per_step` is the measured time of a step,
+    nothing is extrapolated as long as K steps of full slabs fit the budget (AVL_REF_BUDGET_S, default 300 s: always at
+    N = 1); beyond that each slab is scored on a power-of-two row fraction and the line says so.  Rank 0 only."""
+    import synth
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args.steps, args.warmup, budget_s=100.0)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step_extrapolated"],
+    world = max(1, args.gpus)
+    nthreads = host_threads()
+    ctx, blas = blas_threads(nthreads)
+    budget = float(os.environ.get("AVL_REF_BUDGET_S", "300"))
+    with ctx:
+        qs = [synth.index_inputs(1, DIM, NQ, seed=100 + i)[1] for i in range(2)]
+        t0 = time.perf_counter()
+        feat = make_host_slab(N_VOX, DIM, 1000)
+        gen_s = time.perf_counter() - t0
+        probe_rows = 1 << 19
+        cpu_topk_step(feat[:probe_rows], qs[0], TOPK)           # thread pool start-up, page faults
+        t0 = time.perf_counter()
+        cpu_topk_step(feat[:probe_rows], qs[1], TOPK)
+        per_row = (time.perf_counter() - t0) / probe_rows
+        rows = N_VOX
+        while rows > (1 << 18) and per_row * rows * world * (args.steps + min(args.warmup, 1)) > budget:
+            rows //= 2
+        sub = feat[:rows]
+
+        def step(i):
+            for _ in range(world):
+                cpu_topk_step(sub, qs[i % 2], TOPK)
+
+        for i in range(args.warmup):
+            # warm-up on the host is page faults and pool start-up, done above: one full step, the rest on the probe rows
+            step(i) if i == 0 else cpu_topk_step(feat[:probe_rows], qs[i % 2], TOPK)
+        t = []
+        t_all = time.perf_counter()
+        for i in range(args.steps):
+            t0 = time.perf_counter()
+            step(i)
+            t.append(time.perf_counter() - t0)
+        t_all = time.perf_counter() - t_all
+    ms_step = t_all / args.steps * 1e3
+    frac = rows / N_VOX
+    value = NQ * world * frac / (ms_step / 1e3)
+    full = rows == N_VOX
+    cb = {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "blas": blas,
+          "sample": (f"all {N_VOX} rows" if full else f"{rows} of {N_VOX} rows (x{N_VOX // rows} row fraction, value scaled by it)")
+                    + f" x {world} slab(s) x all {NQ} queries per step; numpy float32 `@` through OpenBLAS on {nthreads} threads + "
+                      f"np.argpartition top-{TOPK} on {nthreads} threads; {args.steps} timed steps; slab generated in {gen_s:.1f} s",
+          "ms_per_step_median": statistics.median(t) * 1e3}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"headline: {N_VOX} voxels x {DIM}-d, {NQ} queries, top-{TOPK}; reference CPU path "
-                                   "(numpy/OpenBLAS) on the host cores, bounded sample"},
+            "config": {"workload": f"headline: {N_VOX} voxels x {DIM}-d per slab, {world} slab(s), {NQ} queries per step, top-{TOPK}; "
+                                   "reference CPU path (numpy/OpenBLAS) on the host cores",
+                       "rows_scored_per_slab": rows, "full_size": full, "host_threads": nthreads, "blas": blas,
+                       "value_definition": "queries x 4M-voxel slabs scored per second (N=1: plain queries/s)"},
             "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -657,7 +749,7 @@ def run_gpu(args):
             except Exception as e:  # noqa: BLE001
                 extra["build_error"] = repr(e)
         if not args.no_cpu:
-            cb = cpu_baseline(steps=5, warmup=1)
+            cb = cpu_baseline(steps=5)
             if not args.no_build:
                 try:
                     extra.setdefault("build", {})["cpu_baseline"] = build_cpu_baseline()

@@ -76,12 +76,11 @@ typedef struct avl_index_stats {
   int64_t n_rows;
   int32_t dim;
   int32_t n_queries;
-  int32_t cta_group;          /* tcgen05 variant that ran: 1 / 2 = cta_group of sim_screen.cu, 3 = query-stationary
-                                 2-CTA kernel (queries in TMEM, sim_screen_ts.cu), 0 = no tensor-core kernel */
+  int32_t cta_group;          /* tcgen05 variant that ran: 1 / 2 = cta_group of sim_screen.cu, 0 = no tensor-core kernel */
   int32_t n_launches;         /* kernels launched by the call */
   int64_t n_flagged;          /* argmax: rows whose bf16 margin was inside the error band (re-ranked exactly) */
   int64_t n_candidates;       /* top-k: (row, query) pairs that passed the screen threshold */
-  int32_t n_fallback_queries; /* top-k: queries that overflowed the candidate list -> exact dense path */
+  int32_t n_fallback_queries; /* top-k: queries whose candidate buckets overflowed -> re-scored exactly (on the device) */
   int32_t sample_rows;        /* top-k: rows used for the threshold estimate */
   float ms_screen;            /* CUDA-event time of the main tcgen05 launch (avl_set_profiling(1)), else 0 */
   float ms_total;             /* CUDA-event time of the whole call's device work, else 0 */
@@ -92,7 +91,8 @@ int avl_version(void);              /* 100*major + minor; no CUDA call */
 const char* avl_last_error(void);   /* thread-local message of the last failing call */
 int avl_device_count(int* count);   /* number of CUDA devices (0 on a CPU box) */
 int avl_set_device(int device);     /* cudaSetDevice for the calling thread */
-int avl_set_profiling(int enabled); /* record CUDA events inside index calls (adds a stream sync) */
+int avl_set_profiling(int enabled); /* record CUDA events inside index calls (read through `stats` or
+                                       avl_map_screen_times) */
 
 /* ---- landmark-index path ------------------------------------------------------------- */
 
@@ -126,13 +126,22 @@ int avl_sim_argmax(avl_map* map, const float* queries, int32_t nq, const float* 
 /* Per query the k best rows: out_idx (nq, k) int64, out_score (nq, k) fp32, sorted by
  * (score desc, row asc); slots past n are idx -1 / score -inf.  Scores are the exact ones.
  * Generalises `grid_pos[np.argmax(heat)]` (avlmaps/robot/habitat_lang_robot.py:427-430) and the
- * argsort retrieval precedent (avlmaps/utils/clip_utils.py:86-93) to k > 1. */
+ * argsort retrieval precedent (avlmaps/utils/clip_utils.py:86-93) to k > 1.
+ * With AVL_ON_DEVICE and stats == NULL the call is ASYNCHRONOUS: it enqueues its kernels on `stream` and returns;
+ * the results are ordered on the stream like any kernel's output (the exact fallback for queries whose candidate
+ * buckets overflow is decided on the device).  Host pointers, or stats != NULL, synchronise the stream before
+ * returning.  Calls on one map must be issued from one thread and one stream at a time (they share its workspace). */
 int avl_sim_topk(avl_map* map, const float* queries, int32_t nq, const float* scale, int normalize_map,
                  int32_t k, int64_t* out_idx, float* out_score, int flags, void* stream,
                  avl_index_stats* stats);
 
+/* With avl_set_profiling(1) every avl_sim_topk call records a CUDA-event pair around its main screen launch into a
+ * ring of 256; this reads the times (ms, oldest first) of the calls since the last read into out_ms[0..cap) and
+ * clears the ring.  Synchronises the last recorded event.  *n_out = number written. */
+int avl_map_screen_times(avl_map* map, float* out_ms, int32_t cap, int32_t* n_out);
+
 /* Diagnostic: the raw bf16 tensor-core scores (n, nq) fp32 of the screen kernel, no correction.
- * cta_group = 1 or 2 selects the tcgen05 variant, 3 the query-stationary kernel (0 = engine's choice). */
+ * cta_group = 1 or 2 selects the tcgen05 variant (0 = engine's choice). */
 int avl_sim_screen_dense(avl_map* map, const float* queries, int32_t nq, int32_t cta_group,
                          float* out_scores, int flags, void* stream);
 
@@ -302,13 +311,16 @@ int avl_rank_keys(const uint64_t* keys_all, const int64_t* offsets, int32_t n_sh
  * buffer (avl_p2p_local_handle, avl_p2p_handle_bytes() bytes), gathers the handles of all ranks through any host
  * channel (torch.distributed.all_gather_object in avlmaps_b200/sharded.py) and maps them (avl_p2p_connect).
  * avl_p2p_exchange_merge then takes this slab's (nq, k) result (device pointers, as avl_sim_topk left it in HBM;
- * ids are made global by adding row_offset, or are global already with row_offset = 0), stores it into every peer's buffer with plain peer stores, and merges what the peers
- * delivered -- ONE kernel per query batch, no host round trip, no NCCL call; every rank must call it for every
- * batch with the same nq and k.  out_idx / out_val (nq, k): the global top-k, (score desc, row asc), on every rank.
- * A peer that never delivers trips a ~10 s in-kernel watchdog instead of hanging the GPU; the next call on the object
- * then fails with AVL_ERR_STATE (avl_p2p_status: the source rank that never arrived, or -1).
- * The NCCL all-gather + avl_merge_topk form stays the default; this one is opt-in (AVL_P2P_EXCHANGE=1) until it has
- * been measured on 2 / 8 GPUs. */
+ * ids are made global inside the kernel: + row_offset for a contiguous slab, or a lookup in global_ids (device
+ * pointer, one int64 per slab row) for the slab of a sharded build), stores it into every peer's buffer with plain
+ * peer stores, and merges what the peers delivered -- ONE kernel per query batch, no host round trip, no NCCL call.
+ * Every rank must call it for every batch with the same nq and k, in the same order (the epoch counter is per object);
+ * calls on one object go to one stream at a time.  out_idx / out_val (nq, k): the global top-k, (score desc, row asc),
+ * on every rank.  A peer that never delivers trips a ~10 s in-kernel watchdog instead of hanging the GPU: the queries
+ * it was missing for come back EMPTY (idx -1, score -inf), never merged from stale bytes, and every later call on the
+ * object fails with AVL_ERR_STATE (avl_p2p_status: the source rank that never arrived, or -1).
+ * Default exchange of avlmaps_b200.sharded.ShardedMap (AVL_P2P_EXCHANGE=0 selects the NCCL all-gather +
+ * avl_merge_topk form); both are compared bit for bit on 2 / 4 / 8 GPUs by tools/sharded_index_check.py. */
 typedef struct avl_p2p avl_p2p;
 int avl_p2p_create(int32_t rank, int32_t world, int32_t nq_max, int32_t k_max, avl_p2p** out);
 int avl_p2p_handle_bytes(void);
@@ -316,6 +328,7 @@ int avl_p2p_local_handle(avl_p2p* p, uint8_t* handle);
 int avl_p2p_connect(avl_p2p* p, const uint8_t* handles /* world * avl_p2p_handle_bytes() */);
 int avl_p2p_exchange_merge(avl_p2p* p, const int64_t* idx, const float* val, int32_t nq, int32_t k,
                            int64_t row_offset /* added to every id >= 0: slab-local -> global rows */,
+                           const int64_t* global_ids /* or NULL; replaces row_offset: id -> global_ids[id] */,
                            int64_t* out_idx, float* out_val, int flags, void* stream);
 int avl_p2p_status(avl_p2p* p, int32_t* timed_out_source, void* stream);
 int avl_p2p_destroy(avl_p2p* p);

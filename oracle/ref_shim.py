@@ -176,7 +176,11 @@ def ref_build(map_config: dict, poses: np.ndarray, depths, rgbs, feats, seed: in
         try:
             np.random.seed(seed)
             b = vb.VLMapBuilder(td, cfg, pose_path, rgb_paths, depth_paths, base2cam_tf, base_transform)
+            import time as _time
+
+            _t0 = _time.perf_counter()
             b.create_mobile_base_map()
+            captured["create_mobile_base_map_s"] = _time.perf_counter() - _t0
         finally:
             vb.VLMapBuilder._init_lseg, vb.get_lseg_feat, vb.save_3d_map, vb.load_3d_map = saved
             np.random.shuffle = orig_shuffle

@@ -386,19 +386,6 @@ def test_heat_windowed_search_equals_brute_force(eng, monkeypatch, decay):
         assert (got > 0).sum() > mask.sum() or decay == 0.1
 
 
-def test_query_stationary_variant_matches(eng, monkeypatch):
-    """The opt-in kernel with the queries resident in TMEM (AVL_TS=1) returns the same top-k."""
-    feat, q = synth.index_inputs(40_001, 512, 200, seed=44)
-    scale = np.random.default_rng(5).uniform(0.5, 3.0, 200).astype(np.float32)
-    ref = O.topk(O.scores(feat, q, scale=scale, normalize=True), 16)
-    m = eng.DeviceMap(feat)
-    monkeypatch.setenv("AVL_TS", "1")
-    idx, val = m.topk(q, 16, scale=scale, normalize_map=True)
-    assert m.last_stats["cta_group"] == 3
-    assert np.array_equal(idx, ref[0]) and np.array_equal(val, ref[1])
-    m.close()
-
-
 def _fuse_both_paths(eng, *args, **kw):
     import os
 

@@ -183,12 +183,6 @@ CASES = {
     "screen_cg2_q16": lambda lib, L: case_screen(lib, L, 1000, 512, 16, 2),
     "screen_cg2_q256": lambda lib, L: case_screen(lib, L, 70_000, 512, 256, 2),
     "screen_cg2_q65_d1024": lambda lib, L: case_screen(lib, L, 9000, 1024, 65, 2),
-    "screen_ts_q256": lambda lib, L: case_screen(lib, L, 70_000, 512, 256, 3),
-    "screen_ts_q48_d100": lambda lib, L: case_screen(lib, L, 5_000, 100, 48, 3),
-    "screen_ts_q200_d448": lambda lib, L: case_screen(lib, L, 9_001, 448, 200, 3),
-    "topk_ts_q256_k16": lambda lib, L: case_topk(lib, L, 300_000, 512, 256, 16),
-    "topk_ts_q130_norm_scale": lambda lib, L: case_topk(lib, L, 100_001, 512, 130, 7, normalize=1, use_scale=True),
-    "perf_topk_ts_4m": lambda lib, L: case_perf(lib, L, 4_194_304, 512, 256, 16, "topk"),
     "argmax_cg1_q2": lambda lib, L: case_argmax(lib, L, 10_000, 512, 2, 1),
     "argmax_cg1_q64": lambda lib, L: case_argmax(lib, L, 200_000, 512, 64, 1),
     "argmax_cg2_q64": lambda lib, L: case_argmax(lib, L, 200_000, 512, 64, 2),
