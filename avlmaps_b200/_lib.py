@@ -18,6 +18,7 @@ AVL_OK = 0
 AVL_ON_DEVICE = 1
 AVL_DEPTH_U16_MM = 2
 AVL_MAP_F16 = 4
+AVL_ASYNC = 16
 AVL_FEAT_F16 = 8
 AVL_MAX_QUERIES = 256
 AVL_MAX_TOPK = 128

@@ -27,6 +27,31 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                    \
   } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------
+// The kernels of one top-k call (query_prepare, sample screen, select, screen, finalize, fallback) are launched with
+// programmatic stream serialization: a kernel's CTAs may be scheduled while its predecessor drains, run their
+// data-independent prologue, and block in pdl_wait() until the predecessor has completed and flushed -- the launch
+// latency and the prologue leave the critical path (AVL_PDL=0 launches them the ordinary way).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- screen kernel (sim_screen.cu) -----------------------------------------
 enum ScreenMode : int32_t { kModeDense = 0, kModeArgmax = 1, kModeThresh = 2 };
 
@@ -45,7 +70,8 @@ struct ScreenParams {
   int32_t stages;        // A pipeline depth
   int32_t mode;          // ScreenMode
   int32_t normalize;     // divide by the fp32 row norm
-  int32_t prefetch_tiles; // L2 prefetch distance of the A stream, in tiles per unit (tiled layout: the prefetch warp)
+  uint32_t* tile_ctr;     // global tile counter of the dynamic schedule (never reset)
+  uint32_t tile_base;     // its value before this launch's first fetch
   int32_t a_tiled;        // operand copy of the map is tile-major ([tile][k-block][128 rows][64]), see map_prepare
   int32_t debug_flags;    // perf triage only (AVL_DEBUG_FLAGS): 1 = no MMA, 2 = no A loads, 4 = no epilogue work,
                           // 8 = pre-test always passes, 16 = thresholds +inf (nothing emitted), 32 = TMEM loads only

@@ -25,6 +25,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return AVL_ERR_CUDA;
 }
 static bool g_profiling = false;
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("AVL_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 // ------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -93,6 +97,8 @@ struct Workspace {
   void* fb_scratch = nullptr;    // per-block top-k keys of the exact fallback
   size_t fb_scratch_bytes = 0;
   uint32_t* fb_tickets = nullptr;  // [256]
+  uint32_t* tile_ctr = nullptr;  // [1] tile counter of the screen kernel's dynamic schedule
+  uint32_t tile_base = 0;        // host mirror: the counter's value before the next launch
   float* sample_t = nullptr;
   size_t sample_elems = 0;
   float* fuse_a = nullptr;       // (pairs, n) dense screen scores of the two modalities (avl_fuse_topk)
@@ -151,7 +157,8 @@ static int ws_init(avl_map* m) {
   if ((rc = dev_alloc(&w.scale, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.bq, static_cast<size_t>(AVL_MAX_QUERIES) * m->dpad, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.q_bn, AVL_MAX_QUERIES, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.q_glob, 2, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.q_glob, 4 + AVL_MAX_QUERIES, &m->bytes))) return rc;  // see launch_query_prepare
+  AVL_CUDA(cudaMemset(w.q_glob, 0, (4 + AVL_MAX_QUERIES) * sizeof(float)));
   if ((rc = dev_alloc(&w.thr_t, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.flag_count, 1, &m->bytes))) return rc;
   // counters and overflow flags are adjacent: one 2 KiB read-back into pinned memory per top-k call
@@ -161,6 +168,8 @@ static int ws_init(avl_map* m) {
   if ((rc = dev_alloc(&w.bucket_cnt, static_cast<size_t>(256) * AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.fb_tickets, AVL_MAX_QUERIES, &m->bytes))) return rc;
   AVL_CUDA(cudaMemset(w.fb_tickets, 0, AVL_MAX_QUERIES * sizeof(uint32_t)));
+  if ((rc = dev_alloc(&w.tile_ctr, 1, &m->bytes))) return rc;
+  AVL_CUDA(cudaMemset(w.tile_ctr, 0, sizeof(uint32_t)));
   AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.pin), 2 * AVL_MAX_QUERIES * sizeof(uint32_t), cudaHostAllocDefault));
   if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
@@ -178,7 +187,7 @@ static void ws_free(Workspace& w) {
   cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
   cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small); cudaFree(w.cand_val2);
-  cudaFree(w.bucket_cnt); cudaFree(w.fb_scratch); cudaFree(w.fb_tickets);
+  cudaFree(w.bucket_cnt); cudaFree(w.fb_scratch); cudaFree(w.fb_tickets); cudaFree(w.tile_ctr);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
   if (w.pin) cudaFreeHost(w.pin);
   for (int i = 0; i < 4; ++i)
@@ -337,13 +346,6 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->a_base = m->bf;
   p->tile_stride = 1;
   {
-    static int pf = -1;  // L2 prefetch distance of the A stream (tiles per unit); AVL_PREFETCH_TILES overrides
-    if (pf < 0) {
-      const char* e = getenv("AVL_PREFETCH_TILES");
-      pf = e ? atoi(e) : 0;  // round 1 (row-major copy, prefetch issued by the producer): 0.90 ms without, 1.02-1.31 ms with
-      if (pf < 0 || pf > 16) pf = 0;
-    }
-    p->prefetch_tiles = pf;
     static int dbg = -1;
     if (dbg < 0) {
       const char* e2 = getenv("AVL_DEBUG_FLAGS");
@@ -355,7 +357,11 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->num_tiles = static_cast<int32_t>((m->n + unit - 1) / unit);
 }
 
-static int run_screen(avl_map* m, const QuerySetup& qs, const ScreenParams& p, cudaStream_t s) {
+static int run_screen(avl_map* m, const QuerySetup& qs, ScreenParams& p, cudaStream_t s) {
+  // dynamic tile schedule: one global counter per map, never reset; a launch makes exactly num_tiles fetches
+  p.tile_ctr = m->ws.tile_ctr;
+  p.tile_base = m->ws.tile_base;
+  m->ws.tile_base += static_cast<uint32_t>(p.num_tiles);
   return launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s);
 }
 
@@ -702,7 +708,6 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     p.dense_cs = n_cols;
     p.dense_cols = nq;
     p.dense_lb = 2;
-    p.prefetch_tiles = 0;  // sampled tiles are strided: nothing sequential to prefetch
     if ((rc = run_screen(m, qs, p, s))) return rc;
     if ((rc = launch_select_threshold(w.sample_t, static_cast<int32_t>(n_cols), n_cols, nq, k, w.thr_t, s)))
       return rc;
@@ -744,7 +749,7 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   const bool triage = m->n > 0 && (p.debug_flags & 64);
   if (stats || triage) AVL_CUDA(cudaMemcpyAsync(w.pin, w.cand_cnt, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, cudaMemcpyDeviceToHost, s));
   // device-pointer calls without stats return here, asynchronously: results are ordered on `stream` like any kernel's
-  if (!(flags & AVL_ON_DEVICE) || stats || triage) {
+  if ((!(flags & AVL_ON_DEVICE) && !(flags & AVL_ASYNC)) || stats || triage) {
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk", __FILE__, __LINE__));
   }

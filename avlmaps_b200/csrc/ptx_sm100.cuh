@@ -99,6 +99,52 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
   }
 }
 
+// Cluster-scope variants for a barrier that orders DATA written into this CTA's shared memory by the peer CTA
+// (st.shared::cluster + remote arrive with release.cluster on the writer's side).
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(200000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, volatile uint32_t* dbg, uint32_t tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      if (dbg) {
+        dbg[0] = 0xDEAD0000u | tag;
+        dbg[1] = blockIdx.x;
+        dbg[2] = threadIdx.x;
+        dbg[3] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+// store a word into the same-offset shared-memory location of CTA `cta` of this cluster, then arrive (release at
+// cluster scope) on the same-offset barrier there: the waiter's acquire.cluster wait sees the word
+__device__ __forceinline__ void st_and_arrive_cluster(uint32_t word_addr, uint32_t value, uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra, rb;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %3;\n\t"
+      "mapa.shared::cluster.u32 rb, %2, %3;\n\t"
+      "st.shared::cluster.u32 [ra], %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rb];\n\t"
+      "}\n" ::"r"(word_addr),
+      "r"(value), "r"(bar), "r"(cta)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;

@@ -101,12 +101,17 @@ __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, in
 
 // ------------------------------------------------------------------ query_prepare
 // One block per padded query row: bf16 copy, ||b||, ||b - bf16(b)|| / ||b||.
-// glob[0] = max ratio (rho), glob[1] = max ||b|| (float bits, non-negative => uint order).
+// glob[0] = max ratio (rho), glob[1] = max ||b||: reduced by the LAST block to finish (ticket; it also re-arms the
+// ticket), so no zero-fill precedes the launch -- one stream operation less per query batch.
 __global__ void query_prepare_kernel(const float* __restrict__ q, const float* __restrict__ fold_scale, int32_t nq,
                                      int32_t d, int32_t dpad, __nv_bfloat16* __restrict__ bq,
-                                     float* __restrict__ q_bn, uint32_t* __restrict__ glob, int f16) {
+                                     float* __restrict__ q_bn, float* __restrict__ q_ratio, uint32_t* __restrict__ glob,
+                                     uint32_t* __restrict__ ticket, int f16) {
+  pdl_wait();               // the previous call's finalize / fallback still read q_bn and glob
+  pdl_launch_dependents();
   const int r = blockIdx.x;
   __shared__ double red[2][32];
+  __shared__ uint32_t sh_last;
   double sb = 0.0, sd = 0.0;
   for (int k = threadIdx.x; k < dpad; k += blockDim.x) {
     float x = (r < nq && k < d) ? q[static_cast<size_t>(r) * d + k] : 0.f;
@@ -127,12 +132,37 @@ __global__ void query_prepare_kernel(const float* __restrict__ q, const float* _
   if (threadIdx.x == 0) {
     double tb = 0.0, td = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); ++i) { tb += red[0][i]; td += red[1][i]; }
+    float bn = 0.f, ratio = 0.f;
     if (r < nq) {
-      const float bn = __double2float_ru(sqrt(tb) * (1.0 + 1e-7));
+      bn = __double2float_ru(sqrt(tb) * (1.0 + 1e-7));
+      ratio = (tb > 0.0 ? __double2float_ru(sqrt(td / tb) * (1.0 + 1e-6)) : 0.f) + 2e-6f;
       q_bn[r] = bn;
-      const float ratio = tb > 0.0 ? __double2float_ru(sqrt(td / tb) * (1.0 + 1e-6)) : 0.f;
-      atomicMax(glob + 0, __float_as_uint(ratio + 2e-6f));
-      atomicMax(glob + 1, __float_as_uint(bn));
+    }
+    q_ratio[r] = ratio;  // padded rows: 0
+    __threadfence();
+    sh_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (sh_last) {
+    __threadfence();
+    float mr = 0.f, mb = 0.f;  // both non-negative
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) {
+      mr = fmaxf(mr, __ldcg(q_ratio + i));
+      if (i < nq) mb = fmaxf(mb, __ldcg(q_bn + i));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+      mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    __shared__ float smr[32], smb[32];
+    if (l == 0) { smr[w] = mr; smb[w] = mb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (blockDim.x >> 5); ++i) { mr = fmaxf(mr, smr[i]); mb = fmaxf(mb, smb[i]); }
+      glob[0] = __float_as_uint(mr);
+      glob[1] = __float_as_uint(mb);
+      *ticket = 0u;
     }
   }
 }
@@ -435,6 +465,8 @@ constexpr int kSelThreads = 1024;
 __global__ void __launch_bounds__(kSelThreads)
 select_threshold_kernel(const float* __restrict__ sample_lb, int32_t n_sample, int64_t ld, int32_t k,
                         float* __restrict__ thr_t) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int q = blockIdx.x;
   const float* col = sample_lb + static_cast<int64_t>(q) * ld;
   uint32_t best = 0u;  // 0 = this thread saw no valid row
@@ -465,9 +497,9 @@ select_threshold_kernel(const float* __restrict__ sample_lb, int32_t n_sample, i
 // One block per query.  Gathers its entries from the unified candidate list, finds the k-th best
 // LOWER bound, keeps the entries whose UPPER bound reaches it, re-scores those exactly (fp64) and
 // orders them by (score desc, row asc).
-constexpr int kFinThreads = 1024;
+constexpr int kFinThreads = 512;
 constexpr int kFinMaxGrid = 256;   // CTAs of one screen launch (one per SM)
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kFinThreads, 2)
 topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, const float* __restrict__ q,
                      const float* __restrict__ scale, const float* __restrict__ row_norm,
                      const float* __restrict__ row_c, const float* __restrict__ row_an,
@@ -476,13 +508,16 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
                      const uint32_t* __restrict__ cand_row, const float* __restrict__ cand_val, uint32_t cand_cap,
                      int64_t* __restrict__ out_idx, float* __restrict__ out_score,
                      uint32_t* __restrict__ cand_total, uint32_t* __restrict__ overflow_flags) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ uint8_t sm[];
   uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
-  uint32_t* Uk = Lk + cand_cap;
-  uint32_t* Ix = Uk + cand_cap;
-  // 20 bytes per candidate = 160 KiB: one block per SM.  Measured on B200: packing two blocks per SM (12 bytes per
-  // candidate + a fixed survivor array) made the 256-query finalize slower, 67 vs 57 us
-  unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Ix + cand_cap);
+  uint32_t* Ix = Lk + cand_cap;
+  uint32_t* Uk = Ix + cand_cap;
+  // 12 bytes per candidate = 96 KiB at 8192 candidates, 512 threads: TWO blocks per SM, so the 256 queries of a full
+  // batch are one wave over 148 SMs instead of two.  The exact keys of the survivors live where the upper bounds were
+  // (dead once the survivors are chosen): at most cand_cap / 2 survivors, more flags the query for the exact fallback.
+  unsigned long long* K64 = reinterpret_cast<unsigned long long*>(Uk);
   __shared__ int sh_cnt;
   __shared__ int sh_ns;
   __shared__ uint32_t sh_off[kFinMaxGrid + 1];
@@ -558,6 +593,10 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   }
   __syncthreads();
   const int ns = sh_ns;
+  if (ns > static_cast<int>(cand_cap / 2)) {  // (uniform) the survivors' keys would not fit: massive ties
+    if (threadIdx.x == 0) overflow_flags[qq] = 1u;
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float* b = q + static_cast<size_t>(qq) * d;
   for (int s = warp; s < ns; s += nw) {
@@ -667,6 +706,8 @@ topk_fallback_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const
                      const float* __restrict__ scale, const float* __restrict__ row_norm, int normalize, int32_t k,
                      const uint32_t* __restrict__ overflow_flags, unsigned long long* __restrict__ scratch,
                      uint32_t* __restrict__ tickets, int64_t* __restrict__ out_idx, float* __restrict__ out_score) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int kWarps = kFbThreads / 32;
   __shared__ unsigned long long wl[kWarps][AVL_MAX_TOPK];
   __shared__ int wcnt[kWarps];
@@ -1265,9 +1306,10 @@ int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __
 
 int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, int32_t d, int32_t dpad,
                          int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, int f16, cudaStream_t s) {
-  AVL_CUDA(cudaMemsetAsync(q_glob, 0, 2 * sizeof(float), s));
-  query_prepare_kernel<<<npad, 128, 0, s>>>(q, fold_scale, nq, d, dpad, bq, q_bn,
-                                            reinterpret_cast<uint32_t*>(q_glob), f16);
+  // q_glob: [0] rho, [1] max ||b||, [2] ticket of the last-block reduction (zero at allocation, re-armed by the
+  // kernel), [4 .. 4 + 256) per-row ratios
+  AVL_CUDA(launch_pdl(query_prepare_kernel, dim3(npad), dim3(128), 0, s, q, fold_scale, nq, d, dpad, bq, q_bn, q_glob + 4,
+                      reinterpret_cast<uint32_t*>(q_glob), reinterpret_cast<uint32_t*>(q_glob) + 2, f16));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
@@ -1309,12 +1351,12 @@ int launch_select_threshold(const float* sample_lb, int32_t n_sample, int64_t ld
     set_error("select_threshold: k too large");
     return AVL_ERR_ARG;
   }
-  select_threshold_kernel<<<nq, kSelThreads, 0, s>>>(sample_lb, n_sample, ld, k, thr_t);
+  AVL_CUDA(launch_pdl(select_threshold_kernel, dim3(nq), dim3(kSelThreads), 0, s, sample_lb, n_sample, ld, k, thr_t));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
 
-size_t topk_finalize_smem(uint32_t cand_cap) { return static_cast<size_t>(cand_cap) * 20u; }
+size_t topk_finalize_smem(uint32_t cand_cap) { return static_cast<size_t>(cand_cap) * 12u; }
 
 int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const float* q, int32_t nq,
                          const float* scale, const float* row_norm, const float* row_c, const float* row_an,
@@ -1329,10 +1371,9 @@ int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const flo
   const size_t smem = topk_finalize_smem(cand_cap);
   AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
-  topk_finalize_kernel<<<nq, kFinThreads, smem, s>>>(feat, n_rows, d, q, scale, row_norm, row_c, row_an, q_bn,
-                                                     reinterpret_cast<const uint32_t*>(q_glob), normalize, k,
-                                                     bucket_cnt, grid, cand_bucket, cand_row, cand_val, cand_cap,
-                                                     out_idx, out_score, cand_total, overflow_flags);
+  AVL_CUDA(launch_pdl(topk_finalize_kernel, dim3(nq), dim3(kFinThreads), smem, s, feat, n_rows, d, q, scale, row_norm, row_c,
+                      row_an, q_bn, reinterpret_cast<const uint32_t*>(q_glob), normalize, k, bucket_cnt, grid, cand_bucket,
+                      cand_row, cand_val, cand_cap, out_idx, out_score, cand_total, overflow_flags));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
@@ -1345,9 +1386,8 @@ int launch_topk_fallback(const float* feat, int64_t n, int32_t d, const float* q
                          const float* row_norm, int normalize, int32_t k, const uint32_t* overflow_flags,
                          void* scratch, uint32_t* tickets, int64_t* out_idx, float* out_score, int num_sms,
                          cudaStream_t s) {
-  topk_fallback_kernel<<<2 * num_sms, kFbThreads, 0, s>>>(feat, n, d, q, nq, scale, row_norm, normalize, k, overflow_flags,
-                                                         static_cast<unsigned long long*>(scratch), tickets, out_idx,
-                                                         out_score);
+  AVL_CUDA(launch_pdl(topk_fallback_kernel, dim3(2 * num_sms), dim3(kFbThreads), 0, s, feat, n, d, q, nq, scale, row_norm,
+                      normalize, k, overflow_flags, static_cast<unsigned long long*>(scratch), tickets, out_idx, out_score));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }

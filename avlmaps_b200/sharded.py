@@ -154,6 +154,8 @@ class ShardedMap:
         No eager tensor ops: the slab's result lands in a ring buffer, the exchange kernel makes the ids global."""
         import torch
 
+        if self.world > 1 and not self._use_p2p(k):
+            return PendingTopK(self.topk(queries, k, scale=scale, normalize_map=normalize_map), None)   # NCCL form: in stream order
         nq = queries.shape[0]
         st = self._device_state(queries.device, nq, k)
         i = st["slot"]

@@ -42,6 +42,15 @@ METRIC = "queries/sec over 4M-voxel x 512-d map (256-query batch, fused top-16)"
 UNIT = "queries/s"
 
 
+def workload_config(world: int) -> dict:
+    """`config` of BOTH arms (ours and --impl reference): the same dict, so that the driver can see that they ran the
+    same workload; what differs between the arms is said in cpu_baseline / roofline."""
+    return {"workload": f"headline: {N_VOX} voxels x {DIM}-d per slab, {world} slab(s), {NQ} queries per step, top-{TOPK}",
+            "l2": "per-step input (4.3 GB map per slab) is 34x the 126 MB L2: no flush needed",
+            "map_residency": "map resident (load_map); per-step input = the query batch",
+            "value_definition": "queries x 4M-voxel slabs scored per second (N=1: plain queries/s)"}
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -50,6 +59,35 @@ def load_peaks():
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
             "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_dram_bytes(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a kernel, from the `ncu --page raw --csv` export of
+    this round's `ncu --set full` capture committed under profiles/ (parsed here, at run time) -> (bytes | None, file)."""
+    import csv
+
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r*_ncu_raw_*.csv")):
+        try:
+            rows = list(csv.reader(f.open()))
+        except Exception:  # noqa: BLE001
+            continue
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        try:
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if len(r) > max(ik, ir, iw) and kernel_substr in r[ik]:
+                try:
+                    val = float(r[ir].replace(",", "")) * mult.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * mult.get(units[iw], 1.0)
+                except ValueError:
+                    continue
+                best = (val, f.name)   # the newest round's file wins (sorted by name)
+    return best if best else (None, None)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -254,7 +292,8 @@ def run_reference(args):
     frac = rows / N_VOX
     value = NQ * world * frac / (ms_step / 1e3)
     full = rows == N_VOX
-    cb = {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "blas": blas,
+    cb = {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "blas": blas, "full_size": full,
+          "rows_scored_per_slab": rows,
           "sample": (f"all {N_VOX} rows" if full else f"{rows} of {N_VOX} rows (x{N_VOX // rows} row fraction, value scaled by it)")
                     + f" x {world} slab(s) x all {NQ} queries per step; numpy float32 `@` through OpenBLAS on {nthreads} threads + "
                       f"np.argpartition top-{TOPK} on {nthreads} threads; {args.steps} timed steps; slab generated in {gen_s:.1f} s",
@@ -262,10 +301,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"headline: {N_VOX} voxels x {DIM}-d per slab, {world} slab(s), {NQ} queries per step, top-{TOPK}; "
-                                   "reference CPU path (numpy/OpenBLAS) on the host cores",
-                       "rows_scored_per_slab": rows, "full_size": full, "host_threads": nthreads, "blas": blas,
-                       "value_definition": "queries x 4M-voxel slabs scored per second (N=1: plain queries/s)"},
+            "config": workload_config(world),
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -521,47 +557,107 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: value.  N = 1: the C-ABI call with DEVICE pointers (queries and outputs in HBM);
-    # N > 1: the same call per rank inside ShardedMap.topk, followed by the one NCCL all-gather + merge kernel
+    # ---- device-resident arm: value.  N = 1: the C-ABI call with DEVICE pointers (queries and outputs in HBM), enqueued
+    # asynchronously like any kernel (no host round trip: the exact fallback is decided on the device); N > 1: the same
+    # call per rank inside ShardedMap.topk_async, followed by the ONE exchange + merge kernel over NVLink peer memory
     oi_dev = torch.empty((NQ, TOPK), dtype=torch.int64, device=dev)
     os_dev = torch.empty((NQ, TOPK), dtype=torch.float32, device=dev)
-    st = L.IndexStats()
+    launches_per_step = 6 + (1 if world > 1 else 0)   # query_prepare, sample screen, select, screen, finalize, fallback (+ exchange)
 
     def value_step(i):
         if world == 1:
             L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(qpool[i % 8].data_ptr()), NQ, None, 0, TOPK,
                                      C.c_void_p(oi_dev.data_ptr()), C.c_void_p(os_dev.data_ptr()), L.AVL_ON_DEVICE,
-                                     C.c_void_p(stream.cuda_stream), C.byref(st)))
-            return st.ms_screen, st.n_launches, st.n_candidates, st.cta_group
-        sm.topk(qpool[i % 8], TOPK)
-        d = dmap.last_stats
-        return d["ms_screen"], d["n_launches"], d["n_candidates"], d["cta_group"]
+                                     C.c_void_p(stream.cuda_stream), None))
+            return None
+        return sm.topk_async(qpool[i % 8], TOPK)
 
+    def screen_times():
+        buf = (C.c_float * 256)()
+        nn = C.c_int32(0)
+        L.check(lib.avl_map_screen_times(dmap._h, buf, 256, C.byref(nn)))
+        return [buf[i] for i in range(nn.value)]
+
+    def timed(steps):
+        """`steps` asynchronous steps between two events on the launching stream, barrier + synchronize on both sides;
+        -> (ms of the region, max over ranks; per-launch times of the main screen kernel on this rank)."""
+        screen_times()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        pend = None
+        for i in range(steps):
+            pend = value_step(i)
+        if pend is not None:
+            pend.result()          # the current stream waits for the last exchange: e1 closes the whole job
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), screen_times()
+
+    lib.avl_set_profiling(1)       # one CUDA-event pair around the main screen launch of every call (read after the region)
     for i in range(args.warmup):
-        value_step(i)
-    lib.avl_set_profiling(1)
+        p_ = value_step(i)
+        if p_ is not None:
+            p_.result()
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ms_screen, launches, cands = [], 0, []
-    last_cta_group = 0
-    e0.record(stream)
-    for i in range(args.steps):
-        a, b, c, last_cta_group = value_step(i)
-        ms_screen.append(a)
-        launches += b
-        cands.append(c)
-    e1.record(stream)
-    barrier()
+    t_ms, ms_screen = timed(args.steps)
     clk = clocks.stop() if rank == 0 else None
-    lib.avl_set_profiling(0)
-    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    t_ms = float(t_ms.item())
     value = NQ * world * args.steps / (t_ms / 1e3)
+    launches = launches_per_step * args.steps
+
+    # ---- the same step held for >= 2 s: the power-capped steady state, reported beside the driver's short region
+    sustained_line = None
+    if world == 1 and not args.no_sustained:
+        n_sus = max(200, int(2200.0 / max(t_ms / args.steps, 0.05)))
+        clocks2 = ClockSampler(local)
+        clocks2.start()
+        ts_ms, sus_screen = timed(n_sus)
+        clk2 = clocks2.stop()
+        sustained_line = {"steps": n_sus, "region_s": ts_ms / 1e3, "ms_per_step": ts_ms / n_sus,
+                          "queries_per_s": NQ * n_sus / (ts_ms / 1e3), "kernel_ms": statistics.mean(sus_screen) if sus_screen else None,
+                          "sm_mhz": clk2.get("sm_mhz"), "reasons": clk2.get("reasons")}
+    lib.avl_set_profiling(0)
+    # one call with statistics (synchronises): candidates, fallbacks, variant
+    st = L.IndexStats()
+    L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(qpool[0].data_ptr()), NQ, None, 0, TOPK, C.c_void_p(oi_dev.data_ptr()),
+                             C.c_void_p(os_dev.data_ptr()), L.AVL_ON_DEVICE, C.c_void_p(stream.cuda_stream), C.byref(st)))
+    cands, last_cta_group, n_fallback = [int(st.n_candidates)], int(st.cta_group), int(st.n_fallback_queries)
+
+    # ---- N > 1: parity of the merged result, checked on the GPUs after the timed region: every rank scores its slab
+    # EXACTLY (avl_sim_dense) for 2 queries, the exact per-slab top-k are gathered and merged on the host
+    parity = None
+    if world > 1:
+        from avlmaps_b200.sharded import merge_topk
+
+        mi, mv = sm.topk(qpool[0], TOPK)
+        torch.cuda.synchronize()
+        mi, mv = mi.cpu().numpy().copy(), mv.cpu().numpy().copy()
+        qa = [3, 200]
+        sc = dmap.scores(qpool[0][qa].contiguous())
+        li, lv = [], []
+        for j in range(len(qa)):
+            v, ix = torch.topk(sc[:, j], 4 * TOPK)
+            v, ix = v.cpu().numpy(), ix.cpu().numpy().astype(np.int64)
+            o = np.lexsort((ix, -v.astype(np.float64)))[:TOPK]
+            li.append(ix[o] + rank * N_VOX)
+            lv.append(v[o])
+        gi, gv = [None] * world, [None] * world
+        dist.all_gather_object(gi, np.stack(li))
+        dist.all_gather_object(gv, np.stack(lv))
+        ei, ev = merge_topk(np.stack(gi), np.stack(gv), TOPK)
+        mine_ok = bool(np.array_equal(ei, mi[qa]) and np.array_equal(ev, mv[qa]))
+        oks = [None] * world
+        import hashlib
+
+        dist.all_gather_object(oks, (mine_ok, hashlib.sha256(mi.tobytes() + mv.tobytes()).hexdigest()))
+        parity = bool(all(o[0] for o in oks) and len({o[1] for o in oks}) == 1)
+        del sc
 
     # ---- end-to-end arm: host buffers, H2D of the queries and D2H of the result inside the timed region
     q_host = [torch.empty((NQ, DIM), dtype=torch.float32).pin_memory() for _ in range(8)]
@@ -571,12 +667,20 @@ def run_gpu(args):
     os_host = torch.empty((NQ, TOPK), dtype=torch.float32).pin_memory()
     q_dev = torch.empty((NQ, DIM), dtype=torch.float32, device=dev)
 
+    oi_ring = [torch.empty((NQ, TOPK), dtype=torch.int64).pin_memory() for _ in range(8)]
+    os_ring = [torch.empty((NQ, TOPK), dtype=torch.float32).pin_memory() for _ in range(8)]
+
     def e2e_step(i):
         if world == 1:
-            # the C-ABI call with host pointers: it does the H2D / D2H itself and synchronises
+            # the C-ABI call with HOST pointers (pinned): it enqueues the H2D copy of the batch, the kernels and the D2H
+            # copy of the result and returns (AVL_ASYNC); every batch has its own pinned buffers (ring of 8), and the
+            # host waits for a batch before its buffers are reused -- a serving loop with 8 batches in flight
+            if i >= 8:
+                e2e_done[i % 8].synchronize()
             L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(q_host[i % 8].data_ptr()), NQ, None, 0, TOPK,
-                                     C.c_void_p(oi_host.data_ptr()), C.c_void_p(os_host.data_ptr()), 0,
+                                     C.c_void_p(oi_ring[i % 8].data_ptr()), C.c_void_p(os_ring[i % 8].data_ptr()), L.AVL_ASYNC,
                                      C.c_void_p(stream.cuda_stream), None))
+            e2e_done[i % 8].record(stream)
         else:
             q_dev.copy_(q_host[i % 8], non_blocking=True)
             mi, mv = sm.topk(q_dev, TOPK)
@@ -584,16 +688,23 @@ def run_gpu(args):
             os_host.copy_(mv, non_blocking=True)
             torch.cuda.synchronize()
 
+    e2e_done = [torch.cuda.Event() for _ in range(8)]
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(i)
-    barrier()
+    barrier()                     # synchronises: every result of the region is in host memory
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if world == 1:                # the last batch's result must be the device arm's (same queries)
+        ref_i = oi_dev.cpu()
+        L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(q_host[(args.steps - 1) % 8].data_ptr()), NQ, None, 0, TOPK,
+                                 C.c_void_p(oi_host.data_ptr()), C.c_void_p(os_host.data_ptr()), 0,
+                                 C.c_void_p(stream.cuda_stream), None))
+        assert torch.equal(oi_host, oi_ring[(args.steps - 1) % 8]), "asynchronous host-pointer call returned a different result"
     e2e_value = NQ * world * args.steps / float(te.item())
 
     build_sharded = None
@@ -609,34 +720,36 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the tcgen05 screen), timed live by CUDA events in the library
+    # ---- roofline of the dominant kernel (the tcgen05 screen): CUDA events recorded inside the library around every
+    # main screen launch of the timed region, on the launching stream
     ms_k = statistics.mean(ms_screen)
     flops = 2.0 * N_VOX * DIM * NQ
     achieved = flops / (ms_k * 1e-3) / 1e12
-    # the kernel is timed inside a long step (hundreds of back-to-back launches under the 1 kW power cap):
-    # the sustained cuBLAS figure is the denominator the profiling recipe prescribes; the burst one is kept beside it
+    # a region of tens of milliseconds runs at burst clocks, a region of seconds under the power cap: the profiling
+    # recipe prescribes the burst cuBLAS figure for the former, the sustained one for the latter; both fractions are given
     sustained = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
-    long_step = args.steps >= 50
+    long_step = t_ms >= 500.0
     peak = sustained if long_step else peaks["bf16_tflops"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
-                "peak_kind": "sustained (kernel timed inside a long step)" if long_step else "burst (short run)",
+                "peak_kind": "sustained (region >= 0.5 s)" if long_step else "burst (short region)",
                 "frac_vs_burst_peak": achieved / peaks["bf16_tflops"], "frac_vs_sustained_peak": achieved / sustained,
-                "kernel": {3: "screen_ts_kernel (tcgen05 cta_group::2, queries resident in TMEM, M=256 N=128 K=512 per tile)",
-                           2: "screen_kernel<cta_group::2> (tcgen05 bf16, M=256 N=256 K=512 per tile pair)",
-                           1: "screen_kernel<cta_group::1>"}.get(last_cta_group, "?"),
-                "kernel_ms": ms_k, "peak_source": peaks["source"],
+                "kernel": {2: "screen_kernel<2> (tcgen05 bf16 cta_group::2, M=256 N=256 K=512 per tile pair)",
+                           1: "screen_kernel<1>"}.get(last_cta_group, "?"),
+                "kernel_ms": ms_k, "kernel_launches_timed": len(ms_screen), "peak_source": peaks["source"],
                 "algorithmic_flops": flops, "algorithmic_bytes": N_VOX * DIM * 2 + NQ * DIM * 4 + NQ * TOPK * 12,
-                "hbm_GBps": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9, "hbm_frac": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-    traffic_file = ROOT / "profiles" / "traffic.json"
-    if traffic_file.exists():
-        try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get("screen_kernel_dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            pass
+                "hbm_GBps": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9, "hbm_frac": (N_VOX * DIM * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "step_frac_vs_burst_peak": flops / (t_ms / args.steps * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+    roofline["traffic"], roofline["traffic_source"] = ncu_dram_bytes("screen_kernel")
+    if sustained_line is not None:
+        if sustained_line["kernel_ms"]:
+            sustained_line["frac_vs_sustained_peak"] = flops / (sustained_line["kernel_ms"] * 1e-3) / 1e12 / sustained
+            sustained_line["step_frac_vs_sustained_peak"] = flops / (sustained_line["ms_per_step"] * 1e-3) / 1e12 / sustained
+        roofline["sustained"] = sustained_line
 
-    extra = {"screen_ms_mean": ms_k, "candidates_per_step": statistics.mean(cands), "cta_group": last_cta_group}
-    if dmap16 is not None:
+    extra = {"screen_ms_mean": ms_k, "candidates_per_step": statistics.mean(cands), "cta_group": last_cta_group,
+             "fallback_queries": n_fallback}
+    if dmap16 is not None and not args.no_extra:
         try:
             lib.avl_set_profiling(1)
             for i in range(3):
@@ -661,7 +774,10 @@ def run_gpu(args):
     if build_sharded is not None:
         extra["build_slab_sharded"] = build_sharded
     cb = None
-    if world == 1:
+    if world == 1 and args.no_extra:
+        dmap.close()
+        torch.cuda.empty_cache()
+    if world == 1 and not args.no_extra:
         # BASELINE config 2 (1M x 512, Q = 64): per-voxel argmax and top-16, HBM-bound; bf16 and fp16 operands
         try:
             feat2 = make_shard(torch, 1_000_000, DIM, 5, dev)
@@ -743,6 +859,7 @@ def run_gpu(args):
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             extra["config3_error"] = repr(e)
+    if world == 1:
         if not args.no_build:
             try:
                 extra["build"] = build_extra(torch, engine, L)
@@ -756,17 +873,24 @@ def run_gpu(args):
                 except Exception as e:  # noqa: BLE001
                     extra["build_cpu_baseline_error"] = repr(e)
 
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * TOPK * 12}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"headline: {N_VOX} voxels x {DIM}-d per GPU (slab-sharded, {world} slab(s)), {NQ} queries "
-                                   f"per step, fused top-{TOPK}; bf16 tcgen05 screen + exact fp64-accumulated re-score",
-                       "l2": "per-step input (4.3 GB bf16 map) is 34x the 126 MB L2, no flush needed",
-                       "map_residency": "map uploaded once (load_map); per-step input = the query batch",
-                       "value_definition": "queries x 4M-voxel slabs scored per second (N=1: plain queries/s)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * TOPK * 12},
-            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "extra": extra}
+            "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "extra": extra}
+    if parity is not None:
+        line["parity"] = parity
+        line["config"]["parity"] = parity
+        line["config"]["parity_check"] = "merged top-k == host merge of every slab's exact (avl_sim_dense) top-k, 2 queries, all ranks agree"
+    # the second half of the metric (back-projection frames/s) rides in the keys the driver keeps
+    bld = extra.get("build") if isinstance(extra.get("build"), dict) else None
+    if bld and "roofline" in bld:
+        roofline["build_scatter"] = bld["roofline"]
+        e2e["build"] = bld.get("e2e")
+        line["config"]["workload_build"] = bld.get("workload")
     if cb is not None:
+        if bld and "cpu_baseline" in bld:
+            cb["build"] = bld["cpu_baseline"]
         line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
@@ -781,6 +905,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-build", action="store_true", help="skip the back-projection section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s steady-state region")
+    ap.add_argument("--no-extra", action="store_true", help="skip configs 2 / 3, heat and the fp16-operand line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

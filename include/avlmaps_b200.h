@@ -45,6 +45,11 @@ extern "C" {
                               float64(d) / 1000.0 like `load_depth_img(...) / 1000.0`
                               (vlmap_builder_multi_floor.py:103,128) */
 
+#define AVL_ASYNC 16 /* avl_sim_topk with HOST pointers: enqueue the H2D copy of the queries, the kernels and the D2H copy of
+                         the result on `stream` and return WITHOUT synchronising.  The host buffers must be pinned and must
+                         not be touched until the stream has passed this call (cudaStreamSynchronize / an event): the way
+                         a serving loop keeps several query batches in flight. */
+
 #define AVL_MAP_F16 4 /* avl_map_create: keep the tensor-core copy of the map (and of the queries) in fp16 instead of
                          bf16.  Same tcgen05 kind::f16 rate and bytes; the rounding residual, hence the rigorous error
                          band that decides what is re-scored exactly, is 8x smaller.  Results are identical either
