@@ -33,10 +33,10 @@ EXPORTS = [
     "avl_sim_dense", "avl_sim_argmax", "avl_sim_topk", "avl_sim_screen_dense", "avl_topk_f32", "avl_fuse_topk",
     "avl_heat_from_mask_3d", "avl_merge_topk", "avl_heat2d_sources",
     "avl_builder_create", "avl_builder_destroy", "avl_builder_add_frame", "avl_builder_num_voxels",
-    "avl_builder_num_accepted", "avl_builder_export", "avl_builder_to_map",
+    "avl_builder_num_accepted", "avl_builder_h2d_bytes", "avl_builder_export", "avl_builder_to_map",
     "avl_builder_create_global", "avl_builder_num_rejected_oob",
     "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
-    "avl_builder_set_slab", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
+    "avl_builder_set_slab", "avl_builder_skip_frames", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
     "avl_heat_planar", "avl_heat2d_normalize_lift",
     "avl_p2p_create", "avl_p2p_handle_bytes", "avl_p2p_local_handle", "avl_p2p_connect", "avl_p2p_exchange_merge",
     "avl_p2p_status", "avl_p2p_destroy",
@@ -123,6 +123,8 @@ def load() -> C.CDLL:
     lib.avl_builder_add_frames.argtypes = [vp, C.POINTER(Frame), i32, C.c_int, vp]
     lib.avl_builder_num_voxels.argtypes = [vp, C.POINTER(i64), vp]
     lib.avl_builder_num_accepted.argtypes = [vp, C.POINTER(i64), vp]
+    lib.avl_builder_skip_frames.argtypes = [vp, i32]
+    lib.avl_builder_h2d_bytes.argtypes = [vp, C.POINTER(i64)]
     lib.avl_builder_export.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
     lib.avl_builder_to_map.argtypes = [vp, vp, C.POINTER(vp)]
     lib.avl_builder_create_global.argtypes = [C.POINTER(GlobalGridSpec), C.POINTER(vp)]

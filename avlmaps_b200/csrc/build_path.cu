@@ -18,6 +18,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <sched.h>
 
 #include <cuda_fp16.h>
 
@@ -740,9 +748,107 @@ struct avl_builder {
   float* d_feat_t = nullptr; size_t feat_t_elems = 0;
   uint8_t* d_rgb = nullptr; size_t rgb_bytes = 0;
   int32_t* d_sidx = nullptr; size_t sidx_elems = 0;
+  // sparse hand-off of host-resident (1, D, FH, FW) features (add_frame_sparse): pinned host buffers
+  int32_t* h_cell = nullptr; int32_t* h_fpix = nullptr; size_t h_samples = 0;   // geometry results read back
+  void* h_stage[2] = {nullptr, nullptr}; size_t h_stage_bytes[2] = {0, 0};      // gathered channel rows, double-buffered
+  int32_t* h_cidx[2] = {nullptr, nullptr}; size_t h_cidx_elems[2] = {0, 0};     // compact feature index per sample
+  cudaEvent_t h_ev[2] = {nullptr, nullptr}; bool h_busy[2] = {false, false};
+  int h_next = 0;
+  std::vector<int32_t> h_rank, h_upix;
+  uint64_t h2d_bytes = 0;  // bytes uploaded from host pointers so far (avl_builder_h2d_bytes)
 };
 
 namespace {
+
+// ---------------------------------------------------------------- host threads (feature gather)
+// A small persistent pool: the gather of a frame at depth_sample_rate 100 is ~0.1 ms of work, so threads are not
+// spawned per call.  run(n, f) calls f(i) for i in [0, n) on the pool and the caller.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool p;
+    return p;
+  }
+  int size() const { return static_cast<int>(th_.size()) + 1; }
+  void run(int n, const std::function<void(int)>& f) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &f;
+      n_ = n;
+      next_.store(0);
+      left_ = n;
+      ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return left_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    // the CPUs this process may run on (a container's cpuset), not the machine's: hardware_concurrency() reports the
+    // latter and oversubscribed a 16-CPU cpuset four times over
+    int hc = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) hc = CPU_COUNT(&set);
+    if (hc <= 0) hc = static_cast<int>(std::thread::hardware_concurrency());
+    const char* e = getenv("AVL_HOST_THREADS");
+    int n = e ? atoi(e) : (hc > 0 ? hc : 4);
+    n = std::max(1, std::min(n, 64));
+    for (int i = 1; i < n; ++i) th_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void work() {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) break;
+      (*job_)(i);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--left_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+template <typename T>
+int grow_pinned(T** p, size_t* have, size_t need) {
+  if (*have >= need) return AVL_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *have = 0;
+  AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(p), need * sizeof(T), cudaHostAllocDefault));
+  *have = need;
+  return AVL_OK;
+}
 
 template <typename T>
 int grow(T** p, size_t* have, size_t need) {
@@ -823,7 +929,10 @@ struct BatchItem {
 };
 
 // geometry -> ordered id scan -> scatter for up to kMaxBatch frames whose inputs are on the device
-int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cudaStream_t s) {
+// phase: 1 = geometry only (first-touch keys, per-sample cell / feature pixel / alpha), 2 = id scan + scatter of a
+// batch whose geometry ran, 3 = both.  The split lets a host-resident frame learn WHICH feature pixels it needs
+// (phase 1), gather only those on the host, and fuse (phase 2).
+int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cudaStream_t s, int phase = 3) {
   FrameBatch batch;
   memset(&batch, 0, sizeof(batch));
   int64_t total = 0;
@@ -839,13 +948,13 @@ int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cuda
   batch.nf = nf;
   batch.frame_seq0 = b->frame_seq;
   if (total == 0) {
-    b->frame_seq += static_cast<uint32_t>(nf);
+    if (phase & 2) b->frame_seq += static_cast<uint32_t>(nf);
     return AVL_OK;
   }
   const int32_t n_samples = static_cast<int32_t>(total);
   int rc;
   // ---- scratch
-  if (b->scratch_samples < n_samples) {
+  if ((phase & 1) && b->scratch_samples < n_samples) {
     cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
     cudaFree(b->block_cnt); cudaFree(b->scan_state);
     b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
@@ -863,7 +972,7 @@ int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cuda
     if (!b->ticket) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->ticket), sizeof(uint32_t)));
     b->scratch_samples = n_samples;
   }
-  if ((rc = ensure_capacity(b, n_samples, s))) return rc;
+  if ((phase & 1) && (rc = ensure_capacity(b, n_samples, s))) return rc;
 
   for (int i = 0; i < nf; ++i) {
     FrameGeom& g = batch.g[i];
@@ -883,8 +992,13 @@ int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cuda
   const int d = b->dim;
   const int nblocks = (n_samples + kScanBlock - 1) / kScanBlock;
   const int geom_blocks = std::min((n_samples + 255) / 256, b->num_sms * 8);
-  geom_kernel<<<geom_blocks, 256, 0, s>>>(batch, b->first_key, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap,
-                                          b->counters + 2, b->ticket);
+  if (phase & 1)
+    geom_kernel<<<geom_blocks, 256, 0, s>>>(batch, b->first_key, b->s_cell, b->s_fpix, b->s_alpha, b->s_rgbpix, b->s_wrap,
+                                            b->counters + 2, b->ticket);
+  if (!(phase & 2)) {
+    AVL_CUDA(cudaGetLastError());
+    return AVL_OK;
+  }
   static const bool three_pass = getenv("AVL_BUILD_3PASS") != nullptr;  // the original count / scan / assign kernels (A/B)
   if (three_pass && nf == 1) {
     winner_count_kernel<<<nblocks, kScanBlock, 0, s>>>(b->s_cell, n_samples, b->frame_seq, b->first_key,
@@ -904,6 +1018,125 @@ int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cuda
   AVL_CUDA(cudaGetLastError());
   b->frame_seq += static_cast<uint32_t>(nf);
   return AVL_OK;
+}
+
+// Host-resident (1, D, FH, FW) features, the array get_lseg_feat returns (lseg_utils.py:101-102): 415 MB of float32
+// per 390 x 520 x 512 frame, of which the frame's accepted points read at most 100 k pixel rows (205 MB) at
+// depth_sample_rate 1 and ~3 000 (6 MB) at the reference's default rate 100 (config/map_config/vlmaps.yaml:13).
+// Copying the whole array made the call PCIe-bound at 127 frames/s whatever the rate.  Here the geometry runs first and
+// tells the host WHICH feature pixels are read; the host gathers exactly those, channel row by channel row (one
+// contiguous, sorted pass over each 811 KB channel plane per thread), into pinned staging; the GPU transposes the
+// compact (D, n_used) block and fuses.  The call returns once the caller's arrays have been consumed: the fusion of
+// frame i overlaps the host gather of frame i + 1 (staging is double-buffered).
+template <typename T>
+static void gather_channel_rows(const T* src, size_t plane, const int32_t* upix, int32_t nu, T* dst, int d) {
+  HostPool::get().run(d, [&](int c) {
+    const T* p = src + static_cast<size_t>(c) * plane;
+    T* o = dst + static_cast<size_t>(c) * nu;
+    for (int32_t u = 0; u < nu; ++u) o[u] = p[upix[u]];
+  });
+}
+
+int add_frame_sparse(avl_builder* b, const avl_frame* f, const float* depth_dev, const uint8_t* rgb_dev,
+                     const int32_t* sidx_dev, int32_t n_samples, int flags, cudaStream_t s) {
+  const int d = b->dim;
+  const size_t fpix = static_cast<size_t>(f->fh) * f->fw;
+  const bool f16 = (flags & AVL_FEAT_F16) != 0;
+  const size_t esz = f16 ? sizeof(__half) : sizeof(float);
+  int rc;
+  BatchItem it;
+  it.f = f;
+  it.depth = depth_dev; it.feat = nullptr; it.rgb = rgb_dev; it.sidx = sidx_dev;
+  it.n_samples = n_samples;
+  // ---- 1. geometry on the device, cells and feature pixels back
+  if ((rc = launch_batch(b, &it, 1, flags, s, /*phase=*/1))) return rc;
+  if (b->h_samples < static_cast<size_t>(n_samples)) {
+    if (b->h_cell) cudaFreeHost(b->h_cell);
+    if (b->h_fpix) cudaFreeHost(b->h_fpix);
+    b->h_cell = b->h_fpix = nullptr;
+    b->h_samples = 0;
+    AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->h_cell), n_samples * sizeof(int32_t), cudaHostAllocDefault));
+    AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->h_fpix), n_samples * sizeof(int32_t), cudaHostAllocDefault));
+    b->h_samples = n_samples;
+  }
+  AVL_CUDA(cudaMemcpyAsync(b->h_cell, b->s_cell, n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  AVL_CUDA(cudaMemcpyAsync(b->h_fpix, b->s_fpix, n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  AVL_CUDA(cudaStreamSynchronize(s));
+  // ---- 2. the feature pixels in use, ascending, and every sample's row in the compact block
+  const int slot = b->h_next;
+  b->h_next ^= 1;
+  if (b->h_busy[slot]) {  // the frame that last used this staging slot (two calls ago) must have been uploaded
+    AVL_CUDA(cudaEventSynchronize(b->h_ev[slot]));
+    b->h_busy[slot] = false;
+  }
+  if (!b->h_ev[slot]) AVL_CUDA(cudaEventCreateWithFlags(&b->h_ev[slot], cudaEventDisableTiming));
+  b->h_rank.assign(fpix, 0);
+  int32_t* rank = b->h_rank.data();
+  for (int32_t j = 0; j < n_samples; ++j)
+    if (b->h_cell[j] >= 0) rank[b->h_fpix[j]] = 1;   // accepted points have a feature pixel inside the map (vlmap_builder.py:161)
+  b->h_upix.clear();
+  for (size_t p = 0; p < fpix; ++p) {
+    if (rank[p]) {
+      rank[p] = static_cast<int32_t>(b->h_upix.size());
+      b->h_upix.push_back(static_cast<int32_t>(p));
+    }
+  }
+  const int32_t nu = static_cast<int32_t>(b->h_upix.size());
+  // A frame at depth_sample_rate 1 reads ~40 % of the feature pixels: gathering them touches nearly every cache line
+  // of the 415 MB array on the host and costs what copying all of it over PCIe costs (measured on B200: 10.7 vs 7.9 ms
+  // per frame), so beyond a quarter of the pixels the whole array is uploaded; at the reference's default rate 100 the
+  // frame reads 1.5 % of the pixels and the gather wins 12x (0.63 ms).
+  if (static_cast<size_t>(nu) * 4 > fpix) {
+    if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
+    if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, fpix * d))) return rc;
+    AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * esz, cudaMemcpyHostToDevice, s));
+    b->h2d_bytes += fpix * d * esz;
+    dim3 grid(static_cast<unsigned>((fpix + 63) / 64), static_cast<unsigned>((d + 63) / 64));
+    if (f16)
+      chw16_to_hwc_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(b->d_feat), b->d_feat_t, d, static_cast<int64_t>(fpix));
+    else
+      chw_to_hwc_kernel<<<grid, 256, 0, s>>>(b->d_feat, b->d_feat_t, d, static_cast<int64_t>(fpix));
+    AVL_CUDA(cudaGetLastError());
+    it.feat = b->d_feat_t;   // s_fpix on the device still holds the original feature pixels
+    return launch_batch(b, &it, 1, flags, s, /*phase=*/2);
+  }
+  // ---- 3. gather the channel rows of those pixels into pinned staging
+  if ((rc = grow_pinned(&b->h_cidx[slot], &b->h_cidx_elems[slot], static_cast<size_t>(n_samples)))) return rc;
+  int32_t* cidx = b->h_cidx[slot];
+  for (int32_t j = 0; j < n_samples; ++j) cidx[j] = b->h_cell[j] >= 0 ? rank[b->h_fpix[j]] : 0;
+  const size_t need = std::max<size_t>(static_cast<size_t>(nu) * d * esz, 16);
+  if (b->h_stage_bytes[slot] < need) {
+    if (b->h_stage[slot]) cudaFreeHost(b->h_stage[slot]);
+    b->h_stage[slot] = nullptr;
+    b->h_stage_bytes[slot] = 0;
+    const size_t cap = std::max(need, std::min(fpix / 4 + 1, static_cast<size_t>(n_samples)) * d * esz);  // its largest possible size
+    AVL_CUDA(cudaHostAlloc(&b->h_stage[slot], cap, cudaHostAllocDefault));
+    b->h_stage_bytes[slot] = cap;
+  }
+  if (nu > 0) {
+    if (f16) gather_channel_rows(reinterpret_cast<const uint16_t*>(f->feat), fpix, b->h_upix.data(), nu,
+                                 static_cast<uint16_t*>(b->h_stage[slot]), d);
+    else gather_channel_rows(f->feat, fpix, b->h_upix.data(), nu, static_cast<float*>(b->h_stage[slot]), d);
+  }
+  // ---- 4. upload the compact block, transpose it to pixel-major rows, fuse
+  const size_t nu1 = static_cast<size_t>(std::max(nu, 1));
+  if ((rc = grow(&b->d_feat, &b->feat_elems, nu1 * d))) return rc;
+  if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, nu1 * d))) return rc;
+  AVL_CUDA(cudaMemcpyAsync(b->s_fpix, cidx, n_samples * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  b->h2d_bytes += static_cast<uint64_t>(n_samples) * sizeof(int32_t) + static_cast<uint64_t>(nu) * d * esz;
+  if (nu > 0) {
+    AVL_CUDA(cudaMemcpyAsync(b->d_feat, b->h_stage[slot], static_cast<size_t>(nu) * d * esz, cudaMemcpyHostToDevice, s));
+    dim3 grid(static_cast<unsigned>((nu + 63) / 64), static_cast<unsigned>((d + 63) / 64));
+    if (f16)
+      chw16_to_hwc_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(b->d_feat), b->d_feat_t, d, static_cast<int64_t>(nu));
+    else
+      chw_to_hwc_kernel<<<grid, 256, 0, s>>>(b->d_feat, b->d_feat_t, d, static_cast<int64_t>(nu));
+    AVL_CUDA(cudaGetLastError());
+  }
+  AVL_CUDA(cudaEventRecord(b->h_ev[slot], s));
+  b->h_busy[slot] = true;
+  it.feat = b->d_feat_t;
+  return launch_batch(b, &it, 1, flags, s, /*phase=*/2);
 }
 
 }  // namespace
@@ -988,6 +1221,12 @@ int avl_builder_set_slab(avl_builder* b, int32_t row_lo, int32_t row_hi) {
   return AVL_OK;
 }
 
+int avl_builder_skip_frames(avl_builder* b, int32_t n_frames) {
+  AVL_ARG(b != nullptr && n_frames >= 0, "invalid argument");
+  b->frame_seq += static_cast<uint32_t>(n_frames);  // the skipped frames keep their place in the (frame, sample) order
+  return AVL_OK;
+}
+
 int avl_builder_destroy(avl_builder* b) {
   if (!b) return AVL_OK;
   cudaFree(b->first_key); cudaFree(b->occupied_ids); cudaFree(b->num); cudaFree(b->den); cudaFree(b->rgb_acc);
@@ -995,6 +1234,13 @@ int avl_builder_destroy(avl_builder* b) {
   cudaFree(b->s_alpha); cudaFree(b->s_wrap); cudaFree(b->block_cnt); cudaFree(b->scan_state); cudaFree(b->ticket);
   cudaFree(b->d_depth); cudaFree(b->d_feat); cudaFree(b->d_feat_t);
   cudaFree(b->d_rgb); cudaFree(b->d_sidx);
+  if (b->h_cell) cudaFreeHost(b->h_cell);
+  if (b->h_fpix) cudaFreeHost(b->h_fpix);
+  for (int i = 0; i < 2; ++i) {
+    if (b->h_stage[i]) cudaFreeHost(b->h_stage[i]);
+    if (b->h_cidx[i]) cudaFreeHost(b->h_cidx[i]);
+    if (b->h_ev[i]) cudaEventDestroy(b->h_ev[i]);
+  }
   delete b;
   return AVL_OK;
 }
@@ -1024,14 +1270,22 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   const float* feat = f->feat;
   const uint8_t* rgb = f->rgb;
   const int32_t* sidx = f->sample_idx;
+  // host-resident channel-major features: only the feature pixels the frame's accepted points read are handed over
+  static const bool dense_h2d = getenv("AVL_BUILD_DENSE_H2D") != nullptr;  // A/B: copy the whole (1, D, FH, FW) array
+  const bool sparse = !(flags & AVL_ON_DEVICE) && f->feat_layout == AVL_FEAT_CHW && !dense_h2d && n_samples > 0;
   if (!(flags & AVL_ON_DEVICE)) {
     if ((rc = grow(&b->d_depth, &b->depth_elems, static_cast<size_t>(npix)))) return rc;
-    if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
     AVL_CUDA(cudaMemcpyAsync(b->d_depth, f->depth, depth_bytes, cudaMemcpyHostToDevice, s));
-    AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float)),
-                             cudaMemcpyHostToDevice, s));
     depth = b->d_depth;
-    feat = b->d_feat;
+    b->h2d_bytes += depth_bytes + (f->rgb ? static_cast<uint64_t>(npix) * 3 : 0) +
+                    (f->sample_idx ? static_cast<uint64_t>(n_samples) * sizeof(int32_t) : 0);
+    if (!sparse) {
+      b->h2d_bytes += fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float));
+      if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
+      AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float)),
+                               cudaMemcpyHostToDevice, s));
+      feat = b->d_feat;
+    }
     if (f->rgb) {
       if ((rc = grow(&b->d_rgb, &b->rgb_bytes, static_cast<size_t>(npix) * 3))) return rc;
       AVL_CUDA(cudaMemcpyAsync(b->d_rgb, f->rgb, npix * 3, cudaMemcpyHostToDevice, s));
@@ -1048,6 +1302,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
     b->frame_seq++;
     return AVL_OK;
   }
+  if (sparse) return add_frame_sparse(b, f, depth, rgb, sidx, n_samples, flags, s);
   if (f->feat_layout == AVL_FEAT_CHW) {  // (1, D, FH, FW) -> pixel-major rows for the coalesced gather
     if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, fpix * d))) return rc;
     dim3 grid(static_cast<unsigned>((fpix + 63) / 64), static_cast<unsigned>((d + 63) / 64));
@@ -1116,6 +1371,11 @@ static int read_counter(avl_builder* b, int which, int64_t* n, void* stream) {
 }
 int avl_builder_num_voxels(avl_builder* b, int64_t* n, void* stream) { return read_counter(b, 0, n, stream); }
 int avl_builder_num_accepted(avl_builder* b, int64_t* n, void* stream) { return read_counter(b, 1, n, stream); }
+int avl_builder_h2d_bytes(avl_builder* b, int64_t* n) {
+  AVL_ARG(b != nullptr && n != nullptr, "NULL argument");
+  *n = static_cast<int64_t>(b->h2d_bytes);
+  return AVL_OK;
+}
 int avl_builder_num_rejected_oob(avl_builder* b, int64_t* n, void* stream) { return read_counter(b, 2, n, stream); }
 
 int avl_builder_export(avl_builder* b, float* grid_feat, int32_t* grid_pos, float* weight, int32_t* occupied_ids,

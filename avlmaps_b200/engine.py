@@ -521,6 +521,7 @@ class DeviceBuilder:
         self._h = C.c_void_p()
         L.check(self._lib.avl_builder_create(C.byref(spec), C.byref(self._h)))
         self.n_frames = 0
+        self.mode = 0
 
     @classmethod
     def global_grid(cls, n_row: int, n_col: int, n_height: int, cs: float, pcd_min, dim: int,
@@ -555,6 +556,11 @@ class DeviceBuilder:
     def set_slab(self, row_lo: int, row_hi: int) -> None:
         """Own only the grid rows [row_lo, row_hi) (slab-sharded build, one process per GPU)."""
         L.check(self._lib.avl_builder_set_slab(self._h, int(row_lo), int(row_hi)))
+
+    def skip_frames(self, n: int = 1) -> None:
+        """Slab-sharded build: `n` frames whose frustum cannot reach this builder's rows keep their frame numbers."""
+        L.check(self._lib.avl_builder_skip_frames(self._h, int(n)))
+        self.n_frames += int(n)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -601,6 +607,13 @@ class DeviceBuilder:
         ptr = C.cast(C.addressof(prepared.arr) + start * C.sizeof(L.Frame), C.POINTER(L.Frame))
         L.check(self._lib.avl_builder_add_frames(self._h, ptr, n, prepared.flags, _stream_ptr(stream)))
         self.n_frames += n
+
+    @property
+    def h2d_bytes(self) -> int:
+        """Bytes uploaded from host arrays so far (see avl_builder_h2d_bytes)."""
+        n = C.c_int64()
+        L.check(self._lib.avl_builder_h2d_bytes(self._h, C.byref(n)))
+        return int(n.value)
 
     def _count(self, fn) -> int:
         n = C.c_int64()
@@ -655,6 +668,7 @@ class PreparedFrames:
         self.n = len(frames)
         self.arr = (L.Frame * max(self.n, 1))()
         self.flags, self._keep = 0, []
+        self.frames = frames     # the dicts (ShardedBuilder reads pose / intrinsics / shape for its frustum test)
         for i, fr in enumerate(frames):
             if fr.get("feat") is None:
                 raise ValueError("feat is required")

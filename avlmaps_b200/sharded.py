@@ -252,6 +252,27 @@ class ShardedMap:
         return self.local.argmax(queries, scale=scale, normalize_map=normalize_map)
 
 
+def frame_row_range(shape_hw, kinv, tf, gs: int, cs: float, min_depth: float = 0.1, max_depth: float = 6.0,
+                    mode: int = 0, origin_x: float = 0.0):
+    """Grid rows a frame's points can reach, (lo, hi) inclusive with a 2-cell margin: a conservative host-side test, no
+    depth image needed.  A back-projected point is p = (Kinv @ [u + .5, v + .5, 1]) * z (mapping_utils.py:239-246) and
+    its row depends on g.x = (tf @ [p; 1])[0] only (mapping_utils.py:345-349; vlmap_builder_multi_floor.py:146).  g.x is
+    multilinear in (u, v, z) over the box [0, w] x [0, h] x [min_depth, max_depth], so its extremes sit at the 8 corners."""
+    h, w = shape_hw
+    kinv = np.asarray(kinv, np.float64).reshape(3, 3)
+    tf = np.asarray(tf, np.float64).reshape(4, 4)
+    xs = []
+    for u in (0.0, float(w)):
+        for v in (0.0, float(h)):
+            ray = kinv @ np.array([u, v, 1.0])
+            for z in (float(min_depth), float(max_depth)):
+                xs.append(float(tf[0, :3] @ (ray * z) + tf[0, 3]))
+    x_lo, x_hi = min(xs), max(xs)
+    if mode == 0:    # row = int(gs / 2 - int(x / cs))
+        return int(np.floor(gs / 2 - x_hi / cs)) - 2, int(np.ceil(gs / 2 - x_lo / cs)) + 2
+    return int(np.floor((x_lo - origin_x) / cs)) - 2, int(np.ceil((x_hi - origin_x) / cs)) + 2
+
+
 class ShardedBuilder:
     """Slab-sharded map BUILD: one process per GPU, rank r owns the grid rows
     `slab_bounds(n_rows, world, r)`.  Every rank is fed every frame (depth, pose and the sample list are
@@ -278,17 +299,53 @@ class ShardedBuilder:
         local.set_slab(self.row_lo, self.row_hi)
         self._rank_fn = rank_fn
 
+    # Frames whose camera frustum cannot reach this rank's rows are not handed to the GPU at all (they only keep their
+    # frame number): the geometry and the ordered id scan -- the part of a frame every rank used to repeat -- then
+    # divide over the ranks like the scatter does.  A frame that reaches the slab's rows is processed as before.
+    def _touches(self, depth, kinv, tf, min_depth=0.1, max_depth=6.0) -> bool:
+        if getattr(self.local, "mode", 0) != 0:
+            return True          # global-frame grids: rows wrap like numpy's negative indices; no frame is skipped
+        shape = tuple(depth.shape[-2:])
+        lo, hi = frame_row_range(shape, kinv, tf, int(self.local.grid_shape[0]), float(self.local.cs), min_depth, max_depth)
+        return not (hi < self.row_lo or lo >= self.row_hi)
+
     def add_frame(self, *args, **kwargs):
+        """engine.DeviceBuilder.add_frame's arguments (depth, feat, kinv, k, kfeat, tf, ...)."""
+        if hasattr(self.local, "skip_frames"):
+            names = ("depth", "feat", "kinv", "k", "kfeat", "tf")
+            a = dict(zip(names, args))
+            a.update({n: v for n, v in kwargs.items() if n in names})
+            if all(n in a for n in ("depth", "kinv", "tf")) and not self._touches(
+                    a["depth"], a["kinv"], a["tf"], kwargs.get("min_depth", 0.1), kwargs.get("max_depth", 6.0)):
+                self.n_skipped = getattr(self, "n_skipped", 0) + 1
+                return self.local.skip_frames(1)
         return self.local.add_frame(*args, **kwargs)
 
     def add_frames(self, frames, **kwargs):
-        return self.local.add_frames(frames, **kwargs)
+        return self.add_prepared(self.prepare_frames(frames), **kwargs)
 
     def prepare_frames(self, frames):
-        return self.local.prepare_frames(frames)
+        prep = self.local.prepare_frames(frames)
+        prep.touches = [self._touches(fr["depth"], fr["kinv"], fr["tf"], fr.get("min_depth", 0.1), fr.get("max_depth", 6.0))
+                        for fr in frames]
+        return prep
 
-    def add_prepared(self, prepared, *args, **kwargs):
-        return self.local.add_prepared(prepared, *args, **kwargs)
+    def add_prepared(self, prepared, start: int = 0, count=None, **kwargs):
+        n = prepared.n - start if count is None else count
+        touches = getattr(prepared, "touches", None)
+        if touches is None:
+            return self.local.add_prepared(prepared, start, n, **kwargs)
+        i, end = start, start + n
+        while i < end:     # runs of frames that reach the slab go to the GPU in one call; the gaps are only counted
+            j = i
+            while j < end and touches[j] == touches[i]:
+                j += 1
+            if touches[i]:
+                self.local.add_prepared(prepared, i, j - i, **kwargs)
+            else:
+                self.local.skip_frames(j - i)
+                self.n_skipped = getattr(self, "n_skipped", 0) + (j - i)
+            i = j
 
     def _device(self):
         import torch

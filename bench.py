@@ -380,19 +380,20 @@ def build_sharded_extra(torch, dist, engine, L, world, frames=240, reps=2):
             "scaling": "strong (one map, rows split into slabs)", "features": "HWC, device-resident, identical on every rank"}
 
 
-def build_cpu_baseline(frames=2):
+def build_cpu_baseline(frames=2, rate=1):
     """The reference's sequential fusion loop (vlmap_builder.py:129-178) as the C restatement (oracle/build_oracle.c),
-    one core, on `frames` frames of the same geometry.  The reference itself runs this loop in Python at ~40 k
-    points/s; the C port is the generous baseline."""
+    one core, on `frames` frames of the same geometry.  The reference itself runs this loop in Python at ~30-40 k
+    points/s (profiles/r2_ref_cpu_baselines.json, measured through the shim in the build container); the C port is the
+    generous baseline."""
     import synth
     from oracle import avl_oracle as O
 
     h, w, fh, fw, d, gs, cs, cam_h = 480, 640, 390, 520, DIM, 256, 0.05, 1.6
-    cfg = synth.map_config(gs, cs, cam_h, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
+    cfg = synth.map_config(gs, cs, cam_h, [320, 0, 320, 0, 320, 240, 0, 0, 1], rate)
     poses = synth.circle_poses(frames, radius=2.0)
     depths, _, feats = synth.build_inputs(frames, h, w, fh, fw, d, seed=4, pool=1, depth_lo=0.5, depth_hi=6.0)
     np.random.seed(7)
-    sidx = [O.sample_order(h * w, 1) for _ in range(frames)]
+    sidx = [O.sample_order(h * w, rate) for _ in range(frames)]
     b2c, bt = O.setup_transforms(cfg["pose_info"])
     tfs = O.frame_transforms(poses, b2c, bt)
     calib = np.array(cfg["cam_calib_mat"]).reshape(3, 3)
@@ -403,24 +404,26 @@ def build_cpu_baseline(frames=2):
     dt = time.perf_counter() - t0
     acc = b.num_accepted
     b.close()
-    return {"value": frames / dt, "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"{frames} frames of 480x640 at depth_sample_rate 1 ({acc // frames} accepted points per frame), D = 512, "
-                      "C restatement of the reference's per-point loop; the reference's own Python loop does ~40 k points/s",
+    return {"value": frames / dt, "unit": "frames/s", "cores": 1, "kind": "port", "depth_sample_rate": rate,
+            "sample": f"{frames} frames 480x640, rate {rate}, {acc // frames} points/frame, D=512: C port of the per-point loop, 1 core",
             "points_per_s": acc / dt}
 
 
 def build_extra(torch, engine, L, frames=24, reps=3):
-    """Back-projection frames/s on one GPU: device-resident inputs (HWC and the reference's CHW layout) and the
-    end-to-end host-buffer call (H2D of depth, features and sample list inside the timed region)."""
+    """Back-projection frames/s on one GPU (BASELINE config 4 geometry): device-resident inputs (pixel-major and the
+    reference's channel-major layout) and the end-to-end call with HOST arrays in the layout get_lseg_feat returns --
+    (1, 512, 390, 520) float32 -- at depth_sample_rate 1 and at the reference's default 100, float32 and float16."""
     sc = build_scene(torch, frames)
     h, w, fh, fw, d, gs, cs = sc["h"], sc["w"], sc["fh"], sc["fw"], sc["d"], sc["gs"], sc["cs"]
     tfs, calib, kinv, kfeat, gen, sidx, depths = (sc[k] for k in ("tfs", "calib", "kinv", "kfeat", "gen", "sidx", "depths"))
     cam_h = sc["vh"] * cs
-    out = {}
+    vh = int(cam_h / cs)
+    peaks = load_peaks()
+    out = {"workload": f"config 4: 480x640 RGB-D -> 390x520x{d} features -> {gs}x{gs}x{vh} grid, depth_sample_rate 1"}
     for name, layout in (("hwc", L.FEAT_HWC), ("chw_reference_layout", L.FEAT_CHW)):
         shape = (fh, fw, d) if layout == L.FEAT_HWC else (1, d, fh, fw)
         pool = [torch.randn(shape, device="cuda", generator=gen) * (14.2857 / d ** 0.5) for _ in range(4)]
-        b = engine.DeviceBuilder(gs, int(cam_h / cs), cs, d, capacity=gs * gs * int(cam_h / cs))
+        b = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
         best = None
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -443,65 +446,64 @@ def build_extra(torch, engine, L, frames=24, reps=3):
             nb = 96
             fr = [dict(depth=depths[i % 4], feat=pool[i % 4], kinv=kinv, k=calib, kfeat=kfeat, tf=tfs[i % frames],
                        sample_idx=sidx[i % 4], feat_layout=layout) for i in range(nb)]
-            b = engine.DeviceBuilder(gs, int(cam_h / cs), cs, d, capacity=gs * gs * int(cam_h / cs))
+            b = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
             prep = b.prepare_frames(fr)
             b.add_prepared(prep, 0, 8, stream=torch.cuda.current_stream())  # first call allocates the scratch
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
+            a0 = b.num_accepted
             e0.record()
             for i in range(8, nb, 8):
                 b.add_prepared(prep, i, 8, stream=torch.cuda.current_stream())
             e1.record()
             torch.cuda.synchronize()
             msb = e0.elapsed_time(e1) / (nb - 8)
+            paccb = (b.num_accepted - a0) / (nb - 8)
             out["hwc_batched8"] = {"frames_per_s": 1e3 / msb, "ms_per_frame": msb, "frames_per_call": 8}
+            # HBM roofline of the frame step (geometry + ordered id scan + scatter; the scatter is > 85 % of it):
+            # algorithmic bytes per frame = H*W*4 (depth) + P_acc * (D*4 feature read + 2*D*4 accumulator RMW + 24)
+            byts_b = h * w * 4 + paccb * (3 * d * 4 + 24)
+            traffic, src = ncu_dram_bytes("scatter_kernel")
+            out["roofline"] = {"bound": "hbm", "achieved": byts_b / msb / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": byts_b / msb / 1e6 / peaks["hbm_gbs"], "kernel": "scatter_kernel (+ geom, assign_ids) per frame",
+                               "ms_per_frame": msb, "frames_per_s": 1e3 / msb, "algorithmic_bytes_per_frame": byts_b,
+                               "accepted_points_per_frame": paccb, "traffic": traffic, "traffic_source": src,
+                               "traffic_note": "dram bytes of ONE scatter launch of the ncu capture (its frame count is in the file name)"}
             b.close()
         if layout == L.FEAT_CHW:
-            # end to end through the host-pointer C-ABI call, the layout get_lseg_feat hands over: per frame the
-            # library copies depth (1.2 MB), the (1, 512, 390, 520) fp32 features (415 MB) and the sample list
-            # (1.2 MB) from pinned host memory, transposes, fuses, and synchronises
-            hp = [p_.cpu().pin_memory() for p_ in pool[:2]]
-            hd = [x.cpu().pin_memory() for x in depths[:2]]
-            hs = [x.cpu().pin_memory() for x in sidx[:2]]
-            b = engine.DeviceBuilder(gs, int(cam_h / cs), cs, d, capacity=gs * gs * int(cam_h / cs))
-            n_e2e = 6
-            for i in range(2):
-                b.add_frame(hd[i].numpy(), hp[i].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i].numpy(), feat_layout=layout)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for i in range(n_e2e):
-                b.add_frame(hd[i % 2].numpy(), hp[i % 2].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i % 2].numpy(),
-                            feat_layout=layout)
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n_e2e
-            out["e2e_host_chw"] = {"frames_per_s": 1.0 / dt, "ms_per_frame": dt * 1e3,
-                                   "h2d_bytes_per_frame": h * w * 4 + d * fh * fw * 4 + h * w * 4,
-                                   "h2d_GBps": (h * w * 8 + d * fh * fw * 4) / dt / 1e9,
-                                   "note": "PCIe-bound: 415 MB of fp32 features per frame; a device-side encoder hand-off "
-                                           "(the hwc / chw lines above) removes it"}
-            b.close()
-            if os.environ.get("AVL_BENCH_F16") == "1":
-                # same end-to-end call with the features handed over as float16 (AVL_FEAT_F16: LSeg's output is
-                # fp16-exact, so the map is identical): half the PCIe bytes.  Opt-in until its first GPU run.
-                try:
-                    hp16 = [p_.cpu().to(torch.float16).pin_memory() for p_ in pool[:2]]
-                    b = engine.DeviceBuilder(gs, int(cam_h / cs), cs, d, capacity=gs * gs * int(cam_h / cs))
+            # ---- end to end through the host-pointer C-ABI call, in the layout get_lseg_feat hands over (lseg_utils.py:101-102).
+            # The library reads the geometry back, gathers only the feature pixel rows the accepted points use on the host
+            # threads, uploads those from pinned staging, and returns; the fusion of frame i overlaps the gather of frame i+1.
+            hp = [p_.cpu() for p_ in pool[:2]]
+            hd = [x.cpu() for x in depths[:2]]
+            e2e = {}
+            for rate in (1, 100):
+                np.random.seed(7)
+                from avlmaps_b200.map import VLMapBuilder
+                hs = [VLMapBuilder._sample_order(h * w, rate) for _ in range(2)]
+                for tag, conv in (("f32", lambda t: t.numpy()), ("f16", lambda t: t.to(torch.float16).numpy())):
+                    feats_h = [conv(t) for t in hp]
+                    n_e2e = 8 if rate == 1 else 64
+                    b = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
                     for i in range(2):
-                        b.add_frame(hd[i].numpy(), hp16[i].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i].numpy(), feat_layout=layout)
+                        b.add_frame(hd[i].numpy(), feats_h[i], kinv, calib, kfeat, tfs[i], sample_idx=hs[i], feat_layout=layout)
                     torch.cuda.synchronize()
+                    bytes0, acc0 = b.h2d_bytes, b.num_accepted
                     t0 = time.perf_counter()
                     for i in range(n_e2e):
-                        b.add_frame(hd[i % 2].numpy(), hp16[i % 2].numpy(), kinv, calib, kfeat, tfs[i], sample_idx=hs[i % 2].numpy(),
+                        b.add_frame(hd[i % 2].numpy(), feats_h[i % 2], kinv, calib, kfeat, tfs[i % frames], sample_idx=hs[i % 2],
                                     feat_layout=layout)
                     torch.cuda.synchronize()
-                    dt16 = (time.perf_counter() - t0) / n_e2e
-                    out["e2e_host_chw_f16"] = {"frames_per_s": 1.0 / dt16, "ms_per_frame": dt16 * 1e3,
-                                               "h2d_bytes_per_frame": h * w * 4 + d * fh * fw * 2 + h * w * 4,
-                                               "h2d_GBps": (h * w * 8 + d * fh * fw * 2) / dt16 / 1e9}
+                    dt = (time.perf_counter() - t0) / n_e2e
+                    e2e[f"rate{rate}_{tag}"] = {"value": 1.0 / dt, "unit": "frames/s", "ms_per_frame": dt * 1e3,
+                                                "h2d_bytes_per_frame": (b.h2d_bytes - bytes0) / n_e2e,
+                                                "accepted_points_per_frame": (b.num_accepted - acc0) / n_e2e,
+                                                "h2d_GBps": (b.h2d_bytes - bytes0) / n_e2e / dt / 1e9}
                     b.close()
-                    del hp16
-                except Exception as e:  # noqa: BLE001
-                    out["e2e_host_chw_f16_error"] = repr(e)
+                    del feats_h
+            e2e["note"] = ("host (1,512,390,520) arrays as get_lseg_feat returns them; only the pixel rows in use are uploaded "
+                           "(the full array is 415 MB / frame: 127 frames/s in round 1)")
+            out["e2e"] = e2e
             del hp
         del pool
     return out
@@ -869,7 +871,9 @@ def run_gpu(args):
             cb = cpu_baseline(steps=5)
             if not args.no_build:
                 try:
-                    extra.setdefault("build", {})["cpu_baseline"] = build_cpu_baseline()
+                    cbb = build_cpu_baseline(frames=2, rate=1)
+                    cbb["rate100"] = build_cpu_baseline(frames=8, rate=100)
+                    extra.setdefault("build", {})["cpu_baseline"] = cbb
                 except Exception as e:  # noqa: BLE001
                     extra["build_cpu_baseline_error"] = repr(e)
 

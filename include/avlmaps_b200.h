@@ -241,10 +241,19 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* frame, int flags, voi
  * identical to n_frames avl_builder_add_frame calls.  Host pointers or AVL_FEAT_CHW fall back to that loop. */
 int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_frames, int flags, void* stream);
 
+/* Slab-sharded build: count n_frames frames that were NOT handed to this builder because the caller has shown that
+ * none of their points can fall into its row slab (avlmaps_b200.sharded.frame_row_range: the rows the camera frustum
+ * can reach).  The first-touch order is (frame, sample) over ALL frames of the build, so the skipped frames must
+ * keep their frame numbers. */
+int avl_builder_skip_frames(avl_builder* b, int32_t n_frames);
+
 /* voxels created so far (max_id, vlmap_builder.py:164-170); synchronises the stream. */
 int avl_builder_num_voxels(avl_builder* b, int64_t* n, void* stream);
 /* points that passed the depth / grid / feature-bounds tests so far (P_acc of SURVEY 8d). */
 int avl_builder_num_accepted(avl_builder* b, int64_t* n, void* stream);
+/* bytes the builder has uploaded from HOST pointers so far (depth, sample list, rgb and features; with host-resident
+ * channel-major features only the pixel rows the accepted points read are uploaded) */
+int avl_builder_h2d_bytes(avl_builder* b, int64_t* n);
 
 /* Export arrays[:max_id] + occupied_ids like _save_3d_map (vlmap_builder.py:313-327):
  * grid_feat (V, D) f32, grid_pos (V, 3) i32, weight (V,) f32, occupied_ids (gs, gs, vh) i32,

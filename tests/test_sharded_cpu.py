@@ -218,3 +218,30 @@ def test_sharded_build_world2_gloo():
         p.join(180)
         assert p.exitcode == 0
     assert out.get() is True and out.get() is True
+
+
+def test_frame_row_range_contains_every_row_the_reference_geometry_reaches():
+    """The host-side frustum test that lets a slab's rank skip a frame must never exclude a row a point of that frame
+    falls into: rows from the reference's own arithmetic (mapping_utils.py:239-246, 305-315, 345-349) on random pixels,
+    depths and poses stay inside frame_row_range."""
+    from avlmaps_b200.sharded import frame_row_range
+
+    rng = np.random.default_rng(5)
+    cfg = synth.map_config(256, 0.05, 1.6, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
+    b2c, bt = O.setup_transforms(cfg["pose_info"])
+    poses = synth.circle_poses(40, radius=2.0)
+    tfs = O.frame_transforms(poses, b2c, bt)
+    kinv = np.linalg.inv(np.array(cfg["cam_calib_mat"], np.float64).reshape(3, 3))
+    h, w, gs, cs = 480, 640, 256, 0.05
+    narrow = 0
+    for tf in tfs:
+        lo, hi = frame_row_range((h, w), kinv, tf, gs, cs, 0.1, 6.0)
+        u = rng.integers(0, w, 4000) + 0.5
+        v = rng.integers(0, h, 4000) + 0.5
+        z = rng.uniform(0.1001, 5.9999, 4000)
+        p = (kinv @ np.stack([u, v, np.ones_like(u)])) * z
+        gx = tf[0, :3] @ p + tf[0, 3]
+        rows = (gs / 2 - np.trunc(gx / cs)).astype(np.int64)
+        assert rows.min() >= lo and rows.max() <= hi
+        narrow += (hi - lo) < gs
+    assert narrow > 0      # the test is not vacuous: some frames cannot reach every row

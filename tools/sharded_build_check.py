@@ -100,7 +100,8 @@ def main():
     line = {"n_gpus": world, "frames": frames, "ms_per_frame": best, "frames_per_s": 1e3 / best,
             "voxels_total": res["n_voxels_total"], "voxels_rank0": int(res["global_ids"].size),
             "accepted_points_per_frame": int(acc.item()) / frames, "finalize_s": t_fin,
-            "slab_rows": [sb.row_lo, sb.row_hi], "frames_per_call": batch}
+            "slab_rows": [sb.row_lo, sb.row_hi], "frames_per_call": batch,
+            "frames_skipped_rank0_last_build": int(getattr(sb, "n_skipped", 0))}
     if rank == 0:
         single = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
         feed(single)
