@@ -839,6 +839,45 @@ class HostPool {
   bool stop_ = false;
 };
 
+// Upload from PAGEABLE host memory (a numpy array) at PCIe speed: cudaMemcpyAsync from pageable memory goes through the
+// driver's single-threaded bounce buffer (~10 GB/s measured on B200's host); here the host threads copy 16 MiB chunks
+// into two pinned buffers and each chunk is handed to the copy engine as soon as it is staged.  Returns when the
+// source has been read.
+struct StagedUpload {
+  uint8_t* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool busy[2] = {false, false};
+  static constexpr size_t kChunk = size_t(16) << 20;
+  int copy(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s) {
+    for (int i = 0; i < 2; ++i) {
+      if (!buf[i]) AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&buf[i]), kChunk, cudaHostAllocDefault));
+      if (!ev[i]) AVL_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    const int nt = HostPool::get().size();
+    int slot = 0;
+    for (size_t off = 0; off < bytes; off += kChunk, slot ^= 1) {
+      const size_t n = std::min(kChunk, bytes - off);
+      if (busy[slot]) {
+        AVL_CUDA(cudaEventSynchronize(ev[slot]));
+        busy[slot] = false;
+      }
+      const uint8_t* src = static_cast<const uint8_t*>(src_host) + off;
+      uint8_t* dst = buf[slot];
+      const size_t piece = (n + nt - 1) / nt;
+      HostPool::get().run(nt, [&](int t) {
+        const size_t b0 = static_cast<size_t>(t) * piece;
+        if (b0 < n) memcpy(dst + b0, src + b0, std::min(piece, n - b0));
+      });
+      AVL_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst_dev) + off, dst, n, cudaMemcpyHostToDevice, s));
+      AVL_CUDA(cudaEventRecord(ev[slot], s));
+      busy[slot] = true;
+    }
+    return AVL_OK;
+  }
+  ~StagedUpload() {}  // process teardown: see HeatScratch
+};
+static thread_local StagedUpload g_staged_upload;
+
 template <typename T>
 int grow_pinned(T** p, size_t* have, size_t need) {
   if (*have >= need) return AVL_OK;
@@ -1089,7 +1128,7 @@ int add_frame_sparse(avl_builder* b, const avl_frame* f, const float* depth_dev,
   if (static_cast<size_t>(nu) * 4 > fpix) {
     if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
     if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, fpix * d))) return rc;
-    AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * esz, cudaMemcpyHostToDevice, s));
+    if ((rc = g_staged_upload.copy(b->d_feat, f->feat, fpix * d * esz, s))) return rc;
     b->h2d_bytes += fpix * d * esz;
     dim3 grid(static_cast<unsigned>((fpix + 63) / 64), static_cast<unsigned>((d + 63) / 64));
     if (f16)

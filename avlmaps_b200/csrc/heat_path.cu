@@ -232,6 +232,21 @@ struct HeatScratch {
       cap[i] = 0;
     }
   }
+  // The pool is shared by consecutive calls of this thread.  A device-pointer call returns while its kernels may
+  // still read the pool, so every call records `done` on its stream when it has enqueued its last kernel, and the next
+  // call makes ITS stream wait for that event first: calls on different streams then use the pool one after the other.
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+  cudaError_t acquire(cudaStream_t s) {
+    if (!done) {
+      cudaError_t e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    return pending ? cudaStreamWaitEvent(s, done, 0) : cudaSuccess;
+  }
+  void mark(cudaStream_t s) {
+    if (done && cudaEventRecord(done, s) == cudaSuccess) pending = true;
+  }
   ~HeatScratch() {}  // process teardown: the driver reclaims the memory; calling cudaFree there can race the runtime's own exit
 };
 thread_local HeatScratch g_heat_scratch;
@@ -257,7 +272,8 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
   const bool host = !(flags & AVL_ON_DEVICE);
   do {
     HeatScratch& hs = g_heat_scratch;
-    e = hs.get(HeatScratch::kTargets, static_cast<size_t>(n) * sizeof(int4), reinterpret_cast<void**>(&d_targets));
+    e = hs.acquire(s);
+    if (e == cudaSuccess) e = hs.get(HeatScratch::kTargets, static_cast<size_t>(n) * sizeof(int4), reinterpret_cast<void**>(&d_targets));
     if (e == cudaSuccess) e = hs.get(HeatScratch::kCount, sizeof(uint32_t), reinterpret_cast<void**>(&d_count));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s);
     const int32_t* pos = grid_pos;
@@ -358,6 +374,7 @@ extern "C" int avl_heat_from_mask_3d(const int32_t* grid_pos, const uint8_t* mas
     if (!windowed) heat_kernel<<<blocks, 256, 0, s>>>(pos, msk, n, d_targets, d_count, cell_size, decay_rate, heat);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (host && e == cudaSuccess) e = cudaMemcpyAsync(out_heat, d_heat, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, s);
+    hs.mark(s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   } while (0);
   if (e != cudaSuccess && rc == AVL_OK) rc = cuda_fail(e, "heat_from_mask_3d", __FILE__, __LINE__);

@@ -90,6 +90,10 @@ __global__ void map_prepare_kernel(const float* __restrict__ feat, int64_t n, in
   sa = warp_sum(sa);
   sd = warp_sum(sd);
   sb = warp_sum(sb);
+  // fp16 operands: a row whose values sink into fp16's subnormals (a far point of a fused map is alpha * f with alpha
+  // down to e^-30) loses more to rounding than bf16 would -- its band then covers every query.  Like a value beyond
+  // the fp16 range, such a row makes the map fall back to bf16 operands (same exponent range as fp32).
+  if (f16 && sd > sa * 1.6e-5) bad = true;  // relative residual above 2^-8, bf16's worst case
   if (__any_sync(0xffffffffu, bad) && lane == 0 && nonfinite) atomicExch(nonfinite, 1u);
   if (lane == 0) {
     const float an = __double2float_ru(sqrt(sb) * (1.0 + 1e-7));

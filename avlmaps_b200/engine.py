@@ -162,7 +162,15 @@ class DeviceMap:
     def argmax(self, queries, scale=None, normalize_map: bool = False, stream=None, want_stats: bool = False):
         q, s = self._queries(queries, scale)
         if q.shape[0] > L.AVL_MAX_QUERIES:
-            raise ValueError(f"at most {L.AVL_MAX_QUERIES} queries per argmax call")
+            # the fused kernel holds at most 256 queries; the reference has no limit (vlmap.py:123: np.argmax over any
+            # number of categories), so wider batches take the exact scores and the first maximum per row
+            sc = self.scores(queries, scale=scale, normalize_map=normalize_map, stream=stream)
+            self.last_stats = None
+            if q.device:
+                import torch
+
+                return sc.argmax(dim=1).to(torch.int32)
+            return np.argmax(sc, axis=1).astype(np.int32)
         o, optr = self._out(q.device, (self.n,), np.int32)
         st = L.IndexStats()
         L.check(self._lib.avl_sim_argmax(self._h, q.ptr, q.shape[0], s.ptr, int(normalize_map), optr, _flags(q, s),

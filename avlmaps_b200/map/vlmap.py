@@ -20,11 +20,20 @@ from .map import Map, cfg_get
 from .vlmap_builder import VLMapBuilder
 
 
-def find_similar_category_id(class_name: str, classes_list: List[str]) -> int:
+category_resolver = None   # optional callable(class_name, classes_list) -> one of classes_list (the reference asks an LLM)
+
+
+def find_similar_category_id(class_name: str, classes_list: List[str], resolver=None) -> int:
     """Reference avlmaps/utils/index_utils.py:8-32.  The literal match is kept; the reference's fallback
-    (an OpenAI completion call) is a network service outside this engine."""
+    (an OpenAI completion call) is a network service outside this engine: `resolver(class_name, classes_list) -> str`
+    (or the module-level `category_resolver`) stands in for it when the caller has one."""
     if class_name in classes_list:
         return classes_list.index(class_name)
+    resolver = resolver or category_resolver
+    if resolver is not None:
+        name = resolver(class_name, classes_list)
+        if name in classes_list:
+            return classes_list.index(name)
     raise KeyError(f"'{class_name}' is not one of the initialised categories {classes_list}; the reference "
                    "would ask an OpenAI model for the closest name here")
 

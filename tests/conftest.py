@@ -34,6 +34,14 @@ def lib():
 
 
 def pytest_collection_modifyitems(config, items):
-    # `-m gpu` on a CPU box: fail loudly instead of silently passing on a fallback (there is none)
-    if os.environ.get("AVL_ALLOW_NO_GPU") == "1":
+    """A plain `pytest tests` on a box without a GPU SKIPS the gpu-marked tests (a CPU-only CI run stays green and real CPU
+    regressions stay visible); an explicit `-m gpu` keeps them, so that they FAIL loudly there -- there is no CPU fallback
+    to pass on silently."""
+    if "gpu" in (config.getoption("-m") or ""):
         return
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="needs a B200: run with `-m gpu` under gpurun")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -235,3 +235,19 @@ def test_avlmap_builds_its_pose_converter_on_first_use(tmp_path):
     av2 = AVLMap({"map_config": map_config, "params": {"cs": 0.05}})
     av2.dataloader = sentinel
     assert av2._ensure_dataloader() is sentinel
+
+
+def test_category_lookup_takes_an_optional_resolver():
+    """find_similar_category_id (index_utils.py:8-32): literal match first; the reference then asks an LLM for the closest
+    name -- here a caller-supplied resolver stands in for it, and without one the lookup raises."""
+    import pytest
+
+    from avlmaps_b200.map import vlmap
+
+    cats = ["chair", "table", "sofa"]
+    assert vlmap.find_similar_category_id("table", cats) == 1
+    with pytest.raises(KeyError):
+        vlmap.find_similar_category_id("couch", cats)
+    assert vlmap.find_similar_category_id("couch", cats, resolver=lambda name, lst: "sofa") == 2
+    with pytest.raises(KeyError):
+        vlmap.find_similar_category_id("couch", cats, resolver=lambda name, lst: "bench")

@@ -431,3 +431,18 @@ def test_fusion_degenerate_and_tied_inputs_fall_back_to_the_exact_path(eng):
     assert np.array_equal(gi, wi) and np.array_equal(gh, wh, equal_nan=True)
     mv_.close()
     ma_.close()
+
+
+def test_argmax_over_more_than_256_queries_matches_numpy(eng):
+    """The fused kernel holds 256 queries; the reference has no limit on the number of categories (vlmap.py:123), so a
+    wider batch takes the exact scores and the first maximum per row -- from host and from device arrays."""
+    import torch
+
+    feat, q = synth.index_inputs(5_000, 64, 300, seed=21)
+    q[177] = q[12]                                   # an exact tie across the 256 boundary: the lower index wins
+    ref = O.argmax(O.scores(feat, q))
+    m = eng.DeviceMap(feat)
+    assert np.array_equal(m.argmax(q), ref)
+    got = m.argmax(torch.from_numpy(q).cuda())
+    assert got.dtype == torch.int32 and np.array_equal(got.cpu().numpy(), ref)
+    m.close()
