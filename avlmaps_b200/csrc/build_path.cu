@@ -59,6 +59,7 @@ struct FrameBatch {
   int32_t off[kMaxBatch + 1];     // sample offsets of the frames inside the batch
   int32_t nf;
   uint32_t frame_seq0;            // frame_seq of g[0]
+  int32_t feat_f16;               // feat[] point at __half rows (pixel-major fp16 hand-off), not float
 };
 static_assert(sizeof(FrameBatch) <= 4000, "FrameBatch must fit the kernel parameter space");
 
@@ -659,8 +660,25 @@ scatter_kernel(const __grid_constant__ FrameBatch batch, int32_t d,
     const float wgt = win ? alpha * alpha : alpha;
     const float* __restrict__ feat_hwc = batch.feat[fb];
     const uint8_t* __restrict__ rgb = batch.rgb[fb];
-    const float* f = feat_hwc + static_cast<int64_t>(s_fpix[j]) * d;
     float* o = num + id * d;
+    if (batch.feat_f16) {
+      // pixel-major fp16 rows, what LSeg itself emits (lseg_net.py:318-321: `.half()`): the feature read of a point
+      // is D * 2 bytes instead of D * 4 -- 5 144 instead of 6 168 bytes per accepted point -- and the values are the
+      // very same (fp16 -> fp32 is exact)
+      const __half* fh = reinterpret_cast<const __half*>(feat_hwc) + static_cast<int64_t>(s_fpix[j]) * d;
+      if ((d & 3) == 0) {
+        const uint2* f2 = reinterpret_cast<const uint2*>(fh);
+        for (int c = lane; c < (d >> 2); c += 32) {
+          const uint2 raw = __ldg(f2 + c);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          red_add_v4(o + 4 * c, lo.x * wgt, lo.y * wgt, hi.x * wgt, hi.y * wgt);
+        }
+      } else {
+        for (int c = lane; c < d; c += 32) atomicAdd(o + c, __half2float(fh[c]) * wgt);
+      }
+    } else {
+    const float* f = feat_hwc + static_cast<int64_t>(s_fpix[j]) * d;
     if ((d & 3) == 0) {
       const float4* f4 = reinterpret_cast<const float4*>(f);
       for (int c = lane; c < (d >> 2); c += 32) {
@@ -669,6 +687,7 @@ scatter_kernel(const __grid_constant__ FrameBatch batch, int32_t d,
       }
     } else {
       for (int c = lane; c < d; c += 32) atomicAdd(o + c, f[c] * wgt);
+    }
     }
     if (lane == 0) atomicAdd(den + id, alpha);
     if (rgb && lane >= 1 && lane <= 3) {
@@ -965,6 +984,7 @@ struct BatchItem {
   const avl_frame* f;
   const float* depth; const float* feat; const uint8_t* rgb; const int32_t* sidx;  // device pointers, feat pixel-major
   int32_t n_samples;
+  bool feat_f16 = false;   // feat points at pixel-major __half rows
 };
 
 // geometry -> ordered id scan -> scatter for up to kMaxBatch frames whose inputs are on the device
@@ -986,6 +1006,7 @@ int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cuda
   batch.off[nf] = static_cast<int32_t>(total);
   batch.nf = nf;
   batch.frame_seq0 = b->frame_seq;
+  batch.feat_f16 = (nf > 0 && items[0].feat_f16) ? 1 : 0;
   if (total == 0) {
     if (phase & 2) b->frame_seq += static_cast<uint32_t>(nf);
     return AVL_OK;
@@ -1128,7 +1149,11 @@ int add_frame_sparse(avl_builder* b, const avl_frame* f, const float* depth_dev,
   if (static_cast<size_t>(nu) * 4 > fpix) {
     if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
     if ((rc = grow(&b->d_feat_t, &b->feat_t_elems, fpix * d))) return rc;
-    if ((rc = g_staged_upload.copy(b->d_feat, f->feat, fpix * d * esz, s))) return rc;
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, f->feat) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // an unregistered pointer is not an error here
+    if (pinned) AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * esz, cudaMemcpyHostToDevice, s));   // PCIe speed as it is
+    else if ((rc = g_staged_upload.copy(b->d_feat, f->feat, fpix * d * esz, s))) return rc;
     b->h2d_bytes += fpix * d * esz;
     dim3 grid(static_cast<unsigned>((fpix + 63) / 64), static_cast<unsigned>((d + 63) / 64));
     if (f16)
@@ -1291,10 +1316,6 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   AVL_ARG(static_cast<int64_t>(f->h) * f->w < (int64_t(1) << 31), "frame too large");
   AVL_ARG(f->feat_layout == AVL_FEAT_CHW || f->feat_layout == AVL_FEAT_HWC, "unknown feat_layout");
   const bool feat_f16 = (flags & AVL_FEAT_F16) != 0;
-  if (feat_f16 && f->feat_layout != AVL_FEAT_CHW) {
-    set_error("AVL_FEAT_F16 features are accepted in the AVL_FEAT_CHW layout only");
-    return AVL_ERR_UNSUPPORTED;
-  }
   const int64_t npix = static_cast<int64_t>(f->h) * f->w;
   const int32_t n_samples = f->sample_idx ? f->n_samples : static_cast<int32_t>(npix);
   AVL_ARG(n_samples >= 0 && n_samples <= npix, "n_samples out of range");
@@ -1319,7 +1340,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
     b->h2d_bytes += depth_bytes + (f->rgb ? static_cast<uint64_t>(npix) * 3 : 0) +
                     (f->sample_idx ? static_cast<uint64_t>(n_samples) * sizeof(int32_t) : 0);
     if (!sparse) {
-      b->h2d_bytes += fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float));
+      b->h2d_bytes += fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float));  // d_feat is sized in floats: halves fit
       if ((rc = grow(&b->d_feat, &b->feat_elems, fpix * d))) return rc;
       AVL_CUDA(cudaMemcpyAsync(b->d_feat, f->feat, fpix * d * (feat_f16 ? sizeof(__half) : sizeof(float)),
                                cudaMemcpyHostToDevice, s));
@@ -1358,6 +1379,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
   it.f = f;
   it.depth = depth; it.feat = feat; it.rgb = rgb; it.sidx = sidx;
   it.n_samples = n_samples;
+  it.feat_f16 = feat_f16 && f->feat_layout == AVL_FEAT_HWC;   // channel-major halves were widened by the transposition
   if ((rc = launch_batch(b, &it, 1, flags, s))) return rc;
   if (!(flags & AVL_ON_DEVICE)) AVL_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused per frame
   return AVL_OK;
@@ -1366,7 +1388,7 @@ int avl_builder_add_frame(avl_builder* b, const avl_frame* f, int flags, void* s
 int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_frames, int flags, void* stream) {
   AVL_ARG(b != nullptr && (frames != nullptr || n_frames == 0), "NULL argument");
   AVL_ARG(n_frames >= 0, "n_frames < 0");
-  bool batchable = (flags & AVL_ON_DEVICE) != 0 && !(flags & AVL_FEAT_F16);  // fp16 features: transposed per frame
+  bool batchable = (flags & AVL_ON_DEVICE) != 0;
   for (int i = 0; i < n_frames && batchable; ++i) batchable = frames[i].feat_layout == AVL_FEAT_HWC;
   if (!batchable) {  // host pointers (staged per frame) or channel-major features (transposed per frame): one by one
     for (int i = 0; i < n_frames; ++i) {
@@ -1392,6 +1414,7 @@ int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_fr
       it.f = f;
       it.depth = f->depth; it.feat = f->feat; it.rgb = f->rgb; it.sidx = f->sample_idx;
       it.n_samples = n_samples;  // frames without samples stay in the batch: they still consume a frame_seq
+      it.feat_f16 = (flags & AVL_FEAT_F16) != 0;   // pixel-major fp16 rows, read as they are by the scatter
     }
     const int rc = launch_batch(b, items, used, flags, s);
     if (rc) return rc;

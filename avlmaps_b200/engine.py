@@ -440,8 +440,6 @@ def _fill_frame(depth, feat, kinv, k, kfeat, tf, rgb, sample_idx, feat_layout, m
     """Build the avl_frame struct; returns (frame, flags, keep-alive args)."""
     u16 = _is_u16(depth)
     f16 = _is_f16(feat)
-    if f16 and feat_layout != L.FEAT_CHW:
-        raise ValueError("float16 features are accepted in the CHW layout only (cast to float32 for HWC)")
     d_ = _Arg(depth, np.uint16 if u16 else np.float32, "depth")
     f_ = _Arg(feat, np.float16 if f16 else np.float32, "feat")
     r_ = _Arg(rgb, np.uint8, "rgb")

@@ -472,6 +472,28 @@ def build_extra(torch, engine, L, frames=24, reps=3):
                                "accepted_points_per_frame": paccb, "traffic": traffic, "traffic_source": src,
                                "traffic_note": "dram bytes of ONE scatter launch of the ncu capture (its frame count is in the file name)"}
             b.close()
+            # pixel-major fp16 rows (AVL_FEAT_HWC | AVL_FEAT_F16): what an LSeg that stays on the GPU hands over
+            try:
+                pool16 = [p_.to(torch.float16) for p_ in pool]
+                fr16 = [dict(fr_, feat=pool16[i % 4]) for i, fr_ in enumerate(fr)]
+                b = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
+                prep = b.prepare_frames(fr16)
+                b.add_prepared(prep, 0, 8, stream=torch.cuda.current_stream())
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(8, nb, 8):
+                    b.add_prepared(prep, i, 8, stream=torch.cuda.current_stream())
+                e1.record()
+                torch.cuda.synchronize()
+                ms16 = e0.elapsed_time(e1) / (nb - 8)
+                byts16 = h * w * 4 + paccb * (d * 2 + 2 * d * 4 + 24)
+                out["hwc_f16_batched8"] = {"frames_per_s": 1e3 / ms16, "ms_per_frame": ms16, "algorithmic_GBps": byts16 / ms16 / 1e6,
+                                           "hbm_frac": byts16 / ms16 / 1e6 / peaks["hbm_gbs"]}
+                b.close()
+                del pool16, fr16
+            except Exception as e:  # noqa: BLE001
+                out["hwc_f16_error"] = repr(e)
         if layout == L.FEAT_CHW:
             # ---- end to end through the host-pointer C-ABI call, in the layout get_lseg_feat hands over (lseg_utils.py:101-102).
             # The library reads the geometry back, gathers only the feature pixel rows the accepted points use on the host
@@ -483,7 +505,10 @@ def build_extra(torch, engine, L, frames=24, reps=3):
                 np.random.seed(7)
                 from avlmaps_b200.map import VLMapBuilder
                 hs = [VLMapBuilder._sample_order(h * w, rate) for _ in range(2)]
-                for tag, conv in (("f32", lambda t: t.numpy()), ("f16", lambda t: t.to(torch.float16).numpy())):
+                variants = [("f32", lambda t: t.numpy()), ("f16", lambda t: t.to(torch.float16).numpy())]
+                if rate == 1:   # the same array in page-locked memory: what a producer that pins its output buffer gets
+                    variants.append(("f32_pinned", lambda t: t.pin_memory().numpy()))
+                for tag, conv in variants:
                     feats_h = [conv(t) for t in hp]
                     n_e2e = 8 if rate == 1 else 64
                     b = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)

@@ -55,10 +55,13 @@ extern "C" {
                          band that decides what is re-scored exactly, is 8x smaller.  Results are identical either
                          way.  Falls back to bf16 by itself when a value exceeds the fp16 range. */
 
-#define AVL_FEAT_F16 8 /* avl_builder_add_frame: avl_frame.feat points at fp16 values (AVL_FEAT_CHW layout only).  LSeg emits
+#define AVL_FEAT_F16 8 /* avl_builder_add_frame(s): avl_frame.feat points at fp16 values, in either layout.  LSeg emits
                           `logit_scale * normalize(x).half()` (avlmaps/lseg/modules/models/lseg_net.py:318-321), so the
                           float32 array get_lseg_feat returns holds fp16-exact values; handing the halves over directly
-                          halves the bytes of the hand-off (415 -> 208 MB per 390x520x512 frame) and changes no result. */
+                          halves the bytes of the hand-off (415 -> 208 MB per 390x520x512 frame) and changes no result.
+                          AVL_FEAT_HWC | AVL_FEAT_F16 is the device-side hand-off of an encoder that stays on the GPU:
+                          pixel-major fp16 rows, read as they are by the scatter kernel (no transposition, half the
+                          feature bytes).  bf16 is not offered: it would round LSeg's fp16 values. */
 
 #define AVL_MAX_QUERIES 256 /* per call; larger batches are chunked by the host layer */
 #define AVL_MAX_TOPK 128

@@ -32,14 +32,27 @@ def test_fp16_features_give_the_same_map_as_their_float32_values(lib):
         calib = np.array(cfg["cam_calib_mat"], np.float64).reshape(3, 3)
         want = O.build_map(cfg, poses, depths, rgbs, feats32, sidx, capacity=48 * 48 * 16)
         outs = []
-        for variant in ("f32", "f16_host", "f16_device"):
+        from avlmaps_b200 import _lib as L
+
+        for variant in ("f32", "f16_host", "f16_device", "f16_hwc_device", "f16_hwc_host", "f16_hwc_batched"):
             b = engine.DeviceBuilder(48, 16, 0.1, d)
+            frames = []
             for i in range(3):
                 f = feats32[i] if variant == "f32" else feats16[i]
+                layout = L.FEAT_CHW
+                if "hwc" in variant:      # pixel-major fp16 rows: the hand-off of an encoder that stays on the GPU
+                    f, layout = np.ascontiguousarray(np.transpose(f[0], (1, 2, 0))), L.FEAT_HWC
                 dd, ss, rr = depths[i], sidx[i], rgbs[i]
-                if variant == "f16_device":
+                if variant.endswith("device") or variant.endswith("batched"):
                     f, dd, ss, rr = (torch.from_numpy(x).cuda() for x in (f, dd, ss, rr))
-                b.add_frame(dd, f, np.linalg.inv(calib), calib, O.get_sim_cam_mat(fh, fw), tfs[i], rgb=rr, sample_idx=ss)
+                kw = dict(depth=dd, feat=f, kinv=np.linalg.inv(calib), k=calib, kfeat=O.get_sim_cam_mat(fh, fw), tf=tfs[i], rgb=rr,
+                          sample_idx=ss, feat_layout=layout)
+                if variant.endswith("batched"):
+                    frames.append(kw)
+                else:
+                    b.add_frame(kw.pop("depth"), kw.pop("feat"), kw.pop("kinv"), kw.pop("k"), kw.pop("kfeat"), kw.pop("tf"), **kw)
+            if frames:
+                b.add_frames(frames)      # one geometry / id-scan / scatter launch triple for the three frames
             outs.append(b.export())
             b.close()
         for o in outs:
@@ -49,6 +62,8 @@ def test_fp16_features_give_the_same_map_as_their_float32_values(lib):
         assert np.array_equal(outs[0]["grid_pos"], outs[1]["grid_pos"]) and np.array_equal(outs[1]["grid_pos"], outs[2]["grid_pos"])
         assert np.allclose(outs[0]["grid_feat"], outs[1]["grid_feat"], rtol=1e-5, atol=1e-6)
         assert np.allclose(outs[1]["grid_feat"], outs[2]["grid_feat"], rtol=1e-5, atol=1e-6)
+        for o in outs[3:]:
+            assert np.array_equal(outs[0]["grid_pos"], o["grid_pos"]) and np.allclose(outs[0]["grid_feat"], o["grid_feat"], rtol=1e-5, atol=1e-6)
 
 
 def test_p2p_exchange_with_a_world_of_one(lib):
