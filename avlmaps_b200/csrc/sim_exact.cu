@@ -532,22 +532,29 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
   // flags the query for the exact fallback (adversarial data, massive ties).
   if (threadIdx.x == 0) { sh_ns = 0; sh_bad = 0u; }
   __syncthreads();
+  // all fill counts in one round of loads (one per thread), then one warp scans them from shared memory
+  for (int c = threadIdx.x; c < grid; c += blockDim.x) {
+    const uint32_t v = bucket_cnt[static_cast<size_t>(c) * AVL_MAX_QUERIES + qq];
+    if (v > cand_bucket) sh_bad = 1u;
+    sh_off[c + 1] = v;
+  }
+  __syncthreads();
   if (threadIdx.x < 32) {
     uint32_t run = 0u;
+    if (threadIdx.x == 0) sh_off[0] = 0u;
     for (int c0 = 0; c0 < grid; c0 += 32) {
       const int c = c0 + static_cast<int>(threadIdx.x);
-      const uint32_t v = c < grid ? bucket_cnt[static_cast<size_t>(c) * AVL_MAX_QUERIES + qq] : 0u;
-      if (v > cand_bucket) sh_bad = 1u;
+      const uint32_t v = c < grid ? sh_off[c + 1] : 0u;
       uint32_t x = v;  // inclusive warp scan
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (static_cast<int>(threadIdx.x) >= o) x += y;
       }
-      if (c < grid) sh_off[c] = run + x - v;
+      __syncwarp();
+      if (c < grid) sh_off[c + 1] = run + x;   // exclusive offset of bucket c + 1 = inclusive sum up to c
       run += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (threadIdx.x == 0) sh_off[grid] = run;
   }
   __syncthreads();
   const uint32_t cnt = sh_off[grid];
@@ -557,27 +564,25 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
     return;
   }
   if (threadIdx.x == 0) overflow_flags[qq] = 0u;
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int c = warp; c < grid; c += nw) {
-      const uint32_t o = sh_off[c], m = sh_off[c + 1] - o;
-      const size_t src = (static_cast<size_t>(qq) * grid + c) * cand_bucket;
-      for (uint32_t j = lane; j < m; j += 32) {
-        Ix[o + j] = cand_row[src + j];
-        Lk[o + j] = __float_as_uint(cand_val[src + j]);
-      }
-    }
-  }
-  __syncthreads();
+  // Gather + bounds in ONE pass over the candidates, flattened over the block (a thread finds its candidate's bucket
+  // by bisection of the offsets): the loads of the candidate, of its row statistics and the bound arithmetic pipeline
+  // instead of forming three latency-bound phases, and no warp walks ten buckets one after the other.
   const int n = static_cast<int>(cnt);
   const float rho = __uint_as_float(glob[0]);
   const float bn = q_bn[qq];
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const uint32_t i = Ix[j];
-    const float s = __uint_as_float(Lk[j]);
+    int lo = 0, hi = grid;          // largest c with sh_off[c] <= j
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (sh_off[mid] <= static_cast<uint32_t>(j)) lo = mid; else hi = mid;
+    }
+    const size_t src = (static_cast<size_t>(qq) * grid + lo) * cand_bucket + (static_cast<uint32_t>(j) - sh_off[lo]);
+    const uint32_t i = cand_row[src];
+    const float s = cand_val[src];
     const float r_i = fmaf(rho, row_an[i], row_c[i]);
     const float w_i = normalize ? fmaxf(row_norm[i], 1e-30f) : 1.f;
     const float e = __fmul_ru(r_i, bn);
+    Ix[j] = i;
     Lk[j] = max(f2ord(__fdiv_rd(__fsub_rd(s, e), w_i)), 1u);
     Uk[j] = max(f2ord(__fdiv_ru(__fadd_ru(s, e), w_i)), 1u);
   }

@@ -273,6 +273,44 @@ def frame_row_range(shape_hw, kinv, tf, gs: int, cs: float, min_depth: float = 0
     return int(np.floor((x_lo - origin_x) / cs)) - 2, int(np.ceil((x_hi - origin_x) / cs)) + 2
 
 
+def balanced_row_bounds(frames, gs: int, cs: float, world: int, max_frames: int = 64, pixel_stride: int = 8,
+                        min_depth: float = 0.1, max_depth: float = 6.0):
+    """Row slabs [(lo, hi)] * world that hold about the same number of POINTS each, from a pilot histogram: a subsample
+    of the frames (dicts with depth, kinv, tf as for add_frames) and of their pixels is back-projected on the host
+    (float64 numpy, the reference's formulas; only the row is needed) and the grid rows are cut at the quantiles.
+    Equal row counts leave the centre ranks with 2-3x the points of the edge ranks (the timing is the max over ranks).
+    Every rank must call it with the same frames -- the result is a pure function of them."""
+    hist = np.zeros(gs, np.float64)
+    pick = np.unique(np.linspace(0, len(frames) - 1, min(max_frames, len(frames))).astype(int)) if len(frames) else []
+    for i in pick:
+        fr = frames[i]
+        depth = fr["depth"]
+        depth = depth.detach().cpu().numpy() if hasattr(depth, "detach") else np.asarray(depth)
+        h, w = depth.shape
+        z = depth[::pixel_stride, ::pixel_stride].astype(np.float64)
+        if z.dtype.kind == "u" or depth.dtype == np.uint16:
+            z = z / 1000.0
+        v, u = np.meshgrid(np.arange(0, h, pixel_stride) + 0.5, np.arange(0, w, pixel_stride) + 0.5, indexing="ij")
+        kinv = np.asarray(fr["kinv"], np.float64).reshape(3, 3)
+        tf = np.asarray(fr["tf"], np.float64).reshape(4, 4)
+        ray = kinv @ np.stack([u.ravel(), v.ravel(), np.ones(u.size)])
+        p = ray * z.ravel()
+        ok = (p[2] > fr.get("min_depth", min_depth)) & (p[2] < fr.get("max_depth", max_depth))
+        gx = tf[0, :3] @ p + tf[0, 3]
+        row = (gs / 2 - np.trunc(gx / cs)).astype(np.int64)
+        ok &= (row >= 0) & (row < gs)
+        hist += np.bincount(row[ok], minlength=gs)[:gs]
+    if hist.sum() == 0:
+        return [slab_bounds(gs, world, r) for r in range(world)]
+    cum = np.cumsum(hist) / hist.sum()
+    cuts = [0]
+    for r in range(1, world):
+        c = int(np.searchsorted(cum, r / world)) + 1
+        cuts.append(min(max(c, cuts[-1] + 1), gs - (world - r)))   # every slab keeps at least one row
+    cuts.append(gs)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class ShardedBuilder:
     """Slab-sharded map BUILD: one process per GPU, rank r owns the grid rows
     `slab_bounds(n_rows, world, r)`.  Every rank is fed every frame (depth, pose and the sample list are
@@ -288,14 +326,17 @@ class ShardedBuilder:
     `local` is an engine.DeviceBuilder (anything with set_slab / add_frame / export / export_keys /
     grid_shape); `rank_fn(keys_per_shard, shard) -> int64 ids` defaults to engine.rank_keys."""
 
-    def __init__(self, local, group=None, rank_fn=None):
+    def __init__(self, local, group=None, rank_fn=None, row_bounds=None):
+        """`row_bounds`: this rank's (lo, hi) rows when the slabs are not the equal split -- e.g.
+        balanced_row_bounds(frames, gs, cs, world)[rank]; the slabs of all ranks must tile [0, gs)."""
         import torch.distributed as dist
 
         self.local = local
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.row_lo, self.row_hi = slab_bounds(int(local.grid_shape[0]), self.world, self.rank)
+        self.row_lo, self.row_hi = (int(row_bounds[0]), int(row_bounds[1])) if row_bounds is not None else \
+            slab_bounds(int(local.grid_shape[0]), self.world, self.rank)
         local.set_slab(self.row_lo, self.row_hi)
         self._rank_fn = rank_fn
 

@@ -356,9 +356,14 @@ def build_sharded_extra(torch, dist, engine, L, world, frames=240, reps=2):
     stream = torch.cuda.current_stream()
     fr = [dict(depth=sc["depths"][i % 4], feat=pool[i % 4], kinv=sc["kinv"], k=sc["calib"], kfeat=sc["kfeat"], tf=sc["tfs"][i],
                sample_idx=sc["sidx"][i % 4], feat_layout=L.FEAT_HWC) for i in range(frames)]
+    from avlmaps_b200.sharded import balanced_row_bounds
+
+    rank = dist.get_rank()
+    bounds = balanced_row_bounds(fr, sc["gs"], sc["cs"], world)   # slabs with about the same number of points each
     best, acc = None, 0
     for _ in range(reps):
-        sb = ShardedBuilder(engine.DeviceBuilder(sc["gs"], sc["vh"], sc["cs"], d, capacity=sc["gs"] * sc["gs"] * sc["vh"] // 2))
+        sb = ShardedBuilder(engine.DeviceBuilder(sc["gs"], sc["vh"], sc["cs"], d, capacity=sc["gs"] * sc["gs"] * sc["vh"] // 2),
+                            row_bounds=bounds[rank])
         prep = sb.prepare_frames(fr)   # the 4 buffers are a fixed ring: descriptors marshalled once
         dist.barrier()
         torch.cuda.synchronize()
@@ -379,7 +384,8 @@ def build_sharded_extra(torch, dist, engine, L, world, frames=240, reps=2):
     dist.all_reduce(a)
     return {"frames_per_s": 1e3 / best, "ms_per_frame": best, "frames": frames, "frames_per_call": 8,
             "accepted_points_per_frame_all_ranks": int(a.item()) / frames,
-            "scaling": "strong (one map, rows split into slabs)", "features": "HWC, device-resident, identical on every rank"}
+            "scaling": "strong (one map, rows split into slabs)", "features": "HWC, device-resident, identical on every rank",
+            "slab_rows": [list(b_) for b_ in bounds]}
 
 
 def build_cpu_baseline(frames=2, rate=1):

@@ -245,3 +245,22 @@ def test_frame_row_range_contains_every_row_the_reference_geometry_reaches():
         assert rows.min() >= lo and rows.max() <= hi
         narrow += (hi - lo) < gs
     assert narrow > 0      # the test is not vacuous: some frames cannot reach every row
+
+
+def test_balanced_row_bounds_tile_the_grid_and_even_out_the_points():
+    from avlmaps_b200.sharded import balanced_row_bounds
+
+    cfg = synth.map_config(256, 0.05, 1.6, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
+    b2c, bt = O.setup_transforms(cfg["pose_info"])
+    poses = synth.circle_poses(24, radius=2.0)
+    tfs = O.frame_transforms(poses, b2c, bt)
+    kinv = np.linalg.inv(np.array(cfg["cam_calib_mat"], np.float64).reshape(3, 3))
+    rng = np.random.default_rng(2)
+    frames = [dict(depth=rng.uniform(0.5, 6.0, (480, 640)).astype(np.float32), kinv=kinv, tf=tf) for tf in tfs]
+    for world in (1, 2, 3, 8):
+        b = balanced_row_bounds(frames, 256, 0.05, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == 256
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1)) and all(hi > lo for lo, hi in b)
+    b8 = balanced_row_bounds(frames, 256, 0.05, 8)
+    widths = [hi - lo for lo, hi in b8]
+    assert max(widths) > 2 * min(widths)       # the centre slabs are much narrower than the edge slabs

@@ -31,7 +31,7 @@ def main():
     from avlmaps_b200 import _lib as L
     from avlmaps_b200 import engine
     from avlmaps_b200.map import Map, VLMapBuilder
-    from avlmaps_b200.sharded import ShardedBuilder
+    from avlmaps_b200.sharded import ShardedBuilder, balanced_row_bounds
     from avlmaps_b200.utils.mapping_utils import get_sim_cam_mat
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -61,6 +61,8 @@ def main():
     fr = [dict(depth=depths[i % 4], feat=pool[i % 4], kinv=kinv, k=calib, kfeat=kfeat, tf=tfs[i], sample_idx=sidx[i % 4],
                feat_layout=L.FEAT_HWC) for i in range(frames)]
 
+    bounds = balanced_row_bounds(fr, gs, cs, world)
+
     def feed(b):
         # the 4 depth / feature / sample buffers are a fixed ring (an encoder's output slots): marshal the frame
         # descriptors once, then up to 8 frames per launch triple (avl_builder_add_frames)
@@ -75,7 +77,8 @@ def main():
 
     best = None
     for rep in range(3):
-        sb = ShardedBuilder(engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh // max(world // 2, 1)))
+        sb = ShardedBuilder(engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh // max(world // 2, 1)),
+                            row_bounds=bounds[rank] if os.environ.get("AVL_EQUAL_SLABS") != "1" else None)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
