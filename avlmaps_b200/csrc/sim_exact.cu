@@ -710,16 +710,23 @@ topk_vec_l2_kernel(const unsigned long long* __restrict__ keys, int m, int32_t k
 // keeps the top-k keys of its rows in shared memory, the block merges its warps' lists, the LAST block to finish
 // (ticket) merges the blocks' lists.  keys = (ordered score bits << 32) | ~row: unique, so (score desc, row asc).
 constexpr int kFbThreads = 256;
+constexpr int kFbGroup = 8;   // flagged queries scored per pass over the map
 __global__ void __launch_bounds__(kFbThreads)
 topk_fallback_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const float* __restrict__ q, int32_t nq,
                      const float* __restrict__ scale, const float* __restrict__ row_norm, int normalize, int32_t k,
-                     const uint32_t* __restrict__ overflow_flags, unsigned long long* __restrict__ scratch,
+                     int32_t group, const uint32_t* __restrict__ overflow_flags, unsigned long long* __restrict__ scratch,
                      uint32_t* __restrict__ tickets, int64_t* __restrict__ out_idx, float* __restrict__ out_score) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int kWarps = kFbThreads / 32;
-  __shared__ unsigned long long wl[kWarps][AVL_MAX_TOPK];
-  __shared__ int wcnt[kWarps];
+  extern __shared__ uint8_t fb_sm[];
+  // dynamic: [group][d] doubles of the group's queries (converted once: float -> double conversions run at a quarter
+  // of the fp64 FMA rate and would otherwise be two per product) | [kWarps][group][k] keys (per-warp sorted lists)
+  double* qs = reinterpret_cast<double*>(fb_sm);
+  unsigned long long* wl = reinterpret_cast<unsigned long long*>(fb_sm + static_cast<size_t>(group) * d * 8);
+  __shared__ int wcnt[kWarps][kFbGroup];
+  __shared__ int sh_flagged[AVL_MAX_QUERIES];
+  __shared__ int sh_nflag;
   __shared__ int sh_cnt;
   __shared__ uint32_t sh_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -728,74 +735,128 @@ topk_fallback_kernel(const float* __restrict__ feat, int64_t n, int32_t d, const
   // other cost 24 us per call on B200)
   static_assert(kFbThreads >= AVL_MAX_QUERIES, "one flag per thread");
   if (!__syncthreads_or(static_cast<int>(threadIdx.x) < nq && overflow_flags[threadIdx.x] != 0u)) return;
-  for (int qq = 0; qq < nq; ++qq) {
-    if (!overflow_flags[qq]) continue;  // read-only during this launch: uniform over the grid
-    // ---- phase 1: per-warp top-k of its rows (sorted descending, insertion by lane 0)
-    int cnt = 0;
-    unsigned long long kmin = 0ull;  // smallest kept key once the list is full
-    const float* b = q + static_cast<size_t>(qq) * d;
+  if (threadIdx.x == 0) {  // the flagged queries in ascending order (the flags are read-only during this launch)
+    int c = 0;
+    for (int i = 0; i < nq; ++i)
+      if (overflow_flags[i]) sh_flagged[c++] = i;
+    sh_nflag = c;
+  }
+  __syncthreads();
+  const int nflag = sh_nflag;
+  // Up to `group` flagged queries share ONE pass over the map: a row is loaded once (512 elements at a time, 16 per
+  // lane, in registers) and multiplied into every query of the group, so 256 flagged queries cost 32 passes, not 256.
+  for (int g0 = 0; g0 < nflag; g0 += group) {
+    const int ng = min(group, nflag - g0);
+    for (int e = threadIdx.x; e < ng * d; e += blockDim.x) {
+      const int g = e / d, c = e - g * d;
+      qs[e] = static_cast<double>(q[static_cast<size_t>(sh_flagged[g0 + g]) * d + c]);
+    }
+    __syncthreads();
+    // ---- phase 1: per-warp top-k of its rows for every query of the group (sorted descending, insertion by lane 0)
+    int cnt[kFbGroup];
+    unsigned long long kmin[kFbGroup];
+#pragma unroll
+    for (int g = 0; g < kFbGroup; ++g) { cnt[g] = 0; kmin[g] = 0ull; }
     for (int64_t row = gw; row < n; row += nwarps) {
-      const double dot = warp_dot(feat + row * d, b, d, lane);
-      if (lane == 0) {
-        const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
-        const unsigned long long key = vec_key(canon_score(dot, inv, normalize, scale, qq), row);
-        if (cnt < k || key > kmin) {
-          int pos = cnt < k ? cnt : k - 1;
-          while (pos > 0 && wl[warp][pos - 1] < key) { wl[warp][pos] = wl[warp][pos - 1]; --pos; }
-          wl[warp][pos] = key;
-          if (cnt < k) ++cnt;
-          if (cnt == k) kmin = wl[warp][k - 1];
+      double acc[kFbGroup];
+#pragma unroll
+      for (int g = 0; g < kFbGroup; ++g) acc[g] = 0.0;
+      const float* a = feat + row * d;
+      for (int k0 = 0; k0 < d; k0 += 512) {   // same per-lane order as warp_dot: k = lane, lane + 32, ... ascending
+        float af[16];
+        double av[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const int c = k0 + t * 32 + lane;
+          af[t] = c < d ? __ldg(a + c) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) av[t] = static_cast<double>(af[t]);
+#pragma unroll
+        for (int g = 0; g < kFbGroup; ++g) {
+          if (g < ng) {
+            const double* qg = qs + g * d;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const int c = k0 + t * 32 + lane;
+              if (c < d) acc[g] = fma(av[t], qg[c], acc[g]);
+            }
+          }
+        }
+      }
+      const float inv = normalize ? inv_of_norm(row_norm[row]) : 1.f;
+#pragma unroll
+      for (int g = 0; g < kFbGroup; ++g) {
+        if (g < ng) {
+          const double dot = warp_sum(acc[g]);
+          if (lane == 0) {
+            unsigned long long* list = wl + (static_cast<size_t>(warp) * group + g) * k;
+            const unsigned long long key = vec_key(canon_score(dot, inv, normalize, scale, sh_flagged[g0 + g]), row);
+            if (cnt[g] < k || key > kmin[g]) {
+              int pos = cnt[g] < k ? cnt[g] : k - 1;
+              while (pos > 0 && list[pos - 1] < key) { list[pos] = list[pos - 1]; --pos; }
+              list[pos] = key;
+              if (cnt[g] < k) ++cnt[g];
+              if (cnt[g] == k) kmin[g] = list[k - 1];
+            }
+          }
         }
       }
     }
-    if (lane == 0) wcnt[warp] = cnt;
-    __syncthreads();
-    // ---- phase 2: block merge by rank counting (<= 8 * 128 keys), block list -> scratch[qq][block][k] (0 = nothing)
-    unsigned long long* mine = scratch + (static_cast<size_t>(qq) * gridDim.x + blockIdx.x) * k;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) mine[j] = 0ull;
-    __syncthreads();
-    for (int e = threadIdx.x; e < kWarps * k; e += blockDim.x) {
-      const int w = e / k, j = e - w * k;
-      if (j >= wcnt[w]) continue;
-      const unsigned long long key = wl[w][j];
-      int rank = 0;
-      for (int w2 = 0; w2 < kWarps; ++w2)
-        for (int j2 = 0; j2 < wcnt[w2]; ++j2) rank += (wl[w2][j2] > key) ? 1 : 0;
-      if (rank < k) mine[rank] = key;
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < kFbGroup; ++g) wcnt[warp][g] = cnt[g];
     }
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) sh_last = (atomicAdd(tickets + qq, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (sh_last) {
-      // ---- phase 3 (last block): top-k of the gridDim.x * k block keys
+    for (int g = 0; g < ng; ++g) {
+      const int qq = sh_flagged[g0 + g];
+      // ---- phase 2: block merge by rank counting (<= 8 * 128 keys), block list -> scratch[qq][block][k] (0 = nothing)
+      unsigned long long* mine = scratch + (static_cast<size_t>(qq) * gridDim.x + blockIdx.x) * k;
+      for (int j = threadIdx.x; j < k; j += blockDim.x) mine[j] = 0ull;
+      __syncthreads();
+      for (int e = threadIdx.x; e < kWarps * k; e += blockDim.x) {
+        const int w = e / k, j = e - w * k;
+        if (j >= wcnt[w][g]) continue;
+        const unsigned long long key = wl[(static_cast<size_t>(w) * group + g) * k + j];
+        int rank = 0;
+        for (int w2 = 0; w2 < kWarps; ++w2)
+          for (int j2 = 0; j2 < wcnt[w2][g]; ++j2) rank += (wl[(static_cast<size_t>(w2) * group + g) * k + j2] > key) ? 1 : 0;
+        if (rank < k) mine[rank] = key;
+      }
       __threadfence();
-      const unsigned long long* all = scratch + static_cast<size_t>(qq) * gridDim.x * k;
-      const int m = static_cast<int>(gridDim.x) * k;
-      const int kk = static_cast<int>(min(static_cast<int64_t>(k), n));
-      const unsigned long long t =
-          block_kth_largest<unsigned long long>([&](int j) { return __ldcg(all + j); }, m, kk, &sh_cnt);
-      for (int s = threadIdx.x; s < k; s += blockDim.x) {
-        out_idx[static_cast<size_t>(qq) * k + s] = -1;
-        out_score[static_cast<size_t>(qq) * k + s] = -INFINITY;
+      __syncthreads();
+      if (threadIdx.x == 0) sh_last = (atomicAdd(tickets + qq, 1u) == gridDim.x - 1) ? 1u : 0u;
+      __syncthreads();
+      if (sh_last) {
+        // ---- phase 3 (last block): top-k of the gridDim.x * k block keys
+        __threadfence();
+        const unsigned long long* all = scratch + static_cast<size_t>(qq) * gridDim.x * k;
+        const int m = static_cast<int>(gridDim.x) * k;
+        const int kk = static_cast<int>(min(static_cast<int64_t>(k), n));
+        const unsigned long long t =
+            block_kth_largest<unsigned long long>([&](int j) { return __ldcg(all + j); }, m, kk, &sh_cnt);
+        for (int s = threadIdx.x; s < k; s += blockDim.x) {
+          out_idx[static_cast<size_t>(qq) * k + s] = -1;
+          out_score[static_cast<size_t>(qq) * k + s] = -INFINITY;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+          const unsigned long long key = __ldcg(all + j);
+          if (key == 0ull || key < t) continue;
+          int rank = 0;
+          for (int u = 0; u < m; ++u) {
+            const unsigned long long o = __ldcg(all + u);
+            rank += (o > key) ? 1 : 0;
+          }
+          if (rank < kk) {
+            out_idx[static_cast<size_t>(qq) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+            out_score[static_cast<size_t>(qq) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
+          }
+        }
+        if (threadIdx.x == 0) tickets[qq] = 0u;  // ready for the next call
       }
       __syncthreads();
-      for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        const unsigned long long key = __ldcg(all + j);
-        if (key == 0ull || key < t) continue;
-        int rank = 0;
-        for (int u = 0; u < m; ++u) {
-          const unsigned long long o = __ldcg(all + u);
-          rank += (o > key) ? 1 : 0;
-        }
-        if (rank < kk) {
-          out_idx[static_cast<size_t>(qq) * k + rank] = static_cast<int64_t>(0xFFFFFFFFu - static_cast<uint32_t>(key));
-          out_score[static_cast<size_t>(qq) * k + rank] = ord2f(static_cast<uint32_t>(key >> 32));
-        }
-      }
-      if (threadIdx.x == 0) tickets[qq] = 0u;  // ready for the next call
     }
-    __syncthreads();
   }
 }
 
@@ -1395,9 +1456,14 @@ int launch_topk_fallback(const float* feat, int64_t n, int32_t d, const float* q
                          const float* row_norm, int normalize, int32_t k, const uint32_t* overflow_flags,
                          void* scratch, uint32_t* tickets, int64_t* out_idx, float* out_score, int num_sms,
                          cudaStream_t s) {
-  AVL_CUDA(launch_pdl(topk_fallback_kernel, dim3(2 * num_sms), dim3(kFbThreads), 0, s, feat, n, d, q, nq, scale, row_norm,
-                      normalize, k, overflow_flags, static_cast<unsigned long long*>(scratch), tickets, out_idx, out_score));
-  AVL_CUDA(cudaGetLastError());
+  // queries per pass: bounded by 64 KiB of query vectors (fp64) and 40 KiB of per-warp lists in shared memory
+  int group = kFbGroup;
+  group = std::min<int>(group, std::max<int>(1, 65536 / (d * 8)));
+  group = std::min<int>(group, std::max<int>(1, 40960 / ((kFbThreads / 32) * k * 8)));
+  const size_t smem = static_cast<size_t>(group) * d * 8 + static_cast<size_t>(kFbThreads / 32) * group * k * 8;
+  AVL_CUDA(cudaFuncSetAttribute(topk_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AVL_CUDA(launch_pdl(topk_fallback_kernel, dim3(2 * num_sms), dim3(kFbThreads), smem, s, feat, n, d, q, nq, scale, row_norm,
+                      normalize, k, group, overflow_flags, static_cast<unsigned long long*>(scratch), tickets, out_idx, out_score));
   return AVL_OK;
 }
 

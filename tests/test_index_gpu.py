@@ -70,10 +70,10 @@ def test_topk_and_argmax_vs_oracle(eng, n, d, nq, k, normalize, use_scale):
     m.close()
 
 
-@pytest.mark.parametrize("cg", [1, 2, 3])
+@pytest.mark.parametrize("cg", [1, 2])
 def test_tensor_core_screen_matches_bf16_model(eng, cg):
     """The raw tcgen05 output equals the exact product of the bf16-rounded operands (fp32 accumulate);
-    cg 1/2: operands from shared memory, 3: query-stationary kernel (queries in TMEM)."""
+    cg = cta_group of the kernel (2: the queries are split over an SM pair)."""
     feat, q = synth.index_inputs(3000, 512, 48, seed=3)
 
     def bf16(x):
@@ -88,7 +88,7 @@ def test_tensor_core_screen_matches_bf16_model(eng, cg):
     m.close()
 
 
-@pytest.mark.parametrize("cg", [1, 2, 3])
+@pytest.mark.parametrize("cg", [1, 2])
 def test_f16_operand_mode(eng, cg):
     """AVL_MAP_F16: fp16 tensor-core operands.  (a) the raw screen equals the exact product of the fp16-rounded
     operands; (b) argmax / top-k are the same bits as with bf16 operands and as the oracle, with ~8x fewer rows
@@ -166,6 +166,25 @@ def test_massive_ties_take_the_exact_fallback(eng):
     assert np.array_equal(idx, np.tile(np.arange(8), (3, 1)))
     assert m.last_stats["n_fallback_queries"] == 3
     assert np.array_equal(val, O.topk(O.scores(feat, q), 8)[1])
+    m.close()
+
+
+@pytest.mark.parametrize("n,d,nq,k,normalize", [(30_000, 100, 21, 128, False), (25_000, 1024, 11, 5, True)])
+def test_fallback_scores_groups_of_queries_per_pass(eng, n, d, nq, k, normalize):
+    """Near-duplicate rows (a few prototypes + one-ulp noise): every query's top-k is a near-tie far inside the 16-bit band,
+    so every query overflows into the device-side exact fallback, which scores up to 8 flagged queries per pass over the
+    map (fewer when k or D is large).  Ids, score bits and order must equal the oracle's."""
+    rng = np.random.default_rng(6)
+    protos = rng.standard_normal((4, d)).astype(np.float32)
+    feat = protos[rng.integers(0, 4, n)] * np.float32(3.0)
+    feat *= (1.0 + 1e-7 * rng.integers(-3, 4, (n, 1))).astype(np.float32)
+    q = synth.index_inputs(1, d, nq, seed=8)[1]
+    scale = rng.uniform(0.5, 2.0, nq).astype(np.float32)
+    ref = O.topk(O.scores(feat, q, scale=scale, normalize=normalize), k)
+    m = eng.DeviceMap(feat)
+    idx, val = m.topk(q, k, scale=scale, normalize_map=normalize)
+    assert m.last_stats["n_fallback_queries"] == nq
+    assert np.array_equal(idx, ref[0]) and np.array_equal(val, ref[1])
     m.close()
 
 
