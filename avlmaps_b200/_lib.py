@@ -19,6 +19,7 @@ AVL_ON_DEVICE = 1
 AVL_DEPTH_U16_MM = 2
 AVL_MAP_F16 = 4
 AVL_ASYNC = 16
+AVL_PIPELINED = 32
 AVL_FEAT_F16 = 8
 AVL_MAX_QUERIES = 256
 AVL_MAX_TOPK = 128
@@ -29,7 +30,7 @@ FEAT_CHW, FEAT_HWC = 0, 1
 EXPORTS = [
     "avl_version", "avl_last_error", "avl_device_count", "avl_set_device", "avl_set_profiling",
     "avl_map_create", "avl_map_destroy", "avl_map_shape", "avl_map_device_bytes", "avl_map_operand_f16",
-    "avl_map_screen_times",
+    "avl_map_screen_times", "avl_map_flush", "avl_map_tail_stream",
     "avl_sim_dense", "avl_sim_argmax", "avl_sim_topk", "avl_sim_screen_dense", "avl_topk_f32", "avl_fuse_topk",
     "avl_heat_from_mask_3d", "avl_merge_topk", "avl_heat2d_sources",
     "avl_builder_create", "avl_builder_destroy", "avl_builder_add_frame", "avl_builder_num_voxels",
@@ -105,6 +106,8 @@ def load() -> C.CDLL:
     lib.avl_map_operand_f16.argtypes = [vp]
     lib.avl_map_shape.argtypes = [vp, C.POINTER(i64), C.POINTER(i32)]
     lib.avl_map_screen_times.argtypes = [vp, C.POINTER(C.c_float), i32, C.POINTER(i32)]
+    lib.avl_map_flush.argtypes = [vp, vp]
+    lib.avl_map_tail_stream.argtypes = [vp, C.POINTER(vp)]
     lib.avl_sim_dense.argtypes = [vp, f32p, i32, f32p, C.c_int, f32p, C.c_int, vp]
     lib.avl_sim_argmax.argtypes = [vp, f32p, i32, f32p, C.c_int, vp, C.c_int, vp, C.POINTER(IndexStats)]
     lib.avl_sim_topk.argtypes = [vp, f32p, i32, f32p, C.c_int, i32, vp, vp, C.c_int, vp, C.POINTER(IndexStats)]

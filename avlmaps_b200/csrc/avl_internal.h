@@ -136,7 +136,8 @@ int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const flo
                          const float* row_an, const float* q_bn, const float* q_glob, int normalize,
                          int32_t k, const uint32_t* bucket_cnt, int32_t grid, uint32_t cand_bucket,
                          const uint32_t* cand_row, const float* cand_val, uint32_t fin_cap, int64_t* out_idx,
-                         float* out_score, uint32_t* cand_total, uint32_t* overflow_flags, cudaStream_t s);
+                         float* out_score, uint32_t* cand_total, uint32_t* overflow_flags, uint32_t* gscratch,
+                         cudaStream_t s);
 // exact re-score of the queries whose overflow flag is set, decided on the device (no host round trip)
 int launch_topk_fallback(const float* feat, int64_t n, int32_t d, const float* q, int32_t nq, const float* scale,
                          const float* row_norm, int normalize, int32_t k, const uint32_t* overflow_flags,

@@ -75,6 +75,7 @@ static int encode_kmajor_map(CUtensorMap* out, const void* base, uint64_t rows, 
 }
 
 // ------------------------------------------------------------------ workspace
+constexpr int kQGlobStride = 4 + AVL_MAX_QUERIES;  // floats of one q_glob half (launch_query_prepare)
 struct Workspace {
   float* q = nullptr;          // [256 x d] staged queries (host-pointer calls)
   double* q64 = nullptr;       // [256 x d] queries in fp64 for the exact re-rank
@@ -99,6 +100,17 @@ struct Workspace {
   uint32_t* fb_tickets = nullptr;  // [256]
   uint32_t* tile_ctr = nullptr;  // [1] tile counter of the screen kernel's dynamic schedule
   uint32_t tile_base = 0;        // host mirror: the counter's value before the next launch
+  // pipelined top-k calls (AVL_PIPELINED): the tail of a call (finalize, fallback, result copy) runs on `tail_stream`
+  // next to the following call's screen.  q, scale, q_bn, q_glob, cand_cnt, bucket_cnt, out_idx, out_score and the
+  // candidate arrays hold TWO halves, selected by the parity of the call; every other path uses half 0.
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_main[2] = {nullptr, nullptr};   // the screen of the call of this parity is done
+  cudaEvent_t ev_tail[2] = {nullptr, nullptr};   // its tail is done (the half's buffers may be reused)
+  bool tail_pending[2] = {false, false};
+  uint32_t n_pipelined = 0;
+  cudaEvent_t tl[2][6] = {};                     // AVL_DEBUG_FLAGS & 128: timeline of a pipelined call (timing events)
+  uint32_t* fin_scratch = nullptr;               // [2][256][3 * fin_cap] per-candidate arrays of the finalize beside the screen
+  size_t fin_scratch_elems = 0;
   float* sample_t = nullptr;
   size_t sample_elems = 0;
   float* fuse_a = nullptr;       // (pairs, n) dense screen scores of the two modalities (avl_fuse_topk)
@@ -152,27 +164,37 @@ static int dev_alloc(T** p, size_t count, int64_t* bytes) {
 static int ws_init(avl_map* m) {
   Workspace& w = m->ws;
   int rc;
-  if ((rc = dev_alloc(&w.q, static_cast<size_t>(AVL_MAX_QUERIES) * m->d, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.q, static_cast<size_t>(2 * AVL_MAX_QUERIES) * m->d, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.q64, static_cast<size_t>(AVL_MAX_QUERIES) * m->d, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.scale, AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.scale, 2 * AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.bq, static_cast<size_t>(AVL_MAX_QUERIES) * m->dpad, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.q_bn, AVL_MAX_QUERIES, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.q_glob, 4 + AVL_MAX_QUERIES, &m->bytes))) return rc;  // see launch_query_prepare
-  AVL_CUDA(cudaMemset(w.q_glob, 0, (4 + AVL_MAX_QUERIES) * sizeof(float)));
+  if ((rc = dev_alloc(&w.q_bn, 2 * AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.q_glob, 2 * kQGlobStride, &m->bytes))) return rc;  // see launch_query_prepare
+  AVL_CUDA(cudaMemset(w.q_glob, 0, 2 * kQGlobStride * sizeof(float)));
   if ((rc = dev_alloc(&w.thr_t, AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.flag_count, 1, &m->bytes))) return rc;
   // counters and overflow flags are adjacent: one 2 KiB read-back into pinned memory per top-k call
-  if ((rc = dev_alloc(&w.cand_cnt, 2 * AVL_MAX_QUERIES, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.cand_cnt, 4 * AVL_MAX_QUERIES, &m->bytes))) return rc;
   w.overflow = w.cand_cnt + AVL_MAX_QUERIES;
-  AVL_CUDA(cudaMemset(w.cand_cnt, 0, 2 * AVL_MAX_QUERIES * sizeof(uint32_t)));
-  if ((rc = dev_alloc(&w.bucket_cnt, static_cast<size_t>(256) * AVL_MAX_QUERIES, &m->bytes))) return rc;
+  AVL_CUDA(cudaMemset(w.cand_cnt, 0, 4 * AVL_MAX_QUERIES * sizeof(uint32_t)));
+  if ((rc = dev_alloc(&w.bucket_cnt, static_cast<size_t>(2 * 256) * AVL_MAX_QUERIES, &m->bytes))) return rc;
   if ((rc = dev_alloc(&w.fb_tickets, AVL_MAX_QUERIES, &m->bytes))) return rc;
   AVL_CUDA(cudaMemset(w.fb_tickets, 0, AVL_MAX_QUERIES * sizeof(uint32_t)));
   if ((rc = dev_alloc(&w.tile_ctr, 1, &m->bytes))) return rc;
   AVL_CUDA(cudaMemset(w.tile_ctr, 0, sizeof(uint32_t)));
   AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.pin), 2 * AVL_MAX_QUERIES * sizeof(uint32_t), cudaHostAllocDefault));
-  if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
-  if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.out_idx, static_cast<size_t>(2 * AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
+  if ((rc = dev_alloc(&w.out_score, static_cast<size_t>(2 * AVL_MAX_QUERIES) * AVL_MAX_TOPK, &m->bytes))) return rc;
+  {
+    // lowest priority: the tail fills what the next call's head and screen leave free, it must never delay them
+    int lo = 0, hi = 0;
+    AVL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    AVL_CUDA(cudaStreamCreateWithPriority(&w.tail_stream, cudaStreamNonBlocking, lo));
+  }
+  for (int i = 0; i < 2; ++i) {
+    AVL_CUDA(cudaEventCreateWithFlags(&w.ev_main[i], cudaEventDisableTiming));
+    AVL_CUDA(cudaEventCreateWithFlags(&w.ev_tail[i], cudaEventDisableTiming));
+  }
   AVL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&w.dbg_host), 4096, cudaHostAllocMapped));
   memset(w.dbg_host, 0, 4096);
   AVL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.dbg_dev), w.dbg_host, 0));
@@ -187,7 +209,12 @@ static void ws_free(Workspace& w) {
   cudaFree(w.cand_row); cudaFree(w.cand_val); cudaFree(w.sample_t); cudaFree(w.out_idx);
   cudaFree(w.out_score); cudaFree(w.argmax); cudaFree(w.column); cudaFree(w.topk_scratch);
   cudaFree(w.fuse_a); cudaFree(w.fuse_b); cudaFree(w.fuse_small); cudaFree(w.cand_val2);
-  cudaFree(w.bucket_cnt); cudaFree(w.fb_scratch); cudaFree(w.fb_tickets); cudaFree(w.tile_ctr);
+  cudaFree(w.bucket_cnt); cudaFree(w.fb_scratch); cudaFree(w.fb_tickets); cudaFree(w.tile_ctr); cudaFree(w.fin_scratch);
+  for (int i = 0; i < 2; ++i) {
+    if (w.ev_main[i]) cudaEventDestroy(w.ev_main[i]);
+    if (w.ev_tail[i]) cudaEventDestroy(w.ev_tail[i]);
+  }
+  if (w.tail_stream) cudaStreamDestroy(w.tail_stream);
   if (w.dbg_host) cudaFreeHost(w.dbg_host);
   if (w.pin) cudaFreeHost(w.pin);
   for (int i = 0; i < 4; ++i)
@@ -283,6 +310,8 @@ struct QuerySetup {
   const float* scale_dev = nullptr;  // or null
   int npad = 0;
   int cg = 0;
+  float* q_bn = nullptr;             // per-query ||b|| and the two maxima: the workspace half of this call's parity
+  float* q_glob = nullptr;
   int unit_rows = 0;                 // voxel rows per tile unit of the chosen kernel
   int stages = 0;
   size_t smem = 0;
@@ -292,20 +321,23 @@ struct QuerySetup {
 // stage queries, build bf16 B + norms, pick the kernel variant
 static int setup_queries(avl_map* m, const float* queries, int32_t nq, const float* scale, int flags,
                          int forced_cg, int screen_mode /* ScreenMode of the pass that follows, -1: no screen */,
-                         cudaStream_t s, QuerySetup* qs, bool fold_scale = false) {
+                         cudaStream_t s, QuerySetup* qs, bool fold_scale = false, int parity = 0) {
   Workspace& w = m->ws;
   AVL_ARG(queries != nullptr, "queries is NULL");
   AVL_ARG(nq >= 1 && nq <= AVL_MAX_QUERIES, "nq must be in [1, AVL_MAX_QUERIES]");
+  qs->q_bn = w.q_bn + parity * AVL_MAX_QUERIES;
+  qs->q_glob = w.q_glob + parity * kQGlobStride;
   if (flags & AVL_ON_DEVICE) {
     qs->q_dev = queries;
     qs->scale_dev = scale;
   } else {
-    AVL_CUDA(cudaMemcpyAsync(w.q, queries, static_cast<size_t>(nq) * m->d * sizeof(float),
-                             cudaMemcpyHostToDevice, s));
-    qs->q_dev = w.q;
+    float* qd = w.q + static_cast<size_t>(parity) * AVL_MAX_QUERIES * m->d;
+    AVL_CUDA(cudaMemcpyAsync(qd, queries, static_cast<size_t>(nq) * m->d * sizeof(float), cudaMemcpyHostToDevice, s));
+    qs->q_dev = qd;
     if (scale) {
-      AVL_CUDA(cudaMemcpyAsync(w.scale, scale, static_cast<size_t>(nq) * sizeof(float), cudaMemcpyHostToDevice, s));
-      qs->scale_dev = w.scale;
+      float* sd = w.scale + parity * AVL_MAX_QUERIES;
+      AVL_CUDA(cudaMemcpyAsync(sd, scale, static_cast<size_t>(nq) * sizeof(float), cudaMemcpyHostToDevice, s));
+      qs->scale_dev = sd;
     }
   }
   if (screen_mode < 0) return AVL_OK;
@@ -320,7 +352,7 @@ static int setup_queries(avl_map* m, const float* queries, int32_t nq, const flo
   qs->stages = screen_pick_stages(qs->cg, qs->npad, kblocks, screen_mode);
   qs->smem = screen_smem_bytes(qs->cg, qs->npad, kblocks, qs->stages, screen_mode);
   int rc = launch_query_prepare(qs->q_dev, fold_scale ? qs->scale_dev : nullptr, nq, m->d, m->dpad, qs->npad, w.bq,
-                                w.q_bn, w.q_glob, m->op_f16, s);
+                                qs->q_bn, qs->q_glob, m->op_f16, s);
   if (rc) return rc;
   return encode_kmajor_map(&qs->tmap_b, w.bq, static_cast<uint64_t>(qs->npad), static_cast<uint64_t>(m->dpad),
                            static_cast<uint32_t>(qs->npad / qs->cg), m->op_f16 != 0);
@@ -337,9 +369,9 @@ static void base_params(const avl_map* m, const QuerySetup& qs, int32_t nq, int 
   p->row_norm = m->row_norm;
   p->row_c = m->row_c;
   p->row_an = m->row_an;
-  p->q_bn = m->ws.q_bn;
+  p->q_bn = qs.q_bn;
   p->bq = m->ws.bq;
-  p->q_glob = m->ws.q_glob;
+  p->q_glob = qs.q_glob;
   p->dbg = m->ws.dbg_dev;
   p->op_f16 = m->op_f16;
   p->a_tiled = m->tiled;
@@ -363,6 +395,18 @@ static int run_screen(avl_map* m, const QuerySetup& qs, ScreenParams& p, cudaStr
   p.tile_base = m->ws.tile_base;
   m->ws.tile_base += static_cast<uint32_t>(p.num_tiles);
   return launch_screen(qs.cg, &m->tmap_a, &qs.tmap_b, p, m->num_sms, qs.smem, s);
+}
+
+// Order `s` after the tails of earlier pipelined top-k calls (they run on the map's tail stream and use its workspace).
+static int drain_tails(avl_map* m, cudaStream_t s) {
+  Workspace& w = m->ws;
+  for (int i = 0; i < 2; ++i) {
+    if (w.tail_pending[i]) {
+      AVL_CUDA(cudaStreamWaitEvent(s, w.ev_tail[i], 0));
+      w.tail_pending[i] = false;
+    }
+  }
+  return AVL_OK;
 }
 
 static int scale_positive(const float* scale, int32_t nq, int flags) {
@@ -482,6 +526,7 @@ int avl_map_create(const float* grid_feat, int64_t n, int32_t dim, int flags, vo
 
 int avl_map_destroy(avl_map* m) {
   if (!m) return AVL_OK;
+  if (m->ws.tail_stream) cudaStreamSynchronize(m->ws.tail_stream);
   ws_free(m->ws);
   cudaFree(m->feat); cudaFree(m->bf); cudaFree(m->row_norm); cudaFree(m->row_c); cudaFree(m->row_an);
   delete m;
@@ -503,8 +548,9 @@ int avl_sim_dense(avl_map* m, const float* queries, int32_t nq, const float* sca
   AVL_ARG(m != nullptr && out_scores != nullptr, "NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   QuerySetup qs;
-  int rc = setup_queries(m, queries, nq, scale, flags, 0, -1, s, &qs);
+  int rc = drain_tails(m, s);
   if (rc) return rc;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, -1, s, &qs))) return rc;
   if (m->n == 0) return AVL_OK;
   if (flags & AVL_ON_DEVICE)
     return launch_dense_exact(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map,
@@ -532,8 +578,9 @@ int avl_sim_screen_dense(avl_map* m, const float* queries, int32_t nq, int32_t c
   AVL_ARG(m != nullptr && out_scores != nullptr, "NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   QuerySetup qs;
-  int rc = setup_queries(m, queries, nq, nullptr, flags, cta_group, kModeDense, s, &qs);
+  int rc = drain_tails(m, s);
   if (rc) return rc;
+  if ((rc = setup_queries(m, queries, nq, nullptr, flags, cta_group, kModeDense, s, &qs))) return rc;
   if (m->n == 0) return AVL_OK;
   float* dst = out_scores;
   if (!(flags & AVL_ON_DEVICE))
@@ -570,6 +617,7 @@ int avl_sim_argmax(avl_map* m, const float* queries, int32_t nq, const float* sc
     stats->n_queries = nq;
   }
   if (m->n == 0) return AVL_OK;
+  if ((rc = drain_tails(m, s))) return rc;
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
   QuerySetup qs;
   if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeArgmax, s, &qs, /*fold_scale=*/true))) return rc;
@@ -671,11 +719,40 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     stats->dim = m->d;
     stats->n_queries = nq;
   }
+  // Pipelined form (AVL_PIPELINED, no stats): the tail of this call -- finalize, fallback, result copy -- goes to the
+  // map's tail stream and runs NEXT TO the following call's screen (the finalize keeps its arrays in global memory and
+  // fits beside a screen CTA).  Buffers alternate by the parity of the call; a half is reused only after its tail.
+  const bool pipelined = (flags & AVL_PIPELINED) && !stats && m->n > 0;
+  const int par = pipelined ? static_cast<int>(w.n_pipelined & 1u) : 0;
+  if (pipelined) {
+    if (w.tail_pending[par]) {   // the call two back used this half
+      AVL_CUDA(cudaStreamWaitEvent(s, w.ev_tail[par], 0));
+      w.tail_pending[par] = false;
+    }
+  } else if ((rc = drain_tails(m, s))) {
+    return rc;
+  }
   if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[0], s));
+  static const bool timeline = [] { const char* e = getenv("AVL_DEBUG_FLAGS"); return e && (atoi(e) & 128); }();
+  if (timeline && pipelined) {
+    for (int i = 0; i < 6; ++i)
+      if (!w.tl[par][i]) AVL_CUDA(cudaEventCreate(&w.tl[par][i]));
+    if (w.n_pipelined >= 2 && (w.n_pipelined % 7) == 2) {   // print the call two back (same parity), now complete
+      cudaEventSynchronize(w.tl[par][5]);
+      float t[6] = {0};
+      for (int i = 1; i < 6; ++i) cudaEventElapsedTime(&t[i], w.tl[par][0], w.tl[par][i]);
+      float gap = 0.f;
+      if (w.tl[par ^ 1][0]) cudaEventElapsedTime(&gap, w.tl[par][0], w.tl[par ^ 1][0]);
+      fprintf(stderr, "[avl timeline] head 0 | main start %.3f | main end %.3f | tail start %.3f | finalize end %.3f | tail end %.3f | next call's head starts %.3f ms\n",
+              t[1], t[2], t[3], t[4], t[5], gap);
+    }
+    AVL_CUDA(cudaEventRecord(w.tl[par][0], s));
+  }
   QuerySetup qs;
-  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeThresh, s, &qs))) return rc;
-  int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx;
-  float* d_score = (flags & AVL_ON_DEVICE) ? out_score : w.out_score;
+  if ((rc = setup_queries(m, queries, nq, scale, flags, 0, kModeThresh, s, &qs, false, par))) return rc;
+  const size_t out_half = static_cast<size_t>(par) * AVL_MAX_QUERIES * AVL_MAX_TOPK;
+  int64_t* d_idx = (flags & AVL_ON_DEVICE) ? out_idx : w.out_idx + out_half;
+  float* d_score = (flags & AVL_ON_DEVICE) ? out_score : w.out_score + out_half;
 
   const int64_t unit = qs.unit_rows;
   const int64_t total_units = (m->n + unit - 1) / unit;
@@ -690,9 +767,24 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
   const uint32_t fin_cap = 8192;
   const int grid = screen_grid(qs.cg, m->num_sms, static_cast<int>(std::min<int64_t>(total_units, 1 << 30)));
   const uint32_t bucket = std::min<uint32_t>(fin_cap, std::max<uint32_t>(128u, 4u * fin_cap / static_cast<uint32_t>(std::max(grid, 1))));
-  if ((rc = ensure_cands(m, static_cast<uint32_t>(std::max(grid, 1)) * bucket))) return rc;
+  const uint32_t cand_stride = static_cast<uint32_t>(std::max(grid, 1)) * bucket;   // entries per query
+  if ((rc = ensure_cands(m, pipelined ? 2 * cand_stride : cand_stride))) return rc;
   if ((rc = ensure_sample(m, static_cast<size_t>(std::max<int64_t>(n_sample, 1)) * nq))) return rc;
   if ((rc = ensure_fallback(m, k))) return rc;
+  if (pipelined && w.fin_scratch_elems < static_cast<size_t>(2) * AVL_MAX_QUERIES * 3 * fin_cap) {
+    if ((rc = drain_tails(m, s))) return rc;
+    AVL_CUDA(cudaStreamSynchronize(s));
+    cudaFree(w.fin_scratch);
+    w.fin_scratch = nullptr;
+    w.fin_scratch_elems = 0;
+    if ((rc = dev_alloc(&w.fin_scratch, static_cast<size_t>(2) * AVL_MAX_QUERIES * 3 * fin_cap, &m->bytes))) return rc;
+    w.fin_scratch_elems = static_cast<size_t>(2) * AVL_MAX_QUERIES * 3 * fin_cap;
+  }
+  uint32_t* cand_row = w.cand_row + static_cast<size_t>(par) * AVL_MAX_QUERIES * cand_stride;
+  float* cand_val = w.cand_val + static_cast<size_t>(par) * AVL_MAX_QUERIES * cand_stride;
+  uint32_t* bucket_cnt = w.bucket_cnt + static_cast<size_t>(par) * 256 * AVL_MAX_QUERIES;
+  uint32_t* cand_cnt = w.cand_cnt + par * 2 * AVL_MAX_QUERIES;
+  uint32_t* overflow = cand_cnt + AVL_MAX_QUERIES;
 
   ScreenParams p;
   if (m->n > 0) {
@@ -715,11 +807,12 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     base_params(m, qs, nq, normalize_map, &p);
     p.mode = kModeThresh;
     p.thr_t = w.thr_t;
-    p.cand_cnt = w.bucket_cnt;
-    p.cand_row = w.cand_row;
-    p.cand_val = w.cand_val;
+    p.cand_cnt = bucket_cnt;
+    p.cand_row = cand_row;
+    p.cand_val = cand_val;
     p.cand_bucket = bucket;
     const int slot = w.ring_n % 256;
+    if (timeline && pipelined) AVL_CUDA(cudaEventRecord(w.tl[par][1], s));
     if (g_profiling) {
       AVL_CUDA(cudaEventRecord(w.ev[1], s));
       AVL_CUDA(cudaEventRecord(w.ring_ev[2 * slot], s));
@@ -732,22 +825,46 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
     }
   }
   // phase C: exact re-score of the survivors, final order; totals and overflow flags per query
-  if ((rc = launch_topk_finalize(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, m->row_c,
-                                 m->row_an, w.q_bn, w.q_glob, normalize_map, k, w.bucket_cnt, m->n > 0 ? grid : 0,
-                                 bucket, w.cand_row, w.cand_val, fin_cap, d_idx, d_score, w.cand_cnt, w.overflow, s)))
-    return rc;
   // phase D: queries whose buckets overflowed (adversarial data, massive ties) are re-scored exactly -- decided on
   // the device: the kernel leaves at once when no flag is set, so the call needs no host round trip
-  if ((rc = launch_topk_fallback(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map, k,
-                                 w.overflow, w.fb_scratch, w.fb_tickets, d_idx, d_score, m->num_sms, s)))
+  cudaStream_t ts = s;   // stream of the tail
+  if (pipelined) {
+    ts = w.tail_stream;
+    if (timeline) AVL_CUDA(cudaEventRecord(w.tl[par][2], s));
+    AVL_CUDA(cudaEventRecord(w.ev_main[par], s));
+    AVL_CUDA(cudaStreamWaitEvent(ts, w.ev_main[par], 0));
+    if (timeline) AVL_CUDA(cudaEventRecord(w.tl[par][3], ts));
+  }
+  uint32_t* gscratch = pipelined ? w.fin_scratch + static_cast<size_t>(par) * AVL_MAX_QUERIES * 3 * fin_cap : nullptr;
+  if ((rc = launch_topk_finalize(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, m->row_c,
+                                 m->row_an, qs.q_bn, qs.q_glob, normalize_map, k, bucket_cnt, m->n > 0 ? grid : 0,
+                                 bucket, cand_row, cand_val, fin_cap, d_idx, d_score, cand_cnt, overflow, gscratch, ts)))
     return rc;
-  if (g_profiling) AVL_CUDA(cudaEventRecord(w.ev[3], s));
+  if (timeline && pipelined) AVL_CUDA(cudaEventRecord(w.tl[par][4], ts));
+  if ((rc = launch_topk_fallback(m->feat, m->n, m->d, qs.q_dev, nq, qs.scale_dev, m->row_norm, normalize_map, k,
+                                 overflow, w.fb_scratch, w.fb_tickets, d_idx, d_score, m->num_sms, ts)))
+    return rc;
+  if (timeline && pipelined) AVL_CUDA(cudaEventRecord(w.tl[par][5], ts));
+  if (g_profiling && !pipelined) AVL_CUDA(cudaEventRecord(w.ev[3], s));
   if (!(flags & AVL_ON_DEVICE)) {
-    AVL_CUDA(cudaMemcpyAsync(out_idx, d_idx, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, s));
-    AVL_CUDA(cudaMemcpyAsync(out_score, d_score, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, s));
+    AVL_CUDA(cudaMemcpyAsync(out_idx, d_idx, sizeof(int64_t) * nq * k, cudaMemcpyDeviceToHost, ts));
+    AVL_CUDA(cudaMemcpyAsync(out_score, d_score, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, ts));
+  }
+  if (pipelined) {
+    AVL_CUDA(cudaEventRecord(w.ev_tail[par], ts));
+    w.tail_pending[par] = true;
+    ++w.n_pipelined;
+    // the PREVIOUS call's results become ordered on `stream` here, behind this call's screen; this call's own results
+    // follow with the next call or with avl_map_flush
+    if (w.tail_pending[par ^ 1]) AVL_CUDA(cudaStreamWaitEvent(s, w.ev_tail[par ^ 1], 0));
+    if (!(flags & AVL_ON_DEVICE) && !(flags & AVL_ASYNC)) {
+      cudaError_t e = cudaStreamSynchronize(ts);
+      if (e != cudaSuccess) return check_watchdog(m, cuda_fail(e, "topk (pipelined)", __FILE__, __LINE__));
+    }
+    return AVL_OK;
   }
   const bool triage = m->n > 0 && (p.debug_flags & 64);
-  if (stats || triage) AVL_CUDA(cudaMemcpyAsync(w.pin, w.cand_cnt, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, cudaMemcpyDeviceToHost, s));
+  if (stats || triage) AVL_CUDA(cudaMemcpyAsync(w.pin, cand_cnt, sizeof(uint32_t) * 2 * AVL_MAX_QUERIES, cudaMemcpyDeviceToHost, s));
   // device-pointer calls without stats return here, asynchronously: results are ordered on `stream` like any kernel's
   if ((!(flags & AVL_ON_DEVICE) && !(flags & AVL_ASYNC)) || stats || triage) {
     cudaError_t e = cudaStreamSynchronize(s);
@@ -784,6 +901,17 @@ int avl_sim_topk(avl_map* m, const float* queries, int32_t nq, const float* scal
       cudaEventElapsedTime(&stats->ms_total, w.ev[0], w.ev[3]);
     }
   }
+  return AVL_OK;
+}
+
+int avl_map_flush(avl_map* m, void* stream) {
+  AVL_ARG(m != nullptr, "map is NULL");
+  return drain_tails(m, static_cast<cudaStream_t>(stream));
+}
+
+int avl_map_tail_stream(avl_map* m, void** out_stream) {
+  AVL_ARG(m != nullptr && out_stream != nullptr, "NULL argument");
+  *out_stream = m->ws.tail_stream;
   return AVL_OK;
 }
 
@@ -972,6 +1100,8 @@ int avl_fuse_topk(avl_map* ma, const float* qa, const float* scale_a, int normal
   AVL_ARG(combine >= AVL_FUSE_PRODUCT && combine <= AVL_FUSE_SUM, "unknown combine rule");
   int rc = scale_positive(scale_a, n_pairs, flags);
   if (rc == AVL_OK) rc = scale_positive(scale_b, n_pairs, flags);
+  if (rc == AVL_OK) rc = drain_tails(ma, static_cast<cudaStream_t>(stream));
+  if (rc == AVL_OK) rc = drain_tails(mb, static_cast<cudaStream_t>(stream));
   const bool force_exact = getenv("AVL_FUSE_EXACT") != nullptr;  // A/B and tests of the exact path
   const bool can_screen = rc == AVL_OK && !force_exact && ma != mb && ma->n >= 1024 &&
                           ma->n < (int64_t(1) << 32) - 1;

@@ -511,11 +511,15 @@ topk_finalize_kernel(const float* __restrict__ feat, int64_t n_rows, int32_t d, 
                      int32_t k, const uint32_t* __restrict__ bucket_cnt, int32_t grid, uint32_t cand_bucket,
                      const uint32_t* __restrict__ cand_row, const float* __restrict__ cand_val, uint32_t cand_cap,
                      int64_t* __restrict__ out_idx, float* __restrict__ out_score,
-                     uint32_t* __restrict__ cand_total, uint32_t* __restrict__ overflow_flags) {
+                     uint32_t* __restrict__ cand_total, uint32_t* __restrict__ overflow_flags, uint32_t* gscratch) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ uint8_t sm[];
-  uint32_t* Lk = reinterpret_cast<uint32_t*>(sm);
+  // `gscratch` (pipelined calls): the three per-candidate arrays live in global memory (L2-resident, 12 bytes x cand_cap
+  // per query) instead of shared memory, and the block has 256 threads: it then fits on an SM NEXT TO a CTA of the
+  // persistent screen kernel (which leaves ~15 KiB of shared memory and 22 k registers), so the finalize of one query
+  // batch runs while the next batch's screen streams the map -- slower per block, but off the critical path.
+  uint32_t* Lk = gscratch ? gscratch + static_cast<size_t>(blockIdx.x) * 3 * cand_cap : reinterpret_cast<uint32_t*>(sm);
   uint32_t* Ix = Lk + cand_cap;
   uint32_t* Uk = Ix + cand_cap;
   // 12 bytes per candidate = 96 KiB at 8192 candidates, 512 threads: TWO blocks per SM, so the 256 queries of a full
@@ -1363,6 +1367,15 @@ __global__ void fill_u32_kernel(uint32_t* p, int n, uint32_t v) {
 }  // namespace
 
 // =================================================================== launchers
+// Kernels that may share an SM with a CTA of the screen kernel (217 KiB of shared memory) ask for the maximum
+// shared-memory carveout too: an SM cannot change its L1 / shared split while blocks are resident, so a small kernel
+// that leaves it at the default split keeps the screen CTA out until it has drained (seen as a 2x slower head of the next
+// call when the tail of a pipelined call ran on the default carveout).
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 int launch_map_prepare(const float* feat, int64_t n, int32_t d, int32_t dpad, __nv_bfloat16* bf,
                        float* row_norm, float* row_c, float* row_an, float kappa, int f16, uint32_t* nonfinite,
                        int tiled, cudaStream_t s) {
@@ -1378,6 +1391,7 @@ int launch_query_prepare(const float* q, const float* fold_scale, int32_t nq, in
                          int32_t npad, __nv_bfloat16* bq, float* q_bn, float* q_glob, int f16, cudaStream_t s) {
   // q_glob: [0] rho, [1] max ||b||, [2] ticket of the last-block reduction (zero at allocation, re-armed by the
   // kernel), [4 .. 4 + 256) per-row ratios
+  prefer_max_shared(query_prepare_kernel);
   AVL_CUDA(launch_pdl(query_prepare_kernel, dim3(npad), dim3(128), 0, s, q, fold_scale, nq, d, dpad, bq, q_bn, q_glob + 4,
                       reinterpret_cast<uint32_t*>(q_glob), reinterpret_cast<uint32_t*>(q_glob) + 2, f16));
   AVL_CUDA(cudaGetLastError());
@@ -1421,6 +1435,7 @@ int launch_select_threshold(const float* sample_lb, int32_t n_sample, int64_t ld
     set_error("select_threshold: k too large");
     return AVL_ERR_ARG;
   }
+  prefer_max_shared(select_threshold_kernel);
   AVL_CUDA(launch_pdl(select_threshold_kernel, dim3(nq), dim3(kSelThreads), 0, s, sample_lb, n_sample, ld, k, thr_t));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
@@ -1433,17 +1448,28 @@ int launch_topk_finalize(const float* feat, int64_t n_rows, int32_t d, const flo
                          const float* q_bn, const float* q_glob, int normalize, int32_t k,
                          const uint32_t* bucket_cnt, int32_t grid, uint32_t cand_bucket, const uint32_t* cand_row,
                          const float* cand_val, uint32_t cand_cap, int64_t* out_idx, float* out_score,
-                         uint32_t* cand_total, uint32_t* overflow_flags, cudaStream_t s) {
+                         uint32_t* cand_total, uint32_t* overflow_flags, uint32_t* gscratch, cudaStream_t s) {
   if (grid > kFinMaxGrid) {
     set_error("topk_finalize: screen grid larger than kFinMaxGrid");
     return AVL_ERR_UNSUPPORTED;
+  }
+  prefer_max_shared(topk_finalize_kernel);
+  if (gscratch) {
+    // beside the screen kernel: 128 threads (8 k registers per block: two blocks still fit next to a screen CTA's
+    // 41.5 k -- with 256 threads the SMs that got two blocks had no room for the next call's sample-screen CTA, which
+    // then waited for the finalize and the overlap was lost), no dynamic shared memory
+    AVL_CUDA(launch_pdl(topk_finalize_kernel, dim3(nq), dim3(128), 0, s, feat, n_rows, d, q, scale, row_norm, row_c,
+                        row_an, q_bn, reinterpret_cast<const uint32_t*>(q_glob), normalize, k, bucket_cnt, grid, cand_bucket,
+                        cand_row, cand_val, cand_cap, out_idx, out_score, cand_total, overflow_flags, gscratch));
+    return AVL_OK;
   }
   const size_t smem = topk_finalize_smem(cand_cap);
   AVL_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   AVL_CUDA(launch_pdl(topk_finalize_kernel, dim3(nq), dim3(kFinThreads), smem, s, feat, n_rows, d, q, scale, row_norm, row_c,
                       row_an, q_bn, reinterpret_cast<const uint32_t*>(q_glob), normalize, k, bucket_cnt, grid, cand_bucket,
-                      cand_row, cand_val, cand_cap, out_idx, out_score, cand_total, overflow_flags));
+                      cand_row, cand_val, cand_cap, out_idx, out_score, cand_total, overflow_flags,
+                      static_cast<uint32_t*>(nullptr)));
   AVL_CUDA(cudaGetLastError());
   return AVL_OK;
 }
@@ -1462,6 +1488,7 @@ int launch_topk_fallback(const float* feat, int64_t n, int32_t d, const float* q
   group = std::min<int>(group, std::max<int>(1, 40960 / ((kFbThreads / 32) * k * 8)));
   const size_t smem = static_cast<size_t>(group) * d * 8 + static_cast<size_t>(kFbThreads / 32) * group * k * 8;
   AVL_CUDA(cudaFuncSetAttribute(topk_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  prefer_max_shared(topk_fallback_kernel);
   AVL_CUDA(launch_pdl(topk_fallback_kernel, dim3(2 * num_sms), dim3(kFbThreads), smem, s, feat, n, d, q, nq, scale, row_norm,
                       normalize, k, group, overflow_flags, static_cast<unsigned long long*>(scratch), tickets, out_idx, out_score));
   return AVL_OK;

@@ -179,18 +179,37 @@ class DeviceMap:
         return o
 
     # -- per-query top-k rows
-    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None, out=None, stats: bool = True):
+    def flush(self, stream=None) -> None:
+        """After pipelined top-k calls: make `stream` (default: torch's current stream) wait for their tails."""
+        sp = _stream_ptr(stream) if stream is not None else _current_torch_stream()
+        L.check(self._lib.avl_map_flush(self._h, sp))
+
+    def tail_stream(self):
+        """The stream the tails of pipelined top-k calls run on, as a torch.cuda.ExternalStream."""
+        import torch
+
+        p = C.c_void_p()
+        L.check(self._lib.avl_map_tail_stream(self._h, C.byref(p)))
+        return torch.cuda.ExternalStream(p.value)
+
+    def topk(self, queries, k: int, scale=None, normalize_map: bool = False, stream=None, out=None, stats: bool = True,
+             pipelined: bool = False):
         """out=(idx int64 (Q, k), score float32 (Q, k)) torch CUDA tensors: write there (device path, Q <= 256).
         With out= and stats=False the call is asynchronous: it only enqueues work on `stream` (no host round trip --
-        the exact fallback for overflowed queries is decided on the device) and `last_stats` is not updated."""
+        the exact fallback for overflowed queries is decided on the device) and `last_stats` is not updated.
+        pipelined=True (with out=, stats=False): AVL_PIPELINED -- the call's tail runs on `tail_stream()` next to the
+        following call's screen; its results are ordered on `stream` after the next pipelined call or `flush()`, and
+        queries / out must stay untouched until then."""
         q, s = self._queries(queries, scale)
         if out is not None:
             if not q.device or q.shape[0] > L.AVL_MAX_QUERIES:
                 raise ValueError("out= needs CUDA queries and at most 256 of them")
             st = L.IndexStats() if stats else None
+            fl = _flags(q, s) | (L.AVL_PIPELINED if (pipelined and not stats) else 0)
+            sp = _stream_ptr(stream) if stream is not None else (_current_torch_stream() if pipelined else None)
             L.check(self._lib.avl_sim_topk(self._h, q.ptr, q.shape[0], s.ptr, int(normalize_map), k,
                                            C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
-                                           _flags(q, s), _stream_ptr(stream), C.byref(st) if stats else None))
+                                           fl, sp, C.byref(st) if stats else None))
             if stats:
                 self.last_stats = st.as_dict()
             return out

@@ -164,9 +164,10 @@ class ShardedMap:
         if st["merged"][i] is not None:
             cur.wait_event(st["merged"][i])        # the exchange that last read this ring slot (3 batches ago)
         ti, tv = st["mine"][i]
-        self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv), stats=False)
         if self.world == 1:
+            self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv), stats=False)
             return PendingTopK(self._globalize_single(ti, tv), None)
+        self.local.topk(queries, k, scale=scale, normalize_map=normalize_map, out=(ti, tv), stats=False)
         st["scored"][i].record(cur)
         side = st["side"]
         side.wait_event(st["scored"][i])

@@ -702,11 +702,20 @@ def run_gpu(args):
     os_dev = torch.empty((NQ, TOPK), dtype=torch.float32, device=dev)
     launches_per_step = 6 + (1 if world > 1 else 0)   # query_prepare, sample screen, select, screen, finalize, fallback (+ exchange)
 
+
+    oi_ring_dev = [torch.empty((NQ, TOPK), dtype=torch.int64, device=dev) for _ in range(4)]
+    os_ring_dev = [torch.empty((NQ, TOPK), dtype=torch.float32, device=dev) for _ in range(4)]
+    # AVL_PIPELINED (the call's tail on the map's own stream, next to the following call's screen) is an opt-in: on B200
+    # the overlapped tail slows the power-limited screen by as much as it saves
+    pipe = L.AVL_PIPELINED if os.environ.get("AVL_BENCH_PIPELINE") == "1" else 0
+
     def value_step(i):
         if world == 1:
+            # every batch in flight has its own query and result buffers; avl_map_flush closes the region (a no-op
+            # unless the opt-in pipelined form is used)
             L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(qpool[i % 8].data_ptr()), NQ, None, 0, TOPK,
-                                     C.c_void_p(oi_dev.data_ptr()), C.c_void_p(os_dev.data_ptr()), L.AVL_ON_DEVICE,
-                                     C.c_void_p(stream.cuda_stream), None))
+                                     C.c_void_p(oi_ring_dev[i % 4].data_ptr()), C.c_void_p(os_ring_dev[i % 4].data_ptr()),
+                                     L.AVL_ON_DEVICE | pipe, C.c_void_p(stream.cuda_stream), None))
             return None
         return sm.topk_async(qpool[i % 8], TOPK)
 
@@ -728,6 +737,8 @@ def run_gpu(args):
             pend = value_step(i)
         if pend is not None:
             pend.result()          # the current stream waits for the last exchange: e1 closes the whole job
+        if world == 1:
+            L.check(lib.avl_map_flush(dmap._h, C.c_void_p(stream.cuda_stream)))   # ... and for the tails of every call
         e1.record(stream)
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -816,9 +827,9 @@ def run_gpu(args):
             if i >= 8:
                 e2e_done[i % 8].synchronize()
             L.check(lib.avl_sim_topk(dmap._h, C.c_void_p(q_host[i % 8].data_ptr()), NQ, None, 0, TOPK,
-                                     C.c_void_p(oi_ring[i % 8].data_ptr()), C.c_void_p(os_ring[i % 8].data_ptr()), L.AVL_ASYNC,
-                                     C.c_void_p(stream.cuda_stream), None))
-            e2e_done[i % 8].record(stream)
+                                     C.c_void_p(oi_ring[i % 8].data_ptr()), C.c_void_p(os_ring[i % 8].data_ptr()),
+                                     L.AVL_ASYNC | pipe, C.c_void_p(stream.cuda_stream), None))
+            e2e_done[i % 8].record(tail if pipe else stream)   # the D2H copy of the result is the last thing on that stream
         else:
             q_dev.copy_(q_host[i % 8], non_blocking=True)
             mi, mv = sm.topk(q_dev, TOPK)
@@ -827,6 +838,7 @@ def run_gpu(args):
             torch.cuda.synchronize()
 
     e2e_done = [torch.cuda.Event() for _ in range(8)]
+    tail = dmap.tail_stream() if world == 1 else None
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
     barrier()

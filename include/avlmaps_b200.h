@@ -50,6 +50,15 @@ extern "C" {
                          not be touched until the stream has passed this call (cudaStreamSynchronize / an event): the way
                          a serving loop keeps several query batches in flight. */
 
+#define AVL_PIPELINED 32 /* avl_sim_topk (stats == NULL): the tail of the call -- exact re-score of the survivors, the
+                            device-side fallback and, with host pointers, the copy of the result -- is enqueued on the
+                            map's own tail stream, where it runs next to the FOLLOWING call's screen kernel (a serving
+                            loop hides ~50 us of a ~0.96 ms step that way).  The results of a call are ordered on `stream`
+                            only after the NEXT pipelined call on the map, or after avl_map_flush(map, stream); query,
+                            scale and output buffers of a call must stay untouched until then, so consecutive calls take
+                            distinct buffers.  Work that should follow a call's results directly (the peer exchange of a
+                            slab-sharded map) can be enqueued on avl_map_tail_stream instead. */
+
 #define AVL_MAP_F16 4 /* avl_map_create: keep the tensor-core copy of the map (and of the queries) in fp16 instead of
                          bf16.  Same tcgen05 kind::f16 rate and bytes; the rounding residual, hence the rigorous error
                          band that decides what is re-scored exactly, is 8x smaller.  Results are identical either
@@ -142,6 +151,11 @@ int avl_sim_argmax(avl_map* map, const float* queries, int32_t nq, const float* 
 int avl_sim_topk(avl_map* map, const float* queries, int32_t nq, const float* scale, int normalize_map,
                  int32_t k, int64_t* out_idx, float* out_score, int flags, void* stream,
                  avl_index_stats* stats);
+
+/* Pipelined calls (AVL_PIPELINED): make `stream` wait for the tails of all earlier calls on the map -- their results
+ * are valid for work enqueued on `stream` afterwards.  avl_map_tail_stream: the cudaStream_t those tails run on. */
+int avl_map_flush(avl_map* map, void* stream);
+int avl_map_tail_stream(avl_map* map, void** out_stream);
 
 /* With avl_set_profiling(1) every avl_sim_topk call records a CUDA-event pair around its main screen launch into a
  * ring of 256; this reads the times (ms, oldest first) of the calls since the last read into out_ms[0..cap) and

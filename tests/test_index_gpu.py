@@ -465,3 +465,32 @@ def test_argmax_over_more_than_256_queries_matches_numpy(eng):
     got = m.argmax(torch.from_numpy(q).cuda())
     assert got.dtype == torch.int32 and np.array_equal(got.cpu().numpy(), ref)
     m.close()
+
+
+def test_pipelined_topk_calls_return_the_same_results(eng):
+    """AVL_PIPELINED: the tail of a call (finalize beside the next call's screen, fallback) runs on the map's tail stream.
+    A run of pipelined calls with different query batches, ring buffers and a flush must return what the plain calls
+    return -- including a batch whose queries all overflow into the device-side fallback."""
+    import torch
+
+    feat, _ = synth.index_inputs(60_000, 512, 1, seed=12)
+    feat[40_000:] = feat[7]                              # 20 000 copies of one row: queries near it overflow
+    m = eng.DeviceMap(feat)
+    batches = [synth.index_inputs(1, 512, 256, seed=50 + i)[1] for i in range(5)]
+    batches[2][:40] = feat[7] / np.linalg.norm(feat[7])   # 40 queries aligned with the duplicated row -> fallback
+    want = [m.topk(b, 16) for b in batches]
+    qd = [torch.from_numpy(b).cuda() for b in batches]
+    outs = [(torch.empty((256, 16), dtype=torch.int64, device="cuda"), torch.empty((256, 16), dtype=torch.float32, device="cuda"))
+            for _ in batches]
+    for rep in range(2):
+        for q, o in zip(qd, outs):
+            m.topk(q, 16, out=o, stats=False, pipelined=True)
+        m.flush()
+        torch.cuda.synchronize()
+        for (wi, wv), (oi, ov) in zip(want, outs):
+            assert np.array_equal(oi.cpu().numpy(), wi) and np.array_equal(ov.cpu().numpy(), wv)
+    # a plain call right after pipelined ones (it must wait for their tails by itself)
+    m.topk(qd[0], 16, out=outs[0], stats=False, pipelined=True)
+    i2, v2 = m.topk(batches[1], 16)
+    assert np.array_equal(i2, want[1][0]) and np.array_equal(v2, want[1][1])
+    m.close()

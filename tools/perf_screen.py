@@ -99,7 +99,7 @@ def child(steps: int, n: int, d: int, nq: int, k: int, mode: str):
     smp.join(timeout=1)
     chk = int(oi.sum().item()) if mode == "topk" else int(oa.sum().item())
     # the same calls enqueued asynchronously (device pointers, no stats): the pipelined step the bench's `value` times
-    async_ms = async_scr = None
+    async_ms = async_scr = pipe_ms = pipe_scr = None
     if mode == "topk":
         time.sleep(0.5)
         for _ in range(3):
@@ -120,12 +120,33 @@ def child(steps: int, n: int, d: int, nq: int, k: int, mode: str):
         L.check(lib.avl_map_screen_times(m, buf, 256, C.byref(nn)))
         async_scr = statistics.median(buf[i] for i in range(nn.value)) if nn.value else None
         assert int(oi.sum().item()) == chk, "asynchronous calls returned a different result"
+        # ... and pipelined: the tail of a call runs next to the following call's screen
+        outs = [(torch.empty_like(oi), torch.empty_like(osc)) for _ in range(4)]
+        for _ in range(3):
+            L.check(lib.avl_sim_topk(m, C.c_void_p(q.data_ptr()), nq, None, 0, k, C.c_void_p(outs[0][0].data_ptr()),
+                                     C.c_void_p(outs[0][1].data_ptr()), L.AVL_ON_DEVICE | L.AVL_PIPELINED, None, None))
+        L.check(lib.avl_map_flush(m, None))
+        torch.cuda.synchronize()
+        L.check(lib.avl_map_screen_times(m, buf, 256, C.byref(nn)))
+        e0.record()
+        for i in range(steps):
+            L.check(lib.avl_sim_topk(m, C.c_void_p(q.data_ptr()), nq, None, 0, k, C.c_void_p(outs[i % 4][0].data_ptr()),
+                                     C.c_void_p(outs[i % 4][1].data_ptr()), L.AVL_ON_DEVICE | L.AVL_PIPELINED, None, None))
+        L.check(lib.avl_map_flush(m, None))
+        e1.record()
+        torch.cuda.synchronize()
+        pipe_ms = e0.elapsed_time(e1) / steps
+        L.check(lib.avl_map_screen_times(m, buf, 256, C.byref(nn)))
+        pipe_scr = statistics.median(buf[i] for i in range(nn.value)) if nn.value else None
+        for o in outs[:min(4, steps)]:
+            assert int(o[0].sum().item()) == chk, "pipelined calls returned a different result"
     out = {"steps": steps, "ms_screen_min": min(scr), "ms_screen_med": statistics.median(scr),
            "ms_total_med": statistics.median(tot), "wall_ms": wall, "cands": int(st.n_candidates),
            "flagged": int(st.n_flagged), "fallback": int(st.n_fallback_queries), "cg": int(st.cta_group), "checksum": chk,
            "sm_mhz_med": statistics.median(smp.samples) if smp.samples else None,
            "sm_mhz_min": min(smp.samples) if smp.samples else None,
-           "power_w_max": max(smp.power) if smp.power else None, "async_step_ms": async_ms, "async_screen_med": async_scr}
+           "power_w_max": max(smp.power) if smp.power else None, "async_step_ms": async_ms, "async_screen_med": async_scr,
+           "pipelined_step_ms": pipe_ms, "pipelined_screen_med": pipe_scr}
     lib.avl_map_destroy(m)
     print(json.dumps(out))
 
@@ -168,7 +189,8 @@ def main():
                 print(f"{name:>14s} steps={steps:4d}: screen min {r['ms_screen_min']:.4f} med {r['ms_screen_med']:.4f}  call {r['ms_total_med']:.4f}"
                       f"  wall {r['wall_ms']:.4f}  clk {r['sm_mhz_med']} (min {r['sm_mhz_min']})  P {r['power_w_max']}"
                       f"  cands {r['cands']} fb {r['fallback']} chk {r['checksum']}"
-                      f"  | async step {r.get('async_step_ms') or 0:.4f} screen {r.get('async_screen_med') or 0:.4f}", flush=True)
+                      f"  | async step {r.get('async_step_ms') or 0:.4f} screen {r.get('async_screen_med') or 0:.4f}"
+                      f"  | pipelined step {r.get('pipelined_step_ms') or 0:.4f} screen {r.get('pipelined_screen_med') or 0:.4f}", flush=True)
     if a.out:
         Path(a.out).parent.mkdir(parents=True, exist_ok=True)
         Path(a.out).write_text(json.dumps(rows, indent=1))
