@@ -154,13 +154,14 @@ def test_frame_marshalling_without_a_device():
     # uint16 depth = millimetres -> flag for the kernel's / 1000.0
     _, flags16, _ = engine._fill_frame(depth.astype(np.uint16), feat, k, k, k, tf, None, None, L.FEAT_CHW, 0.1, 100.0, dim=5)
     assert flags16 == L.AVL_DEPTH_U16_MM
-    # float16 features are handed over as they are (AVL_FEAT_F16, CHW only); float32 features carry no such flag
+    # float16 features are handed over as they are (AVL_FEAT_F16), channel-major or pixel-major; float32 carries no flag
     feat16 = feat.astype(np.float16)
     fr16, flagsf16, keep16 = engine._fill_frame(depth, feat16, k, k, k, tf, None, sidx, L.FEAT_CHW, 0.1, 6.0, dim=5)
     assert flagsf16 == L.AVL_FEAT_F16 and keep16[1].keep.dtype == np.float16 and fr16.feat == feat16.ctypes.data
     assert (fr16.fh, fr16.fw) == (fr.fh, fr.fw) and flags == 0
-    with pytest.raises(ValueError, match="CHW layout only"):
-        engine._fill_frame(depth, np.zeros((3, 4, 5), np.float16), k, k, k, tf, None, sidx, L.FEAT_HWC, 0.1, 6.0, dim=5)
+    hwc16 = np.zeros((3, 4, 5), np.float16)       # pixel-major fp16 rows: the hand-off of an encoder that stays on the GPU
+    frh, flagsh, keeph = engine._fill_frame(depth, hwc16, k, k, k, tf, None, sidx, L.FEAT_HWC, 0.1, 6.0, dim=5)
+    assert flagsh == L.AVL_FEAT_F16 and (frh.fh, frh.fw, frh.feat_layout) == (3, 4, L.FEAT_HWC) and frh.feat == hwc16.ctypes.data
     # sample_idx=None means every pixel (NULL pointer); an EMPTY list must stay distinguishable (non-NULL, 0 samples)
     fr_all, _, _ = engine._fill_frame(depth, feat, k, k, k, tf, None, None, L.FEAT_CHW, 0.1, 6.0, dim=5)
     fr_none, _, _ = engine._fill_frame(depth, feat, k, k, k, tf, None, sidx[:0], L.FEAT_CHW, 0.1, 6.0, dim=5)
