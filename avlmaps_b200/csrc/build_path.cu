@@ -49,7 +49,9 @@ struct FrameGeom {
 // Up to kMaxBatch frames per launch triple (geometry, id scan, scatter): the samples of the frames are simply
 // concatenated -- the first-touch key (frame_seq << 32 | position in the frame's sample list) already orders them.
 // Passed by value as a __grid_constant__ kernel parameter (< 4 KiB), so a batch costs no upload.
-constexpr int kMaxBatch = 8;
+constexpr int kMaxBatch = 16;  // 7.7 KiB of kernel parameters (CUDA >= 12.1 allows 32 KiB on sm_70+).  8 was enough on the GPUs
+                               // next to the host cores; on the far socket of an 8-GPU box a launch costs ~50 us of
+                               // host time, and 3 launches per 8 frames left those ranks of a slab build host-bound
 struct FrameBatch {
   FrameGeom g[kMaxBatch];
   const float* depth[kMaxBatch];
@@ -61,7 +63,7 @@ struct FrameBatch {
   uint32_t frame_seq0;            // frame_seq of g[0]
   int32_t feat_f16;               // feat[] point at __half rows (pixel-major fp16 hand-off), not float
 };
-static_assert(sizeof(FrameBatch) <= 4000, "FrameBatch must fit the kernel parameter space");
+static_assert(sizeof(FrameBatch) <= 16000, "FrameBatch must fit the kernel parameter space");
 
 __device__ __forceinline__ int batch_frame_of(const FrameBatch& b, int gidx) {
   int f = 0;

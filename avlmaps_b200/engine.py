@@ -612,7 +612,7 @@ class DeviceBuilder:
     def add_frames(self, frames, stream=None):
         """Several consecutive frames in one call: `frames` is a list of dicts with add_frame's arguments
         (depth, feat, kinv, k, kfeat, tf and optionally rgb, sample_idx, feat_layout, min_depth, max_depth).  With torch
-        CUDA tensors and pixel-major features up to 8 frames share one launch triple; same result as a loop."""
+        CUDA tensors and pixel-major features up to 16 frames share one launch triple; same result as a loop."""
         if len(frames) == 0:
             return
         self.add_prepared(PreparedFrames(self, frames), stream=stream)

@@ -252,7 +252,7 @@ int avl_builder_destroy(avl_builder* b);
  * Frames must be added in the reference's frame order. */
 int avl_builder_add_frame(avl_builder* b, const avl_frame* frame, int flags, void* stream);
 
-/* Several consecutive frames in one call.  With device pointers and pixel-major features the samples of up to 8
+/* Several consecutive frames in one call.  With device pointers and pixel-major features the samples of up to 16
  * frames are concatenated into ONE geometry / id-scan / scatter launch triple (the first-touch key already orders
  * them by frame, then sample), which amortises the launch and tail cost of the small kernels; the result is
  * identical to n_frames avl_builder_add_frame calls.  Host pointers or AVL_FEAT_CHW fall back to that loop. */

@@ -366,9 +366,9 @@ def test_full_size_c4_properties(eng):
     assert np.all(a["weight"] > 0) and np.allclose(a["weight"], c["weight"], rtol=1e-4)
 
 
-@pytest.mark.parametrize("n_frames", [1, 5, 8, 11])
+@pytest.mark.parametrize("n_frames", [1, 5, 8, 11, 16, 19])
 def test_batched_frames_equal_frame_by_frame(eng, n_frames):
-    """avl_builder_add_frames: up to 8 frames share one geometry / id-scan / scatter launch triple.  ids, positions,
+    """avl_builder_add_frames: up to 16 frames share one geometry / id-scan / scatter launch triple.  ids, positions,
     accepted-point counts are identical to a loop of add_frame, and both match the C oracle; includes a frame
     without samples in the middle and frames with different sample counts."""
     import torch

@@ -58,7 +58,7 @@ def main():
     vh = int(cam_h / cs)
     stream = torch.cuda.current_stream()
 
-    batch = int(os.environ.get("AVL_BATCH", "8"))
+    batch = int(os.environ.get("AVL_BATCH", "16"))
     fr = [dict(depth=depths[i % 4], feat=pool[i % 4], kinv=kinv, k=calib, kfeat=kfeat, tf=tfs[i], sample_idx=sidx[i % 4],
                feat_layout=L.FEAT_HWC) for i in range(frames)]
 
@@ -66,7 +66,7 @@ def main():
 
     def feed(b, prep=None, start=0):
         # the 4 depth / feature / sample buffers are a fixed ring (an encoder's output slots): marshal the frame
-        # descriptors once, then up to 8 frames per launch triple (avl_builder_add_frames)
+        # descriptors once, then up to 16 frames per launch triple (avl_builder_add_frames)
         prep = prep or b.prepare_frames(fr)
         for i in range(start, frames, batch):
             b.add_prepared(prep, i, min(batch, frames - i), stream=stream)
