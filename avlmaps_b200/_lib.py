@@ -23,6 +23,7 @@ AVL_PIPELINED = 32
 AVL_FEAT_F16 = 8
 AVL_MAX_QUERIES = 256
 AVL_MAX_TOPK = 128
+AVL_MAX_BATCH = 16     # frames per launch triple (kMaxBatch in csrc/build_path.cu)
 FUSE_PRODUCT, FUSE_MAX, FUSE_SUM = 0, 1, 2
 FEAT_CHW, FEAT_HWC = 0, 1
 
@@ -37,7 +38,7 @@ EXPORTS = [
     "avl_builder_num_accepted", "avl_builder_h2d_bytes", "avl_builder_export", "avl_builder_to_map",
     "avl_builder_create_global", "avl_builder_num_rejected_oob",
     "avl_bounds_create", "avl_bounds_destroy", "avl_bounds_add_frame", "avl_bounds_get",
-    "avl_builder_set_slab", "avl_builder_skip_frames", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
+    "avl_builder_set_slab", "avl_builder_skip_frames", "avl_builder_reserve", "avl_builder_export_keys", "avl_rank_keys", "avl_builder_import", "avl_builder_add_frames",
     "avl_heat_planar", "avl_heat2d_normalize_lift",
     "avl_p2p_create", "avl_p2p_handle_bytes", "avl_p2p_local_handle", "avl_p2p_connect", "avl_p2p_exchange_merge",
     "avl_p2p_status", "avl_p2p_destroy",
@@ -127,6 +128,7 @@ def load() -> C.CDLL:
     lib.avl_builder_num_voxels.argtypes = [vp, C.POINTER(i64), vp]
     lib.avl_builder_num_accepted.argtypes = [vp, C.POINTER(i64), vp]
     lib.avl_builder_skip_frames.argtypes = [vp, i32]
+    lib.avl_builder_reserve.argtypes = [vp, i64, vp]
     lib.avl_builder_h2d_bytes.argtypes = [vp, C.POINTER(i64)]
     lib.avl_builder_export.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
     lib.avl_builder_to_map.argtypes = [vp, vp, C.POINTER(vp)]

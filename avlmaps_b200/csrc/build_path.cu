@@ -1017,6 +1017,30 @@ struct BatchItem {
   bool feat_f16 = false;   // feat points at pixel-major __half rows
 };
 
+// per-sample scratch of one launch triple (cell, feature pixel, colour pixel, alpha, wrap flag) + the scan's block state;
+// grown (never shrunk) to the largest batch seen, or ahead of time through avl_builder_reserve
+int grow_scratch(avl_builder* b, int64_t n_samples, cudaStream_t s) {
+  if (b->scratch_samples >= n_samples) return AVL_OK;
+  cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
+  cudaFree(b->block_cnt); cudaFree(b->scan_state);
+  b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
+  b->scan_state = nullptr;
+  b->scratch_samples = 0;
+  const size_t n = static_cast<size_t>(n_samples);
+  const size_t nb = (n + kScanBlock - 1) / kScanBlock;
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_cell), n * sizeof(int32_t)));
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_fpix), n * sizeof(int32_t)));
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_rgbpix), n * sizeof(int32_t)));
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_alpha), n * sizeof(float)));
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_wrap), n));
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->block_cnt), nb * sizeof(uint32_t)));
+  AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->scan_state), nb * sizeof(unsigned long long)));
+  AVL_CUDA(cudaMemsetAsync(b->scan_state, 0xff, nb * sizeof(unsigned long long), s));
+  if (!b->ticket) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->ticket), sizeof(uint32_t)));
+  b->scratch_samples = n_samples;
+  return AVL_OK;
+}
+
 // geometry -> ordered id scan -> scatter for up to kMaxBatch frames whose inputs are on the device
 // phase: 1 = geometry only (first-touch keys, per-sample cell / feature pixel / alpha), 2 = id scan + scatter of a
 // batch whose geometry ran, 3 = both.  The split lets a host-resident frame learn WHICH feature pixels it needs
@@ -1044,24 +1068,7 @@ int launch_batch(avl_builder* b, const BatchItem* items, int nf, int flags, cuda
   const int32_t n_samples = static_cast<int32_t>(total);
   int rc;
   // ---- scratch
-  if ((phase & 1) && b->scratch_samples < n_samples) {
-    cudaFree(b->s_cell); cudaFree(b->s_fpix); cudaFree(b->s_rgbpix); cudaFree(b->s_alpha); cudaFree(b->s_wrap);
-    cudaFree(b->block_cnt); cudaFree(b->scan_state);
-    b->s_cell = b->s_fpix = b->s_rgbpix = nullptr; b->s_alpha = nullptr; b->s_wrap = nullptr; b->block_cnt = nullptr;
-    b->scan_state = nullptr;
-    b->scratch_samples = 0;
-    const size_t n = static_cast<size_t>(n_samples);
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_cell), n * sizeof(int32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_fpix), n * sizeof(int32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_rgbpix), n * sizeof(int32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_alpha), n * sizeof(float)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->s_wrap), n));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->block_cnt), ((n + kScanBlock - 1) / kScanBlock) * sizeof(uint32_t)));
-    AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->scan_state), ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long)));
-    AVL_CUDA(cudaMemsetAsync(b->scan_state, 0xff, ((n + kScanBlock - 1) / kScanBlock) * sizeof(unsigned long long), s));
-    if (!b->ticket) AVL_CUDA(cudaMalloc(reinterpret_cast<void**>(&b->ticket), sizeof(uint32_t)));
-    b->scratch_samples = n_samples;
-  }
+  if ((phase & 1) && (rc = grow_scratch(b, n_samples, s))) return rc;
   if ((phase & 1) && (rc = ensure_capacity(b, n_samples, s))) return rc;
 
   for (int i = 0; i < nf; ++i) {
@@ -1326,6 +1333,11 @@ int avl_builder_skip_frames(avl_builder* b, int32_t n_frames) {
   AVL_ARG(b != nullptr && n_frames >= 0, "invalid argument");
   b->frame_seq += static_cast<uint32_t>(n_frames);  // the skipped frames keep their place in the (frame, sample) order
   return AVL_OK;
+}
+
+int avl_builder_reserve(avl_builder* b, int64_t samples_per_call, void* stream) {
+  AVL_ARG(b != nullptr && samples_per_call >= 0 && samples_per_call < (int64_t(1) << 31), "invalid argument");
+  return grow_scratch(b, samples_per_call, static_cast<cudaStream_t>(stream));
 }
 
 int avl_builder_destroy(avl_builder* b) {

@@ -621,7 +621,16 @@ class DeviceBuilder:
         """Marshal a list of frame dicts (see add_frames) once.  For producers that write into a fixed ring of device
         buffers (an encoder's output slots): only the pose changes per frame -- `PreparedFrames.set_tf(i, tf)` -- and
         `add_prepared` then costs one ctypes call instead of ~25 us of Python per frame."""
-        return PreparedFrames(self, frames)
+        prep = PreparedFrames(self, frames)
+        if prep.n and (prep.flags & L.AVL_ON_DEVICE):
+            # scratch for the largest call add_prepared can make, now -- not in the middle of the frame loop
+            per_frame = max((f.n_samples if f.sample_idx else f.h * f.w) for f in prep.arr[:prep.n])
+            self.reserve(min(prep.n, L.AVL_MAX_BATCH) * per_frame)
+        return prep
+
+    def reserve(self, samples_per_call: int, stream=None) -> None:
+        """Allocate the per-sample scratch for calls of up to `samples_per_call` samples ahead of time."""
+        L.check(self._lib.avl_builder_reserve(self._h, int(samples_per_call), _stream_ptr(stream)))
 
     def add_prepared(self, prepared: "PreparedFrames", start: int = 0, count: Optional[int] = None, stream=None):
         n = prepared.n - start if count is None else count

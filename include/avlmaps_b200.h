@@ -264,6 +264,12 @@ int avl_builder_add_frames(avl_builder* b, const avl_frame* frames, int32_t n_fr
  * keep their frame numbers. */
 int avl_builder_skip_frames(avl_builder* b, int32_t n_frames);
 
+/* Allocate the per-sample scratch of a launch triple for calls of up to samples_per_call samples (the sum over the
+ * frames of one avl_builder_add_frames call) ahead of time.  Without it the scratch grows -- cudaFree + cudaMalloc,
+ * which synchronise the device -- inside the first call that needs more, i.e. somewhere in the frame loop of a slab
+ * build whose first frames are skipped.  No reference counterpart (the reference allocates per frame in numpy). */
+int avl_builder_reserve(avl_builder* b, int64_t samples_per_call, void* stream);
+
 /* voxels created so far (max_id, vlmap_builder.py:164-170); synchronises the stream. */
 int avl_builder_num_voxels(avl_builder* b, int64_t* n, void* stream);
 /* points that passed the depth / grid / feature-bounds tests so far (P_acc of SURVEY 8d). */
