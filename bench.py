@@ -1051,6 +1051,9 @@ def run_gpu(args):
         roofline["build_scatter"] = bld["roofline"]
         e2e["build"] = bld.get("e2e")
         line["config"]["workload_build"] = bld.get("workload")
+    if build_sharded is not None:
+        # N > 1: the strong-scaling line of the slab-sharded build (one map, rows split over the ranks)
+        roofline["build_slab_sharded"] = build_sharded
     if cb is not None:
         if bld and "cpu_baseline" in bld:
             cb["build"] = bld["cpu_baseline"]

@@ -444,3 +444,40 @@ def test_frames_without_valid_depth_and_non_finite_depths(eng):
     assert_build_equal(out, ref)
     assert b.num_accepted == ref["num_accepted"]
     b.close()
+
+
+def test_scratch_reserved_ahead_or_grown_in_the_loop_builds_the_same_map(eng):
+    """avl_builder_reserve only moves the scratch allocation out of the frame loop: a builder whose scratch was
+    reserved for the largest call, one whose reservation is too small (grows inside add_frames) and one that never
+    reserved produce identical maps; a negative size is an argument error."""
+    import torch
+
+    n_frames = 6
+    cfg, poses, depths, rgbs, feats, sidx = random_scene(n_frames, 60, 80, 49, 65, 16, 48, 0.1, 1.6,
+                                                         [40, 0, 40, 0, 40, 30, 0, 0, 1], 2, seed=5, radius=0.3)
+    ref = O.build_map(cfg, poses, depths, rgbs, feats, sidx, capacity=48 * 48 * 16)
+    cs, gs = cfg["cell_size"], cfg["grid_size"]
+    vh = int(cfg["pose_info"]["camera_height"] / cs)
+    tfs, calib, kinv = scene_mats(cfg, poses)
+    frames = [dict(depth=torch.from_numpy(depths[i]).cuda(),
+                   feat=torch.from_numpy(np.ascontiguousarray(feats[i][0].transpose(1, 2, 0))).cuda(), kinv=kinv, k=calib,
+                   kfeat=O.get_sim_cam_mat(49, 65), tf=tf, rgb=torch.from_numpy(rgbs[i]).cuda(),
+                   sample_idx=torch.from_numpy(sidx[i]).cuda(), feat_layout=1) for i, tf in enumerate(tfs)]
+    total = sum(int(s.size) for s in sidx)
+    outs = []
+    for reserve in (None, 7, total, 4 * total):
+        b = eng.DeviceBuilder(gs, vh, cs, 16)
+        if reserve is not None:
+            b.reserve(reserve)
+        b.add_frames(frames[:2])
+        b.add_frames(frames[2:])
+        assert b.num_accepted == ref["num_accepted"]
+        outs.append(b.export())
+        if reserve == total:
+            with pytest.raises(Exception):
+                b.reserve(-1)
+        b.close()
+    assert_build_equal(outs[0], ref)
+    for o in outs[1:]:
+        assert np.array_equal(o["grid_pos"], outs[0]["grid_pos"]) and np.array_equal(o["occupied_ids"], outs[0]["occupied_ids"])
+        assert np.allclose(o["grid_feat"], outs[0]["grid_feat"], rtol=1e-4, atol=1e-6)
