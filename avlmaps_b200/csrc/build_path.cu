@@ -1337,7 +1337,11 @@ int avl_builder_skip_frames(avl_builder* b, int32_t n_frames) {
 
 int avl_builder_reserve(avl_builder* b, int64_t samples_per_call, void* stream) {
   AVL_ARG(b != nullptr && samples_per_call >= 0 && samples_per_call < (int64_t(1) << 31), "invalid argument");
-  return grow_scratch(b, samples_per_call, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = grow_scratch(b, samples_per_call, s);
+  if (rc) return rc;
+  AVL_CUDA(cudaStreamSynchronize(s));  // a set-up call: the scan state is initialised before ANY stream's first frame
+  return AVL_OK;
 }
 
 int avl_builder_destroy(avl_builder* b) {
