@@ -264,3 +264,68 @@ def test_balanced_row_bounds_tile_the_grid_and_even_out_the_points():
     b8 = balanced_row_bounds(frames, 256, 0.05, 8)
     widths = [hi - lo for lo, hi in b8]
     assert max(widths) > 2 * min(widths)       # the centre slabs are much narrower than the edge slabs
+
+
+def test_prepared_frames_are_fed_as_runs_and_skipped_frames_keep_their_numbers():
+    """ShardedBuilder.add_prepared: frames whose frustum cannot reach the slab are counted (skip_frames), the others go
+    to the local builder in runs, in order, so that every frame keeps its number in the (frame, sample) first-touch
+    order; whatever the batch boundaries, the calls cover each frame exactly once.  A skipped frame really has no
+    point in the slab (rows by the reference's arithmetic)."""
+    from types import SimpleNamespace
+
+    from avlmaps_b200.sharded import ShardedBuilder
+
+    class Recorder:
+        grid_shape, cs, mode = (256, 256, 32), 0.05, 0
+
+        def __init__(self):
+            self.calls, self.seq = [], 0
+
+        def set_slab(self, lo, hi):
+            self.slab = (lo, hi)
+
+        def prepare_frames(self, frames):
+            return SimpleNamespace(n=len(frames), frames=frames)
+
+        def add_prepared(self, prep, start, count, **kw):
+            assert count > 0
+            self.calls.append(("add", self.seq, start, count))
+            self.seq += count
+
+        def skip_frames(self, n):
+            self.calls.append(("skip", self.seq, None, n))
+            self.seq += n
+
+    cfg = synth.map_config(256, 0.05, 1.6, [320, 0, 320, 0, 320, 240, 0, 0, 1], 1)
+    b2c, bt = O.setup_transforms(cfg["pose_info"])
+    tfs = O.frame_transforms(synth.circle_poses(60, radius=2.0), b2c, bt)
+    kinv = np.linalg.inv(np.array(cfg["cam_calib_mat"], np.float64).reshape(3, 3))
+    depth = np.zeros((480, 640), np.float32)
+    frames = [dict(depth=depth, kinv=kinv, tf=tf) for tf in tfs]
+    rng = np.random.default_rng(1)
+    for bounds in ((0, 54), (120, 141), (202, 256)):
+        for batch in (1, 7, 16):
+            rec = Recorder()
+            sb = ShardedBuilder(rec, row_bounds=bounds)
+            assert rec.slab == bounds
+            prep = sb.prepare_frames(frames)
+            for i in range(0, 60, batch):
+                sb.add_prepared(prep, i, min(batch, 60 - i), stream=None)
+            assert rec.seq == 60
+            covered = []
+            for kind, seq, start, n in rec.calls:
+                covered += list(range(seq, seq + n))
+                if kind == "add":
+                    assert start == seq                       # the frame number on the device == its index in the list
+                    assert all(prep.touches[start:start + n])
+                else:
+                    assert not any(prep.touches[seq:seq + n])
+            assert covered == list(range(60))
+            assert getattr(sb, "n_skipped", 0) == sum(1 for t in prep.touches if not t)
+        assert 0 < sum(prep.touches) < 60 or bounds == (120, 141)
+        for i in np.nonzero(~np.array(prep.touches))[0]:
+            u, v = rng.integers(0, 640, 2000) + 0.5, rng.integers(0, 480, 2000) + 0.5
+            z = rng.uniform(0.1001, 5.9999, 2000)
+            p = (kinv @ np.stack([u, v, np.ones_like(u)])) * z
+            rows = (128 - np.trunc((tfs[i][0, :3] @ p + tfs[i][0, 3]) / 0.05)).astype(np.int64)
+            assert not np.any((rows >= bounds[0]) & (rows < bounds[1]))
