@@ -132,6 +132,8 @@ class ShardedMap:
 
         st = getattr(self, "_dev", None)
         if st is None or st["nq"] != nq or st["k"] != k:
+            if st is not None:
+                st["side"].synchronize()   # exchanges in flight still read the ring that is about to be released
             st = {"nq": nq, "k": k, "slot": 0,
                   "mine": [(torch.empty((nq, k), dtype=torch.int64, device=device),
                             torch.empty((nq, k), dtype=torch.float32, device=device)) for _ in range(self._RING)],
